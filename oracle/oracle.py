@@ -1,0 +1,335 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
+
+ctypes front-end to ``liboracle.so`` (our CPU restatement, ``oracle_*.cpp``) and, when present, to
+``_ref/liboracle_fc.so`` (the unmodified reference ``FastClusterWrapper.cpp`` compiled by ``make ref``).
+Importers allowed: ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``.
+The product package ``fluidaudio_b200`` must never import this module (tests enforce it).
+
+Pipeline glue restated here (pure Python, O(N)):
+  * ``ahc_cluster``      AHCClustering.cluster            AHCClustering.swift:20-67
+  * ``vbx_refine``       VBxClustering.refine             VBxClustering.swift:41-165
+  * ``diarize_cluster``  OfflineDiarizerManager.cluster   OfflineDiarizerManager.swift:270-384 (+591-611)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+_REF = os.path.join(_HERE, "_ref", "liboracle_fc.so")
+_REFERENCE_ROOT = "/root/reference"
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so (always possible) and _ref/liboracle_fc.so (only where /root/reference exists)."""
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_mel.cpp", "oracle_cluster.cpp", "oracle_adapters.cpp")]
+    stale = force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "all"])
+    ref_src = os.path.join(_REFERENCE_ROOT, "Sources/FastClusterWrapper/FastClusterWrapper.cpp")
+    if os.path.exists(ref_src) and (force or not os.path.exists(_REF)):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "ref"])
+
+
+class MelConfig(C.Structure):
+    _fields_ = [
+        ("sample_rate", C.c_int32), ("n_mels", C.c_int32), ("n_fft", C.c_int32), ("hop_length", C.c_int32),
+        ("win_length", C.c_int32), ("preemph", C.c_float), ("pad_to", C.c_int32), ("log_floor", C.c_float),
+        ("log_floor_mode", C.c_int32), ("window_periodic", C.c_int32), ("precision", C.c_int32),
+    ]
+
+
+class VbxConfig(C.Structure):
+    _fields_ = [("Fa", C.c_double), ("Fb", C.c_double), ("max_iterations", C.c_int32), ("epsilon", C.c_double),
+                ("init_smoothing", C.c_double)]
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        L = C.CDLL(_LIB)
+        L.oracle_mel_hann.argtypes = [C.c_int32, C.c_int32, _f32p]
+        L.oracle_mel_filterbank.argtypes = [C.c_int32, C.c_int32, C.c_int32, _f32p]
+        L.oracle_mel_frame_count.argtypes = [C.POINTER(MelConfig), C.c_int64, C.c_int32, C.c_int64]
+        L.oracle_mel_frame_count.restype = C.c_int64
+        for name in ("oracle_mel_compute_flat_transposed",):
+            f = getattr(L, name)
+            f.argtypes = [C.POINTER(MelConfig), C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_int64,
+                          C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+            f.restype = C.c_int64
+        L.oracle_mel_compute_flat.argtypes = [C.POINTER(MelConfig), C.c_void_p, C.c_int64, C.c_float, C.c_void_p,
+                                              C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.oracle_mel_compute_flat.restype = C.c_int64
+        L.oracle_mel_compute_legacy.argtypes = [C.POINTER(MelConfig), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                                C.POINTER(C.c_int64)]
+        L.oracle_mel_compute_legacy.restype = C.c_int64
+        L.oracle_l2_normalize_rows.argtypes = [_f64p, C.c_int64, C.c_int64, _f64p]
+        L.oracle_centroid_linkage.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.oracle_centroid_linkage.restype = C.c_int32
+        L.oracle_dendrogram_cut.argtypes = [_f64p, C.c_int64, C.c_double, _i32p]
+        L.oracle_vbx_refine.argtypes = [_f64p, C.c_int64, C.c_int64, _f64p, C.c_int64, C.c_void_p,
+                                        C.POINTER(VbxConfig), C.c_int32, _f64p, _f64p, _f64p, _i32p]
+        L.oracle_vbx_refine.restype = C.c_int32
+        L.oracle_compute_centroids.argtypes = [_f64p, C.c_int64, C.c_int64, _f64p, _f64p, C.c_int32, _f64p, _i32p]
+        L.oracle_compute_centroids.restype = C.c_int32
+        L.oracle_centroids_from_clusters.argtypes = [_f64p, C.c_int64, C.c_int64, _i32p, _f64p, C.c_int32]
+        L.oracle_centroids_from_clusters.restype = C.c_int32
+        L.oracle_assign_embeddings.argtypes = [_f64p, C.c_int64, C.c_int64, _f64p, C.c_int32, _i32p, C.c_void_p]
+        L.oracle_linear_resample.argtypes = [_f32p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_void_p]
+        L.oracle_linear_resample.restype = C.c_int64
+        L.oracle_normalize_per_feature.argtypes = [_f32p, C.c_int64, C.c_int32, C.c_int64]
+        L.oracle_transpose_tm.argtypes = [_f32p, C.c_int64, C.c_int32, _f32p]
+        _lib = L
+    return _lib
+
+
+def ref_available() -> bool:
+    return os.path.exists(_REF)
+
+
+def ref():
+    """The compiled, unmodified reference FastClusterWrapper (None if it was never built here)."""
+    global _ref
+    if _ref is None and os.path.exists(_REF):
+        R = C.CDLL(_REF)
+        R.fastcluster_compute_centroid_linkage.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]
+        R.fastcluster_compute_centroid_linkage.restype = C.c_int
+        _ref = R
+    return _ref
+
+
+# ------------------------------------------------------------------------------------------------ mel
+def mel_config(sample_rate=16000, n_mels=128, n_fft=512, hop_length=160, win_length=400, preemph=0.97, pad_to=0,
+               log_floor=2.0 ** -24, log_floor_mode=0, window_periodic=False, precision=0) -> MelConfig:
+    return MelConfig(sample_rate, n_mels, n_fft, hop_length, win_length, preemph, pad_to, log_floor,
+                     log_floor_mode, int(window_periodic), precision)
+
+
+def hann_window(length=400, periodic=False) -> np.ndarray:
+    out = np.zeros(length, np.float32)
+    lib().oracle_mel_hann(length, int(periodic), out)
+    return out
+
+
+def mel_filterbank(n_fft=512, n_mels=128, sample_rate=16000) -> np.ndarray:
+    out = np.zeros((n_mels, n_fft // 2 + 1), np.float32)
+    lib().oracle_mel_filterbank(n_fft, n_mels, sample_rate, out)
+    return out
+
+
+def mel_frame_count(cfg: MelConfig, n: int, mode: int = 0, expected: int = -1) -> int:
+    return int(lib().oracle_mel_frame_count(C.byref(cfg), n, mode, expected))
+
+
+def mel_flat_transposed(cfg: MelConfig, audio: np.ndarray, last=0.0, padding_mode=0, expected_frames=None):
+    """computeFlatTransposed: returns (mel [Tp x nMels] float32, melLength, numFrames)."""
+    audio = np.ascontiguousarray(audio, np.float32)
+    exp = -1 if expected_frames is None else int(expected_frames)
+    ml, nf = C.c_int64(), C.c_int64()
+    need = lib().oracle_mel_compute_flat_transposed(C.byref(cfg), audio.ctypes.data, audio.size, last, padding_mode,
+                                                    exp, None, 0, C.byref(ml), C.byref(nf))
+    out = np.zeros(need, np.float32)
+    lib().oracle_mel_compute_flat_transposed(C.byref(cfg), audio.ctypes.data, audio.size, last, padding_mode, exp,
+                                             out.ctypes.data, need, C.byref(ml), C.byref(nf))
+    if ml.value == 0:
+        return out, 0, 1
+    return out.reshape(nf.value, cfg.n_mels), ml.value, nf.value
+
+
+def mel_flat(cfg: MelConfig, audio: np.ndarray, last=0.0):
+    """computeFlat: returns (mel [nMels x Tp], melLength, numFrames)."""
+    audio = np.ascontiguousarray(audio, np.float32)
+    ml, nf = C.c_int64(), C.c_int64()
+    need = lib().oracle_mel_compute_flat(C.byref(cfg), audio.ctypes.data, audio.size, last, None, 0, C.byref(ml),
+                                         C.byref(nf))
+    out = np.zeros(need, np.float32)
+    lib().oracle_mel_compute_flat(C.byref(cfg), audio.ctypes.data, audio.size, last, out.ctypes.data, need,
+                                  C.byref(ml), C.byref(nf))
+    if ml.value == 0:
+        return out, 0, 1
+    return out.reshape(cfg.n_mels, nf.value), ml.value, nf.value
+
+
+def mel_legacy(cfg: MelConfig, audio: np.ndarray):
+    """compute(audio:): returns (mel [nMels x T], melLength)."""
+    audio = np.ascontiguousarray(audio, np.float32)
+    ml = C.c_int64()
+    need = lib().oracle_mel_compute_legacy(C.byref(cfg), audio.ctypes.data, audio.size, None, 0, C.byref(ml))
+    if need <= 0:
+        return np.zeros((0,), np.float32), 0
+    out = np.zeros(need, np.float32)
+    lib().oracle_mel_compute_legacy(C.byref(cfg), audio.ctypes.data, audio.size, out.ctypes.data, need, C.byref(ml))
+    return out.reshape(cfg.n_mels, ml.value), ml.value
+
+
+def normalize_per_feature(x: np.ndarray, valid_frames: int) -> np.ndarray:
+    y = np.ascontiguousarray(x, np.float32).copy()
+    lib().oracle_normalize_per_feature(y, y.shape[0], y.shape[1], valid_frames)
+    return y
+
+
+def linear_resample(planar: np.ndarray, in_rate: float, out_rate: float) -> np.ndarray:
+    """planar: [channels x frames] float32."""
+    planar = np.ascontiguousarray(planar, np.float32)
+    ch, frames = planar.shape
+    n = lib().oracle_linear_resample(planar, frames, ch, in_rate, out_rate, None)
+    out = np.zeros(n, np.float32)
+    lib().oracle_linear_resample(planar, frames, ch, in_rate, out_rate, out.ctypes.data)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ clustering
+def l2_normalize_rows(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.zeros_like(x)
+    lib().oracle_l2_normalize_rows(x, x.shape[0], x.shape[1], out)
+    return out
+
+
+def centroid_linkage(x: np.ndarray, use_ref: bool = False):
+    """Returns (status, Z [(N-1) x 4]).  use_ref=True calls the compiled reference instead of the restatement."""
+    x = np.ascontiguousarray(x, np.float64)
+    n, d = x.shape
+    z = np.zeros((max(n - 1, 0), 4), np.float64)
+    zp = z.ctypes.data if z.size else C.cast(C.create_string_buffer(8), C.c_void_p).value
+    if use_ref:
+        st = ref().fastcluster_compute_centroid_linkage(x.ctypes.data, n, d, zp, z.size)
+    else:
+        st = lib().oracle_centroid_linkage(x.ctypes.data, n, d, zp, z.size)
+    return int(st), z
+
+
+def dendrogram_cut(z: np.ndarray, count: int, threshold: float) -> np.ndarray:
+    labels = np.zeros(count, np.int32)
+    zz = np.ascontiguousarray(z, np.float64).reshape(-1)
+    if zz.size == 0:
+        zz = np.zeros(4, np.float64)
+    lib().oracle_dendrogram_cut(zz, count, threshold, labels)
+    return labels
+
+
+def ahc_cluster(features: np.ndarray, threshold: float, use_ref: bool = False) -> np.ndarray:
+    """AHCClustering.cluster (AHCClustering.swift:20-67) incl. guards and the FFI-failure fallback."""
+    features = np.asarray(features, np.float64)
+    count = features.shape[0]
+    if count == 0:
+        return np.zeros(0, np.int32)
+    if features.ndim < 2 or features.shape[1] == 0:
+        return np.zeros(count, np.int32)
+    if count == 1:
+        return np.zeros(1, np.int32)
+    normalized = l2_normalize_rows(features)
+    status, z = centroid_linkage(normalized, use_ref=use_ref)
+    if status != 0:
+        return np.arange(count, dtype=np.int32)
+    return dendrogram_cut(z, count, threshold)
+
+
+@dataclass
+class VBxOutput:
+    gamma: np.ndarray
+    pi: np.ndarray
+    hard: np.ndarray
+    num_clusters: int
+    elbos: np.ndarray
+
+
+def vbx_refine(rho: np.ndarray, psi: np.ndarray, initial: np.ndarray, Fa=0.07, Fb=0.8, max_iterations=20,
+               epsilon=1e-4, init_smoothing=7.0) -> VBxOutput:
+    rho = np.ascontiguousarray(rho, np.float64)
+    T = rho.shape[0]
+    if T == 0 or rho.ndim < 2 or rho.shape[1] == 0:
+        return VBxOutput(np.zeros((0, 0)), np.zeros(0), np.zeros(0, np.int32), 0, np.zeros(0))
+    D = rho.shape[1]
+    psi = np.ascontiguousarray(psi, np.float64)
+    initial = np.ascontiguousarray(initial, np.int32)
+    S = max(1, len(set(initial.tolist())))
+    gamma = np.zeros((T, S), np.float64)
+    pi = np.zeros(S, np.float64)
+    elbos = np.zeros(max(max_iterations, 1), np.float64)
+    hard = np.zeros(T, np.int32)
+    cfg = VbxConfig(Fa, Fb, max_iterations, epsilon, init_smoothing)
+    init_ptr = initial.ctypes.data if initial.size else None
+    iters = lib().oracle_vbx_refine(rho, T, D, psi if psi.size else np.zeros(1), psi.size, init_ptr, C.byref(cfg), S,
+                                    gamma, pi, elbos, hard)
+    return VBxOutput(gamma, pi, hard, S, elbos[:iters].copy())
+
+
+def compute_centroids(train: np.ndarray, vbx: VBxOutput, initial: np.ndarray) -> np.ndarray:
+    """computeCentroids (OfflineDiarizerManager.swift:613-691) with the from-clusters fallback (:693-746)."""
+    train = np.ascontiguousarray(train, np.float64)
+    T, dim = train.shape
+    if vbx.gamma.size and vbx.pi.size and np.any(vbx.pi > 1e-7):
+        S = vbx.pi.size
+        cents = np.zeros((S, dim), np.float64)
+        who = np.zeros(S, np.int32)
+        limit = min(vbx.gamma.shape[0], T)
+        K = lib().oracle_compute_centroids(train[:limit].copy(), limit, dim,
+                                           np.ascontiguousarray(vbx.gamma[:limit]), vbx.pi, S, cents, who)
+        return cents[:K].copy()
+    initial = np.ascontiguousarray(initial, np.int32)
+    if T == 0 or initial.size != T:
+        return np.zeros((0, dim))
+    cap = len(set(initial.tolist()))
+    cents = np.zeros((cap, dim), np.float64)
+    K = lib().oracle_centroids_from_clusters(train, T, dim, initial, cents, cap)
+    return cents[:K].copy()
+
+
+def assign_embeddings(emb: np.ndarray, centroids: np.ndarray, want_scores=False):
+    emb = np.ascontiguousarray(emb, np.float64)
+    centroids = np.ascontiguousarray(centroids, np.float64)
+    N, dim = emb.shape
+    K = centroids.shape[0]
+    labels = np.zeros(N, np.int32)
+    scores = np.zeros((N, max(K, 1)), np.float64) if want_scores else None
+    lib().oracle_assign_embeddings(emb, N, dim, centroids if K else np.zeros((1, dim)), K, labels,
+                                   scores.ctypes.data if want_scores else None)
+    return (labels, scores) if want_scores else labels
+
+
+@dataclass
+class ClusterResult:
+    labels: np.ndarray          # final assignment for all N embeddings (P3)
+    initial: np.ndarray         # AHC labels of the training subset (A1)
+    vbx: VBxOutput
+    centroids: np.ndarray
+    training_indices: np.ndarray
+
+
+def diarize_cluster(emb256: np.ndarray, rho128: np.ndarray, psi: np.ndarray, threshold=0.6, Fa=0.07, Fb=0.8,
+                    max_iterations=20, epsilon=1e-4, use_ref: bool = False) -> ClusterResult:
+    """OfflineDiarizerManager.cluster(_:) lines 286-375, unconstrained argmax assignment."""
+    emb32 = np.ascontiguousarray(emb256, np.float32)
+    feats = emb32.astype(np.float64)                      # :286  Float -> Double
+    rho = np.ascontiguousarray(rho128, np.float64)
+    finite = np.isfinite(emb32).all(axis=1)               # :591-611
+    idx = np.nonzero(finite)[0]
+    if idx.size == 0:
+        idx = np.arange(feats.shape[0])
+    train, train_rho = feats[idx], rho[idx]
+    if train.shape[0] >= 2:
+        initial = ahc_cluster(train, threshold, use_ref=use_ref)
+    else:
+        initial = np.zeros(train.shape[0], np.int32)
+    vbx = vbx_refine(train_rho, psi, initial, Fa, Fb, max_iterations, epsilon)
+    cents = compute_centroids(train, vbx, initial)
+    if cents.shape[0] == 0:
+        cents = feats.mean(axis=0, keepdims=True)         # computeFallbackCentroids :748-786
+    labels = assign_embeddings(feats, cents)
+    return ClusterResult(labels, initial, vbx, cents, idx)

@@ -1,0 +1,557 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
+//
+// CPU restatement (plain C++, single thread, IEEE double, no FMA contraction: build with
+// -ffp-contract=off) of FluidAudio's offline clustering backend.  Only tests/, smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library.
+//
+// Follows:
+//   A2  Sources/FluidAudio/Diarizer/Offline/Clustering/AHCClustering.swift:70-105   normalizeFeatures
+//   A3  Sources/FastClusterWrapper/FastClusterWrapper.cpp:26-147,196-244 + fastcluster_internal.hpp:1625-1800
+//       (generic_linkage_vector_alternative<METHOD_VECTOR_CENTROID>), heap :778-937, list :299-350
+//   A5  FastClusterWrapper.cpp:149-192  SciPy-format rows
+//   A6  AHCClustering.swift:112-121,124-197  clampDistanceThreshold + assignmentsFromDendrogram
+//   A7  AHCClustering.swift:200-210  remapClusterIds
+//   V1/V2 Sources/FluidAudio/Diarizer/Offline/Clustering/VBxClustering.swift:41-165,167-664
+//   P2  Sources/FluidAudio/Diarizer/Offline/Core/OfflineDiarizerManager.swift:613-691 computeCentroids
+//   P3  OfflineDiarizerManager.swift:789-883 centroidScores / assignEmbeddings / normalize / dot
+//
+// Parity status:
+//   * A3 is PINNED: oracle/_ref/liboracle_fc.so is the unmodified reference C++ compiled here; tests require
+//     this restatement to reproduce its dendrogram bit for bit (ids and IEEE doubles) on random, clustered,
+//     duplicate-heavy and lattice inputs.
+//   * A1/A6/A7 are pinned at label level by the reference's own unit tests (AHCClusteringTests.swift).
+//   * V1/V2/P2/P3: "parity unpinned" beyond this restatement — no reference test executes VBx and its BLAS /
+//     vForce calls are closed-source Accelerate (summation order unknown).  Sums here are sequential in index
+//     order; hard labels are the contract.
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+#include <algorithm>
+
+namespace {
+
+// ---- indexed binary min-heap with the exact sift rules of fastcluster_internal.hpp:778-937 -------------
+// Keys live in an external array `key`; `at[pos]` is the element at heap position pos and `where[elem]`
+// its inverse.  Tie behaviour (strict '<' when sifting up, '>=' tests when sifting down, left child first)
+// is what decides which of several equal-distance pairs merges first, so it is restated exactly.
+struct NNHeap {
+    double *key;
+    int size;
+    std::vector<int> at, where;
+    NNHeap(double *key_, int count, int universe, int first) : key(key_), size(count), at(count), where(universe) {
+        for (int i = 0; i < count; ++i) {
+            where[i + first] = i;
+            at[i] = i + first;
+        }
+    }
+    double val(int pos) const { return key[at[pos]]; }
+    void swap_pos(int a, int b) {
+        std::swap(at[a], at[b]);
+        where[at[a]] = a;
+        where[at[b]] = b;
+    }
+    void sift_up(int pos) {
+        while (pos > 0) {
+            const int parent = (pos - 1) >> 1;
+            if (!(val(pos) < val(parent))) break;
+            swap_pos(pos, parent);
+            pos = parent;
+        }
+    }
+    void sift_down(int pos) {
+        for (;;) {
+            int child = 2 * pos + 1;
+            if (child >= size) break;
+            if (val(child) >= val(pos)) {
+                ++child;
+                if (child >= size || val(child) >= val(pos)) break;
+            } else if (child + 1 < size && val(child + 1) < val(child)) {
+                ++child;
+            }
+            swap_pos(pos, child);
+            pos = child;
+        }
+    }
+    void heapify() {
+        for (int pos = size >> 1; pos > 0;) {
+            --pos;
+            sift_down(pos);
+        }
+    }
+    int top() const { return at[0]; }
+    void raise_key(int elem, double v) {  // new value >= old
+        key[elem] = v;
+        sift_down(where[elem]);
+    }
+    void lower_key(int elem, double v) {  // new value <= old
+        key[elem] = v;
+        sift_up(where[elem]);
+    }
+    void erase(int elem) {
+        --size;
+        const int pos = where[elem];
+        where[at[size]] = pos;
+        at[pos] = at[size];
+        if (val(size) <= key[elem]) sift_up(pos); else sift_down(pos);
+    }
+    void rename(int old_elem, int new_elem, double v) {
+        where[new_elem] = where[old_elem];
+        at[where[new_elem]] = new_elem;
+        if (v <= key[old_elem]) lower_key(new_elem, v); else raise_key(new_elem, v);
+    }
+};
+
+// ascending list of live node ids with O(1) removal (fastcluster_internal.hpp:299-350)
+struct LiveList {
+    int head = 0;
+    std::vector<int> next, prev;
+    explicit LiveList(int n) : next(n + 1), prev(n + 1) {
+        for (int i = 0; i < n; ++i) {
+            prev[i + 1] = i;
+            next[i] = i + 1;
+        }
+    }
+    void drop(int id) {
+        if (id == head) head = next[id];
+        else {
+            next[prev[id]] = next[id];
+            prev[next[id]] = prev[id];
+        }
+        next[id] = 0;
+    }
+    bool dead(int id) const { return next[id] == 0; }
+};
+
+struct NanFound {};
+
+} // namespace
+
+extern "C" {
+
+// A2: row-wise L2 normalisation, scale = norm>0 ? 1/sqrt(sum x^2) : 0
+void oracle_l2_normalize_rows(const double *x, int64_t n, int64_t d, double *out) {
+    for (int64_t r = 0; r < n; ++r) {
+        double s = 0;
+        for (int64_t k = 0; k < d; ++k) s += x[r * d + k] * x[r * d + k];
+        const double scale = s > 0 ? 1.0 / std::sqrt(s) : 0.0;
+        for (int64_t k = 0; k < d; ++k) out[r * d + k] = x[r * d + k] * scale;
+    }
+}
+
+// A3+A5: same status codes as FastClusterWrapper.h:11-19
+int32_t oracle_centroid_linkage(const double *data, uint64_t point_count, uint64_t dimension, double *Z,
+                                uint64_t z_len) {
+    if (!data || !Z) return 1;
+    if (point_count == 0) return 0;
+    if (dimension == 0) return 1;
+    if (point_count > 0x7fffffffull || dimension > 0x7fffffffull) return 2;
+    const uint64_t need = point_count > 1 ? (point_count - 1) * 4 : 0;
+    if (z_len < need) return 3;
+    if (point_count == 1) return 0;
+    try {
+        const int N = (int)point_count, D = (int)dimension;
+        std::vector<double> merged((size_t)(N - 1) * D);
+        std::vector<int> weight(2 * N - 1, 0);
+        for (int i = 0; i < N; ++i) weight[i] = 1;
+        auto vec = [&](int id) -> const double * {
+            return id < N ? data + (size_t)id * D : merged.data() + (size_t)(id - N) * D;
+        };
+        auto sqdist = [&](int a, int b) -> double {
+            const double *pa = vec(a), *pb = vec(b);
+            double s = 0;
+            for (int k = 0; k < D; ++k) {
+                const double diff = pa[k] - pb[k];
+                s += diff * diff;
+            }
+            if (s != s) throw NanFound();
+            return s;
+        };
+        std::vector<int> nn(2 * N - 2);
+        std::vector<double> nnd(2 * N - 2);
+        LiveList live(2 * N - 1);
+        NNHeap heap(nnd.data(), N - 1, 2 * N - 2, 1);
+        std::vector<int> ma(N - 1), mb(N - 1);
+        std::vector<double> md(N - 1);
+
+        for (int i = 1; i < N; ++i) {
+            double best = std::numeric_limits<double>::infinity();
+            int arg = 0;
+            for (int j = 0; j < i; ++j) {
+                const double t = sqdist(i, j);
+                if (t < best) {
+                    best = t;
+                    arg = j;
+                }
+            }
+            nnd[i] = best;
+            nn[i] = arg;
+        }
+        heap.heapify();
+        for (int step = 0; step < N - 1; ++step) {
+            const int fresh = N + step;
+            int a = heap.top();
+            while (live.dead(nn[a])) {
+                int j = live.head;
+                nn[a] = j;
+                double best = sqdist(a, j);
+                for (j = live.next[j]; j < a; j = live.next[j]) {
+                    const double t = sqdist(a, j);
+                    if (t < best) {
+                        best = t;
+                        nn[a] = j;
+                    }
+                }
+                heap.raise_key(a, best);
+                a = heap.top();
+            }
+            const int b = nn[a];
+            live.drop(a);
+            live.drop(b);
+            ma[step] = a;
+            mb[step] = b;
+            md[step] = nnd[a];
+            if (step < N - 2) {
+                double *pn = merged.data() + (size_t)step * D;
+                const double *pa = vec(a), *pb = vec(b);
+                const double wa = (double)weight[a], wb = (double)weight[b];
+                const double den = wa + wb;
+                for (int k = 0; k < D; ++k) pn[k] = (pa[k] * wa + pb[k] * wb) / den;
+                weight[fresh] = weight[a] + weight[b];
+                int j = live.head;
+                nn[fresh] = j;
+                double best = sqdist(j, fresh);
+                for (j = live.next[j]; j < fresh; j = live.next[j]) {
+                    const double t = sqdist(j, fresh);
+                    if (t < best) {
+                        best = t;
+                        nn[fresh] = j;
+                    }
+                }
+                if (b < live.head) heap.erase(live.head); else heap.erase(b);
+                heap.rename(a, fresh, best);
+            }
+        }
+        // postprocess: sqrt of every merge distance, then SciPy rows (min id, max id, dist, size)
+        for (int s = 0; s < N - 1; ++s) {
+            const int lo = std::min(ma[s], mb[s]), hi = std::max(ma[s], mb[s]);
+            const double sz = (lo < N ? 1.0 : Z[(size_t)(lo - N) * 4 + 3]) + (hi < N ? 1.0 : Z[(size_t)(hi - N) * 4 + 3]);
+            Z[(size_t)s * 4 + 0] = (double)lo;
+            Z[(size_t)s * 4 + 1] = (double)hi;
+            Z[(size_t)s * 4 + 2] = std::sqrt(md[s]);
+            Z[(size_t)s * 4 + 3] = sz;
+        }
+        return 0;
+    } catch (const std::bad_alloc &) {
+        return 4;
+    } catch (const NanFound &) {
+        return 5;
+    } catch (...) {
+        return 255;
+    }
+}
+
+// A6 + A7: threshold clamp, top-down cut using each node's own merge distance, relabel by first appearance.
+void oracle_dendrogram_cut(const double *Z, int64_t count, double threshold, int32_t *labels) {
+    if (count <= 0) return;
+    if (count == 1) {
+        labels[0] = 0;
+        return;
+    }
+    double thr;
+    if (threshold != threshold) thr = 0;
+    else thr = std::max(0.0, std::min(2.0, threshold));
+    const int64_t total = 2 * count - 1;
+    std::vector<int64_t> left(total, -1), right(total, -1);
+    std::vector<double> dist(total, 0.0);
+    for (int64_t m = 0; m < count - 1; ++m) {
+        left[count + m] = (int64_t)Z[m * 4];
+        right[count + m] = (int64_t)Z[m * 4 + 1];
+        dist[count + m] = Z[m * 4 + 2];
+    }
+    std::vector<int64_t> assign(count, -1), stack{total - 1}, queue;
+    int64_t next_label = 0;
+    while (!stack.empty()) {
+        const int64_t node = stack.back();
+        stack.pop_back();
+        if (node < 0) continue;
+        if (node < count) {
+            if (assign[node] == -1) assign[node] = next_label++;
+            continue;
+        }
+        if (dist[node] <= thr) {
+            const int64_t label = next_label++;
+            queue.assign(1, node);
+            while (!queue.empty()) {
+                const int64_t cur = queue.back();
+                queue.pop_back();
+                if (cur < count) assign[cur] = label;
+                else {
+                    if (left[cur] >= 0) queue.push_back(left[cur]);
+                    if (right[cur] >= 0) queue.push_back(right[cur]);
+                }
+            }
+        } else {
+            if (left[node] >= 0) stack.push_back(left[node]);
+            if (right[node] >= 0) stack.push_back(right[node]);
+        }
+    }
+    for (int64_t i = 0; i < count; ++i)
+        if (assign[i] == -1) assign[i] = next_label++;
+    // remapClusterIds
+    std::vector<int64_t> map(next_label, -1);
+    int64_t next_id = 0;
+    for (int64_t i = 0; i < count; ++i) {
+        if (map[assign[i]] < 0) map[assign[i]] = next_id++;
+        labels[i] = (int32_t)map[assign[i]];
+    }
+}
+
+struct oracle_vbx_config {
+    double Fa;              // 0.07
+    double Fb;              // 0.8
+    int32_t max_iterations; // 20
+    double epsilon;         // 1e-4
+    double init_smoothing;  // 7.0
+};
+
+// V1+V2.  features: T x D row-major (rho), phi: D (psi), init: T labels (may be null -> uniform gamma).
+// gamma out: T x S, pi out: S, elbos out: max(max_iterations,1) capacity, hard: T.
+// Returns the number of iterations run; *speakers = S.
+int32_t oracle_vbx_refine(const double *features, int64_t T, int64_t D, const double *phi_in, int64_t phi_len,
+                          const int32_t *init, const oracle_vbx_config *cfg, int32_t S, double *gamma, double *pi,
+                          double *elbos, int32_t *hard) {
+    std::vector<double> phi(D);
+    if (phi_len != D) std::fill(phi.begin(), phi.end(), 1.0);            // :72-76
+    else for (int64_t d = 0; d < D; ++d) phi[d] = phi_in[d];
+    // initial gamma (:100-113)
+    std::fill(gamma, gamma + T * S, 0.0);
+    if (init) {
+        for (int64_t t = 0; t < T; ++t) {
+            const int32_t sp = std::max(0, std::min(init[t], S - 1));
+            gamma[t * S + sp] = 1.0;
+        }
+    } else {
+        for (int64_t i = 0; i < T * S; ++i) gamma[i] = 1.0 / (double)S;
+    }
+    std::vector<double> row(S);
+    if (cfg->init_smoothing >= 0.0) {  // :190-219
+        for (int64_t t = 0; t < T; ++t) {
+            double *g = gamma + t * S;
+            double mx = -std::numeric_limits<double>::max();
+            for (int s = 0; s < S; ++s) {
+                row[s] = g[s] * cfg->init_smoothing;
+                mx = std::max(mx, row[s]);
+            }
+            double sum = 0;
+            for (int s = 0; s < S; ++s) {
+                row[s] = std::exp(row[s] - mx);
+                sum += row[s];
+            }
+            if (sum <= 0.0 || !std::isfinite(sum)) for (int s = 0; s < S; ++s) g[s] = 1.0 / (double)S;
+            else {
+                const double inv = 1.0 / sum;
+                for (int s = 0; s < S; ++s) g[s] = row[s] * inv;
+            }
+        }
+    }
+    for (int64_t t = 0; t < T; ++t) {  // :221-235
+        double *g = gamma + t * S;
+        double sum = 0;
+        for (int s = 0; s < S; ++s) sum += g[s];
+        if (sum <= 0.0 || !std::isfinite(sum)) for (int s = 0; s < S; ++s) g[s] = 1.0 / (double)S;
+        else {
+            const double inv = 1.0 / sum;
+            for (int s = 0; s < S; ++s) g[s] *= inv;
+        }
+    }
+    for (int s = 0; s < S; ++s) pi[s] = 1.0 / (double)S;
+    std::vector<double> phic(D), sq(D);
+    for (int64_t d = 0; d < D; ++d) {
+        phic[d] = std::max(phi[d], 1e-12);
+        sq[d] = std::sqrt(phic[d]);
+    }
+    std::vector<double> rho((size_t)T * D), G(T);
+    const double log_const = (double)D * std::log(2.0 * M_PI);
+    for (int64_t t = 0; t < T; ++t) {
+        double ss = 0;
+        for (int64_t d = 0; d < D; ++d) {
+            rho[t * D + d] = features[t * D + d] * sq[d];
+            ss += features[t * D + d] * features[t * D + d];
+        }
+        G[t] = -0.5 * (ss + log_const);
+    }
+    const double ratio = cfg->Fa / cfg->Fb;
+    std::vector<double> invL((size_t)S * D), alpha((size_t)S * D), gsum(S), phiTerm(S), logP((size_t)T * S), logPi(S);
+    double prev = -std::numeric_limits<double>::max();
+    int32_t iterations = 0;
+    const int32_t cap = std::max(cfg->max_iterations, 1);
+    for (int i = 0; i < cap; ++i) elbos[i] = 0.0;
+    for (int32_t it = 0; it < cfg->max_iterations; ++it) {
+        iterations = it + 1;
+        for (int s = 0; s < S; ++s) gsum[s] = 0;
+        for (int64_t t = 0; t < T; ++t)
+            for (int s = 0; s < S; ++s) gsum[s] += gamma[t * S + s];
+        for (int s = 0; s < S; ++s) {
+            const double w = ratio * gsum[s];
+            for (int64_t d = 0; d < D; ++d) invL[s * D + d] = 1.0 / std::max(1.0 + w * phic[d], 1e-12);
+        }
+        // temp = gamma^T rho  (S x D), then alpha = ratio * invL .* temp
+        std::fill(alpha.begin(), alpha.end(), 0.0);
+        for (int64_t t = 0; t < T; ++t)
+            for (int s = 0; s < S; ++s) {
+                const double g = gamma[t * S + s];
+                for (int64_t d = 0; d < D; ++d) alpha[s * D + d] += g * rho[t * D + d];
+            }
+        for (size_t i = 0; i < alpha.size(); ++i) alpha[i] = (alpha[i] * invL[i]) * ratio;
+        for (int s = 0; s < S; ++s) {
+            double sum = 0;
+            for (int64_t d = 0; d < D; ++d) sum += (alpha[s * D + d] * alpha[s * D + d] + invL[s * D + d]) * phic[d];
+            phiTerm[s] = sum;
+        }
+        for (int64_t t = 0; t < T; ++t)
+            for (int s = 0; s < S; ++s) {
+                double acc = 0;
+                for (int64_t d = 0; d < D; ++d) acc += rho[t * D + d] * alpha[s * D + d];
+                logP[t * S + s] = ((acc + (-0.5 * phiTerm[s])) + G[t]) * cfg->Fa;
+            }
+        for (int s = 0; s < S; ++s) logPi[s] = std::log(std::max(pi[s], 1e-8));
+        double ll = 0;
+        for (int64_t t = 0; t < T; ++t) {
+            double mx = -std::numeric_limits<double>::max();
+            for (int s = 0; s < S; ++s) {
+                row[s] = logP[t * S + s] + logPi[s];
+                mx = std::max(mx, row[s]);
+            }
+            double sum = 0;
+            for (int s = 0; s < S; ++s) {
+                row[s] = std::exp(row[s] - mx);
+                sum += row[s];
+            }
+            double *g = gamma + t * S;
+            if (sum <= 0.0 || !std::isfinite(sum)) {
+                for (int s = 0; s < S; ++s) g[s] = 1.0 / (double)S;
+                ll += mx;
+            } else {
+                const double inv = 1.0 / sum;
+                for (int s = 0; s < S; ++s) g[s] = row[s] * inv;
+                ll += mx + std::log(sum);
+            }
+        }
+        for (int s = 0; s < S; ++s) pi[s] = 0;
+        for (int64_t t = 0; t < T; ++t)
+            for (int s = 0; s < S; ++s) pi[s] += gamma[t * S + s];
+        double ps = 0;
+        for (int s = 0; s < S; ++s) ps += pi[s];
+        if (ps > 0.0 && std::isfinite(ps)) {
+            const double inv = 1.0 / ps;
+            for (int s = 0; s < S; ++s) pi[s] *= inv;
+        } else for (int s = 0; s < S; ++s) pi[s] = 1.0 / (double)S;
+        double sLog = 0, sInv = 0, sA2 = 0;
+        for (size_t i = 0; i < invL.size(); ++i) {
+            sLog += std::log(invL[i]);
+            sInv += invL[i];
+            sA2 += alpha[i] * alpha[i];
+        }
+        const double elbo = ll + cfg->Fb * 0.5 * (sLog - sInv - sA2 + (double)invL.size());
+        if (it < cap) elbos[it] = elbo;
+        if (it > 0 && std::fabs(elbo - prev) < cfg->epsilon) {
+            prev = elbo;
+            break;
+        }
+        prev = elbo;
+    }
+    for (int64_t t = 0; t < T; ++t) {  // first max wins (:144-146)
+        int best = 0;
+        for (int s = 1; s < S; ++s)
+            if (gamma[t * S + best] < gamma[t * S + s]) best = s;
+        hard[t] = best;
+    }
+    return iterations;
+}
+
+// P2: gamma/pi weighted centroids over UN-normalised training embeddings, speakers with pi > 1e-7.
+// centroids out capacity S x dim.  Returns K (number of centroids); speaker_of[k] = VBx speaker index.
+int32_t oracle_compute_centroids(const double *emb, int64_t T, int64_t dim, const double *gamma, const double *pi,
+                                 int32_t S, double *centroids, int32_t *speaker_of) {
+    int32_t K = 0;
+    for (int s = 0; s < S; ++s) {
+        if (!(pi[s] > 1e-7)) continue;
+        double *c = centroids + (size_t)K * dim;
+        for (int64_t k = 0; k < dim; ++k) c[k] = 0;
+        double den = 0;
+        for (int64_t t = 0; t < T; ++t) {
+            const double w = gamma[t * S + s];
+            if (!(w > 0)) continue;
+            den += w;
+            for (int64_t k = 0; k < dim; ++k) c[k] += w * emb[t * dim + k];  // cblas_daxpy
+        }
+        if (den > 0) for (int64_t k = 0; k < dim; ++k) c[k] /= den;
+        else for (int64_t k = 0; k < dim; ++k) c[k] = 0;
+        if (speaker_of) speaker_of[K] = s;
+        ++K;
+    }
+    return K;
+}
+
+// computeCentroidsFromClusters (:693-746): plain means per distinct label, ordered by label value.
+int32_t oracle_centroids_from_clusters(const double *emb, int64_t T, int64_t dim, const int32_t *clusters,
+                                       double *centroids, int32_t cap) {
+    std::vector<int32_t> keys(clusters, clusters + T);
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    if ((int64_t)keys.size() > cap) return -(int32_t)keys.size();
+    for (size_t k = 0; k < keys.size(); ++k) {
+        double *c = centroids + k * dim;
+        for (int64_t j = 0; j < dim; ++j) c[j] = 0;
+        int64_t cnt = 0;
+        for (int64_t t = 0; t < T; ++t)
+            if (clusters[t] == keys[k]) {
+                for (int64_t j = 0; j < dim; ++j) c[j] += 1.0 * emb[t * dim + j];
+                ++cnt;
+            }
+        if (cnt > 0) for (int64_t j = 0; j < dim; ++j) c[j] /= (double)cnt;
+    }
+    return (int32_t)keys.size();
+}
+
+// P3: cosine of every embedding vs every centroid, argmax with strict '>' (first max wins).
+// scores out (optional): N x K.
+void oracle_assign_embeddings(const double *emb, int64_t N, int64_t dim, const double *centroids, int32_t K,
+                              int32_t *labels, double *scores) {
+    if (K <= 0) {
+        for (int64_t i = 0; i < N; ++i) labels[i] = 0;
+        return;
+    }
+    auto normalize = [&](const double *v, double *o) {
+        double ss = 0;
+        for (int64_t k = 0; k < dim; ++k) ss += v[k] * v[k];
+        if (ss <= 0) {
+            for (int64_t k = 0; k < dim; ++k) o[k] = v[k];
+            return;
+        }
+        const double sc = 1.0 / std::sqrt(ss);
+        for (int64_t k = 0; k < dim; ++k) o[k] = v[k] * sc;
+    };
+    std::vector<double> cn((size_t)K * dim), en(dim);
+    for (int c = 0; c < K; ++c) normalize(centroids + (size_t)c * dim, cn.data() + (size_t)c * dim);
+    for (int64_t i = 0; i < N; ++i) {
+        normalize(emb + i * dim, en.data());
+        int best = 0;
+        double best_score = -std::numeric_limits<double>::infinity();
+        for (int c = 0; c < K; ++c) {
+            double dot = 0;
+            for (int64_t k = 0; k < dim; ++k) dot += en[k] * cn[(size_t)c * dim + k];
+            if (scores) scores[i * K + c] = dot;
+            if (dot > best_score) {
+                best_score = dot;
+                best = c;
+            }
+        }
+        labels[i] = best;
+    }
+}
+
+} // extern "C"
