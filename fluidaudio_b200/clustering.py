@@ -1,0 +1,218 @@
+"""Host-side mirror of the offline clustering backend's Swift surface.
+
+* ``AHCClustering.cluster``      Sources/FluidAudio/Diarizer/Offline/Clustering/AHCClustering.swift:20-67
+* ``VBxClustering.refine``       Sources/FluidAudio/Diarizer/Offline/Clustering/VBxClustering.swift:41-165
+* ``VBxOutput``                  Sources/FluidAudio/Diarizer/Offline/Core/OfflineDiarizerTypes.swift:629-702
+* ``OfflineDiarizerConfig``      OfflineDiarizerTypes.swift:33-454 (only the clustering knobs)
+* ``OfflineClusterer.cluster``   OfflineDiarizerManager.cluster(_:) lines 286-375 of
+                                 Sources/FluidAudio/Diarizer/Offline/Core/OfflineDiarizerManager.swift
+* ``centroid_linkage``           the reference's C symbol fastcluster_compute_centroid_linkage
+                                 (Sources/FastClusterWrapper/include/FastClusterWrapper.h:34-40)
+
+Every computation runs in libfluidaudio_b200.so on the GPU; this file only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+
+@dataclass
+class ClusteringConfig:           # OfflineDiarizerConfig.Clustering.community
+    threshold: float = 0.6
+    warm_start_fa: float = 0.07
+    warm_start_fb: float = 0.8
+
+
+@dataclass
+class VBxConfig:                  # OfflineDiarizerConfig.VBx.community
+    max_iterations: int = 20
+    convergence_tolerance: float = 1e-4
+
+
+@dataclass
+class OfflineDiarizerConfig:
+    clustering: ClusteringConfig = field(default_factory=ClusteringConfig)
+    vbx: VBxConfig = field(default_factory=VBxConfig)
+
+    @property
+    def clustering_threshold(self) -> float:
+        return self.clustering.threshold
+
+    def _c_vbx(self) -> _lib.VbxConfig:
+        return _lib.VbxConfig(self.clustering.warm_start_fa, self.clustering.warm_start_fb, self.vbx.max_iterations,
+                              self.vbx.convergence_tolerance, 7.0)
+
+    def _c_cluster(self) -> _lib.ClusterConfig:
+        return _lib.ClusterConfig(self.clustering.threshold, self._c_vbx())
+
+
+def centroid_linkage(normalized_rows: np.ndarray):
+    """Calls the drop-in C symbol.  Returns (status, Z [(N-1) x 4])."""
+    x = np.ascontiguousarray(normalized_rows, np.float64)
+    n, d = x.shape
+    z = np.zeros((max(n - 1, 0), 4), np.float64)
+    zbuf = z if z.size else np.zeros(4, np.float64)
+    st = _lib.load().fastcluster_compute_centroid_linkage(x.ctypes.data, n, d, zbuf.ctypes.data, z.size)
+    return int(st), z
+
+
+def l2_normalize_rows(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.zeros_like(x)
+    _lib.check(_lib.load().fa_l2_normalize_rows(x.ctypes.data, x.shape[0], x.shape[1], out.ctypes.data),
+               "fa_l2_normalize_rows")
+    return out
+
+
+def dendrogram_cut(z: np.ndarray, count: int, threshold: float) -> np.ndarray:
+    labels = np.zeros(count, np.int32)
+    zz = np.ascontiguousarray(z, np.float64).reshape(-1)
+    _lib.check(_lib.load().fa_dendrogram_cut(zz.ctypes.data if zz.size else None, count, float(threshold),
+                                             labels.ctypes.data if count else None), "fa_dendrogram_cut")
+    return labels
+
+
+class AHCClustering:
+    def cluster(self, embedding_features, threshold: float) -> np.ndarray:
+        rows = list(embedding_features) if not isinstance(embedding_features, np.ndarray) else embedding_features
+        count = len(rows)
+        if count == 0:
+            return np.zeros(0, np.int32)
+        x = np.asarray(rows, np.float64)
+        if x.ndim < 2 or x.shape[1] == 0:
+            return np.zeros(count, np.int32)
+        x = np.ascontiguousarray(x)
+        labels = np.zeros(count, np.int32)
+        _lib.check(_lib.load().fa_ahc_cluster(x.ctypes.data, count, x.shape[1], float(threshold), labels.ctypes.data),
+                   "fa_ahc_cluster")
+        return labels
+
+
+@dataclass
+class VBxOutput:
+    gamma: np.ndarray
+    pi: np.ndarray
+    hard_clusters: np.ndarray
+    num_clusters: int
+    elbos: np.ndarray
+    centroids: np.ndarray = field(default_factory=lambda: np.zeros((0, 0)))
+    was_adjusted: bool = False
+
+    active_cluster_epsilon = 1e-7
+
+    @property
+    def active_cluster_count(self) -> int:
+        if self.pi.size == 0:
+            return self.num_clusters
+        return int((self.pi > self.active_cluster_epsilon).sum())
+
+    @property
+    def assigned_cluster_count(self) -> int:
+        if self.gamma.size == 0:
+            return self.active_cluster_count
+        return int(np.unique(self.gamma.argmax(axis=1)).size)
+
+
+class VBxClustering:
+    def __init__(self, config: OfflineDiarizerConfig | None = None, psi: np.ndarray | None = None):
+        self.config = config or OfflineDiarizerConfig()
+        self.psi = None if psi is None else np.ascontiguousarray(psi, np.float64)
+
+    def refine(self, rho_features, initial_clusters) -> VBxOutput:
+        rho = np.asarray(rho_features, np.float64)
+        if rho.size == 0 or rho.ndim < 2 or rho.shape[1] == 0:
+            return VBxOutput(np.zeros((0, 0)), np.zeros(0), np.zeros(0, np.int32), 0, np.zeros(0))
+        rho = np.ascontiguousarray(rho)
+        T, D = rho.shape
+        init = np.ascontiguousarray(initial_clusters, np.int32)
+        S = max(1, len(set(init.tolist())))
+        cfg = self.config._c_vbx()
+        cap = max(cfg.max_iterations, 1)
+        gamma = np.zeros((T, S), np.float64)
+        pi = np.zeros(S, np.float64)
+        elbos = np.zeros(cap, np.float64)
+        hard = np.zeros(T, np.int32)
+        its = C.c_int32()
+        psi = self.psi
+        _lib.check(_lib.load().fa_vbx_refine(rho.ctypes.data, T, D, _lib.ptr(psi), 0 if psi is None else psi.size,
+                                             init.ctypes.data if init.size else None, S, C.byref(cfg),
+                                             gamma.ctypes.data, pi.ctypes.data, elbos.ctypes.data, hard.ctypes.data,
+                                             C.byref(its)), "fa_vbx_refine")
+        return VBxOutput(gamma, pi, hard, S, elbos[: its.value].copy())
+
+
+def compute_centroids(training_embeddings: np.ndarray, vbx: VBxOutput) -> np.ndarray:
+    emb = np.ascontiguousarray(training_embeddings, np.float64)
+    T, dim = emb.shape
+    S = vbx.pi.size
+    cents = np.zeros((S, dim), np.float64)
+    k = C.c_int32()
+    _lib.check(_lib.load().fa_compute_centroids(emb.ctypes.data, T, dim,
+                                                np.ascontiguousarray(vbx.gamma).ctypes.data,
+                                                np.ascontiguousarray(vbx.pi).ctypes.data, S, cents.ctypes.data,
+                                                C.byref(k)), "fa_compute_centroids")
+    return cents[: k.value].copy()
+
+
+def assign_embeddings(embedding_features: np.ndarray, centroids: np.ndarray, want_scores: bool = False):
+    emb = np.ascontiguousarray(embedding_features, np.float64)
+    cen = np.ascontiguousarray(centroids, np.float64)
+    N, dim = emb.shape
+    K = cen.shape[0]
+    labels = np.zeros(N, np.int32)
+    scores = np.zeros((N, max(K, 1)), np.float64) if want_scores else None
+    _lib.check(_lib.load().fa_assign_embeddings(emb.ctypes.data, N, dim, cen.ctypes.data if K else None, K,
+                                                labels.ctypes.data, _lib.ptr(scores)), "fa_assign_embeddings")
+    return (labels, scores) if want_scores else labels
+
+
+@dataclass
+class ClusterResult:
+    labels: np.ndarray
+    initial: np.ndarray
+    centroids: np.ndarray
+    info: dict
+
+
+class OfflineClusterer:
+    """The clustering phase of OfflineDiarizerManager.cluster(_:) (embeddings -> per-embedding speaker labels)."""
+
+    def __init__(self, config: OfflineDiarizerConfig | None = None, psi: np.ndarray | None = None):
+        self.config = config or OfflineDiarizerConfig()
+        self.psi = None if psi is None else np.ascontiguousarray(psi, np.float64)
+
+    def cluster(self, embedding256: np.ndarray, rho128: np.ndarray, max_centroids: int = 64) -> ClusterResult:
+        emb = np.ascontiguousarray(embedding256, np.float32)
+        rho = np.ascontiguousarray(rho128, np.float64)
+        N, E = emb.shape
+        R = rho.shape[1]
+        labels = np.zeros(N, np.int32)
+        initial = np.zeros(N, np.int32)
+        cents = np.zeros((max_centroids, E), np.float64)
+        info = _lib.ClusterInfo()
+        cfg = self.config._c_cluster()
+        _lib.check(_lib.load().fa_diarize_cluster(emb.ctypes.data, rho.ctypes.data, N, E, R, _lib.ptr(self.psi),
+                                                  C.byref(cfg), labels.ctypes.data, initial.ctypes.data,
+                                                  cents.ctypes.data, max_centroids, C.byref(info)),
+                   "fa_diarize_cluster")
+        d = {f: getattr(info, f) for f, _ in _lib.ClusterInfo._fields_}
+        return ClusterResult(labels, initial, cents[: min(info.centroid_count, max_centroids)].copy(), d)
+
+    def cluster_batch(self, embedding256: np.ndarray, rho128: np.ndarray, set_offsets) -> tuple[np.ndarray, list]:
+        emb = np.ascontiguousarray(embedding256, np.float32)
+        rho = np.ascontiguousarray(rho128, np.float64)
+        offs = np.ascontiguousarray(set_offsets, np.int64)
+        count = offs.size - 1
+        labels = np.zeros(emb.shape[0], np.int32)
+        infos = (_lib.ClusterInfo * max(count, 1))()
+        cfg = self.config._c_cluster()
+        _lib.check(_lib.load().fa_diarize_cluster_batch(emb.ctypes.data, rho.ctypes.data, offs.ctypes.data, count,
+                                                        emb.shape[1], rho.shape[1], _lib.ptr(self.psi), C.byref(cfg),
+                                                        labels.ctypes.data, infos), "fa_diarize_cluster_batch")
+        out = [{f: getattr(infos[i], f) for f, _ in _lib.ClusterInfo._fields_} for i in range(count)]
+        return labels, out

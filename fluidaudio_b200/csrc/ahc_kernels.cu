@@ -1,0 +1,757 @@
+// Centroid-linkage agglomerative clustering on one B200, bit-compatible with the reference's
+// fastcluster_compute_centroid_linkage (Sources/FastClusterWrapper/FastClusterWrapper.cpp:196-244 driving
+// fastcluster_internal.hpp:1625-1800).
+//
+// Why it can be bit-exact: every squared distance is accumulated exactly as the C++ does it
+// (FastClusterWrapper.cpp:44-52): sum = sum + (a[k]-b[k])*(a[k]-b[k]) for k = 0..D-1 in order, each operation
+// individually rounded (__dsub_rn/__dmul_rn/__dadd_rn: no FMA contraction, no tree reduction); merged
+// centroids use (a*wa + b*wb)/(wa+wb) with the same four roundings (:89-100); and the pair chosen at every
+// step comes out of the same heap rules (ahc_core.cuh).  Parallelism is ACROSS pairs, never inside one sum:
+// one thread owns one (i,j) chain.
+//
+// Kernels
+//   ahc_stage_kernel      input rows -> node store (row-major) + scan copy (k-major, coalesced across nodes)
+//   ahc_init_nn_kernel    N(N-1)/2 distances, tiled: 128 i-threads x 16 j-accumulators, k-chunks through smem;
+//                         per (i, j-range) lexicographic (distance, j) minimum
+//   ahc_init_reduce_kernel  per-i minimum over j-ranges -> nearest neighbour + key of the heap
+//   ahc_merge_kernel      persistent, cooperative: CTA 0 = master (heap, live list, merge log; one warp),
+//                         CTAs 1.. = workers (one node per thread).  Per merge step the master publishes one
+//                         command (release store), workers build the new centroid, scan their nodes against
+//                         it (256-long chain each, node data streamed from L2), reduce to one candidate per
+//                         CTA and signal (release add); the master folds the <=147 candidates and updates
+//                         the heap.  N-1 dependent steps, no kernel launch or host round trip inside.
+#include "ahc_core.cuh"
+#include "ahc_plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <vector>
+
+namespace fa {
+namespace ahc {
+
+#define FA_CUDA_TRY(expr)                                                                               \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            fa::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return e__ == cudaErrorMemoryAllocation ? FA_ALLOCATION_FAILURE : FA_CUDA_ERROR;            \
+        }                                                                                               \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ sync helpers
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ double sq_step(double sum, double a, double b) {
+    const double diff = __dsub_rn(a, b);
+    return __dadd_rn(sum, __dmul_rn(diff, diff));
+}
+
+// ------------------------------------------------------------------------------------------------ staging
+// in: [N x D] row-major.  rows[0..N) = in; cols[k*Ns + i] = in[i*D + k].
+__global__ void ahc_stage_kernel(const double *__restrict__ in, double *__restrict__ rows, double *__restrict__ cols,
+                                 int N, int D, int Ns) {
+    __shared__ double tile[32][33];
+    const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, k = k0 + tx;
+        double v = 0.0;
+        if (i < N && k < D) {
+            v = in[(size_t)i * D + k];
+            rows[(size_t)i * D + k] = v;
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, i = i0 + tx;
+        if (k < D && i < Ns) cols[(size_t)k * Ns + i] = tile[tx][r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ initial NN
+constexpr int kTI = 128;   // i per CTA (one thread each)
+constexpr int kTJ = 16;    // j accumulators per thread
+constexpr int kKC = 32;    // k chunk staged in shared memory
+constexpr int kJR = 512;   // j range per CTA (grid.y)
+
+__global__ void __launch_bounds__(kTI) ahc_init_nn_kernel(const double *__restrict__ cols, int N, int D, int Ns,
+                                                           Cand *__restrict__ partial, int *error) {
+    __shared__ double sj[kKC][kTJ];
+    const int t = threadIdx.x;
+    const int i = blockIdx.x * kTI + t;
+    const int jr0 = blockIdx.y * kJR;
+    const int i_last = min(N, (int)(blockIdx.x + 1) * kTI) - 1;   // largest i of this CTA
+    double best = INFINITY;
+    int arg = INT_MAX;
+    if (jr0 < i_last) {
+        const int jr1 = min(jr0 + kJR, i_last);   // pairs need j < i <= i_last
+        bool bad = false;
+        for (int j0 = jr0; j0 < jr1; j0 += kTJ) {
+            double acc[kTJ];
+#pragma unroll
+            for (int jj = 0; jj < kTJ; ++jj) acc[jj] = 0.0;
+            for (int k0 = 0; k0 < D; k0 += kKC) {
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < (kKC * kTJ) / kTI; ++u) {
+                    const int idx = t + kTI * u;
+                    const int kk = idx / kTJ, jj = idx % kTJ;
+                    const int k = k0 + kk, j = j0 + jj;
+                    sj[kk][jj] = (k < D && j < N) ? cols[(size_t)k * Ns + j] : 0.0;
+                }
+                __syncthreads();
+                if (i < N) {
+                    const int kn = min(kKC, D - k0);
+#pragma unroll 4
+                    for (int kk = 0; kk < kn; ++kk) {
+                        const double xi = cols[(size_t)(k0 + kk) * Ns + i];
+#pragma unroll
+                        for (int jj = 0; jj < kTJ; ++jj) acc[jj] = sq_step(acc[jj], xi, sj[kk][jj]);
+                    }
+                }
+            }
+            if (i < N) {
+#pragma unroll
+                for (int jj = 0; jj < kTJ; ++jj) {
+                    const int j = j0 + jj;
+                    if (j < i && j < jr1) {
+                        const double d = acc[jj];
+                        if (d != d) bad = true;
+                        if (d < best) {   // ascending j + strict '<'  ==  lexicographic (d, j) minimum
+                            best = d;
+                            arg = j;
+                        }
+                    }
+                }
+            }
+        }
+        if (bad) atomicExch(error, 1);
+    }
+    if (i < N) {
+        Cand c;
+        c.d = best;
+        c.id = arg;
+        partial[(size_t)blockIdx.y * N + i] = c;
+    }
+}
+
+__global__ void ahc_init_reduce_kernel(const Cand *__restrict__ partial, int N, int ranges, double *key, int *nn) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 1 || i >= N) return;
+    double best = INFINITY;
+    int arg = 0;   // reference initialises idx = 0 and min = +inf (fastcluster_internal.hpp:1654-1656)
+    for (int r = 0; r < ranges; ++r) {
+        const Cand c = partial[(size_t)r * N + i];
+        if (c.id != INT_MAX && c.d < best) {
+            best = c.d;
+            arg = c.id;
+        }
+    }
+    key[i] = best;
+    nn[i] = arg;
+}
+
+// ------------------------------------------------------------------------------------------------ merge loop
+constexpr int kMergeThreads = 256;
+constexpr int kMaxRounds = 8;
+enum { CMD_MERGE = 1, CMD_RESCAN = 2, CMD_EXIT = 3 };
+
+__device__ __forceinline__ void cand_min(double &d, int &id, double od, int oid) {
+    if (cand_less(od, oid, d, id)) {
+        d = od;
+        id = oid;
+    }
+}
+
+__device__ void ahc_master(Problem &P, int W) {
+    const int lane = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    const int N = P.N;
+    // live list and per-node bookkeeping, built by the whole warp
+    for (int i = lane; i < 2 * N - 1; i += 32) {
+        P.live_prev[i + 1] = i;
+        P.live_next[i] = i + 1;
+        if (i < N) {
+            P.weight[i] = 1;
+            P.slot_of[i] = i;
+        }
+    }
+    __syncwarp();
+    NnHeap heap{P.key, P.heap_at, P.heap_where, P.heap_size};
+    LiveList live{P.live_next, P.live_prev, 0};
+    unsigned seq = 0, arrivals = 0;
+    bool failed = false;
+
+    auto publish = [&](const Command &c) {   // lane 0
+        *P.cmd = c;
+        st_release_u32(P.seq, ++seq);
+    };
+    auto collect = [&](double &d, int &id) {   // whole warp; result valid in every lane
+        arrivals += (unsigned)W;
+        if (lane == 0) {
+            while (ld_acquire_u32(P.arrive) < arrivals) {
+            }
+        }
+        __syncwarp();
+        d = INFINITY;
+        id = INT_MAX;
+        for (int w = lane; w < W; w += 32) {
+            const double od = __ldcg(&P.partial[w].d);
+            const int oid = __ldcg(&P.partial[w].id);
+            cand_min(d, id, od, oid);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(full, d, o);
+            const int oid = __shfl_xor_sync(full, id, o);
+            cand_min(d, id, od, oid);
+        }
+        if (__ldcg(P.error) != 0) failed = true;
+    };
+
+    for (int step = 0; step < N - 1 && !failed; ++step) {
+        const int fresh = N + step;
+        int a = 0;
+        for (;;) {   // make sure the heap top has a live nearest neighbour (lazy repair, :1706-1734)
+            int stale = 0;
+            if (lane == 0) {
+                a = heap.top();
+                stale = live.dead(P.nn[a]) ? 1 : 0;
+            }
+            stale = __shfl_sync(full, stale, 0);
+            a = __shfl_sync(full, a, 0);
+            if (!stale) break;
+            if (lane == 0) {
+                Command c{};
+                c.type = CMD_RESCAN;
+                c.fresh = a;
+                c.limit = a;
+                c.slot_a = c.slot_b = -1;
+                publish(c);
+            }
+            double d;
+            int id;
+            collect(d, id);
+            if (failed) break;
+            if (lane == 0) {
+                P.nn[a] = id;
+                heap.raise_key(a, d);
+            }
+            __syncwarp();
+        }
+        if (failed) break;
+        int b = 0;
+        if (lane == 0) {
+            b = P.nn[a];
+            live.drop(a);
+            live.drop(b);
+            P.merge_a[step] = a;
+            P.merge_b[step] = b;
+            P.merge_d[step] = P.key[a];
+        }
+        if (step < N - 2) {
+            if (lane == 0) {
+                Command c{};
+                c.type = CMD_MERGE;
+                c.a = a;
+                c.b = b;
+                c.fresh = fresh;
+                c.slot_a = P.slot_of[a];
+                c.slot_b = P.slot_of[b];
+                c.limit = fresh;
+                c.wa = (double)P.weight[a];
+                c.wb = (double)P.weight[b];
+                publish(c);
+                P.weight[fresh] = P.weight[a] + P.weight[b];
+                P.slot_of[fresh] = P.slot_of[a];
+            }
+            double d;
+            int id;
+            collect(d, id);
+            if (failed) break;
+            if (lane == 0) {
+                P.nn[fresh] = id;
+                if (b < live.head) heap.erase(live.head); else heap.erase(b);
+                heap.rename(a, fresh, d);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) P.steps_done = step + 1;
+    }
+    if (lane == 0) {
+        Command c{};
+        c.type = CMD_EXIT;
+        publish(c);
+    }
+}
+
+__global__ void __launch_bounds__(kMergeThreads, 1) ahc_merge_kernel(Problem *pp) {
+    extern __shared__ double smem_d[];
+    Problem P = *pp;
+    const int W = (int)gridDim.x - 1;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < 32) ahc_master(P, W);
+        return;
+    }
+    const int wb = (int)blockIdx.x - 1;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int N = P.N, D = P.D, Ns = P.Ns;
+    double *v = smem_d;                                   // [D] target vector
+    double *red_d = smem_d + D;                           // [warps]
+    int *red_id = reinterpret_cast<int *>(red_d + kMergeThreads / 32);
+    __shared__ Command sc;
+
+    const int rounds = (Ns + W * kMergeThreads - 1) / (W * kMergeThreads);
+    int ids[kMaxRounds];
+#pragma unroll
+    for (int r = 0; r < kMaxRounds; ++r) {
+        const int s = (r * W + wb) * kMergeThreads + t;
+        ids[r] = (r < rounds && s < N) ? s : -1;
+    }
+    unsigned expect = 0;
+    for (;;) {
+        ++expect;
+        if (t == 0) {
+            while (ld_acquire_u32(P.seq) < expect) {
+            }
+            const int *src = reinterpret_cast<const int *>(P.cmd);
+            int *dst = reinterpret_cast<int *>(&sc);
+#pragma unroll
+            for (int q = 0; q < (int)(sizeof(Command) / sizeof(int)); ++q) dst[q] = __ldcg(src + q);
+        }
+        __syncthreads();
+        const Command c = sc;
+        if (c.type == CMD_EXIT) break;
+        if (c.type == CMD_MERGE) {
+            const double *ra = P.rows + (size_t)c.a * D, *rb = P.rows + (size_t)c.b * D;
+            const double den = __dadd_rn(c.wa, c.wb);
+            for (int k = t; k < D; k += kMergeThreads) {
+                const double xa = __ldcg(ra + k), xb = __ldcg(rb + k);
+                v[k] = __ddiv_rn(__dadd_rn(__dmul_rn(xa, c.wa), __dmul_rn(xb, c.wb)), den);
+            }
+            __syncthreads();
+            // the CTA that owns slot_a stores the new node: scan copy (its own column) + node store (new row)
+            const int owner = (c.slot_a / kMergeThreads) % W;
+            if (owner == wb) {
+                double *row = P.rows + (size_t)c.fresh * D;
+                for (int k = t; k < D; k += kMergeThreads) {
+                    P.cols[(size_t)k * Ns + c.slot_a] = v[k];
+                    row[k] = v[k];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kMaxRounds; ++r) {
+                const int s = (r * W + wb) * kMergeThreads + t;
+                if (r < rounds) {
+                    if (s == c.slot_a) ids[r] = c.fresh;
+                    else if (s == c.slot_b) ids[r] = -1;
+                }
+            }
+        } else {
+            const double *rt = P.rows + (size_t)c.fresh * D;
+            for (int k = t; k < D; k += kMergeThreads) v[k] = __ldcg(rt + k);
+            __syncthreads();
+        }
+        // ---- scan: one sequential chain per owned live node with id < limit ------------------------------
+        double best = INFINITY;
+        int best_id = INT_MAX;
+        bool bad = false;
+#pragma unroll
+        for (int r = 0; r < kMaxRounds; ++r) {
+            if (r < rounds) {
+                const int id = ids[r];
+                if (id >= 0 && id < c.limit) {
+                    const int s = (r * W + wb) * kMergeThreads + t;
+                    const double *col = P.cols + s;
+                    double sum = 0.0;
+                    int k = 0;
+                    for (; k + 8 <= D; k += 8) {
+                        double x[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) x[u] = __ldcg(col + (size_t)(k + u) * Ns);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) sum = sq_step(sum, x[u], v[k + u]);
+                    }
+                    for (; k < D; ++k) sum = sq_step(sum, __ldcg(col + (size_t)k * Ns), v[k]);
+                    if (sum != sum) bad = true;
+                    cand_min(best, best_id, sum, id);
+                }
+            }
+        }
+        if (bad) atomicExch(P.error, 1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oid = __shfl_xor_sync(0xffffffffu, best_id, o);
+            cand_min(best, best_id, od, oid);
+        }
+        if (lane == 0) {
+            red_d[warp] = best;
+            red_id[warp] = best_id;
+        }
+        __syncthreads();
+        if (t == 0) {
+            for (int w2 = 1; w2 < kMergeThreads / 32; ++w2) cand_min(best, best_id, red_d[w2], red_id[w2]);
+            __stcg(&P.partial[wb].d, best);
+            __stcg(&P.partial[wb].id, best_id);
+            __threadfence();
+            red_release_add_u32(P.arrive, 1u);
+        }
+        // sc / red_* are rewritten only after the next command's barrier
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+// Row-wise L2 normalisation with the oracle's (= AHCClustering.normalizeFeatures') operation order:
+// s = sum_k x*x sequentially, scale = s > 0 ? 1/sqrt(s) : 0, out = x*scale.
+__global__ void ahc_normalize_rows_kernel(const double *__restrict__ in, double *__restrict__ out, int rows, int dim) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const double *x = in + (size_t)r * dim;
+    double s = 0.0;
+    for (int k = 0; k < dim; ++k) s = __dadd_rn(s, __dmul_rn(x[k], x[k]));
+    const double scale = s > 0.0 ? __ddiv_rn(1.0, __dsqrt_rn(s)) : 0.0;
+    double *o = out + (size_t)r * dim;
+    for (int k = 0; k < dim; ++k) o[k] = __dmul_rn(x[k], scale);
+}
+
+__global__ void ahc_widen_kernel(const float *__restrict__ in, double *__restrict__ out, long long count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (double)in[i];
+}
+
+int launch_normalize_rows(const double *d_in, double *d_out, int rows, int dim, cudaStream_t s) {
+    if (rows <= 0) return FA_OK;
+    ahc_normalize_rows_kernel<<<(rows + 127) / 128, 128, 0, s>>>(d_in, d_out, rows, dim);
+    FA_CUDA_TRY(cudaGetLastError());
+    return FA_OK;
+}
+
+int launch_widen_rows(const float *d_in, double *d_out, long long count, cudaStream_t s) {
+    if (count <= 0) return FA_OK;
+    ahc_widen_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_in, d_out, count);
+    FA_CUDA_TRY(cudaGetLastError());
+    return FA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ host solver
+Solver::~Solver() { release(); }
+
+void Solver::release() {
+    if (d_pool) cudaFree(d_pool);
+    if (d_input) cudaFree(d_input);
+    if (h_pool) cudaFreeHost(h_pool);
+    d_pool = nullptr;
+    d_input = nullptr;
+    h_pool = nullptr;
+    pool_bytes = h_pool_bytes = input_cap = 0;
+}
+
+int Solver::init(cudaStream_t s, int worker_limit) {
+    stream = s;
+    int dev = 0;
+    FA_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    FA_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        fa::set_error("fluidaudio_b200 requires an sm_100a device, found sm_%d%d", prop.major, prop.minor);
+        return FA_NO_DEVICE;
+    }
+    int coop = 0;
+    FA_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) {
+        fa::set_error("device does not support cooperative launch");
+        return FA_UNSUPPORTED;
+    }
+    num_sms = prop.multiProcessorCount;
+    max_workers = std::max(1, std::min(num_sms - 1, worker_limit > 0 ? worker_limit : num_sms - 1));
+    return FA_OK;
+}
+
+namespace {
+struct Carver {
+    size_t off = 0;
+    template <typename T> size_t take(size_t count) {
+        off = (off + 255) & ~size_t(255);
+        const size_t at = off;
+        off += count * sizeof(T);
+        return at;
+    }
+};
+struct Layout {
+    size_t rows, cols, key, nn, heap_at, heap_where, live_next, live_prev, weight, slot_of, merge_a, merge_b, merge_d,
+        cmd, seq, arrive, partial, error, init_partial, problem, total;
+    int ranges;
+};
+Layout make_layout(int N, int D, int Ns, int workers) {
+    Layout L{};
+    Carver c;
+    L.rows = c.take<double>((size_t)(2 * N - 1) * D);
+    L.cols = c.take<double>((size_t)D * Ns);
+    L.key = c.take<double>((size_t)2 * N);
+    L.nn = c.take<int>((size_t)2 * N);
+    L.heap_at = c.take<int>((size_t)N);
+    L.heap_where = c.take<int>((size_t)2 * N);
+    L.live_next = c.take<int>((size_t)2 * N + 2);
+    L.live_prev = c.take<int>((size_t)2 * N + 2);
+    L.weight = c.take<int>((size_t)2 * N);
+    L.slot_of = c.take<int>((size_t)2 * N);
+    L.merge_a = c.take<int>((size_t)N);
+    L.merge_b = c.take<int>((size_t)N);
+    L.merge_d = c.take<double>((size_t)N);
+    L.cmd = c.take<Command>(1);
+    L.seq = c.take<unsigned>(64);      // own 256-byte line
+    L.arrive = c.take<unsigned>(64);   // own 256-byte line
+    L.partial = c.take<Cand>((size_t)workers + 1);
+    L.error = c.take<int>(64);
+    L.ranges = (N + kJR - 1) / kJR;
+    L.init_partial = c.take<Cand>((size_t)L.ranges * N);
+    L.problem = c.take<Problem>(1);
+    L.total = (c.off + 255) & ~size_t(255);
+    return L;
+}
+} // namespace
+
+int Solver::ensure_pool(int N, int D) {
+    const int Ns = (N + 31) & ~31;
+    const Layout L = make_layout(N, D, Ns, max_workers);
+    if (L.total > pool_bytes) {
+        if (d_pool) cudaFree(d_pool);
+        d_pool = nullptr;
+        pool_bytes = 0;
+        FA_CUDA_TRY(cudaMalloc(&d_pool, L.total));
+        pool_bytes = L.total;
+    }
+    const size_t hneed = sizeof(double) * (size_t)(3 * N + 8) + sizeof(int) * (size_t)(6 * N + 64);
+    if (hneed > h_pool_bytes) {
+        if (h_pool) cudaFreeHost(h_pool);
+        h_pool = nullptr;
+        h_pool_bytes = 0;
+        FA_CUDA_TRY(cudaMallocHost(&h_pool, hneed));
+        h_pool_bytes = hneed;
+    }
+    return FA_OK;
+}
+
+int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
+    if (N < 2) return FA_OK;
+    const int Ns = (N + 31) & ~31;
+    int workers = std::min(max_workers, (Ns + kMergeThreads - 1) / kMergeThreads);
+    workers = std::max(workers, 1);
+    if ((long long)workers * kMergeThreads * kMaxRounds < Ns) {
+        fa::set_error("point count %d exceeds the capacity of the merge kernel (%lld)", N,
+                      (long long)workers * kMergeThreads * kMaxRounds);
+        return FA_RUNTIME_ERROR;
+    }
+    const size_t smem = sizeof(double) * (size_t)D + (sizeof(double) + sizeof(int)) * (kMergeThreads / 32) + 16;
+    if (smem > 200 * 1024) {
+        fa::set_error("dimension %d too large for the merge kernel's shared-memory target vector", D);
+        return FA_RUNTIME_ERROR;
+    }
+    int st = ensure_pool(N, D);
+    if (st != FA_OK) return st;
+    const Layout L = make_layout(N, D, Ns, max_workers);
+    char *base = static_cast<char *>(d_pool);
+    Problem P{};
+    P.N = N;
+    P.D = D;
+    P.Ns = Ns;
+    P.rows = reinterpret_cast<double *>(base + L.rows);
+    P.cols = reinterpret_cast<double *>(base + L.cols);
+    P.key = reinterpret_cast<double *>(base + L.key);
+    P.nn = reinterpret_cast<int *>(base + L.nn);
+    P.heap_at = reinterpret_cast<int *>(base + L.heap_at);
+    P.heap_where = reinterpret_cast<int *>(base + L.heap_where);
+    P.live_next = reinterpret_cast<int *>(base + L.live_next);
+    P.live_prev = reinterpret_cast<int *>(base + L.live_prev);
+    P.weight = reinterpret_cast<int *>(base + L.weight);
+    P.slot_of = reinterpret_cast<int *>(base + L.slot_of);
+    P.merge_a = reinterpret_cast<int *>(base + L.merge_a);
+    P.merge_b = reinterpret_cast<int *>(base + L.merge_b);
+    P.merge_d = reinterpret_cast<double *>(base + L.merge_d);
+    P.cmd = reinterpret_cast<Command *>(base + L.cmd);
+    P.seq = reinterpret_cast<unsigned *>(base + L.seq);
+    P.arrive = reinterpret_cast<unsigned *>(base + L.arrive);
+    P.partial = reinterpret_cast<Cand *>(base + L.partial);
+    P.error = reinterpret_cast<int *>(base + L.error);
+    Cand *init_partial = reinterpret_cast<Cand *>(base + L.init_partial);
+    Problem *d_prob = reinterpret_cast<Problem *>(base + L.problem);
+
+    // pinned host mirrors
+    char *hb = static_cast<char *>(h_pool);
+    double *h_key = reinterpret_cast<double *>(hb);
+    double *h_md = h_key + 2 * N + 4;
+    int *h_nn = reinterpret_cast<int *>(h_md + N + 4);
+    int *h_at = h_nn + 2 * N;
+    int *h_where = h_at + N;
+    int *h_ma = h_where + 2 * N;
+    int *h_mb = h_ma + N;
+    int *h_err = h_mb + N;
+
+    cudaEvent_t ev[4];
+    for (auto &e : ev) FA_CUDA_TRY(cudaEventCreate(&e));
+    auto drop_events = [&]() {
+        for (auto &e : ev) cudaEventDestroy(e);
+    };
+
+    FA_CUDA_TRY(cudaMemsetAsync(base + L.seq, 0, 256, stream));
+    FA_CUDA_TRY(cudaMemsetAsync(base + L.arrive, 0, 256, stream));
+    FA_CUDA_TRY(cudaMemsetAsync(base + L.error, 0, 256, stream));
+    FA_CUDA_TRY(cudaEventRecord(ev[0], stream));
+    {
+        dim3 grid((Ns + 31) / 32, (D + 31) / 32), block(32, 8);
+        ahc_stage_kernel<<<grid, block, 0, stream>>>(d_rows, P.rows, P.cols, N, D, Ns);
+        FA_CUDA_TRY(cudaGetLastError());
+        dim3 g2((N + kTI - 1) / kTI, L.ranges);
+        ahc_init_nn_kernel<<<g2, kTI, 0, stream>>>(P.cols, N, D, Ns, init_partial, P.error);
+        FA_CUDA_TRY(cudaGetLastError());
+        ahc_init_reduce_kernel<<<(N + 127) / 128, 128, 0, stream>>>(init_partial, N, L.ranges, P.key, P.nn);
+        FA_CUDA_TRY(cudaGetLastError());
+        launches += 3;
+    }
+    FA_CUDA_TRY(cudaEventRecord(ev[1], stream));
+    FA_CUDA_TRY(cudaMemcpyAsync(h_key, P.key, sizeof(double) * N, cudaMemcpyDeviceToHost, stream));
+    FA_CUDA_TRY(cudaMemcpyAsync(h_err, P.error, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    FA_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (*h_err != 0) {
+        drop_events();
+        fa::set_error("NaN distance between input vectors");
+        return FA_RUNTIME_ERROR;   // reference: nan_error -> FASTCLUSTER_WRAPPER_RUNTIME_ERROR
+    }
+    // heapify on the host (fastcluster_internal.hpp:1682): O(N), ~50 us, avoids ~1 ms of serial device work
+    {
+        NnHeap heap{h_key, h_at, h_where, 0};
+        heap.build(N - 1, 1);
+        P.heap_size = heap.size;
+    }
+    FA_CUDA_TRY(cudaMemcpyAsync(P.heap_at, h_at, sizeof(int) * (N - 1), cudaMemcpyHostToDevice, stream));
+    FA_CUDA_TRY(cudaMemcpyAsync(P.heap_where, h_where, sizeof(int) * (2 * N - 2), cudaMemcpyHostToDevice, stream));
+    FA_CUDA_TRY(cudaMemcpyAsync(d_prob, &P, sizeof(Problem), cudaMemcpyHostToDevice, stream));
+    FA_CUDA_TRY(cudaEventRecord(ev[2], stream));
+    {
+        FA_CUDA_TRY(cudaFuncSetAttribute(ahc_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void *args[] = {&d_prob};
+        FA_CUDA_TRY(cudaLaunchCooperativeKernel((void *)ahc_merge_kernel, dim3(workers + 1), dim3(kMergeThreads), args,
+                                                smem, stream));
+        ++launches;
+    }
+    FA_CUDA_TRY(cudaEventRecord(ev[3], stream));
+    FA_CUDA_TRY(cudaMemcpyAsync(h_ma, P.merge_a, sizeof(int) * (N - 1), cudaMemcpyDeviceToHost, stream));
+    FA_CUDA_TRY(cudaMemcpyAsync(h_mb, P.merge_b, sizeof(int) * (N - 1), cudaMemcpyDeviceToHost, stream));
+    FA_CUDA_TRY(cudaMemcpyAsync(h_md, P.merge_d, sizeof(double) * (N - 1), cudaMemcpyDeviceToHost, stream));
+    FA_CUDA_TRY(cudaMemcpyAsync(h_err, P.error, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    FA_CUDA_TRY(cudaStreamSynchronize(stream));
+    cudaEventElapsedTime(&last_ms[0], ev[0], ev[1]);
+    cudaEventElapsedTime(&last_ms[1], ev[1], ev[2]);
+    cudaEventElapsedTime(&last_ms[2], ev[2], ev[3]);
+    cudaEventElapsedTime(&last_ms[3], ev[0], ev[3]);
+    drop_events();
+    if (*h_err != 0) {
+        fa::set_error("NaN distance during merging");
+        return FA_RUNTIME_ERROR;
+    }
+    // SciPy rows in merge order (FastClusterWrapper.cpp:128-130,169-192): sqrt of the squared distance,
+    // smaller id first, size = sum of the children's sizes
+    for (int s = 0; s < N - 1; ++s) {
+        const int lo = std::min(h_ma[s], h_mb[s]), hi = std::max(h_ma[s], h_mb[s]);
+        const double sz = (lo < N ? 1.0 : Z[(size_t)(lo - N) * 4 + 3]) + (hi < N ? 1.0 : Z[(size_t)(hi - N) * 4 + 3]);
+        Z[(size_t)s * 4 + 0] = (double)lo;
+        Z[(size_t)s * 4 + 1] = (double)hi;
+        Z[(size_t)s * 4 + 2] = std::sqrt(h_md[s]);
+        Z[(size_t)s * 4 + 3] = sz;
+    }
+    return FA_OK;
+}
+
+int Solver::linkage_host(const double *rows_host, size_t N, size_t D, double *Z, size_t z_len) {
+    // argument contract of FastClusterWrapper.cpp:203-223
+    if (!rows_host || !Z) return FA_INVALID_ARGUMENT;
+    if (N == 0) return FA_OK;
+    if (D == 0) return FA_INVALID_ARGUMENT;
+    if (N > 0x7fffffffull || D > 0x7fffffffull) return FA_INDEX_OVERFLOW;
+    if (z_len < (N > 1 ? (N - 1) * 4 : 0)) return FA_OUTPUT_TOO_SMALL;
+    if (N == 1) return FA_OK;
+    const size_t count = N * D;
+    if (count > input_cap) {
+        if (d_input) cudaFree(d_input);
+        d_input = nullptr;
+        input_cap = 0;
+        FA_CUDA_TRY(cudaMalloc(&d_input, count * sizeof(double)));
+        input_cap = count;
+    }
+    FA_CUDA_TRY(cudaMemcpyAsync(d_input, rows_host, count * sizeof(double), cudaMemcpyHostToDevice, stream));
+    return linkage_device(d_input, (int)N, (int)D, Z);
+}
+
+// Swift-side cut (AHCClustering.swift:112-121 clamp, :124-197 traversal, :200-210 relabel)
+void dendrogram_cut(const double *Z, long long count, double threshold, int32_t *labels) {
+    if (count <= 0) return;
+    if (count == 1) {
+        labels[0] = 0;
+        return;
+    }
+    const double thr = (threshold != threshold) ? 0.0 : std::max(0.0, std::min(2.0, threshold));
+    const long long total = 2 * count - 1;
+    std::vector<long long> lc(total, -1), rc(total, -1);
+    std::vector<double> nd(total, 0.0);
+    for (long long m = 0; m + 1 < count; ++m) {
+        lc[count + m] = (long long)Z[m * 4];
+        rc[count + m] = (long long)Z[m * 4 + 1];
+        nd[count + m] = Z[m * 4 + 2];
+    }
+    std::vector<long long> lab(count, -1), todo, sub;
+    todo.push_back(total - 1);
+    long long next = 0;
+    while (!todo.empty()) {
+        const long long node = todo.back();
+        todo.pop_back();
+        if (node < 0) continue;
+        if (node < count) {
+            if (lab[node] < 0) lab[node] = next++;
+            continue;
+        }
+        if (nd[node] <= thr) {          // whole subtree is one cluster
+            const long long id = next++;
+            sub.assign(1, node);
+            while (!sub.empty()) {
+                const long long cur = sub.back();
+                sub.pop_back();
+                if (cur < count) lab[cur] = id;
+                else {
+                    if (lc[cur] >= 0) sub.push_back(lc[cur]);
+                    if (rc[cur] >= 0) sub.push_back(rc[cur]);
+                }
+            }
+        } else {                        // split: left pushed first, so the right child is visited first
+            if (lc[node] >= 0) todo.push_back(lc[node]);
+            if (rc[node] >= 0) todo.push_back(rc[node]);
+        }
+    }
+    for (long long i = 0; i < count; ++i)
+        if (lab[i] < 0) lab[i] = next++;
+    std::vector<int32_t> canon((size_t)next, -1);
+    int32_t fresh = 0;
+    for (long long i = 0; i < count; ++i) {
+        if (canon[lab[i]] < 0) canon[lab[i]] = fresh++;
+        labels[i] = canon[lab[i]];
+    }
+}
+
+} // namespace ahc
+} // namespace fa

@@ -1,0 +1,718 @@
+// Fused log-mel frontend for sm_100a:  pre-emphasis -> Hann window -> 512-point real FFT -> |.|^2 ->
+// Slaney mel filterbank -> log, one persistent CTA per SM.
+//
+// Re-implements Sources/FluidAudio/Shared/AudioMelSpectrogram.swift:325-456 (computeFlatTransposed),
+// :185-292 (computeFlat) and :132-178 (compute) — the three differ only in (pad, window offset, pre-emphasis,
+// output layout), which are kernel parameters here.
+//
+// Data flow per tile of 32 frames (kTileFrames):
+//   HBM --cp.async.bulk (TMA 1-D, mbarrier complete_tx)--> raw[2]   double-buffered, prefetched one tile ahead
+//   raw --pre-emphasis--> ptile                                       all threads
+//   ptile --one warp per frame: FFT256 + recombination--> power[32][257]
+//   power --lane = frame, warp = mel: banded dot + log--> otile / HBM
+// HBM traffic is the algorithmic minimum: every sample is read once (plus a 352-sample halo per tile) and
+// every log-mel value is written once, both fully coalesced.
+//
+// The mel filterbank is applied as a BANDED contraction on the FP32 pipe, not as a tensor-core GEMM: each
+// FFT bin feeds at most two triangular filters, so the dense [T x 257] x [257 x nMels] product is >97 % zeros
+// (514 useful MACs per frame out of 20 560 at 80 mels), and bf16 operands cannot meet the 1e-4 log-mel parity
+// bound.  See DESIGN.md §4.
+#include "mel_core.cuh"
+#include "mel_plan.h"
+
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace fa {
+namespace mel {
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk copy global -> shared (TMA engine), completion signalled on an mbarrier.  SASS: UBLKCP.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ kernel
+struct TileGeom {
+    int unit;          // index into units[]
+    long long f0;      // first frame of the tile (absolute frame index inside the clip)
+    int nf;            // frames in this tile (1..32)
+    long long a0;      // audio index of ptile[0]  (= f0*hop - pad)
+    long long base;    // audio index of raw[0]    (= floor4(a0 - 1), may be negative)
+    long long gs, ge;  // bulk-copied audio range [gs, ge), both multiples of 4 (empty if ge <= gs)
+};
+
+__device__ __forceinline__ TileGeom tile_geom(const MelLaunch &P, int tile) {
+    // units are sorted by tile_begin; binary search for the unit that owns this tile
+    int lo = 0, hi = P.num_units - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (P.units[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    const MelUnit &u = P.units[lo];
+    TileGeom g;
+    g.unit = lo;
+    g.f0 = u.frame_begin + (long long)kTileFrames * (tile - u.tile_begin);
+    const long long rem = u.frame_begin + u.frame_count - g.f0;
+    g.nf = rem < kTileFrames ? (int)rem : kTileFrames;
+    g.a0 = g.f0 * P.hop - P.pad;
+    const long long need0 = g.a0 - 1;
+    g.base = (need0 >= 0) ? (need0 & ~3LL) : -(((-need0) + 3) & ~3LL);
+    long long ge = (g.a0 + P.pt_len + 3) & ~3LL;
+    const long long n4 = u.n & ~3LL;
+    if (ge > n4) ge = n4;
+    g.gs = g.base < 0 ? 0 : g.base;
+    g.ge = ge;
+    if (!P.use_tma) g.ge = g.gs;   // nothing is bulk-copied: every sample comes through the read-only path
+    return g;
+}
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) mel512_kernel(const MelLaunch P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float *raw0 = reinterpret_cast<float *>(smem);
+    float *raw1 = raw0 + P.raw_cap;
+    float *ptile = raw1 + P.raw_cap;
+    float *fftbuf = ptile + P.pt_cap;                       // kWarps * 2 * kFftPad
+    float *power = fftbuf + kWarps * 2 * kFftPad;           // 32 * 257
+    float *otile = power + kTileFrames * kPowStride;        // 32 * (n_mels + 1)
+    float *fbw = otile + kTileFrames * (P.n_mels + 1);      // fb_nnz_cap
+    int *fblo = reinterpret_cast<int *>(fbw + P.fb_cap);    // n_mels
+    int *fbhi = fblo + P.n_mels;
+    int *fboff = fbhi + P.n_mels;
+    uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(fboff + P.n_mels) + 7) & ~uintptr_t(7));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < P.fb_nnz; i += kWarps * 32) fbw[i] = P.fb_w[i];
+    for (int i = tid; i < P.n_mels; i += kWarps * 32) {
+        fblo[i] = P.fb_lo[i];
+        fbhi[i] = P.fb_hi[i];
+        fboff[i] = P.fb_off[i];
+    }
+    LaneTables T;
+    load_lane_tables(lane, P.win_tab, P.in_tab, P.tw256, P.tw512, T);
+    __syncthreads();
+
+    float *sre = fftbuf + warp * 2 * kFftPad;
+    float *sim = sre + kFftPad;
+
+    auto issue = [&](int tile, int buf) {   // thread 0 only
+        const TileGeom g = tile_geom(P, tile);
+        float *dst = buf ? raw1 : raw0;
+        if (g.ge > g.gs) {
+            const MelUnit &u = P.units[g.unit];
+            const uint32_t bytes = (uint32_t)((g.ge - g.gs) * 4);
+            mbar_expect_tx(&bars[buf], bytes);
+            bulk_g2s(dst + (g.gs - g.base), P.audio + u.audio_off + g.gs, bytes, &bars[buf]);
+        } else {
+            mbar_arrive(&bars[buf]);
+        }
+    };
+
+    int it = 0;
+    if (tid == 0 && (int)blockIdx.x < P.total_tiles) issue(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+        const TileGeom g = tile_geom(P, tile);
+        const MelUnit u = P.units[g.unit];
+        if (tid == 0) {
+            const int next = tile + gridDim.x;
+            if (next < P.total_tiles) {
+                fence_proxy_async();   // generic-proxy reads of raw[buf^1] (previous tile) precede this async write
+                issue(next, buf ^ 1);
+            }
+        }
+        mbar_wait(&bars[buf], parity);
+
+        // ---- phase 1: pre-emphasis into ptile (zero outside [0, n)) -------------------------------------
+        {
+            const float *raw = buf ? raw1 : raw0;
+            const float *gaudio = P.audio + u.audio_off;
+            auto sample = [&](long long i) -> float {   // x(i) for -1 <= i < n
+                if (i >= g.gs && i < g.ge) return raw[i - g.base];
+                if (i < 0) return u.last;
+                return __ldg(gaudio + i);
+            };
+            const float a = P.preemph;
+            for (int t = tid; t < P.pt_len; t += kWarps * 32) {
+                const long long i = g.a0 + t;
+                float v = 0.0f;
+                if (i >= 0 && i < u.n) {
+                    const float x = sample(i);
+                    if (a == 0.0f) v = x;
+                    else if (i == 0) v = preemph_first(x, u.last, a);
+                    else v = preemph_rest(x, sample(i - 1), a);
+                }
+                ptile[t] = v;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: one warp per frame: FFT + power ----------------------------------------------------
+        for (int fi = warp; fi < g.nf; fi += kWarps) {
+            const float *pf = ptile + fi * P.hop;
+            pass1(lane, pf, T, sre, sim);
+            __syncwarp();
+            pass2(lane, T, sre, sim);
+            __syncwarp();
+            float re[8], im[8];
+            pass3_load(lane, sre, sim, re, im);
+            __syncwarp();
+            pass3_store(lane, re, im, sre, sim);
+            __syncwarp();
+            post_power(lane, sre, sim, T, power + fi * kPowStride);
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---- phase 3: mel filterbank + log; lane = frame, warp strides over mel bins --------------------
+        {
+            const bool live = lane < g.nf;
+            const float *prow = power + lane * kPowStride;
+            const long long f = g.f0 + lane;
+            for (int m = warp; m < P.n_mels; m += kWarps) {
+                float v = 0.0f;
+                if (live) v = log_value(mel_dot(prow, fbw + fboff[m], fblo[m], fbhi[m]), P.log_floor, P.log_clamped);
+                if (P.layout == 0) otile[lane * (P.n_mels + 1) + m] = v;
+                else if (live) P.out[u.out_off + (long long)m * u.out_stride + f] = v;
+            }
+        }
+        if (P.layout == 0) {
+            __syncthreads();
+            // time-major tile is contiguous in HBM: rows f0..f0+nf, n_mels floats each
+            float *dst = P.out + u.out_off + g.f0 * P.n_mels;
+            for (int fi = warp; fi < g.nf; fi += kWarps)
+                for (int m = lane; m < P.n_mels; m += 32) dst[fi * P.n_mels + m] = otile[fi * (P.n_mels + 1) + m];
+        }
+        // next iteration's phase-1 barrier orders these reads against the next tile's writes
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host plan
+static float swift_float_pi() {
+    const uint32_t bits = 0x40490FDAu;   // Swift's Float.pi is rounded toward zero
+    float f;
+    std::memcpy(&f, &bits, 4);
+    return f;
+}
+
+// AudioMelSpectrogram.swift:553-562
+void build_window(int length, bool periodic, std::vector<float> &w) {
+    w.resize(length);
+    const float divisor = periodic ? (float)length : (float)(length - 1);
+    const float pi = swift_float_pi();
+    for (int i = 0; i < length; ++i) {
+        const float phase = 2.0f * pi * (float)i / divisor;
+        w[i] = 0.5f * (1.0f - cosf(phase));
+    }
+}
+
+// AudioMelSpectrogram.swift:564-642 (Slaney mel scale, Slaney area normalisation, Float32 arithmetic)
+void build_filterbank(int n_fft, int n_mels, int sample_rate, std::vector<float> &fb) {
+    const int bins = n_fft / 2 + 1;
+    const float f_sp = 200.0f / 3.0f, min_log_hz = 1000.0f;
+    const float min_log_mel = min_log_hz / f_sp;
+    const float log_step = logf(6.4f) / 27.0f;
+    auto to_mel = [&](float hz) { return hz >= min_log_hz ? min_log_mel + logf(hz / min_log_hz) / log_step : hz / f_sp; };
+    auto to_hz = [&](float mel) {
+        return mel >= min_log_mel ? min_log_hz * expf(log_step * (mel - min_log_mel)) : f_sp * mel;
+    };
+    const float mel_lo = to_mel(0.0f), mel_hi = to_mel((float)sample_rate / 2.0f);
+    std::vector<float> edge(n_mels + 2), freq(bins);
+    for (int i = 0; i < n_mels + 2; ++i) edge[i] = to_hz(mel_lo + (float)i * (mel_hi - mel_lo) / (float)(n_mels + 1));
+    for (int i = 0; i < bins; ++i) freq[i] = (float)i * (float)sample_rate / (float)n_fft;
+    fb.assign((size_t)n_mels * bins, 0.0f);
+    for (int m = 0; m < n_mels; ++m) {
+        const float l = edge[m], c = edge[m + 1], r = edge[m + 2];
+        const float norm = 2.0f / (r - l);
+        for (int b = 0; b < bins; ++b) {
+            const float f = freq[b];
+            if (f >= l && f < c) fb[(size_t)m * bins + b] = norm * (f - l) / (c - l);
+            else if (f >= c && f <= r) fb[(size_t)m * bins + b] = norm * (r - f) / (r - c);
+        }
+    }
+}
+
+#define FA_CUDA_TRY(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            fa::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return FA_CUDA_ERROR;                                                           \
+        }                                                                                   \
+    } while (0)
+
+static constexpr int kWarpsPerCta = 16;
+
+MelPlan::~MelPlan() { release(); }
+
+void MelPlan::release() {
+    auto fr = [](auto *&p) {
+        if (p) cudaFree(p);
+        p = nullptr;
+    };
+    for (int m = 0; m < 2; ++m) {
+        fr(d_win_tab_mode[m]);
+        fr(d_in_tab_mode[m]);
+    }
+    fr(d_tw256);
+    fr(d_tw512);
+    fr(d_fb_w);
+    fr(d_fb_lo);
+    fr(d_fb_hi);
+    fr(d_fb_off);
+    fr(d_units);
+    fr(d_audio);
+    fr(d_out);
+    d_audio_cap = d_out_cap = 0;
+    if (h_units) cudaFreeHost(h_units);
+    h_units = nullptr;
+    units_cap = 0;
+    for (auto &s : streams)
+        if (s) cudaStreamDestroy(s), s = nullptr;
+    for (auto &e : events)
+        if (e) cudaEventDestroy(e);
+    events.clear();
+}
+
+int MelPlan::init(const MelConfig &c) {
+    cfg = c;
+    if (cfg.pad_to < 1) cfg.pad_to = 1;   // AudioMelSpectrogram.swift:72
+    if (cfg.n_mels <= 0 || cfg.hop_length <= 0 || cfg.win_length <= 0 || cfg.n_fft <= 0 || cfg.sample_rate <= 0) {
+        fa::set_error("mel config: all sizes must be positive");
+        return FA_INVALID_ARGUMENT;
+    }
+    if (cfg.n_fft != kNfft || (cfg.hop_length & 1) || cfg.win_length > kNfft || cfg.n_mels > 512 ||
+        cfg.hop_length > 1024) {
+        fa::set_error("mel config unsupported by the sm_100a kernel: need nFFT == 512, even hop <= 1024, win <= 512, "
+                      "nMels <= 512 (got nFFT=%d hop=%d win=%d nMels=%d)",
+                      cfg.n_fft, cfg.hop_length, cfg.win_length, cfg.n_mels);
+        return FA_UNSUPPORTED;
+    }
+    build_window(cfg.win_length, cfg.window_periodic != 0, window);
+    build_filterbank(cfg.n_fft, cfg.n_mels, cfg.sample_rate, filterbank);
+
+    // banded filterbank: per mel the contiguous range of non-zero bins
+    std::vector<float> w;
+    std::vector<int> lo(cfg.n_mels), hi(cfg.n_mels), off(cfg.n_mels);
+    for (int m = 0; m < cfg.n_mels; ++m) {
+        int a = kBins, b = 0;
+        for (int k = 0; k < kBins; ++k)
+            if (filterbank[(size_t)m * kBins + k] != 0.0f) {
+                a = std::min(a, k);
+                b = k + 1;
+            }
+        if (b == 0) a = 0;
+        lo[m] = a;
+        hi[m] = b;
+        off[m] = (int)w.size();
+        for (int k = a; k < b; ++k) w.push_back(filterbank[(size_t)m * kBins + k]);
+    }
+    fb_nnz = (int)w.size();
+
+    int dev = 0;
+    FA_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    FA_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    num_sms = prop.multiProcessorCount;
+    if (prop.major != 10) {
+        fa::set_error("fluidaudio_b200 requires an sm_100a device, found sm_%d%d", prop.major, prop.minor);
+        return FA_NO_DEVICE;
+    }
+
+    std::vector<float> win_tab(kNfft, 0.0f);
+    std::vector<uint8_t> in_tab(kNfft, 0);
+    for (int mode = 0; mode < 2; ++mode) {   // 0: centred window (offset (nFFT-win)/2); 1: legacy compute(), offset 0
+        const int off_w = mode == 0 ? (cfg.n_fft - cfg.win_length) / 2 : 0;
+        std::fill(win_tab.begin(), win_tab.end(), 0.0f);
+        std::fill(in_tab.begin(), in_tab.end(), 0);
+        for (int j = 0; j < cfg.win_length; ++j) {
+            win_tab[off_w + j] = window[j];
+            in_tab[off_w + j] = 1;
+        }
+        FA_CUDA_TRY(cudaMalloc(&d_win_tab_mode[mode], kNfft * sizeof(float)));
+        FA_CUDA_TRY(cudaMalloc(&d_in_tab_mode[mode], kNfft));
+        FA_CUDA_TRY(cudaMemcpy(d_win_tab_mode[mode], win_tab.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice));
+        FA_CUDA_TRY(cudaMemcpy(d_in_tab_mode[mode], in_tab.data(), kNfft, cudaMemcpyHostToDevice));
+    }
+    std::vector<cpx> tw256(256), tw512(256);
+    for (int k = 0; k < 256; ++k) {
+        tw256[k] = {(float)std::cos(2.0 * M_PI * k / 256.0), (float)-std::sin(2.0 * M_PI * k / 256.0)};
+        tw512[k] = {(float)std::cos(2.0 * M_PI * k / 512.0), (float)-std::sin(2.0 * M_PI * k / 512.0)};
+    }
+    FA_CUDA_TRY(cudaMalloc(&d_tw256, 256 * sizeof(cpx)));
+    FA_CUDA_TRY(cudaMalloc(&d_tw512, 256 * sizeof(cpx)));
+    FA_CUDA_TRY(cudaMemcpy(d_tw256, tw256.data(), 256 * sizeof(cpx), cudaMemcpyHostToDevice));
+    FA_CUDA_TRY(cudaMemcpy(d_tw512, tw512.data(), 256 * sizeof(cpx), cudaMemcpyHostToDevice));
+    FA_CUDA_TRY(cudaMalloc(&d_fb_w, std::max<size_t>(1, w.size()) * sizeof(float)));
+    FA_CUDA_TRY(cudaMalloc(&d_fb_lo, cfg.n_mels * sizeof(int)));
+    FA_CUDA_TRY(cudaMalloc(&d_fb_hi, cfg.n_mels * sizeof(int)));
+    FA_CUDA_TRY(cudaMalloc(&d_fb_off, cfg.n_mels * sizeof(int)));
+    if (!w.empty()) FA_CUDA_TRY(cudaMemcpy(d_fb_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    FA_CUDA_TRY(cudaMemcpy(d_fb_lo, lo.data(), cfg.n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    FA_CUDA_TRY(cudaMemcpy(d_fb_hi, hi.data(), cfg.n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    FA_CUDA_TRY(cudaMemcpy(d_fb_off, off.data(), cfg.n_mels * sizeof(int), cudaMemcpyHostToDevice));
+
+    pt_len = (kTileFrames - 1) * cfg.hop_length + kNfft;
+    pt_cap = (pt_len + 3) & ~3;
+    raw_cap = (pt_len + 1 + 3 + 3 + 3) & ~3;
+    fb_cap = (fb_nnz + 3) & ~3;
+    smem_bytes = sizeof(float) * ((size_t)2 * raw_cap + pt_cap + (size_t)kWarpsPerCta * 2 * kFftPad +
+                                  (size_t)kTileFrames * kPowStride + (size_t)kTileFrames * (cfg.n_mels + 1) + fb_cap) +
+                 sizeof(int) * 3 * (size_t)cfg.n_mels + 8 + 2 * sizeof(uint64_t);
+    if (smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+        fa::set_error("mel config needs %zu bytes of shared memory per CTA, device allows %zu", smem_bytes,
+                      (size_t)prop.sharedMemPerBlockOptin);
+        return FA_UNSUPPORTED;
+    }
+    FA_CUDA_TRY(cudaFuncSetAttribute(mel512_kernel<kWarpsPerCta>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes));
+    for (auto &s : streams) FA_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    return FA_OK;
+}
+
+long long MelPlan::frame_count(long long n, int mode, long long expected) const {
+    long long computed;   // C++ integer division truncates toward zero exactly like Swift's Int '/'
+    if (mode == 0) computed = 1 + (n + 2 * (long long)(cfg.n_fft / 2) - cfg.win_length) / cfg.hop_length;
+    else if (mode == 1) computed = std::max<long long>(0, (n - cfg.n_fft) / cfg.hop_length + 1);
+    else computed = 1 + (n - cfg.win_length) / cfg.hop_length;
+    return expected >= 0 ? expected : computed;
+}
+
+int MelPlan::ensure_units(int count) {
+    if (count <= units_cap) return FA_OK;
+    if (d_units) cudaFree(d_units);
+    if (h_units) cudaFreeHost(h_units);
+    d_units = nullptr;
+    h_units = nullptr;
+    units_cap = std::max(count, 64);
+    FA_CUDA_TRY(cudaMalloc(&d_units, units_cap * sizeof(MelUnit)));
+    FA_CUDA_TRY(cudaMallocHost(&h_units, units_cap * sizeof(MelUnit)));
+    return FA_OK;
+}
+
+int MelPlan::ensure_staging(size_t audio_floats, size_t out_floats) {
+    if (audio_floats > d_audio_cap) {
+        if (d_audio) cudaFree(d_audio);
+        d_audio = nullptr;
+        d_audio_cap = 0;
+        FA_CUDA_TRY(cudaMalloc(&d_audio, audio_floats * sizeof(float)));
+        d_audio_cap = audio_floats;
+    }
+    if (out_floats > d_out_cap) {
+        if (d_out) cudaFree(d_out);
+        d_out = nullptr;
+        d_out_cap = 0;
+        FA_CUDA_TRY(cudaMalloc(&d_out, out_floats * sizeof(float)));
+        d_out_cap = out_floats;
+    }
+    return FA_OK;
+}
+
+int MelPlan::ensure_events(size_t count) {
+    while (events.size() < count) {
+        cudaEvent_t e;
+        FA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        events.push_back(e);
+    }
+    return FA_OK;
+}
+
+int MelPlan::launch(const float *d_audio_base, float *d_out_base, int first, int count, int total_tiles, int mode,
+                    int layout, cudaStream_t stream, bool aligned16) {
+    if (total_tiles <= 0) return FA_OK;
+    MelLaunch P{};
+    P.audio = d_audio_base;
+    P.out = d_out_base;
+    P.units = d_units + first;
+    P.num_units = count;
+    P.total_tiles = total_tiles;
+    P.hop = cfg.hop_length;
+    P.pad = mode == 0 ? cfg.n_fft / 2 : 0;
+    P.preemph = mode == 2 ? 0.0f : cfg.preemph;
+    P.n_mels = cfg.n_mels;
+    P.log_floor = cfg.log_floor;
+    P.log_clamped = cfg.log_floor_mode;
+    P.layout = layout;
+    P.win_tab = d_win_tab_mode[mode == 2 ? 1 : 0];
+    P.in_tab = d_in_tab_mode[mode == 2 ? 1 : 0];
+    P.tw256 = d_tw256;
+    P.tw512 = d_tw512;
+    P.fb_w = d_fb_w;
+    P.fb_lo = d_fb_lo;
+    P.fb_hi = d_fb_hi;
+    P.fb_off = d_fb_off;
+    P.fb_nnz = fb_nnz;
+    P.fb_cap = fb_cap;
+    P.pt_len = pt_len;
+    P.pt_cap = pt_cap;
+    P.raw_cap = raw_cap;
+    P.use_tma = aligned16 ? 1 : 0;
+    const int grid = std::min(total_tiles, num_sms);
+    mel512_kernel<kWarpsPerCta><<<grid, kWarpsPerCta * 32, smem_bytes, stream>>>(P);
+    FA_CUDA_TRY(cudaGetLastError());
+    ++launches;
+    return FA_OK;
+}
+
+static inline long long ceil_to(long long v, long long m) { return ((v + m - 1) / m) * m; }
+static inline int tiles_of(long long frames) { return (int)((frames + kTileFrames - 1) / kTileFrames); }
+
+// Shape rules shared by every entry point.  Returns false for the reference's "empty" guard
+// (AudioMelSpectrogram.swift:135-137, :199-201, :349-351).
+static bool shape_of(const MelPlan &p, long long n, int mode, long long expected, long long &T, long long &Tp) {
+    T = p.frame_count(n, mode, mode == 0 || mode == 1 ? expected : -1);
+    if (T <= 0 || n <= 0) return false;
+    Tp = mode == 2 ? T : ceil_to(T, p.cfg.pad_to);
+    return true;
+}
+
+int MelPlan::compute_device(const float *d_in, long long n, float last, int mode, long long expected, int layout,
+                            float *d_out_buf, long long out_len, long long *mel_length, long long *num_frames,
+                            cudaStream_t stream) {
+    long long T, Tp;
+    if (!shape_of(*this, n, mode, expected, T, Tp)) {
+        if (mel_length) *mel_length = 0;
+        if (num_frames) *num_frames = mode == 2 ? 0 : 1;
+        if (mode != 2) {
+            if (out_len < cfg.n_mels) return FA_OUTPUT_TOO_SMALL;
+            FA_CUDA_TRY(cudaMemsetAsync(d_out_buf, 0, cfg.n_mels * sizeof(float), stream));
+        }
+        return FA_OK;
+    }
+    if (mel_length) *mel_length = T;
+    if (num_frames) *num_frames = Tp;
+    if (out_len < Tp * cfg.n_mels) {
+        fa::set_error("mel output needs %lld floats, buffer has %lld", Tp * cfg.n_mels, out_len);
+        return FA_OUTPUT_TOO_SMALL;
+    }
+    int st = ensure_units(1);
+    if (st != FA_OK) return st;
+    if (Tp > T) FA_CUDA_TRY(cudaMemsetAsync(d_out_buf, 0, Tp * cfg.n_mels * sizeof(float), stream));
+    h_units[0] = MelUnit{0, n, 0, Tp, 0, T, last, 0};
+    FA_CUDA_TRY(cudaMemcpyAsync(d_units, h_units, sizeof(MelUnit), cudaMemcpyHostToDevice, stream));
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
+    return launch(d_in, d_out_buf, 0, 1, tiles_of(T), mode, layout, stream, aligned);
+}
+
+int MelPlan::compute_batch_device(const float *d_in, const long long *offsets, int count, const float *last, int mode,
+                                  int layout, float *d_out_buf, const long long *out_offsets, long long *mel_lengths,
+                                  long long *num_frames, cudaStream_t stream) {
+    int st = ensure_units(count);
+    if (st != FA_OK) return st;
+    int tiles = 0, used = 0;
+    bool aligned = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
+    for (int i = 0; i < count; ++i) {
+        const long long n = offsets[i + 1] - offsets[i];
+        long long T, Tp;
+        if (!shape_of(*this, n, mode, -1, T, Tp)) {
+            if (mel_lengths) mel_lengths[i] = 0;
+            if (num_frames) num_frames[i] = mode == 2 ? 0 : 1;
+            if (mode != 2) FA_CUDA_TRY(cudaMemsetAsync(d_out_buf + out_offsets[i], 0, cfg.n_mels * sizeof(float), stream));
+            continue;
+        }
+        if (mel_lengths) mel_lengths[i] = T;
+        if (num_frames) num_frames[i] = Tp;
+        if (Tp > T) FA_CUDA_TRY(cudaMemsetAsync(d_out_buf + out_offsets[i], 0, Tp * cfg.n_mels * sizeof(float), stream));
+        if (offsets[i] & 3) aligned = false;
+        h_units[used] = MelUnit{offsets[i], n, out_offsets[i], Tp, 0, T, last ? last[i] : 0.0f, tiles};
+        tiles += tiles_of(T);
+        ++used;
+    }
+    if (!used) return FA_OK;
+    FA_CUDA_TRY(cudaMemcpyAsync(d_units, h_units, used * sizeof(MelUnit), cudaMemcpyHostToDevice, stream));
+    return launch(d_in, d_out_buf, 0, used, tiles, mode, layout, stream, aligned);
+}
+
+// Host buffers in, host buffers out.  A long clip is cut into units of `chunk` frames: unit c's samples are copied
+// on the H2D stream while unit c-1 runs on the compute stream and unit c-2's rows return on the D2H stream.
+int MelPlan::compute_host(const float *audio, long long n, float last, int mode, long long expected, int layout,
+                          float *out, long long out_len, long long *mel_length, long long *num_frames) {
+    long long T, Tp;
+    if (!shape_of(*this, n, mode, expected, T, Tp)) {
+        if (mel_length) *mel_length = 0;
+        if (num_frames) *num_frames = mode == 2 ? 0 : 1;
+        if (mode != 2) {
+            if (out_len < cfg.n_mels) return FA_OUTPUT_TOO_SMALL;
+            for (int m = 0; m < cfg.n_mels; ++m) out[m] = 0.0f;   // padValue
+        }
+        return FA_OK;
+    }
+    if (mel_length) *mel_length = T;
+    if (num_frames) *num_frames = Tp;
+    const long long need = Tp * cfg.n_mels;
+    if (out_len < need) {
+        fa::set_error("mel output needs %lld floats, buffer has %lld", need, out_len);
+        return FA_OUTPUT_TOO_SMALL;
+    }
+    int st = ensure_staging((size_t)n + 8, (size_t)need);
+    if (st != FA_OK) return st;
+    const long long kMinChunk = 4096, kMaxChunks = 24;
+    long long chunk = std::max(kMinChunk, ceil_to((T + kMaxChunks - 1) / kMaxChunks, kTileFrames));
+    const int chunks = (int)((T + chunk - 1) / chunk);
+    st = ensure_units(chunks);
+    if (st != FA_OK) return st;
+    st = ensure_events(2 * (size_t)chunks);
+    if (st != FA_OK) return st;
+    cudaStream_t s_in = streams[0], s_k = streams[1], s_out = streams[2];
+    for (int c = 0; c < chunks; ++c) {
+        const long long fb = c * chunk, fc = std::min(chunk, T - fb);
+        h_units[c] = MelUnit{0, n, 0, Tp, fb, fc, last, 0};
+    }
+    FA_CUDA_TRY(cudaMemcpyAsync(d_units, h_units, chunks * sizeof(MelUnit), cudaMemcpyHostToDevice, s_k));
+    if (Tp > T) FA_CUDA_TRY(cudaMemsetAsync(d_out, 0, need * sizeof(float), s_k));
+    const long long pad = mode == 0 ? cfg.n_fft / 2 : 0;
+    long long copied = 0;
+    for (int c = 0; c < chunks; ++c) {
+        const long long f_end = h_units[c].frame_begin + h_units[c].frame_count;            // exclusive
+        long long s_end = std::min(n, (f_end - 1) * cfg.hop_length + kNfft - pad);          // samples needed so far
+        if (c == chunks - 1) s_end = n;
+        if (s_end > copied) {
+            FA_CUDA_TRY(cudaMemcpyAsync(d_audio + copied, audio + copied, (s_end - copied) * sizeof(float),
+                                        cudaMemcpyHostToDevice, s_in));
+            copied = s_end;
+        }
+        FA_CUDA_TRY(cudaEventRecord(events[2 * c], s_in));
+        FA_CUDA_TRY(cudaStreamWaitEvent(s_k, events[2 * c], 0));
+        st = launch(d_audio, d_out, c, 1, tiles_of(h_units[c].frame_count), mode, layout, s_k, true);
+        if (st != FA_OK) return st;
+        FA_CUDA_TRY(cudaEventRecord(events[2 * c + 1], s_k));
+        FA_CUDA_TRY(cudaStreamWaitEvent(s_out, events[2 * c + 1], 0));
+        const long long fb = h_units[c].frame_begin, fc = h_units[c].frame_count;
+        if (layout == 0) {
+            const long long rows = (c == chunks - 1) ? (Tp - fb) : fc;   // last unit also returns the zero pad rows
+            FA_CUDA_TRY(cudaMemcpyAsync(out + fb * cfg.n_mels, d_out + fb * cfg.n_mels, rows * cfg.n_mels * sizeof(float),
+                                        cudaMemcpyDeviceToHost, s_out));
+        } else {
+            const long long cols = (c == chunks - 1) ? (Tp - fb) : fc;
+            FA_CUDA_TRY(cudaMemcpy2DAsync(out + fb, Tp * sizeof(float), d_out + fb, Tp * sizeof(float),
+                                          cols * sizeof(float), cfg.n_mels, cudaMemcpyDeviceToHost, s_out));
+        }
+    }
+    FA_CUDA_TRY(cudaStreamSynchronize(s_out));
+    FA_CUDA_TRY(cudaStreamSynchronize(s_k));
+    return FA_OK;
+}
+
+// Batch of clips, host buffers: clips are grouped so that copies and kernels of successive groups overlap.
+int MelPlan::compute_batch_host(const float *audio, const long long *offsets, int count, const float *last, int mode,
+                                int layout, float *out, const long long *out_offsets, long long *mel_lengths,
+                                long long *num_frames) {
+    if (count <= 0) return FA_OK;
+    // device-side packing: clip i starts at a 4-float aligned offset so that every tile can use the TMA path
+    std::vector<long long> doff(count + 1), dout(count + 1);
+    long long a = 0, o = 0;
+    std::vector<long long> Ts(count), Tps(count);
+    for (int i = 0; i < count; ++i) {
+        const long long n = offsets[i + 1] - offsets[i];
+        doff[i] = a;
+        a += ceil_to(n, 4) + 4;
+        dout[i] = o;
+        long long T, Tp;
+        if (!shape_of(*this, n, mode, -1, T, Tp)) {
+            Ts[i] = 0;
+            Tps[i] = 0;
+            o += cfg.n_mels;
+        } else {
+            Ts[i] = T;
+            Tps[i] = Tp;
+            o += Tp * cfg.n_mels;
+        }
+    }
+    doff[count] = a;
+    dout[count] = o;
+    int st = ensure_staging((size_t)a + 8, (size_t)o);
+    if (st != FA_OK) return st;
+    st = ensure_units(count);
+    if (st != FA_OK) return st;
+    const int groups = std::min(count, 16);
+    st = ensure_events(2 * (size_t)groups);
+    if (st != FA_OK) return st;
+    cudaStream_t s_in = streams[0], s_k = streams[1], s_out = streams[2];
+    // all unit descriptors first (one small copy), then per group: H2D, kernel, D2H
+    std::vector<int> g_first(groups + 1), g_units(groups + 1, 0), g_tiles(groups, 0);
+    int used = 0;
+    for (int g = 0; g < groups; ++g) {
+        const int c0 = (int)((long long)count * g / groups), c1 = (int)((long long)count * (g + 1) / groups);
+        g_first[g] = used;
+        int tiles = 0;
+        for (int i = c0; i < c1; ++i) {
+            if (mel_lengths) mel_lengths[i] = Ts[i];
+            if (num_frames) num_frames[i] = Ts[i] ? Tps[i] : (mode == 2 ? 0 : 1);
+            if (!Ts[i]) continue;
+            h_units[used] = MelUnit{doff[i], offsets[i + 1] - offsets[i], dout[i], Tps[i], 0, Ts[i], last ? last[i] : 0.0f, tiles};
+            tiles += tiles_of(Ts[i]);
+            ++used;
+        }
+        g_tiles[g] = tiles;
+    }
+    g_first[groups] = used;
+    if (used) FA_CUDA_TRY(cudaMemcpyAsync(d_units, h_units, used * sizeof(MelUnit), cudaMemcpyHostToDevice, s_k));
+    FA_CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)o * sizeof(float), s_k));
+    for (int g = 0; g < groups; ++g) {
+        const int c0 = (int)((long long)count * g / groups), c1 = (int)((long long)count * (g + 1) / groups);
+        for (int i = c0; i < c1; ++i) {
+            const long long n = offsets[i + 1] - offsets[i];
+            if (n > 0)
+                FA_CUDA_TRY(cudaMemcpyAsync(d_audio + doff[i], audio + offsets[i], n * sizeof(float), cudaMemcpyHostToDevice, s_in));
+        }
+        FA_CUDA_TRY(cudaEventRecord(events[2 * g], s_in));
+        FA_CUDA_TRY(cudaStreamWaitEvent(s_k, events[2 * g], 0));
+        st = launch(d_audio, d_out, g_first[g], g_first[g + 1] - g_first[g], g_tiles[g], mode, layout, s_k, true);
+        if (st != FA_OK) return st;
+        FA_CUDA_TRY(cudaEventRecord(events[2 * g + 1], s_k));
+        FA_CUDA_TRY(cudaStreamWaitEvent(s_out, events[2 * g + 1], 0));
+        for (int i = c0; i < c1; ++i) {
+            const long long len = dout[i + 1] - dout[i];
+            FA_CUDA_TRY(cudaMemcpyAsync(out + out_offsets[i], d_out + dout[i], len * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+        }
+    }
+    FA_CUDA_TRY(cudaStreamSynchronize(s_out));
+    FA_CUDA_TRY(cudaStreamSynchronize(s_k));
+    return FA_OK;
+}
+
+} // namespace mel
+} // namespace fa

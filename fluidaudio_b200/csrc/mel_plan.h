@@ -1,0 +1,118 @@
+// Host-side plan + launch descriptors of the fused log-mel kernel (see mel_kernels.cu).
+#pragma once
+
+#include "fa_common.cuh"
+#include <cuda_runtime.h>
+#include <vector>
+
+namespace fa {
+namespace mel {
+
+struct cpx;
+
+// Mirrors the parameters of AudioMelSpectrogram.init (AudioMelSpectrogram.swift:59-70).
+struct MelConfig {
+    int32_t sample_rate;
+    int32_t n_mels;
+    int32_t n_fft;
+    int32_t hop_length;
+    int32_t win_length;
+    float preemph;
+    int32_t pad_to;
+    float log_floor;
+    int32_t log_floor_mode;    // 0 additive log(x + floor), 1 clamped log(max(x, floor))
+    int32_t window_periodic;
+};
+
+// One unit of work = a run of frames of one clip.  A long clip is cut into several units so that H2D copies,
+// kernels and D2H copies of successive units overlap; a batch of clips is simply many units in one launch.
+struct MelUnit {
+    long long audio_off;     // float offset of the clip's sample 0 inside the audio buffer (multiple of 4 for TMA)
+    long long n;             // samples in the clip
+    long long out_off;       // float offset of the clip's output inside the output buffer
+    long long out_stride;    // mel-major layout: row stride (= padded frame count); unused for time-major
+    long long frame_begin;   // first frame of this unit
+    long long frame_count;   // frames in this unit
+    float last;              // lastAudioSample (pre-emphasis state), x[-1]
+    int tile_begin;          // first tile index of this unit inside its launch
+};
+
+struct MelLaunch {
+    const float *audio;
+    float *out;
+    const MelUnit *units;
+    int num_units;
+    int total_tiles;
+    int hop;
+    int pad;            // audio index of buffer position j of frame f is f*hop + j - pad
+    float preemph;
+    int n_mels;
+    float log_floor;
+    int log_clamped;
+    int layout;         // 0 time-major [T x nMels], 1 mel-major [nMels x stride]
+    const float *win_tab;
+    const uint8_t *in_tab;
+    const cpx *tw256;
+    const cpx *tw512;
+    const float *fb_w;
+    const int *fb_lo;
+    const int *fb_hi;
+    const int *fb_off;
+    int fb_nnz, fb_cap;
+    int pt_len, pt_cap, raw_cap;
+    int use_tma;
+};
+
+struct MelPlan {
+    MelConfig cfg{};
+    std::vector<float> window;       // [win]
+    std::vector<float> filterbank;   // [n_mels x 257] dense, as the reference exposes it (getFilterbank)
+    int fb_nnz = 0, fb_cap = 0;
+    int pt_len = 0, pt_cap = 0, raw_cap = 0;
+    size_t smem_bytes = 0;
+    int num_sms = 0;
+    long long launches = 0;          // kernels launched through this plan (bench.py reports it)
+
+    float *d_win_tab_mode[2] = {nullptr, nullptr};
+    uint8_t *d_in_tab_mode[2] = {nullptr, nullptr};
+    cpx *d_tw256 = nullptr, *d_tw512 = nullptr;
+    float *d_fb_w = nullptr;
+    int *d_fb_lo = nullptr, *d_fb_hi = nullptr, *d_fb_off = nullptr;
+
+    MelUnit *d_units = nullptr, *h_units = nullptr;
+    int units_cap = 0;
+    float *d_audio = nullptr, *d_out = nullptr;   // staging for the host-buffer entry points
+    size_t d_audio_cap = 0, d_out_cap = 0;
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};   // h2d, compute, d2h
+    std::vector<cudaEvent_t> events;
+
+    ~MelPlan();
+    void release();
+    int init(const MelConfig &c);
+    long long frame_count(long long n, int mode, long long expected) const;
+    int ensure_units(int count);
+    int ensure_staging(size_t audio_floats, size_t out_floats);
+    int ensure_events(size_t count);
+    // kernel launch over units [first, first+count) already resident in d_units
+    int launch(const float *d_audio_base, float *d_out_base, int first, int count, int total_tiles, int mode,
+               int layout, cudaStream_t stream, bool aligned16);
+
+    // mode: 0 .center, 1 .prePadded, 2 legacy compute(); layout: 0 time-major, 1 mel-major
+    int compute_device(const float *d_in, long long n, float last, int mode, long long expected, int layout,
+                       float *d_out_buf, long long out_len, long long *mel_length, long long *num_frames,
+                       cudaStream_t stream);
+    int compute_host(const float *audio, long long n, float last, int mode, long long expected, int layout,
+                     float *out, long long out_len, long long *mel_length, long long *num_frames);
+    int compute_batch_host(const float *audio, const long long *offsets, int count, const float *last, int mode,
+                           int layout, float *out, const long long *out_offsets, long long *mel_lengths,
+                           long long *num_frames);
+    int compute_batch_device(const float *d_in, const long long *offsets, int count, const float *last, int mode,
+                             int layout, float *d_out_buf, const long long *out_offsets, long long *mel_lengths,
+                             long long *num_frames, cudaStream_t stream);
+};
+
+void build_window(int length, bool periodic, std::vector<float> &w);
+void build_filterbank(int n_fft, int n_mels, int sample_rate, std::vector<float> &fb);
+
+} // namespace mel
+} // namespace fa

@@ -1,0 +1,172 @@
+"""Host-side mirror of ``AudioMelSpectrogram`` (Sources/FluidAudio/Shared/AudioMelSpectrogram.swift:18-121).
+
+Same constructor parameters, same three entry points (``compute`` :132, ``compute_flat`` :185,
+``compute_flat_transposed`` :299/:325), same return tuples, same "empty" guards, same non-thread-safety
+(one instance per stream of calls).  All arithmetic happens in the sm_100a kernel behind ``fa_mel_*``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import _lib
+
+
+class PaddingMode(enum.IntEnum):
+    center = 0        # AudioMelSpectrogram.PaddingMode.center
+    pre_padded = 1    # .prePadded
+
+
+class LogFloorMode(enum.IntEnum):
+    additive = 0
+    clamped = 1
+
+
+_TIME_MAJOR, _MEL_MAJOR = 0, 1
+_LEGACY = 2
+
+
+class AudioMelSpectrogram:
+    def __init__(self, sample_rate: int = 16000, n_mels: int = 128, n_fft: int = 512, hop_length: int = 160,
+                 win_length: int = 400, preemph: float = 0.97, pad_to: int = 0, log_floor: float = 2.0 ** -24,
+                 log_floor_mode: LogFloorMode = LogFloorMode.additive, window_periodic: bool = False):
+        self.sample_rate, self.n_mels, self.n_fft = sample_rate, n_mels, n_fft
+        self.hop_length, self.win_length, self.preemph = hop_length, win_length, preemph
+        self.pad_to = max(1, pad_to)
+        self._L = _lib.load()
+        cfg = _lib.MelConfig(sample_rate, n_mels, n_fft, hop_length, win_length, preemph, pad_to, log_floor,
+                             int(log_floor_mode), int(bool(window_periodic)))
+        h = C.c_void_p()
+        _lib.check(self._L.fa_mel_create(C.byref(cfg), C.byref(h)), "fa_mel_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._L.fa_mel_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- debug getters (:486-493) ---------------------------------------------------------------------------
+    def get_hann_window(self) -> np.ndarray:
+        out = np.zeros(self.win_length, np.float32)
+        _lib.check(self._L.fa_mel_get_window(self._h, out.ctypes.data, out.size), "fa_mel_get_window")
+        return out
+
+    def get_filterbank(self) -> np.ndarray:
+        out = np.zeros((self.n_mels, self.n_fft // 2 + 1), np.float32)
+        _lib.check(self._L.fa_mel_get_filterbank(self._h, out.ctypes.data, out.size), "fa_mel_get_filterbank")
+        return out
+
+    def frame_count(self, sample_count: int, padding_mode: int = PaddingMode.center, expected=None) -> int:
+        return int(self._L.fa_mel_frame_count(self._h, sample_count, int(padding_mode),
+                                              -1 if expected is None else int(expected)))
+
+    # ---- host-buffer entry points ---------------------------------------------------------------------------
+    def _run(self, audio, last, mode, expected, layout, out=None):
+        audio = np.ascontiguousarray(audio, np.float32)
+        n = audio.size
+        T = self.frame_count(n, mode, None if mode == _LEGACY else expected)
+        empty = T <= 0 or n == 0
+        Tp = 1 if empty else (T if mode == _LEGACY else -(-T // self.pad_to) * self.pad_to)
+        need = self.n_mels * Tp
+        if out is None:
+            out = np.empty(need, np.float32)
+        elif out.size < need:
+            raise ValueError(f"output buffer too small: need {need} floats")
+        ml, nf = C.c_int64(), C.c_int64()
+        _lib.check(self._L.fa_mel_compute(self._h, _lib.ptr(audio) if n else None, n, float(last), int(mode),
+                                          -1 if expected is None else int(expected), layout, out.ctypes.data,
+                                          out.size, C.byref(ml), C.byref(nf)), "fa_mel_compute")
+        return out, int(ml.value), int(nf.value)
+
+    def compute(self, audio):
+        """``compute(audio:)`` → (mel [1, nMels, T], melLength).  No pre-emphasis, no centre padding."""
+        out, ml, _ = self._run(audio, 0.0, _LEGACY, None, _MEL_MAJOR)
+        if ml == 0:
+            return np.zeros((0,), np.float32), 0
+        return out[: self.n_mels * ml].reshape(1, self.n_mels, ml), ml
+
+    def compute_flat(self, audio, last_audio_sample: float = 0.0):
+        """``computeFlat`` → (mel flat [nMels * numFrames] mel-major, melLength, numFrames)."""
+        out, ml, nf = self._run(audio, last_audio_sample, PaddingMode.center, None, _MEL_MAJOR)
+        return out[: self.n_mels * nf], ml, nf
+
+    def compute_flat_transposed(self, audio, last_audio_sample: float = 0.0,
+                                padding_mode: PaddingMode = PaddingMode.center, expected_frame_count=None, out=None):
+        """``computeFlatTransposed`` → (mel flat [numFrames * nMels] time-major, melLength, numFrames)."""
+        out, ml, nf = self._run(audio, last_audio_sample, padding_mode, expected_frame_count, _TIME_MAJOR, out)
+        return out[: self.n_mels * nf], ml, nf
+
+    # ---- batch of independent clips (BASELINE config 4) -------------------------------------------------------
+    def compute_batch(self, clips, last_samples=None, padding_mode: PaddingMode = PaddingMode.center,
+                      time_major: bool = True, packed_audio=None, offsets=None, out=None):
+        """``clips``: list of float32 arrays (or pass ``packed_audio`` + ``offsets``).  Returns
+        (out flat float32, out_offsets int64 [count+1], mel_lengths int64, num_frames int64)."""
+        if packed_audio is None:
+            clips = [np.ascontiguousarray(c, np.float32).reshape(-1) for c in clips]
+            offsets = np.zeros(len(clips) + 1, np.int64)
+            offsets[1:] = np.cumsum([c.size for c in clips])
+            packed_audio = np.concatenate(clips) if clips else np.zeros(0, np.float32)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        count = offsets.size - 1
+        out_offsets = np.zeros(count + 1, np.int64)
+        for i in range(count):
+            n = int(offsets[i + 1] - offsets[i])
+            T = self.frame_count(n, padding_mode)
+            Tp = 1 if (T <= 0 or n == 0) else -(-T // self.pad_to) * self.pad_to
+            out_offsets[i + 1] = out_offsets[i] + Tp * self.n_mels
+        if out is None:
+            out = np.empty(int(out_offsets[-1]), np.float32)
+        ml = np.zeros(count, np.int64)
+        nf = np.zeros(count, np.int64)
+        last = None if last_samples is None else np.ascontiguousarray(last_samples, np.float32)
+        _lib.check(self._L.fa_mel_compute_batch(self._h, packed_audio.ctypes.data, offsets.ctypes.data, count,
+                                                _lib.ptr(last), int(padding_mode), 0 if time_major else 1,
+                                                out.ctypes.data, out_offsets.ctypes.data, ml.ctypes.data,
+                                                nf.ctypes.data), "fa_mel_compute_batch")
+        return out, out_offsets, ml, nf
+
+    # ---- device-resident entry point (kernel-only timing, pipelines that keep audio in HBM) -------------------
+    def compute_device(self, d_audio: "_lib.DeviceBuffer", sample_count: int, d_out: "_lib.DeviceBuffer",
+                       last_audio_sample: float = 0.0, padding_mode: PaddingMode = PaddingMode.center,
+                       expected_frame_count=None, time_major: bool = True):
+        ml, nf = C.c_int64(), C.c_int64()
+        _lib.check(self._L.fa_mel_compute_device(self._h, d_audio.ptr, sample_count, float(last_audio_sample),
+                                                 int(padding_mode),
+                                                 -1 if expected_frame_count is None else int(expected_frame_count),
+                                                 0 if time_major else 1, d_out.ptr, d_out.nbytes // 4,
+                                                 C.byref(ml), C.byref(nf)), "fa_mel_compute_device")
+        return int(ml.value), int(nf.value)
+
+    def compute_batch_device(self, d_audio, offsets, d_out, out_offsets, padding_mode=PaddingMode.center,
+                             time_major: bool = True):
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        out_offsets = np.ascontiguousarray(out_offsets, np.int64)
+        count = offsets.size - 1
+        ml = np.zeros(count, np.int64)
+        nf = np.zeros(count, np.int64)
+        _lib.check(self._L.fa_mel_compute_batch_device(self._h, d_audio.ptr, offsets.ctypes.data, count, None,
+                                                       int(padding_mode), 0 if time_major else 1, d_out.ptr,
+                                                       out_offsets.ctypes.data, ml.ctypes.data, nf.ctypes.data),
+                   "fa_mel_compute_batch_device")
+        return ml, nf
+
+
+def normalize_per_feature(mel_time_major: np.ndarray, valid_frames: int) -> np.ndarray:
+    """UnifiedMelExtractor.normalizePerFeature (UnifiedMelExtractor.swift:88-113) on a [frames x nMels] array."""
+    x = np.ascontiguousarray(mel_time_major, np.float32).copy()
+    _lib.check(_lib.load().fa_mel_normalize_per_feature(x.ctypes.data, x.shape[0], x.shape[1], int(valid_frames)),
+               "fa_mel_normalize_per_feature")
+    return x
+
+
+def to_channel_major(mel_time_major: np.ndarray) -> np.ndarray:
+    """NemotronMelExtractor.melSpectrogram's [T x M] → [1, M, T] re-layout (NemotronMelExtractor.swift:44-67)."""
+    return np.ascontiguousarray(mel_time_major.T)[None]

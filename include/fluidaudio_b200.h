@@ -1,0 +1,183 @@
+/* fluidaudio_b200 — C ABI of the B200-native (sm_100a) implementation of FluidAudio's two CPU hot paths.
+ *
+ * Every entry point is what a Swift/cgo/ctypes FFI binding for that piece of the reference would bind:
+ * plain pointers and sizes, caller-owned buffers, an int status, no exception ever crosses the boundary
+ * (same conventions as the reference's only C boundary, Sources/FastClusterWrapper/include/FastClusterWrapper.h).
+ * There is NO CPU fallback: without an sm_100a device every compute call returns FA_NO_DEVICE.
+ *
+ * Reference interfaces replaced (paths relative to the FluidAudio repository):
+ *   fa_mel_*             Sources/FluidAudio/Shared/AudioMelSpectrogram.swift:18-121 (class + init),
+ *                        :132 compute, :185 computeFlat, :299/:325 computeFlatTransposed, :486-493 getters
+ *   fa_linear_resample   Sources/FluidAudio/Shared/AudioConverter.swift:388-442 (linearResample)
+ *   fa_l2_normalize_rows Sources/FluidAudio/Diarizer/Offline/Clustering/AHCClustering.swift:70-105
+ *   fastcluster_compute_centroid_linkage  (declared in FastClusterWrapper.h, same symbol as the reference)
+ *   fa_ahc_cluster       AHCClustering.swift:20-67  (AHCClustering.cluster)
+ *   fa_dendrogram_cut    AHCClustering.swift:112-121,124-210
+ *   fa_vbx_refine        Sources/FluidAudio/Diarizer/Offline/Clustering/VBxClustering.swift:41-165 (refine)
+ *   fa_compute_centroids Sources/FluidAudio/Diarizer/Offline/Core/OfflineDiarizerManager.swift:613-691
+ *   fa_assign_embeddings OfflineDiarizerManager.swift:789-822
+ *   fa_diarize_cluster   OfflineDiarizerManager.swift:270-384 (cluster(_:), clustering phase)
+ */
+#ifndef FLUIDAUDIO_B200_H
+#define FLUIDAUDIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    FA_STATUS_OK = 0,
+    FA_STATUS_INVALID_ARGUMENT = 1,
+    FA_STATUS_INDEX_OVERFLOW = 2,
+    FA_STATUS_OUTPUT_TOO_SMALL = 3,
+    FA_STATUS_ALLOCATION_FAILURE = 4,
+    FA_STATUS_RUNTIME_ERROR = 5,   /* e.g. NaN distance, as the reference's nan_error */
+    FA_STATUS_NO_DEVICE = 6,       /* no sm_100a GPU visible: there is deliberately no CPU fallback */
+    FA_STATUS_CUDA_ERROR = 7,
+    FA_STATUS_UNSUPPORTED = 8,
+    FA_STATUS_UNKNOWN_ERROR = 255
+} fa_status;
+
+/* ---- runtime ------------------------------------------------------------------------------------------- */
+const char *fa_version(void);
+const char *fa_last_error(void);            /* thread-local text of the last failure */
+int32_t fa_device_count(void);              /* sm_100a devices visible */
+fa_status fa_set_device(int32_t ordinal);   /* binds the calling thread; one process per GPU is the intended use */
+fa_status fa_device_synchronize(void);
+int64_t fa_kernel_launch_count(void);       /* kernels this library has launched in this process */
+
+/* Pinned host memory and device memory for callers that want the copy engines / resident buffers. */
+fa_status fa_host_alloc(size_t bytes, void **out);
+fa_status fa_host_free(void *p);
+fa_status fa_device_alloc(size_t bytes, void **out);
+fa_status fa_device_free(void *p);
+fa_status fa_memcpy_h2d(void *dst_device, const void *src_host, size_t bytes);
+fa_status fa_memcpy_d2h(void *dst_host, const void *src_device, size_t bytes);
+
+/* Device-side timing of a region on the library's default stream (CUDA events). */
+fa_status fa_timer_start(void);
+fa_status fa_timer_stop_ms(float *elapsed_ms);
+
+/* ---- log-mel frontend ---------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t sample_rate;     /* 16000 */
+    int32_t n_mels;          /* 128 (reference default); 80 in BASELINE config 2 */
+    int32_t n_fft;           /* 512 */
+    int32_t hop_length;      /* 160 */
+    int32_t win_length;      /* 400 */
+    float preemph;           /* 0.97 */
+    int32_t pad_to;          /* 0 -> 1 */
+    float log_floor;         /* 2^-24 */
+    int32_t log_floor_mode;  /* 0 = additive log(x+floor), 1 = clamped log(max(x,floor)) */
+    int32_t window_periodic; /* 0 = symmetric Hann, 1 = periodic */
+} fa_mel_config;
+
+enum { FA_MEL_PAD_CENTER = 0, FA_MEL_PAD_PREPADDED = 1, FA_MEL_LEGACY_COMPUTE = 2 };
+enum { FA_MEL_TIME_MAJOR = 0 /* [T x nMels], computeFlatTransposed */, FA_MEL_MEL_MAJOR = 1 /* [nMels x T], computeFlat / compute */ };
+
+typedef struct fa_mel fa_mel;   /* one handle per stream of calls: like the Swift class it is not thread-safe */
+
+void fa_mel_default_config(fa_mel_config *cfg);
+fa_status fa_mel_create(const fa_mel_config *cfg, fa_mel **out);
+void fa_mel_destroy(fa_mel *mel);
+fa_status fa_mel_get_window(const fa_mel *mel, float *out, size_t len);       /* getHannWindow(): win_length floats */
+fa_status fa_mel_get_filterbank(const fa_mel *mel, float *out, size_t len);   /* getFilterbank(): n_mels x (n_fft/2+1) */
+/* frames the reference would produce; expected_frames < 0 means nil */
+int64_t fa_mel_frame_count(const fa_mel *mel, int64_t sample_count, int32_t padding_mode, int64_t expected_frames);
+
+/* Host buffers in and out (the drop-in call).  On return *mel_length = valid frames, *num_frames = padded frames;
+ * out receives num_frames*n_mels floats in `layout`.  Mirrors computeFlatTransposed / computeFlat / compute. */
+fa_status fa_mel_compute(fa_mel *mel, const float *audio, size_t sample_count, float last_audio_sample,
+                         int32_t padding_mode, int64_t expected_frames, int32_t layout, float *out, size_t out_len,
+                         int64_t *mel_length, int64_t *num_frames);
+/* Same with buffers already resident in HBM (asynchronous on the library stream). */
+fa_status fa_mel_compute_device(fa_mel *mel, const float *d_audio, size_t sample_count, float last_audio_sample,
+                                int32_t padding_mode, int64_t expected_frames, int32_t layout, float *d_out,
+                                size_t out_len, int64_t *mel_length, int64_t *num_frames);
+/* Batch of independent clips.  Clip i is audio[offsets[i] .. offsets[i+1]); its output starts at out_offsets[i]
+ * and holds num_frames[i]*n_mels floats (use fa_mel_frame_count to size it).  last_samples may be NULL. */
+fa_status fa_mel_compute_batch(fa_mel *mel, const float *audio, const int64_t *offsets, int32_t clip_count,
+                               const float *last_samples, int32_t padding_mode, int32_t layout, float *out,
+                               const int64_t *out_offsets, int64_t *mel_lengths, int64_t *num_frames);
+fa_status fa_mel_compute_batch_device(fa_mel *mel, const float *d_audio, const int64_t *offsets, int32_t clip_count,
+                                      const float *last_samples, int32_t padding_mode, int32_t layout, float *d_out,
+                                      const int64_t *out_offsets, int64_t *mel_lengths, int64_t *num_frames);
+
+/* NeMo per-feature normalisation of a time-major [frames x n_mels] buffer, in place (host buffer).
+ * UnifiedMelExtractor.normalizePerFeature, Sources/FluidAudio/ASR/Parakeet/Unified/UnifiedMelExtractor.swift:88-113 */
+fa_status fa_mel_normalize_per_feature(float *x, int64_t frames, int32_t n_mels, int64_t valid_frames);
+
+/* AudioConverter.linearResample: planar [channels x frames] -> mono at out_rate.  Returns the sample count
+ * through *out_count; call with out == NULL to size the buffer. */
+fa_status fa_linear_resample(const float *planar, int64_t frames, int32_t channels, double in_rate, double out_rate,
+                             float *out, int64_t out_cap, int64_t *out_count);
+
+/* ---- offline clustering backend ------------------------------------------------------------------------ */
+fa_status fa_l2_normalize_rows(const double *x, size_t rows, size_t dim, double *out);
+
+/* AHCClustering.cluster: rows are NOT yet normalised; labels are canonical (first appearance order). */
+fa_status fa_ahc_cluster(const double *features, size_t count, size_t dim, double threshold, int32_t *labels);
+
+/* Swift-side dendrogram cut + relabel on a SciPy-format linkage Z [(count-1) x 4]. */
+fa_status fa_dendrogram_cut(const double *Z, size_t count, double threshold, int32_t *labels);
+
+typedef struct {
+    double Fa;               /* 0.07 */
+    double Fb;               /* 0.8 */
+    int32_t max_iterations;  /* 20 */
+    double epsilon;          /* 1e-4 */
+    double init_smoothing;   /* 7.0 */
+} fa_vbx_config;
+void fa_vbx_default_config(fa_vbx_config *cfg);
+
+/* VBxClustering.refine.  rho: T x D; psi: psi_len doubles (identity if psi_len != D); initial: T labels.
+ * speakers = number of distinct initial labels (the caller sizes gamma [T x speakers], pi [speakers],
+ * elbos [max(max_iterations,1)], hard [T]).  *iterations receives the number of EM iterations run. */
+fa_status fa_vbx_refine(const double *rho, size_t T, size_t D, const double *psi, size_t psi_len,
+                        const int32_t *initial, int32_t speakers, const fa_vbx_config *cfg, double *gamma,
+                        double *pi, double *elbos, int32_t *hard, int32_t *iterations);
+
+/* computeCentroids (gamma/pi weighted, speakers with pi > 1e-7).  centroids capacity speakers x dim.
+ * *centroid_count receives K. */
+fa_status fa_compute_centroids(const double *embeddings, size_t T, size_t dim, const double *gamma, const double *pi,
+                               int32_t speakers, double *centroids, int32_t *centroid_count);
+
+/* assignEmbeddings: cosine against every centroid, first maximum wins.  scores may be NULL (else N x K). */
+fa_status fa_assign_embeddings(const double *embeddings, size_t N, size_t dim, const double *centroids, int32_t K,
+                               int32_t *labels, double *scores);
+
+typedef struct {
+    double threshold;        /* 0.6  OfflineDiarizerConfig.clusteringThreshold */
+    fa_vbx_config vbx;       /* warmStartFa/Fb, VBx.maxIterations, convergenceTolerance */
+} fa_cluster_config;
+void fa_cluster_default_config(fa_cluster_config *cfg);
+
+typedef struct {
+    int32_t training_count;    /* embeddings that survived the NaN/Inf filter */
+    int32_t initial_clusters;  /* AHC cluster count (= VBx speaker count S) */
+    int32_t vbx_iterations;
+    int32_t centroid_count;    /* K */
+    float ms_normalize, ms_ahc, ms_cut, ms_vbx, ms_assign, ms_total;   /* device/host stage times */
+} fa_cluster_info;
+
+/* OfflineDiarizerManager.cluster(_:) lines 286-375 (unconstrained argmax assignment):
+ *   emb256: N x emb_dim float32; rho: N x rho_dim float64; psi: rho_dim.  labels: N final assignments.
+ * Optional outputs (may be NULL): initial [N] AHC labels of the training rows (-1 for filtered rows),
+ * centroids [max_centroids x emb_dim], info. */
+fa_status fa_diarize_cluster(const float *emb256, const double *rho, size_t N, size_t emb_dim, size_t rho_dim,
+                             const double *psi, const fa_cluster_config *cfg, int32_t *labels, int32_t *initial,
+                             double *centroids, int32_t max_centroids, fa_cluster_info *info);
+
+/* Many independent embedding sets (meetings) on this GPU.  Set m is rows [set_offsets[m], set_offsets[m+1]).
+ * Several sets are clustered concurrently on disjoint SM partitions. */
+fa_status fa_diarize_cluster_batch(const float *emb256, const double *rho, const int64_t *set_offsets,
+                                   int32_t set_count, size_t emb_dim, size_t rho_dim, const double *psi,
+                                   const fa_cluster_config *cfg, int32_t *labels, fa_cluster_info *infos);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUIDAUDIO_B200_H */

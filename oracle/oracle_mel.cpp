@@ -19,10 +19,13 @@
 // mat-vec, cos/log/exp come from Apple Accelerate / libm (closed).  This restatement is therefore the
 // oracle by construction: every operation is done in IEEE float32 in the order the Swift source states;
 // where the Swift delegates to a closed library the mathematically defined operation is used
-// (DFT = radix-2 Cooley-Tukey in float32 with double-precision-rounded twiddles; mat-vec = sequential
-// float32 accumulation in bin order; vDSP_vsma = fused multiply-add).  A float64 evaluation of the same
-// pipeline (precision=1) is provided so tests can measure both the oracle's and the GPU's distance from
-// exact arithmetic.  "Parity pinned" only for structure: frame counts, shapes, window/filterbank
+// (mat-vec = sequential float32 accumulation in bin order; vDSP_vsma = fused multiply-add).  The DFT is the one
+// place where "the reference's float32 algorithm" cannot be restated (vDSP_DFT_zop is closed): the oracle
+// therefore uses the implementation-independent definition — the DFT of the float32 frame evaluated in
+// float64 and rounded ONCE to float32 (precision = 0), which every float32 FFT, vDSP's included, approximates
+// to within its own rounding noise.  Two more evaluations are provided so that tests can report the spread:
+// precision = 2 runs a float32 radix-2 Cooley-Tukey instead (a second, independent float32 FFT), precision = 1
+// runs the whole pipeline in float64 (distance from exact arithmetic).  "Parity pinned" only for structure: frame counts, shapes, window/filterbank
 // properties (AudioMelSpectrogramTests.swift, EouChunkSizeFrameCountTests.swift).
 
 #include <cmath>
@@ -44,7 +47,8 @@ struct oracle_mel_config {
     float   log_floor;       // 2^-24
     int32_t log_floor_mode;  // 0 additive, 1 clamped
     int32_t window_periodic; // 0 symmetric, 1 periodic
-    int32_t precision;       // 0 = float32 pipeline (the oracle), 1 = float64 evaluation (error budget only)
+    int32_t precision;       // 0 = float32 pipeline, DFT correctly rounded (THE oracle); 1 = all float64;
+                             // 2 = float32 pipeline with a float32 radix-2 FFT (spread indicator)
 };
 
 // Swift's Float.pi is pi rounded TOWARD ZERO (0x40490FDA), not to nearest.
@@ -204,6 +208,8 @@ struct MelCore {
     std::vector<float> window;
     std::vector<float> fb;
     Fft<T> fft;
+    Fft<double> fft_exact;
+    std::vector<double> dframe, dre, dim;
     std::vector<T> frame, re, im, power;
 
     explicit MelCore(const oracle_mel_config &cfg) : c(cfg) {
@@ -213,6 +219,12 @@ struct MelCore {
         fb.resize((size_t)c.n_mels * bins);
         oracle_mel_filterbank(c.n_fft, c.n_mels, c.sample_rate, fb.data());
         fft.init(c.n_fft);
+        if (sizeof(T) == 4 && c.precision == 0) {
+            fft_exact.init(c.n_fft);
+            dframe.assign(c.n_fft, 0);
+            dre.assign(c.n_fft, 0);
+            dim.assign(c.n_fft, 0);
+        }
         frame.assign(c.n_fft, 0);
         re.assign(c.n_fft, 0);
         im.assign(c.n_fft, 0);
@@ -226,7 +238,16 @@ struct MelCore {
     // frame[] already filled.  Writes n_mels log values through `store(m, value)`.
     template <typename Store>
     void finish_frame(Store store) {
-        fft.forward_real(frame.data(), re.data(), im.data());
+        if (sizeof(T) == 4 && c.precision == 0) {
+            for (int i = 0; i < c.n_fft; ++i) dframe[i] = (double)frame[i];
+            fft_exact.forward_real(dframe.data(), dre.data(), dim.data());
+            for (int b = 0; b < bins; ++b) {
+                re[b] = (T)dre[b];   // single rounding to float32
+                im[b] = (T)dim[b];
+            }
+        } else {
+            fft.forward_real(frame.data(), re.data(), im.data());
+        }
         for (int b = 0; b < bins; ++b) power[b] = re[b] * re[b] + im[b] * im[b];
         for (int m = 0; m < c.n_mels; ++m) {
             T acc = 0;

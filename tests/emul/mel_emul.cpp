@@ -1,0 +1,72 @@
+// Host lane-emulator for fluidaudio_b200/csrc/mel_core.cuh (CPU test-suite only).
+// Runs the exact per-lane functions the CUDA kernel runs, one lane at a time, phase by phase, for every
+// frame of a clip, so the index math / twiddles / bank layout of the device code is checked without a GPU.
+//   extern "C" int mel_emul(audio, n, last, hop, win, off, pad, preemph, n_mels, fb[n_mels*257],
+//                           window[win], log_floor, clamped, T, out[T*n_mels])
+#include "../../fluidaudio_b200/csrc/mel_core.cuh"
+#include <cmath>
+#include <vector>
+#include <cstring>
+
+using namespace fa::mel;
+
+extern "C" int mel_emul(const float *audio, long long n, float last, int hop, int win, int off, int pad, float preemph,
+                        int n_mels, const float *fb, const float *window, float log_floor, int clamped, long long T,
+                        float *out) {
+    if (hop & 1) return 1;
+    std::vector<float> win_tab(kNfft, 0.0f);
+    std::vector<uint8_t> in_tab(kNfft, 0);
+    for (int j = 0; j < kNfft; ++j)
+        if (j >= off && j < off + win) {
+            win_tab[j] = window[j - off];
+            in_tab[j] = 1;
+        }
+    std::vector<cpx> tw256(256), tw512(256);
+    for (int k = 0; k < 256; ++k) {
+        tw256[k] = {(float)std::cos(2.0 * M_PI * k / 256.0), (float)-std::sin(2.0 * M_PI * k / 256.0)};
+        tw512[k] = {(float)std::cos(2.0 * M_PI * k / 512.0), (float)-std::sin(2.0 * M_PI * k / 512.0)};
+    }
+    std::vector<LaneTables> tabs(32);
+    for (int l = 0; l < 32; ++l) load_lane_tables(l, win_tab.data(), in_tab.data(), tw256.data(), tw512.data(), tabs[l]);
+    // sparse filterbank ranges
+    std::vector<int> lo(n_mels), hi(n_mels);
+    for (int m = 0; m < n_mels; ++m) {
+        int a = kBins, b = 0;
+        for (int k = 0; k < kBins; ++k)
+            if (fb[(size_t)m * kBins + k] != 0.0f) {
+                a = std::min(a, k);
+                b = k + 1;
+            }
+        if (b == 0) a = 0;
+        lo[m] = a;
+        hi[m] = b;
+    }
+    alignas(16) float sre[kFftPad], sim[kFftPad];
+    alignas(16) float pf[kNfft + 8];
+    std::vector<float> prow(kBins);
+    for (long long f = 0; f < T; ++f) {
+        for (int j = 0; j < kNfft; ++j) {
+            const long long i = f * hop + j - pad;
+            float v = 0.0f;
+            if (i >= 0 && i < n) {
+                if (preemph == 0.0f) v = audio[i];
+                else if (i == 0) v = preemph_first(audio[0], last, preemph);
+                else v = preemph_rest(audio[i], audio[i - 1], preemph);
+            }
+            pf[j] = v;
+        }
+        std::memset(sre, 0, sizeof(sre));
+        std::memset(sim, 0, sizeof(sim));
+        for (int l = 0; l < 32; ++l) pass1(l, pf, tabs[l], sre, sim);
+        for (int l = 0; l < 32; ++l) pass2(l, tabs[l], sre, sim);
+        float re[32][8], im[32][8];
+        for (int l = 0; l < 32; ++l) pass3_load(l, sre, sim, re[l], im[l]);
+        for (int l = 0; l < 32; ++l) pass3_store(l, re[l], im[l], sre, sim);
+        for (int l = 0; l < 32; ++l) post_power(l, sre, sim, tabs[l], prow.data());
+        for (int m = 0; m < n_mels; ++m) {
+            const float acc = mel_dot(prow.data(), fb + (size_t)m * kBins + lo[m], lo[m], hi[m]);
+            out[f * n_mels + m] = log_value(acc, log_floor, clamped);
+        }
+    }
+    return 0;
+}
