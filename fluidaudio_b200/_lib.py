@@ -56,7 +56,8 @@ EXPORTED_SYMBOLS = [
     "fa_mel_compute_device", "fa_mel_compute_batch", "fa_mel_compute_batch_device", "fa_mel_normalize_per_feature",
     "fa_linear_resample", "fa_l2_normalize_rows", "fa_ahc_cluster", "fa_dendrogram_cut", "fa_vbx_default_config",
     "fa_vbx_refine", "fa_compute_centroids", "fa_assign_embeddings", "fa_cluster_default_config",
-    "fa_diarize_cluster", "fa_diarize_cluster_batch", "fastcluster_compute_centroid_linkage",
+    "fa_diarize_cluster", "fa_diarize_cluster_batch", "fa_ahc_last_stage_ms",
+    "fastcluster_compute_centroid_linkage",
 ]
 
 _lib = None
@@ -113,6 +114,8 @@ def load():
     L.fa_diarize_cluster.argtypes = [vp, vp, sz, sz, sz, vp, C.POINTER(ClusterConfig), vp, vp, vp, i32,
                                      C.POINTER(ClusterInfo)]
     L.fa_diarize_cluster_batch.argtypes = [vp, vp, vp, i32, sz, sz, vp, C.POINTER(ClusterConfig), vp, vp]
+    L.fa_ahc_last_stage_ms.argtypes = [vp]
+    L.fa_ahc_last_stage_ms.restype = None
     L.fastcluster_compute_centroid_linkage.argtypes = [vp, sz, sz, vp, sz]
     L.fastcluster_compute_centroid_linkage.restype = C.c_int
     _lib = L

@@ -15,21 +15,24 @@
 namespace fa {
 namespace ahc {
 
-// Heap over elements identified by node id.  key[] is indexed by node id, at[] by heap position,
-// where[] by node id.  All arrays live in caller-provided memory (global memory on the device).
-struct NnHeap {
+// Heap over elements identified by SLOT (a slot holds one live node; a merged node inherits the slot of its first
+// parent, so "rename old -> new node" is a key update in place).  key[] and where[] are indexed by slot, at[] by
+// heap position.  The arrays live wherever the caller puts them: shared memory for the device master when they
+// fit (Idx = uint16_t, 12 bytes per slot), global memory otherwise, plain host memory for the heapify.
+template <typename Idx>
+struct NnHeapT {
     double *key;
-    int *at;
-    int *where;
+    Idx *at;
+    Idx *where;
     int size;
 
     FA_HD double val(int pos) const { return key[at[pos]]; }
     FA_HD void swap_pos(int a, int b) {
-        const int ea = at[a], eb = at[b];
+        const Idx ea = at[a], eb = at[b];
         at[a] = eb;
         at[b] = ea;
-        where[eb] = a;
-        where[ea] = b;
+        where[eb] = (Idx)a;
+        where[ea] = (Idx)b;
     }
     FA_HD void sift_up(int pos) {
         while (pos > 0) {
@@ -54,67 +57,66 @@ struct NnHeap {
             pos = child;
         }
     }
-    // identity layout over ids first..first+count-1, then Floyd heap construction
+    // identity layout over slots first..first+count-1, then Floyd heap construction
     FA_HD void build(int count, int first) {
         size = count;
         for (int i = 0; i < count; ++i) {
-            at[i] = i + first;
-            where[i + first] = i;
+            at[i] = (Idx)(i + first);
+            where[i + first] = (Idx)i;
         }
         for (int pos = size >> 1; pos > 0;) {
             --pos;
             sift_down(pos);
         }
     }
-    FA_HD int top() const { return at[0]; }
-    FA_HD void raise_key(int id, double v) {   // v >= old key
-        key[id] = v;
-        sift_down(where[id]);
+    FA_HD int top() const { return (int)at[0]; }
+    FA_HD void raise_key(int slot, double v) {   // v >= old key
+        key[slot] = v;
+        sift_down((int)where[slot]);
     }
-    FA_HD void lower_key(int id, double v) {   // v <= old key
-        key[id] = v;
-        sift_up(where[id]);
+    FA_HD void lower_key(int slot, double v) {   // v <= old key
+        key[slot] = v;
+        sift_up((int)where[slot]);
     }
-    FA_HD void erase(int id) {
+    // reference: binary_min_heap::replace(old, new, v) with old and new sharing a slot
+    FA_HD void replace_key(int slot, double v) {
+        if (v <= key[slot]) lower_key(slot, v); else raise_key(slot, v);
+    }
+    FA_HD void erase(int slot) {
         --size;
-        const int pos = where[id];
-        const int moved = at[size];
-        where[moved] = pos;
+        const int pos = (int)where[slot];
+        const Idx moved = at[size];
+        where[moved] = (Idx)pos;
         at[pos] = moved;
-        if (key[moved] <= key[id]) sift_up(pos); else sift_down(pos);
-    }
-    FA_HD void rename(int old_id, int new_id, double v) {
-        const int pos = where[old_id];
-        where[new_id] = pos;
-        at[pos] = new_id;
-        if (v <= key[old_id]) lower_key(new_id, v); else raise_key(new_id, v);
+        if (key[moved] <= key[slot]) sift_up(pos); else sift_down(pos);
     }
 };
 
-// Ascending list of live node ids 0..count-1 with O(1) unlink; next[id] == 0 marks a dead id.
-struct LiveList {
-    int *next;
-    int *prev;
+// Set of live node ids 0..count-1 as a bitmap; `head` is the smallest live id (the reference's
+// doubly_linked_list::start, fastcluster_internal.hpp:299-350 — only start / is_inactive / remove are needed by
+// the control plane, the ordered traversal is done by the scan kernels).
+struct LiveSet {
+    unsigned *bits;
+    int count;
     int head;
 
-    FA_HD void build(int count) {
-        head = 0;
-        for (int i = 0; i < count; ++i) {
-            prev[i + 1] = i;
-            next[i] = i + 1;
-        }
-    }
     FA_HD void drop(int id) {
+        bits[id >> 5] &= ~(1u << (id & 31));
         if (id == head) {
-            head = next[id];
-        } else {
-            const int p = prev[id], n = next[id];
-            next[p] = n;
-            prev[n] = p;
+            int w = id >> 5;
+            unsigned word = bits[w] & ~((2u << (id & 31)) - 1u);   // bits above id in the same word
+            const int words = (count + 31) >> 5;
+            while (word == 0u && ++w < words) word = bits[w];
+            if (word == 0u) {
+                head = count;
+            } else {
+                int b = 0;
+                while (!((word >> b) & 1u)) ++b;
+                head = (w << 5) + b;
+            }
         }
-        next[id] = 0;
     }
-    FA_HD bool dead(int id) const { return next[id] == 0; }
+    FA_HD bool dead(int id) const { return ((bits[id >> 5] >> (id & 31)) & 1u) == 0u; }
 };
 
 // (distance, node id) candidates are ordered lexicographically: the scan "first strict minimum in ascending id

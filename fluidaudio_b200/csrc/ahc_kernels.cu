@@ -151,9 +151,16 @@ __global__ void __launch_bounds__(kTI) ahc_init_nn_kernel(const double *__restri
     }
 }
 
-__global__ void ahc_init_reduce_kernel(const Cand *__restrict__ partial, int N, int ranges, double *key, int *nn) {
+__global__ void ahc_init_reduce_kernel(const Cand *__restrict__ partial, int N, int ranges, double *key, int *nn,
+                                       int *node_weight) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 1 || i >= N) return;
+    if (i >= N) return;
+    node_weight[i] = 1;
+    if (i < 1) {
+        key[0] = INFINITY;
+        nn[0] = 0;
+        return;
+    }
     double best = INFINITY;
     int arg = 0;   // reference initialises idx = 0 and min = +inf (fastcluster_internal.hpp:1654-1656)
     for (int r = 0; r < ranges; ++r) {
@@ -168,9 +175,30 @@ __global__ void ahc_init_reduce_kernel(const Cand *__restrict__ partial, int N, 
 }
 
 // ------------------------------------------------------------------------------------------------ merge loop
-constexpr int kMergeThreads = 256;
-constexpr int kMaxRounds = 8;
+constexpr int kMergeThreads = 128;
+constexpr int kMaxRounds = 16;    // streamed mode only: slots per thread
 enum { CMD_MERGE = 1, CMD_RESCAN = 2, CMD_EXIT = 3 };
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 ld_acquire_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(u64 *p, u64 v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 pack_cmd(int type, unsigned counter, int a, int b) {
+    return ((u64)type << 62) | ((u64)(counter & 0x3fffu) << 48) | ((u64)(unsigned)a << 24) | (u64)(unsigned)b;
+}
 
 __device__ __forceinline__ void cand_min(double &d, int &id, double od, int oid) {
     if (cand_less(od, oid, d, id)) {
@@ -179,42 +207,79 @@ __device__ __forceinline__ void cand_min(double &d, int &id, double od, int oid)
     }
 }
 
-__device__ void ahc_master(Problem &P, int W) {
+// Master: one warp of CTA 0.  Lane 0 runs the reference's control flow (fastcluster_internal.hpp:1685-1799);
+// the other lanes poll and fold the per-CTA candidates.  Heap, nearest-neighbour table, slot->node table and
+// live bitmap sit in shared memory: every ld.acquire of a polling loop invalidates this SM's L1, and a sift
+// through L2-resident arrays would cost ~100 dependent 300-cycle loads per step.
+template <typename Idx>
+__device__ void ahc_master(const Problem &P, int W, unsigned char *sm) {
     const int lane = threadIdx.x;
     const unsigned full = 0xffffffffu;
     const int N = P.N;
-    // live list and per-node bookkeeping, built by the whole warp
-    for (int i = lane; i < 2 * N - 1; i += 32) {
-        P.live_prev[i + 1] = i;
-        P.live_next[i] = i + 1;
-        if (i < N) {
-            P.weight[i] = 1;
-            P.slot_of[i] = i;
+    const int words = (2 * N - 1 + 31) >> 5;
+    double *key = P.key;
+    Idx *at = static_cast<Idx *>(P.heap_at), *where = static_cast<Idx *>(P.heap_where);
+    int *nn = P.nn, *node_of = P.node_of;
+    unsigned *bits = P.live_bits;
+    if (P.smem_level >= 1) {
+        size_t off = 0;
+        auto take = [&](size_t bytes) {
+            unsigned char *p = sm + off;
+            off = (off + bytes + 15) & ~size_t(15);
+            return p;
+        };
+        double *s_key = reinterpret_cast<double *>(take(sizeof(double) * N));
+        Idx *s_at = reinterpret_cast<Idx *>(take(sizeof(Idx) * N));
+        Idx *s_where = reinterpret_cast<Idx *>(take(sizeof(Idx) * N));
+        unsigned *s_bits = reinterpret_cast<unsigned *>(take(sizeof(unsigned) * words));
+        for (int i = lane; i < N; i += 32) {
+            s_key[i] = key[i];
+            s_where[i] = where[i];
+            if (i < N - 1) s_at[i] = at[i];
         }
+        for (int i = lane; i < words; i += 32) s_bits[i] = 0xffffffffu;
+        key = s_key;
+        at = s_at;
+        where = s_where;
+        bits = s_bits;
+        if (P.smem_level >= 2) {
+            int *s_nn = reinterpret_cast<int *>(take(sizeof(int) * N));
+            for (int i = lane; i < N; i += 32) s_nn[i] = nn[i];
+            nn = s_nn;
+        }
+        if (P.smem_level >= 3) {
+            int *s_node = reinterpret_cast<int *>(take(sizeof(int) * N));
+            for (int i = lane; i < N; i += 32) s_node[i] = i;
+            node_of = s_node;
+        }
+    } else {
+        for (int i = lane; i < words; i += 32) bits[i] = 0xffffffffu;
     }
+    if (P.smem_level < 3)
+        for (int i = lane; i < N; i += 32) node_of[i] = i;
+    for (int i = lane; i < N; i += 32) P.slot_of[i] = i;
     __syncwarp();
-    NnHeap heap{P.key, P.heap_at, P.heap_where, P.heap_size};
-    LiveList live{P.live_next, P.live_prev, 0};
-    unsigned seq = 0, arrivals = 0;
+
+    NnHeapT<Idx> heap{key, at, where, P.heap_size};
+    LiveSet live{bits, 2 * N - 1, 0};
+    unsigned counter = 0;
     bool failed = false;
 
-    auto publish = [&](const Command &c) {   // lane 0
-        *P.cmd = c;
-        st_release_u32(P.seq, ++seq);
+    auto publish = [&](int type, int a, int b) {   // lane 0
+        st_release_u64(P.cmd, pack_cmd(type, ++counter, a, b));
     };
-    auto collect = [&](double &d, int &id) {   // whole warp; result valid in every lane
-        arrivals += (unsigned)W;
-        if (lane == 0) {
-            while (ld_acquire_u32(P.arrive) < arrivals) {
-            }
-        }
-        __syncwarp();
+    auto collect = [&](unsigned tag, double &d, int &id) {   // whole warp; result valid in every lane
         d = INFINITY;
         id = INT_MAX;
+        bool bad = false;
         for (int w = lane; w < W; w += 32) {
-            const double od = __ldcg(&P.partial[w].d);
-            const int oid = __ldcg(&P.partial[w].id);
-            cand_min(d, id, od, oid);
+            u64 it;
+            do {
+                it = ld_acquire_u64(&P.results[w].id_tag);
+            } while ((unsigned)it != tag);
+            const int oid = (int)(it >> 32);
+            const double od = __longlong_as_double((long long)ld_relaxed_u64(&P.results[w].d_bits));
+            if (oid == -2) bad = true; else cand_min(d, id, od, oid);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -222,198 +287,234 @@ __device__ void ahc_master(Problem &P, int W) {
             const int oid = __shfl_xor_sync(full, id, o);
             cand_min(d, id, od, oid);
         }
-        if (__ldcg(P.error) != 0) failed = true;
+        if (__any_sync(full, bad)) failed = true;
     };
 
     for (int step = 0; step < N - 1 && !failed; ++step) {
         const int fresh = N + step;
-        int a = 0;
-        for (;;) {   // make sure the heap top has a live nearest neighbour (lazy repair, :1706-1734)
+        int sa = 0;   // slot of the heap top
+        for (;;) {    // lazy repair of a stale nearest neighbour (:1706-1734)
             int stale = 0;
             if (lane == 0) {
-                a = heap.top();
-                stale = live.dead(P.nn[a]) ? 1 : 0;
+                sa = heap.top();
+                stale = live.dead(nn[sa]) ? 1 : 0;
+                if (stale) publish(CMD_RESCAN, node_of[sa], 0);
             }
             stale = __shfl_sync(full, stale, 0);
-            a = __shfl_sync(full, a, 0);
             if (!stale) break;
-            if (lane == 0) {
-                Command c{};
-                c.type = CMD_RESCAN;
-                c.fresh = a;
-                c.limit = a;
-                c.slot_a = c.slot_b = -1;
-                publish(c);
-            }
+            counter = __shfl_sync(full, counter, 0);
             double d;
             int id;
-            collect(d, id);
+            collect(counter, d, id);
             if (failed) break;
             if (lane == 0) {
-                P.nn[a] = id;
-                heap.raise_key(a, d);
+                nn[sa] = id;
+                heap.raise_key(sa, d);
             }
             __syncwarp();
         }
         if (failed) break;
-        int b = 0;
+        int a = 0, b = 0, sb = 0;
         if (lane == 0) {
-            b = P.nn[a];
+            a = node_of[sa];
+            b = nn[sa];
+            if (step < N - 2) publish(CMD_MERGE, a, b);   // workers start while the bookkeeping below runs
             live.drop(a);
             live.drop(b);
             P.merge_a[step] = a;
             P.merge_b[step] = b;
-            P.merge_d[step] = P.key[a];
+            P.merge_d[step] = key[sa];
+            if (step < N - 2) {
+                sb = P.slot_of[b];
+                node_of[sa] = fresh;
+                node_of[sb] = -1;
+                P.slot_of[fresh] = sa;
+            }
         }
         if (step < N - 2) {
-            if (lane == 0) {
-                Command c{};
-                c.type = CMD_MERGE;
-                c.a = a;
-                c.b = b;
-                c.fresh = fresh;
-                c.slot_a = P.slot_of[a];
-                c.slot_b = P.slot_of[b];
-                c.limit = fresh;
-                c.wa = (double)P.weight[a];
-                c.wb = (double)P.weight[b];
-                publish(c);
-                P.weight[fresh] = P.weight[a] + P.weight[b];
-                P.slot_of[fresh] = P.slot_of[a];
-            }
+            counter = __shfl_sync(full, counter, 0);
             double d;
             int id;
-            collect(d, id);
+            collect(counter, d, id);
             if (failed) break;
             if (lane == 0) {
-                P.nn[fresh] = id;
-                if (b < live.head) heap.erase(live.head); else heap.erase(b);
-                heap.rename(a, fresh, d);
+                nn[sa] = id;
+                if (b < live.head) heap.erase(P.slot_of[live.head]); else heap.erase(sb);   // :1792-1796
+                heap.replace_key(sa, d);                                                    // :1797
             }
             __syncwarp();
         }
-        if (lane == 0) P.steps_done = step + 1;
     }
     if (lane == 0) {
-        Command c{};
-        c.type = CMD_EXIT;
-        publish(c);
+        if (failed) *P.error = 1;
+        publish(CMD_EXIT, 0, 0);
     }
 }
 
-__global__ void __launch_bounds__(kMergeThreads, 1) ahc_merge_kernel(Problem *pp) {
-    extern __shared__ double smem_d[];
-    Problem P = *pp;
+__global__ void __launch_bounds__(kMergeThreads, 1) ahc_merge_kernel(const Problem *pp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Problem P = *pp;
     const int W = (int)gridDim.x - 1;
     if (blockIdx.x == 0) {
-        if (threadIdx.x < 32) ahc_master(P, W);
+        if (threadIdx.x < 32) {
+            if (P.idx16) ahc_master<uint16_t>(P, W, smem_raw); else ahc_master<int>(P, W, smem_raw);
+        }
         return;
     }
     const int wb = (int)blockIdx.x - 1;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int N = P.N, D = P.D, Ns = P.Ns;
-    double *v = smem_d;                                   // [D] target vector
-    double *red_d = smem_d + D;                           // [warps]
+    double *v = reinterpret_cast<double *>(smem_raw);       // [D] target vector
+    double *red_d = v + ((D + 1) & ~1);                     // [warps]
     int *red_id = reinterpret_cast<int *>(red_d + kMergeThreads / 32);
-    __shared__ Command sc;
+    double *sv = red_d + kMergeThreads / 32 + kMergeThreads / 32;   // resident node vectors [D x SP], k-major
+    __shared__ u64 s_cmd;
+    __shared__ int s_owner;
 
-    const int rounds = (Ns + W * kMergeThreads - 1) / (W * kMergeThreads);
+    const bool resident = P.resident != 0;
+    const int SP = P.slots_per_cta;
+    const int rounds = resident ? 1 : (Ns + W * kMergeThreads - 1) / (W * kMergeThreads);
     int ids[kMaxRounds];
 #pragma unroll
-    for (int r = 0; r < kMaxRounds; ++r) {
-        const int s = (r * W + wb) * kMergeThreads + t;
-        ids[r] = (r < rounds && s < N) ? s : -1;
+    for (int r = 0; r < kMaxRounds; ++r) ids[r] = -1;
+    if (resident) {
+        const int s = wb * SP + t;
+        if (t < SP && s < N) {
+            ids[0] = s;
+            for (int k = 0; k < D; ++k) sv[k * SP + t] = P.cols[(size_t)k * Ns + s];   // coalesced over t
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < kMaxRounds; ++r) {
+            const int s = (r * W + wb) * kMergeThreads + t;
+            ids[r] = (r < rounds && s < N) ? s : -1;
+        }
     }
     unsigned expect = 0;
+    int merges = 0;
     for (;;) {
         ++expect;
         if (t == 0) {
-            while (ld_acquire_u32(P.seq) < expect) {
-            }
-            const int *src = reinterpret_cast<const int *>(P.cmd);
-            int *dst = reinterpret_cast<int *>(&sc);
-#pragma unroll
-            for (int q = 0; q < (int)(sizeof(Command) / sizeof(int)); ++q) dst[q] = __ldcg(src + q);
+            u64 c;
+            do {
+                c = ld_acquire_u64(P.cmd);
+            } while ((unsigned)((c >> 48) & 0x3fffu) != (expect & 0x3fffu));
+            s_cmd = c;
+            s_owner = -1;
         }
         __syncthreads();
-        const Command c = sc;
-        if (c.type == CMD_EXIT) break;
-        if (c.type == CMD_MERGE) {
-            const double *ra = P.rows + (size_t)c.a * D, *rb = P.rows + (size_t)c.b * D;
-            const double den = __dadd_rn(c.wa, c.wb);
+        const u64 c = s_cmd;
+        const int type = (int)(c >> 62);
+        const int a = (int)((c >> 24) & 0xffffffu), b = (int)(c & 0xffffffu);
+        if (type == CMD_EXIT) break;
+        int limit;
+        if (type == CMD_MERGE) {
+            const int fresh = N + merges;
+            ++merges;
+            const double wa = (double)__ldcg(P.node_weight + a), wbv = (double)__ldcg(P.node_weight + b);
+            const double *ra = P.rows + (size_t)a * D, *rb = P.rows + (size_t)b * D;
+            const double den = __dadd_rn(wa, wbv);
             for (int k = t; k < D; k += kMergeThreads) {
                 const double xa = __ldcg(ra + k), xb = __ldcg(rb + k);
-                v[k] = __ddiv_rn(__dadd_rn(__dmul_rn(xa, c.wa), __dmul_rn(xb, c.wb)), den);
+                v[k] = __ddiv_rn(__dadd_rn(__dmul_rn(xa, wa), __dmul_rn(xb, wbv)), den);
             }
-            __syncthreads();
-            // the CTA that owns slot_a stores the new node: scan copy (its own column) + node store (new row)
-            const int owner = (c.slot_a / kMergeThreads) % W;
-            if (owner == wb) {
-                double *row = P.rows + (size_t)c.fresh * D;
-                for (int k = t; k < D; k += kMergeThreads) {
-                    P.cols[(size_t)k * Ns + c.slot_a] = v[k];
-                    row[k] = v[k];
-                }
-            }
+            // the thread holding a turns into `fresh`, the one holding b goes idle
 #pragma unroll
             for (int r = 0; r < kMaxRounds; ++r) {
-                const int s = (r * W + wb) * kMergeThreads + t;
                 if (r < rounds) {
-                    if (s == c.slot_a) ids[r] = c.fresh;
-                    else if (s == c.slot_b) ids[r] = -1;
+                    if (ids[r] == a) {
+                        ids[r] = fresh;
+                        s_owner = resident ? t : (r * W + wb) * kMergeThreads + t;
+                    } else if (ids[r] == b) {
+                        ids[r] = -1;
+                    }
                 }
             }
+            __syncthreads();
+            const int os = s_owner;
+            if (os >= 0) {   // this CTA holds the slot: store the new node (scan copy + node-store row + weight)
+                double *row = P.rows + (size_t)fresh * D;
+                for (int k = t; k < D; k += kMergeThreads) {
+                    if (resident) sv[k * SP + os] = v[k]; else P.cols[(size_t)k * Ns + os] = v[k];
+                    row[k] = v[k];
+                }
+                if (t == 0) P.node_weight[fresh] = (int)(wa + wbv);
+            }
+            limit = fresh;
         } else {
-            const double *rt = P.rows + (size_t)c.fresh * D;
+            const double *rt = P.rows + (size_t)a * D;
             for (int k = t; k < D; k += kMergeThreads) v[k] = __ldcg(rt + k);
             __syncthreads();
+            limit = a;
         }
         // ---- scan: one sequential chain per owned live node with id < limit ------------------------------
         double best = INFINITY;
         int best_id = INT_MAX;
         bool bad = false;
+        if (resident) {
+            const int id = ids[0];
+            if (id >= 0 && id < limit) {
+                const double *col = sv + t;
+                double sum = 0.0;
+                int k = 0;
+                for (; k + 8 <= D; k += 8) {
+                    double x[8];
 #pragma unroll
-        for (int r = 0; r < kMaxRounds; ++r) {
-            if (r < rounds) {
-                const int id = ids[r];
-                if (id >= 0 && id < c.limit) {
-                    const int s = (r * W + wb) * kMergeThreads + t;
-                    const double *col = P.cols + s;
-                    double sum = 0.0;
-                    int k = 0;
-                    for (; k + 8 <= D; k += 8) {
-                        double x[8];
+                    for (int u = 0; u < 8; ++u) x[u] = col[(k + u) * SP];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) x[u] = __ldcg(col + (size_t)(k + u) * Ns);
+                    for (int u = 0; u < 8; ++u) sum = sq_step(sum, x[u], v[k + u]);
+                }
+                for (; k < D; ++k) sum = sq_step(sum, col[k * SP], v[k]);
+                if (sum != sum) bad = true;
+                best = sum;
+                best_id = id;
+            }
+        } else {
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) sum = sq_step(sum, x[u], v[k + u]);
+            for (int r = 0; r < kMaxRounds; ++r) {
+                if (r < rounds) {
+                    const int id = ids[r];
+                    if (id >= 0 && id < limit) {
+                        const int s = (r * W + wb) * kMergeThreads + t;
+                        const double *col = P.cols + s;
+                        double sum = 0.0;
+                        int k = 0;
+                        for (; k + 16 <= D; k += 16) {
+                            double x[16];
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) x[u] = __ldcg(col + (size_t)(k + u) * Ns);
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) sum = sq_step(sum, x[u], v[k + u]);
+                        }
+                        for (; k < D; ++k) sum = sq_step(sum, __ldcg(col + (size_t)k * Ns), v[k]);
+                        if (sum != sum) bad = true;
+                        cand_min(best, best_id, sum, id);
                     }
-                    for (; k < D; ++k) sum = sq_step(sum, __ldcg(col + (size_t)k * Ns), v[k]);
-                    if (sum != sum) bad = true;
-                    cand_min(best, best_id, sum, id);
                 }
             }
         }
-        if (bad) atomicExch(P.error, 1);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double od = __shfl_xor_sync(0xffffffffu, best, o);
             const int oid = __shfl_xor_sync(0xffffffffu, best_id, o);
             cand_min(best, best_id, od, oid);
         }
+        const bool warp_bad = __any_sync(0xffffffffu, bad);
         if (lane == 0) {
             red_d[warp] = best;
-            red_id[warp] = best_id;
+            red_id[warp] = warp_bad ? -2 : best_id;
         }
         __syncthreads();
         if (t == 0) {
-            for (int w2 = 1; w2 < kMergeThreads / 32; ++w2) cand_min(best, best_id, red_d[w2], red_id[w2]);
-            __stcg(&P.partial[wb].d, best);
-            __stcg(&P.partial[wb].id, best_id);
-            __threadfence();
-            red_release_add_u32(P.arrive, 1u);
+            bool any_bad = red_id[0] == -2;
+            if (any_bad) best_id = INT_MAX, best = INFINITY;
+            for (int w2 = 1; w2 < kMergeThreads / 32; ++w2) {
+                if (red_id[w2] == -2) any_bad = true; else cand_min(best, best_id, red_d[w2], red_id[w2]);
+            }
+            st_relaxed_u64(&P.results[wb].d_bits, (u64)__double_as_longlong(best));
+            st_release_u64(&P.results[wb].id_tag, ((u64)(unsigned)(any_bad ? -2 : best_id) << 32) | (u64)expect);
         }
-        // sc / red_* are rewritten only after the next command's barrier
+        // s_cmd / red_* / s_owner are rewritten only after the next command's barrier
     }
 }
 
@@ -451,6 +552,9 @@ int launch_widen_rows(const float *d_in, double *d_out, long long count, cudaStr
 }
 
 // ------------------------------------------------------------------------------------------------ host solver
+thread_local float g_last_ms[4] = {0, 0, 0, 0};
+const float *last_stage_ms() { return g_last_ms; }
+
 Solver::~Solver() { release(); }
 
 void Solver::release() {
@@ -495,8 +599,8 @@ struct Carver {
     }
 };
 struct Layout {
-    size_t rows, cols, key, nn, heap_at, heap_where, live_next, live_prev, weight, slot_of, merge_a, merge_b, merge_d,
-        cmd, seq, arrive, partial, error, init_partial, problem, total;
+    size_t rows, cols, node_weight, key, nn, heap_at, heap_where, node_of, slot_of, live_bits, merge_a, merge_b, merge_d,
+        cmd, results, error, init_partial, problem, total;
     int ranges;
 };
 Layout make_layout(int N, int D, int Ns, int workers) {
@@ -504,27 +608,34 @@ Layout make_layout(int N, int D, int Ns, int workers) {
     Carver c;
     L.rows = c.take<double>((size_t)(2 * N - 1) * D);
     L.cols = c.take<double>((size_t)D * Ns);
-    L.key = c.take<double>((size_t)2 * N);
-    L.nn = c.take<int>((size_t)2 * N);
-    L.heap_at = c.take<int>((size_t)N);
-    L.heap_where = c.take<int>((size_t)2 * N);
-    L.live_next = c.take<int>((size_t)2 * N + 2);
-    L.live_prev = c.take<int>((size_t)2 * N + 2);
-    L.weight = c.take<int>((size_t)2 * N);
+    L.node_weight = c.take<int>((size_t)2 * N);
+    L.key = c.take<double>((size_t)N + 2);
+    L.nn = c.take<int>((size_t)N + 2);
+    L.heap_at = c.take<int>((size_t)N + 2);
+    L.heap_where = c.take<int>((size_t)N + 2);
+    L.node_of = c.take<int>((size_t)N + 2);
     L.slot_of = c.take<int>((size_t)2 * N);
+    L.live_bits = c.take<unsigned>((size_t)(2 * N + 31) / 32 + 2);
     L.merge_a = c.take<int>((size_t)N);
     L.merge_b = c.take<int>((size_t)N);
     L.merge_d = c.take<double>((size_t)N);
-    L.cmd = c.take<Command>(1);
-    L.seq = c.take<unsigned>(64);      // own 256-byte line
-    L.arrive = c.take<unsigned>(64);   // own 256-byte line
-    L.partial = c.take<Cand>((size_t)workers + 1);
+    L.cmd = c.take<unsigned long long>(32);   // own 256-byte line
+    L.results = c.take<ResultSlot>((size_t)workers + 1);
     L.error = c.take<int>(64);
     L.ranges = (N + kJR - 1) / kJR;
     L.init_partial = c.take<Cand>((size_t)L.ranges * N);
     L.problem = c.take<Problem>(1);
     L.total = (c.off + 255) & ~size_t(255);
     return L;
+}
+// bytes of master state staged in shared memory at each level (must mirror ahc_master's carving)
+size_t master_smem_bytes(int N, int level) {
+    auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
+    const size_t words = (size_t)(2 * N - 1 + 31) >> 5;
+    size_t b = up(sizeof(double) * N) + 2 * up(sizeof(uint16_t) * N) + up(sizeof(unsigned) * words);
+    if (level >= 2) b += up(sizeof(int) * N);
+    if (level >= 3) b += up(sizeof(int) * N);
+    return b;
 }
 } // namespace
 
@@ -538,7 +649,7 @@ int Solver::ensure_pool(int N, int D) {
         FA_CUDA_TRY(cudaMalloc(&d_pool, L.total));
         pool_bytes = L.total;
     }
-    const size_t hneed = sizeof(double) * (size_t)(3 * N + 8) + sizeof(int) * (size_t)(6 * N + 64);
+    const size_t hneed = sizeof(double) * (size_t)(2 * N + 16) + sizeof(int) * (size_t)(4 * N + 64);
     if (hneed > h_pool_bytes) {
         if (h_pool) cudaFreeHost(h_pool);
         h_pool = nullptr;
@@ -552,18 +663,38 @@ int Solver::ensure_pool(int N, int D) {
 int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     if (N < 2) return FA_OK;
     const int Ns = (N + 31) & ~31;
-    int workers = std::min(max_workers, (Ns + kMergeThreads - 1) / kMergeThreads);
-    workers = std::max(workers, 1);
-    if ((long long)workers * kMergeThreads * kMaxRounds < Ns) {
-        fa::set_error("point count %d exceeds the capacity of the merge kernel (%lld)", N,
-                      (long long)workers * kMergeThreads * kMaxRounds);
-        return FA_RUNTIME_ERROR;
-    }
-    const size_t smem = sizeof(double) * (size_t)D + (sizeof(double) + sizeof(int)) * (kMergeThreads / 32) + 16;
-    if (smem > 200 * 1024) {
+    // master placement: slot-indexed heap (+ nn, + node_of) in shared memory when it fits
+    const size_t smem_cap = 227 * 1024 - 512;
+    int level = 0;
+    if (N <= 65535)
+        for (int l = 1; l <= 3; ++l)
+            if (master_smem_bytes(N, l) <= smem_cap) level = l;
+    const bool idx16 = level >= 1;
+    // worker placement: resident (each CTA keeps <= 128 node vectors in shared memory) when the whole problem fits
+    // into max_workers CTAs, else streamed from the k-major global copy
+    const size_t worker_fixed = sizeof(double) * (size_t)((D + 1) & ~1) + 2 * sizeof(double) * (kMergeThreads / 32) + 64;
+    if (worker_fixed + sizeof(double) * D > smem_cap) {
         fa::set_error("dimension %d too large for the merge kernel's shared-memory target vector", D);
         return FA_RUNTIME_ERROR;
     }
+    const int cap_slots = (int)std::min<size_t>(kMergeThreads, (smem_cap - worker_fixed) / (sizeof(double) * (size_t)D));
+    bool resident = cap_slots >= 1 && (long long)cap_slots * max_workers >= N;
+    int workers, slots_per_cta = 0;
+    size_t worker_smem = worker_fixed;
+    if (resident) {
+        // enough CTAs to hold every node, but no more than needed: the per-step barrier cost grows with CTA count
+        workers = std::min(max_workers, std::max(1, (N + cap_slots - 1) / cap_slots));
+        slots_per_cta = (N + workers - 1) / workers;
+        worker_smem += sizeof(double) * (size_t)D * slots_per_cta;
+    } else {
+        workers = std::max(1, std::min(max_workers, (Ns + kMergeThreads - 1) / kMergeThreads));
+        if ((long long)workers * kMergeThreads * kMaxRounds < Ns) {
+            fa::set_error("point count %d exceeds the capacity of the merge kernel (%lld)", N,
+                          (long long)workers * kMergeThreads * kMaxRounds);
+            return FA_RUNTIME_ERROR;
+        }
+    }
+    const size_t smem = std::max(worker_smem, level ? master_smem_bytes(N, level) : (size_t)0);
     int st = ensure_pool(N, D);
     if (st != FA_OK) return st;
     const Layout L = make_layout(N, D, Ns, max_workers);
@@ -574,33 +705,34 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     P.Ns = Ns;
     P.rows = reinterpret_cast<double *>(base + L.rows);
     P.cols = reinterpret_cast<double *>(base + L.cols);
+    P.node_weight = reinterpret_cast<int *>(base + L.node_weight);
     P.key = reinterpret_cast<double *>(base + L.key);
     P.nn = reinterpret_cast<int *>(base + L.nn);
-    P.heap_at = reinterpret_cast<int *>(base + L.heap_at);
-    P.heap_where = reinterpret_cast<int *>(base + L.heap_where);
-    P.live_next = reinterpret_cast<int *>(base + L.live_next);
-    P.live_prev = reinterpret_cast<int *>(base + L.live_prev);
-    P.weight = reinterpret_cast<int *>(base + L.weight);
+    P.heap_at = base + L.heap_at;
+    P.heap_where = base + L.heap_where;
+    P.node_of = reinterpret_cast<int *>(base + L.node_of);
     P.slot_of = reinterpret_cast<int *>(base + L.slot_of);
+    P.live_bits = reinterpret_cast<unsigned *>(base + L.live_bits);
     P.merge_a = reinterpret_cast<int *>(base + L.merge_a);
     P.merge_b = reinterpret_cast<int *>(base + L.merge_b);
     P.merge_d = reinterpret_cast<double *>(base + L.merge_d);
-    P.cmd = reinterpret_cast<Command *>(base + L.cmd);
-    P.seq = reinterpret_cast<unsigned *>(base + L.seq);
-    P.arrive = reinterpret_cast<unsigned *>(base + L.arrive);
-    P.partial = reinterpret_cast<Cand *>(base + L.partial);
+    P.cmd = reinterpret_cast<unsigned long long *>(base + L.cmd);
+    P.results = reinterpret_cast<ResultSlot *>(base + L.results);
     P.error = reinterpret_cast<int *>(base + L.error);
+    P.resident = resident ? 1 : 0;
+    P.slots_per_cta = slots_per_cta;
+    P.idx16 = idx16 ? 1 : 0;
+    P.smem_level = level;
     Cand *init_partial = reinterpret_cast<Cand *>(base + L.init_partial);
     Problem *d_prob = reinterpret_cast<Problem *>(base + L.problem);
 
     // pinned host mirrors
     char *hb = static_cast<char *>(h_pool);
     double *h_key = reinterpret_cast<double *>(hb);
-    double *h_md = h_key + 2 * N + 4;
-    int *h_nn = reinterpret_cast<int *>(h_md + N + 4);
-    int *h_at = h_nn + 2 * N;
-    int *h_where = h_at + N;
-    int *h_ma = h_where + 2 * N;
+    double *h_md = h_key + N + 4;
+    int *h_at = reinterpret_cast<int *>(h_md + N + 4);   // N ints (reused as uint16 when idx16)
+    int *h_where = h_at + N + 2;
+    int *h_ma = h_where + N + 2;
     int *h_mb = h_ma + N;
     int *h_err = h_mb + N;
 
@@ -610,8 +742,8 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
         for (auto &e : ev) cudaEventDestroy(e);
     };
 
-    FA_CUDA_TRY(cudaMemsetAsync(base + L.seq, 0, 256, stream));
-    FA_CUDA_TRY(cudaMemsetAsync(base + L.arrive, 0, 256, stream));
+    FA_CUDA_TRY(cudaMemsetAsync(base + L.cmd, 0, 256, stream));
+    FA_CUDA_TRY(cudaMemsetAsync(base + L.results, 0, sizeof(ResultSlot) * (size_t)(max_workers + 1), stream));
     FA_CUDA_TRY(cudaMemsetAsync(base + L.error, 0, 256, stream));
     FA_CUDA_TRY(cudaEventRecord(ev[0], stream));
     {
@@ -621,7 +753,8 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
         dim3 g2((N + kTI - 1) / kTI, L.ranges);
         ahc_init_nn_kernel<<<g2, kTI, 0, stream>>>(P.cols, N, D, Ns, init_partial, P.error);
         FA_CUDA_TRY(cudaGetLastError());
-        ahc_init_reduce_kernel<<<(N + 127) / 128, 128, 0, stream>>>(init_partial, N, L.ranges, P.key, P.nn);
+        ahc_init_reduce_kernel<<<(N + 127) / 128, 128, 0, stream>>>(init_partial, N, L.ranges, P.key, P.nn,
+                                                                     P.node_weight);
         FA_CUDA_TRY(cudaGetLastError());
         launches += 3;
     }
@@ -635,13 +768,22 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
         return FA_RUNTIME_ERROR;   // reference: nan_error -> FASTCLUSTER_WRAPPER_RUNTIME_ERROR
     }
     // heapify on the host (fastcluster_internal.hpp:1682): O(N), ~50 us, avoids ~1 ms of serial device work
-    {
-        NnHeap heap{h_key, h_at, h_where, 0};
+    size_t idx_bytes;
+    if (idx16) {
+        NnHeapT<uint16_t> heap{h_key, reinterpret_cast<uint16_t *>(h_at), reinterpret_cast<uint16_t *>(h_where), 0};
+        heap.where[0] = 0;
         heap.build(N - 1, 1);
         P.heap_size = heap.size;
+        idx_bytes = sizeof(uint16_t);
+    } else {
+        NnHeapT<int> heap{h_key, h_at, h_where, 0};
+        heap.where[0] = 0;
+        heap.build(N - 1, 1);
+        P.heap_size = heap.size;
+        idx_bytes = sizeof(int);
     }
-    FA_CUDA_TRY(cudaMemcpyAsync(P.heap_at, h_at, sizeof(int) * (N - 1), cudaMemcpyHostToDevice, stream));
-    FA_CUDA_TRY(cudaMemcpyAsync(P.heap_where, h_where, sizeof(int) * (2 * N - 2), cudaMemcpyHostToDevice, stream));
+    FA_CUDA_TRY(cudaMemcpyAsync(P.heap_at, h_at, idx_bytes * (N - 1), cudaMemcpyHostToDevice, stream));
+    FA_CUDA_TRY(cudaMemcpyAsync(P.heap_where, h_where, idx_bytes * N, cudaMemcpyHostToDevice, stream));
     FA_CUDA_TRY(cudaMemcpyAsync(d_prob, &P, sizeof(Problem), cudaMemcpyHostToDevice, stream));
     FA_CUDA_TRY(cudaEventRecord(ev[2], stream));
     {
@@ -661,6 +803,7 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     cudaEventElapsedTime(&last_ms[1], ev[1], ev[2]);
     cudaEventElapsedTime(&last_ms[2], ev[2], ev[3]);
     cudaEventElapsedTime(&last_ms[3], ev[0], ev[3]);
+    for (int q = 0; q < 4; ++q) g_last_ms[q] = last_ms[q];
     drop_events();
     if (*h_err != 0) {
         fa::set_error("NaN distance during merging");

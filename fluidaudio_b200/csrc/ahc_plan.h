@@ -8,16 +8,17 @@
 namespace fa {
 namespace ahc {
 
-// One command from the master thread to the worker CTAs of the persistent merge kernel.
-struct Command {
-    int type;        // 1 = MERGE (build node `fresh` from a,b then scan), 2 = RESCAN (scan for node `target`), 3 = EXIT
-    int a, b;        // node ids being merged
-    int fresh;       // id of the new node (MERGE) / target node id (RESCAN)
-    int slot_a;      // slot holding a: becomes the slot of `fresh`
-    int slot_b;      // slot holding b: becomes empty
-    int limit;       // only nodes with id < limit are candidates
-    int pad;
-    double wa, wb;   // member counts of a and b as doubles
+// Master -> workers: ONE 64-bit word, written with st.release and polled with ld.acquire (8-byte accesses are
+// single-copy atomic, so sequence tag and payload can never tear):
+//   [63:62] type (1 MERGE a,b | 2 RESCAN for node a | 3 EXIT)   [61:48] command counter mod 2^14
+//   [47:24] node id a                                           [23:0]  node id b
+// The id of a freshly merged node is implicit (N + number of MERGE commands so far).  Workers find the slots of
+// a and b themselves (every thread knows which node its slot holds) and read member counts from node_weight[].
+// Workers -> master: one 16-byte slot per worker CTA, {distance bits, (node id << 32) | command counter},
+// second word written with st.release; the master warp polls the slots directly (no atomic counter).
+struct ResultSlot {
+    unsigned long long d_bits;
+    unsigned long long id_tag;
 };
 
 // Everything the persistent kernel needs, resident in HBM.
@@ -25,25 +26,26 @@ struct Problem {
     int N, D, Ns;            // points, dimension, slot stride (N rounded up to 32)
     double *rows;            // [(2N-1) x D] node store, row-major: rows 0..N-1 = input, N.. = merged centroids
     double *cols;            // [D x Ns]     scan copy, k-major: cols[k*Ns + slot]
-    // master state
-    double *key;             // [2N-2] nearest-neighbour distance per node id (heap keys)
-    int *nn;                 // [2N-2] nearest neighbour per node id
-    int *heap_at;            // [N-1]
-    int *heap_where;         // [2N-2]
-    int *live_next;          // [2N]
-    int *live_prev;          // [2N]
-    int *weight;             // [2N-1] member count per node
-    int *slot_of;            // [2N-1] slot per node
+    int *node_weight;        // [2N-1] member count per node id (written by the CTA that creates the node)
+    // master state, slot-indexed; staged into shared memory when it fits (idx16 != 0)
+    double *key;             // [N]   nearest-neighbour squared distance of the node in each slot (heap keys)
+    int *nn;                 // [N]   nearest neighbour (node id) of the node in each slot
+    void *heap_at;           // [N-1] heap position -> slot   (uint16_t if idx16 else int)
+    void *heap_where;        // [N]   slot -> heap position
+    int *node_of;            // [N]   node id held by each slot (-1 when empty)
+    int *slot_of;            // [2N-1] slot of each node id
+    unsigned *live_bits;     // [(2N-1+31)/32]
     int *merge_a, *merge_b;  // [N-1] merge log
     double *merge_d;         // [N-1] squared distance of each merge
     // synchronisation
-    Command *cmd;            // 1
-    unsigned *seq;           // command sequence number (release/acquire)
-    unsigned *arrive;        // worker arrival counter (monotonic)
-    Cand *partial;           // [workers] per-CTA minima
-    int *error;              // 0 ok, 1 NaN distance
+    unsigned long long *cmd; // command word
+    ResultSlot *results;     // [workers]
+    int *error;              // 0 ok, 1 NaN distance (host-visible copy)
     int heap_size;           // after host heapify
-    int steps_done;          // (debug) merges completed
+    int idx16;               // heap index arrays are uint16_t and the master state lives in shared memory
+    int smem_level;          // how much master state fits in smem: 1 = heap, 2 = + nn, 3 = + node_of
+    int resident;            // 1: every worker keeps its nodes' vectors in shared memory; 0: streamed from `cols`
+    int slots_per_cta;       // resident mode: slots [w*slots_per_cta, (w+1)*slots_per_cta) belong to worker w
 };
 
 struct Solver {
@@ -71,6 +73,10 @@ struct Solver {
     int linkage_host(const double *rows_host, size_t N, size_t D, double *Z_host, size_t z_len);
     int ensure_pool(int N, int D);
 };
+
+// [0] initial nearest-neighbour kernels, [1] heapify + copies, [2] merge kernel, [3] total (ms) of the calling
+// thread's most recent linkage
+const float *last_stage_ms();
 
 // Standalone kernels used by the clustering pipeline
 int launch_normalize_rows(const double *d_in, double *d_out, int rows, int dim, cudaStream_t s);

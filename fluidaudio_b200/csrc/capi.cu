@@ -733,6 +733,12 @@ FA_API fastcluster_wrapper_status fastcluster_compute_centroid_linkage(const dou
     }
 }
 
+FA_API void fa_ahc_last_stage_ms(float *out4) {
+    if (!out4) return;
+    const float *m = ahc::last_stage_ms();
+    for (int q = 0; q < 4; ++q) out4[q] = m[q];
+}
+
 FA_API fa_status fa_l2_normalize_rows(const double *x, size_t rows, size_t dim, double *out) {
     if (!x || !out) return FA_STATUS_INVALID_ARGUMENT;
     if (rows == 0 || dim == 0) return FA_STATUS_OK;

@@ -121,6 +121,10 @@ fa_status fa_l2_normalize_rows(const double *x, size_t rows, size_t dim, double 
 /* AHCClustering.cluster: rows are NOT yet normalised; labels are canonical (first appearance order). */
 fa_status fa_ahc_cluster(const double *features, size_t count, size_t dim, double threshold, int32_t *labels);
 
+/* Device time of the calling thread's most recent linkage: [0] initial nearest-neighbour pass, [1] heapify + copies,
+ * [2] persistent merge kernel, [3] total (ms).  Diagnostics only. */
+void fa_ahc_last_stage_ms(float *out4);
+
 /* Swift-side dendrogram cut + relabel on a SciPy-format linkage Z [(count-1) x 4]. */
 fa_status fa_dendrogram_cut(const double *Z, size_t count, double threshold, int32_t *labels);
 

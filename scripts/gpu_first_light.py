@@ -78,7 +78,10 @@ def ahc_part():
         x = O.l2_normalize_rows(emb.astype(np.float64))
         t = time.time(); st, z = cl.centroid_linkage(x); dt = time.time() - t
         t = time.time(); st2, z2 = O.centroid_linkage(x, use_ref=O.ref_available()); dt2 = time.time() - t
+        ms = np.zeros(4, np.float32); _lib.load().fa_ahc_last_stage_ms(ms.ctypes.data)
+        print("   stages", ms)
         print(f"AHC N={N} status={st}/{st2} bit-exact={np.array_equal(z, z2)} gpu={dt*1e3:.1f} ms cpu={dt2*1e3:.1f} ms", flush=True)
+        if st != 0: print("   last error:", _lib.load().fa_last_error())
         if not np.array_equal(z, z2) and N <= 100: print(z[:5], z2[:5])
     rng = np.random.default_rng(0)
     base = rng.standard_normal((50, 8)); x = np.repeat(base, 4, axis=0)[rng.permutation(200)]
@@ -92,7 +95,8 @@ def ahc_part():
     x = O.l2_normalize_rows(emb.astype(np.float64))
     for rep in range(2):
         t = time.time(); st, z = cl.centroid_linkage(x); dt = time.time() - t
-        print(f"AHC N=10000 gpu={dt*1e3:.1f} ms status={st}", flush=True)
+        ms = np.zeros(4, np.float32); _lib.load().fa_ahc_last_stage_ms(ms.ctypes.data)
+        print(f"AHC N=10000 gpu={dt*1e3:.1f} ms status={st} stages(init,heapify,merge,total)={ms}", flush=True)
     np.save("gpurun_out/z10000.npy", z)
 
 def pipe_part():

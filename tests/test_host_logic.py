@@ -1,0 +1,219 @@
+"""CPU tests of the product's host side (no GPU needed, no compute calls into the CUDA library):
+
+* the C-ABI library loads and exports every symbol the public headers declare;
+* argument contracts that are decided before any device work (the reference's own status codes);
+* "no CPU fallback": without a B200 every compute entry point fails loudly;
+* the product never touches oracle/;
+* the device code's per-lane FFT / mel math and the merge kernel's control plane, compiled for the host from the
+  SAME headers the kernels use (tests/emul/*.cpp), against the oracle and the reference goldens;
+* sharding helpers, including a 2-rank gloo run.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from fluidaudio_b200 import _lib, sharding, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _lib.load()
+
+
+def _declared_functions(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(fa_[a-z0-9_]+|fastcluster_compute_centroid_linkage)\s*\(", text))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = _declared_functions("fluidaudio_b200.h") | _declared_functions("FastClusterWrapper.h")
+    assert "fastcluster_compute_centroid_linkage" in declared and len(declared) >= 35
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert declared <= exported, f"declared but not exported: {sorted(declared - exported)}"
+    assert set(_lib.EXPORTED_SYMBOLS) == declared
+    # nothing but the C ABI leaks out of the shared object
+    assert all(s.startswith("fa_") or s.startswith("fastcluster_") for s in exported), sorted(exported)[:10]
+
+
+def test_reference_argument_contract_needs_no_device(lib):
+    """FastClusterWrapper.cpp:203-223 — these statuses are decided before any clustering work."""
+    f = lib.fastcluster_compute_centroid_linkage
+    x = np.ones((3, 2))
+    z = np.zeros(8)
+    assert f(None, 3, 2, z.ctypes.data, 8) == 1
+    assert f(x.ctypes.data, 3, 2, None, 8) == 1
+    assert f(x.ctypes.data, 0, 2, z.ctypes.data, 8) == 0
+    assert f(x.ctypes.data, 3, 0, z.ctypes.data, 8) == 1
+    assert f(x.ctypes.data, 2 ** 31, 2, z.ctypes.data, 8) == 2
+    assert f(x.ctypes.data, 3, 2 ** 31, z.ctypes.data, 8) == 2
+    assert f(x.ctypes.data, 3, 2, z.ctypes.data, 7) == 3
+    assert f(x.ctypes.data, 1, 2, z.ctypes.data, 0) == 0
+    assert np.all(z == 0)
+
+
+def test_swift_level_guards_need_no_device(lib):
+    from fluidaudio_b200.clustering import AHCClustering
+    ahc = AHCClustering()
+    assert ahc.cluster([], 0.7).size == 0                                   # AHCClusteringTests.swift:12-15
+    assert ahc.cluster(np.zeros((3, 0)), 0.7).tolist() == [0, 0, 0]         # :137-145
+    labels = np.zeros(1, np.int32)
+    assert lib.fa_ahc_cluster(np.ones((1, 3)).ctypes.data, 1, 3, 0.7, labels.ctypes.data) == 0 and labels[0] == 0
+
+
+def test_no_cpu_fallback_without_a_device(lib):
+    if _lib.device_count() > 0:
+        pytest.skip("a B200 is visible here; the no-device behaviour is exercised on CPU-only boxes")
+    from fluidaudio_b200.mel import AudioMelSpectrogram
+    from fluidaudio_b200.clustering import OfflineClusterer, centroid_linkage
+    with pytest.raises(_lib.FluidAudioError) as e:
+        AudioMelSpectrogram()
+    assert e.value.status == 6 and "no CPU fallback" in str(e.value)
+    emb, _ = synth.speaker_embeddings(50, 16, 2)
+    with pytest.raises(_lib.FluidAudioError):
+        OfflineClusterer().cluster(emb, emb.astype(np.float64))
+    st, _ = centroid_linkage(np.eye(3))
+    assert st == 5      # the Swift caller maps a non-zero status to identity labels (AHCClustering.swift:52-55)
+
+
+def test_product_never_imports_or_links_the_oracle():
+    pkg = os.path.join(ROOT, "fluidaudio_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or name == "Makefile":
+                text = open(os.path.join(dirpath, name), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{name} imports oracle"
+                assert "liboracle" not in text and "oracle_" not in text, f"{name} references the oracle"
+    out = subprocess.check_output(["ldd", _lib.LIB_PATH], text=True)
+    assert "oracle" not in out
+
+
+def test_helpers_that_run_on_the_host(lib, oracle):
+    x = (np.arange(24, dtype=np.float32).reshape(6, 4) ** 1.5)
+    y = x.copy()
+    assert lib.fa_mel_normalize_per_feature(y.ctypes.data, 6, 4, 4) == 0
+    assert np.array_equal(y, oracle.normalize_per_feature(x, 4))
+    planar = np.ascontiguousarray(np.random.default_rng(0).standard_normal((3, 1000)), np.float32)
+    for rin, rout in ((48000, 16000), (44100, 16000), (8000, 16000), (16000, 16000)):
+        n = C.c_int64()
+        assert lib.fa_linear_resample(planar.ctypes.data, 1000, 3, rin, rout, None, 0, C.byref(n)) == 0
+        out = np.zeros(n.value, np.float32)
+        assert lib.fa_linear_resample(planar.ctypes.data, 1000, 3, rin, rout, out.ctypes.data, out.size, C.byref(n)) == 0
+        ref = oracle.linear_resample(planar, rin, rout)
+        assert np.array_equal(out, ref)
+        assert abs(out.size - 1000 * rout / rin) <= 0.01 * 1000 * rout / rin + 1      # AudioConverterTests.swift:129-176
+    from fluidaudio_b200.clustering import dendrogram_cut
+    rng = np.random.default_rng(5)
+    for n in (2, 7, 40):
+        xx = oracle.l2_normalize_rows(rng.standard_normal((n, 3)))
+        _, z = oracle.centroid_linkage(xx)
+        for thr in (0.0, 0.5, 1.0, 2.5, float("nan")):
+            assert np.array_equal(dendrogram_cut(z, n, thr), oracle.dendrogram_cut(z, n, thr))
+
+
+# ------------------------------------------------------------------------------------------------ device code on the host
+def _compile(src, out):
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", out,
+                           os.path.join(ROOT, "tests", "emul", src)])
+    return C.CDLL(out)
+
+
+def test_kernel_lane_math_matches_oracle(tmp_path, oracle):
+    """mel_core.cuh (the per-lane FFT256 / recombination / banded mel / log the CUDA kernel runs) emulated lane by
+    lane on the host vs the oracle: same frames, |delta log-mel| <= 1e-4."""
+    L = _compile("mel_emul.cpp", str(tmp_path / "libmel_emul.so"))
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L.mel_emul.argtypes = [f32p, C.c_longlong, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, f32p,
+                           f32p, C.c_float, C.c_int, C.c_longlong, f32p]
+    for nm, gen, n in ((80, synth.tone_noise_audio, 16000 * 4 + 137), (128, synth.speech_like_audio, 16000 * 3)):
+        a = gen(n)
+        ref, T, _ = oracle.mel_flat_transposed(oracle.mel_config(n_mels=nm), a)
+        out = np.zeros((T, nm), np.float32)
+        assert L.mel_emul(a, a.size, 0.0, 160, 400, 56, 256, np.float32(0.97), nm, oracle.mel_filterbank(512, nm),
+                          oracle.hann_window(), np.float32(2.0 ** -24), 0, T, out) == 0
+        assert np.abs(out - ref).max() <= 1e-4
+    # legacy compute(): window at offset 0, no padding, no pre-emphasis
+    a = synth.tone_noise_audio(8000)
+    ref, T = oracle.mel_legacy(oracle.mel_config(n_mels=80), a)
+    out = np.zeros((T, 80), np.float32)
+    assert L.mel_emul(a, a.size, 0.0, 160, 400, 0, 0, np.float32(0.0), 80, oracle.mel_filterbank(512, 80),
+                      oracle.hann_window(), np.float32(2.0 ** -24), 0, T, out) == 0
+    assert np.abs(out.T - ref).max() <= 1e-4
+
+
+def test_merge_control_plane_matches_reference_goldens(tmp_path, golden_dir, oracle):
+    """ahc_core.cuh (slot-indexed heap + live bitmap, the code the device master warp runs) driven on the host in the
+    merge kernel's order: dendrograms must equal the reference's bit for bit."""
+    L = _compile("ahc_emul.cpp", str(tmp_path / "libahc_emul.so"))
+    g = np.load(os.path.join(golden_dir, "ahc_reference.npz"))
+    for name in sorted({k.rsplit("__", 1)[0] for k in g.files}):
+        x = np.ascontiguousarray(g[name + "__x"])
+        z = np.zeros((x.shape[0] - 1, 4))
+        assert L.ahc_emul(x.ctypes.data_as(C.c_void_p), x.shape[0], x.shape[1], z.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(z, g[name + "__z"]), name
+    rng = np.random.default_rng(17)
+    for n, d in ((300, 8), (257, 3)):
+        x = np.round(rng.standard_normal((n, d)), 1)          # coarse grid: many exactly tied distances
+        z = np.zeros((n - 1, 4))
+        assert L.ahc_emul(x.ctypes.data_as(C.c_void_p), n, d, z.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(z, oracle.centroid_linkage(x)[1])
+    bad = rng.standard_normal((10, 3)); bad[4, 1] = np.nan
+    assert L.ahc_emul(bad.ctypes.data_as(C.c_void_p), 10, 3, np.zeros((9, 4)).ctypes.data_as(C.c_void_p)) == 5
+
+
+# ------------------------------------------------------------------------------------------------ sharding
+def test_sharding_partitions():
+    for count, world in ((512, 8), (64, 8), (10, 4), (3, 8), (0, 2)):
+        seen = []
+        for r in range(world):
+            seen += list(sharding.contiguous_shard(count, r, world))
+        assert seen == list(range(count))
+        sizes = [len(sharding.contiguous_shard(count, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+    costs = [sharding.ahc_cost(n) for n in (5000, 100, 3000, 3000, 800, 4500, 50, 2000)]
+    parts = sharding.lpt_partition(costs, 3)
+    assert sorted(sum(parts, [])) == list(range(8))
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert max(loads) <= 1.34 * sum(costs) / 3          # LPT bound (4/3 - 1/3m) on the makespan
+    assert sharding.lpt_partition(costs, 3) == parts    # deterministic
+
+
+_WORKER = r"""
+import os, sys, numpy as np
+sys.path.insert(0, {root!r})
+from fluidaudio_b200 import sharding
+d = sharding.init_distributed("gloo")
+mine = sharding.contiguous_shard(10, d.rank, d.world)
+labels = np.array([100 * d.rank + i for i in mine], np.int32)
+sharding.barrier(d)
+mx = sharding.all_reduce_max(d, 1.5 + d.rank)
+sm = sharding.all_reduce_sum(d, len(mine))
+got = sharding.gather_labels(d, labels, [len(sharding.contiguous_shard(10, r, d.world)) for r in range(d.world)])
+if d.is_root:
+    assert mx == 2.5 and sm == 10.0, (mx, sm)
+    assert got.tolist() == [0, 1, 2, 3, 4, 105, 106, 107, 108, 109], got.tolist()
+    print("GLOO_OK")
+sharding.finalize(d)
+"""
+
+
+def test_two_rank_gloo_plumbing(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GLOO_OK" in out.stdout

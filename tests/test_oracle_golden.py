@@ -1,0 +1,315 @@
+"""CPU tests that PIN THE ORACLE (oracle/ is test infrastructure; see its headers).
+
+1. against the compiled, unmodified reference C++ (oracle/_ref/liboracle_fc.so, only where it was built) and
+   against golden dendrograms that reference produced (tests/golden/ahc_reference.npz, always available);
+2. against an independent implementation (scipy centroid linkage; numpy float64 mel pipeline);
+3. against the reference's own unit tests, ported as known-answer tests:
+   Tests/FluidAudioTests/Diarizer/Offline/AHCClusteringTests.swift, ASR/Parakeet/Streaming/
+   AudioMelSpectrogramTests.swift, EouChunkSizeFrameCountTests.swift, Diarizer/Offline/VDSPOperationsTests.swift.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from fluidaudio_b200 import synth
+
+
+# ------------------------------------------------------------------------------------------------ AHC: pinning
+def test_restatement_reproduces_reference_goldens_bit_exact(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ahc_reference.npz"))
+    names = sorted({k.rsplit("__", 1)[0] for k in g.files})
+    assert len(names) >= 6
+    for name in names:
+        x, z_ref = g[name + "__x"], g[name + "__z"]
+        st, z = oracle.centroid_linkage(x)
+        assert st == 0
+        assert np.array_equal(z, z_ref), f"{name}: restatement differs from the reference dendrogram"
+
+
+def test_restatement_equals_compiled_reference_on_fresh_inputs(oracle):
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built on this box (needs /root/reference)")
+    rng = np.random.default_rng(7)
+    for n, d in ((2, 3), (3, 1), (17, 4), (200, 16), (600, 256)):
+        x = rng.standard_normal((n, d))
+        st1, z1 = oracle.centroid_linkage(x)
+        st2, z2 = oracle.centroid_linkage(x, use_ref=True)
+        assert st1 == st2 == 0 and np.array_equal(z1, z2)
+    x = np.repeat(rng.standard_normal((30, 6)), 5, axis=0)[rng.permutation(150)]   # exact ties
+    assert np.array_equal(oracle.centroid_linkage(x)[1], oracle.centroid_linkage(x, use_ref=True)[1])
+
+
+def test_large_reference_hashes_match_restatement(oracle, golden_dir):
+    meta = json.load(open(os.path.join(golden_dir, "ahc_large.json")))
+    m = meta["c5_5000x256_seed0"]
+    emb, _ = synth.speaker_embeddings(m["n"], 256, m["speakers"], weights=m["weights"], seed=m["seed"])
+    x = oracle.l2_normalize_rows(emb.astype(np.float64))
+    st, z = oracle.centroid_linkage(x)
+    assert st == 0
+    assert hashlib.sha256(z.tobytes()).hexdigest() == m["z_sha256"]
+    labels = oracle.dendrogram_cut(z, m["n"], 0.6)
+    assert hashlib.sha256(labels.tobytes()).hexdigest() == m["labels_sha256"]
+    assert labels.max() + 1 == m["clusters"]
+
+
+def test_status_codes_match_reference_contract(oracle):
+    import ctypes as C
+    L = oracle.lib()
+    x = np.ones((3, 2))
+    z = np.zeros(8)
+    assert L.oracle_centroid_linkage(None, 3, 2, z.ctypes.data, 8) == 1
+    assert L.oracle_centroid_linkage(x.ctypes.data, 0, 2, z.ctypes.data, 8) == 0
+    assert L.oracle_centroid_linkage(x.ctypes.data, 3, 0, z.ctypes.data, 8) == 1
+    assert L.oracle_centroid_linkage(x.ctypes.data, 3, 2, z.ctypes.data, 7) == 3
+    assert L.oracle_centroid_linkage(x.ctypes.data, 1, 2, z.ctypes.data, 0) == 0
+    assert L.oracle_centroid_linkage(x.ctypes.data, 2 ** 31, 2, z.ctypes.data, 8) == 2
+    bad = np.array([[0.0, 1.0], [np.nan, 0.0], [1.0, 1.0]])
+    assert oracle.centroid_linkage(bad)[0] == 5
+    if oracle.ref_available():
+        assert oracle.centroid_linkage(bad, use_ref=True)[0] == 5
+
+
+def test_restatement_agrees_with_scipy_centroid_linkage(oracle):
+    from scipy.cluster.hierarchy import linkage
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((300, 12))
+    st, z = oracle.centroid_linkage(x)
+    zs = linkage(x, method="centroid")
+    assert np.array_equal(z[:, :2], zs[:, :2]) and np.array_equal(z[:, 3], zs[:, 3])
+    assert np.abs(z[:, 2] - zs[:, 2]).max() < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ AHC: reference KATs
+def test_ahc_empty_single_and_zero_dim(oracle):
+    for use_ref in {False, oracle.ref_available()}:
+        assert oracle.ahc_cluster(np.zeros((0, 3)), 0.7, use_ref).size == 0
+        assert oracle.ahc_cluster(np.array([[1.0, 0, 0]]), 0.7, use_ref).tolist() == [0]
+        assert oracle.ahc_cluster(np.zeros((3, 0)), 0.7, use_ref).tolist() == [0, 0, 0]
+
+
+def test_ahc_reference_unit_tests(oracle):
+    for use_ref in {False, oracle.ref_available()}:
+        same = oracle.ahc_cluster(np.tile([1.0, 2.0, 3.0], (5, 1)), 0.7, use_ref)
+        assert len(set(same.tolist())) == 1
+        g1 = [[1.0, 0, 0], [0.9, 0.1, 0], [0.95, 0.05, 0]]
+        g2 = [[0, 1.0, 0], [0, 0.9, 0.1], [0, 0.95, 0.05]]
+        r = oracle.ahc_cluster(np.array(g1 + g2), 0.8, use_ref)
+        assert len(set(r[:3].tolist())) == 1 and len(set(r[3:].tolist())) == 1 and r[0] != r[3]
+        four = np.array([[1.0, 0, 0], [0.9, 0.1, 0], [0, 1.0, 0], [0, 0.9, 0.1]])
+        assert len(set(oracle.ahc_cluster(four, 0.5, use_ref).tolist())) == 2
+        assert len(set(oracle.ahc_cluster(four, 1.5, use_ref).tolist())) == 1
+        eye = np.eye(3)
+        ids = sorted(set(oracle.ahc_cluster(eye, 0.5, use_ref).tolist()))
+        assert ids == list(range(len(ids)))
+        assert len(set(oracle.ahc_cluster(eye, 2.0, use_ref).tolist())) == 1
+        assert len(set(oracle.ahc_cluster(eye, 0.0, use_ref).tolist())) == 3
+
+
+def test_cut_is_the_swift_traversal_not_scipy_fcluster(oracle):
+    """Centroid linkage has inversions; the Swift cut uses each node's own distance."""
+    def py_cut(z, n, thr):
+        thr = 0.0 if np.isnan(thr) else max(0.0, min(2.0, thr))
+        left = {n + m: int(z[m, 0]) for m in range(n - 1)}
+        right = {n + m: int(z[m, 1]) for m in range(n - 1)}
+        dist = {n + m: z[m, 2] for m in range(n - 1)}
+        lab, nxt, stack = [-1] * n, 0, [2 * n - 2]
+        while stack:
+            node = stack.pop()
+            if node < n:
+                if lab[node] == -1:
+                    lab[node] = nxt; nxt += 1
+                continue
+            if dist[node] <= thr:
+                q = [node]
+                while q:
+                    c = q.pop()
+                    if c < n: lab[c] = nxt
+                    else: q += [left[c], right[c]]
+                nxt += 1
+            else:
+                stack += [left[node], right[node]]
+        remap, out = {}, []
+        for v in lab:
+            remap.setdefault(v, len(remap)); out.append(remap[v])
+        return np.array(out, np.int32)
+    rng = np.random.default_rng(11)
+    inversions = 0
+    for trial in range(40):
+        n = int(rng.integers(5, 60))
+        x = oracle.l2_normalize_rows(rng.standard_normal((n, 3)))
+        _, z = oracle.centroid_linkage(x)
+        inversions += int((np.diff(z[:, 2]) < 0).any())
+        for thr in (0.0, 0.3, 0.8, 1.2, 2.0, 5.0, -1.0, float("nan")):
+            assert np.array_equal(oracle.dendrogram_cut(z, n, thr), py_cut(z, n, thr))
+    assert inversions > 0
+
+
+def test_l2_normalize_matches_reference_vdsp_test(oracle):
+    # VDSPOperationsTests.swift: l2Normalize([3,4]) == [0.6, 0.8]; zero rows stay zero (AHCClustering.swift:88)
+    out = oracle.l2_normalize_rows(np.array([[3.0, 4.0], [0.0, 0.0]]))
+    assert np.allclose(out[0], [0.6, 0.8], atol=1e-15) and np.all(out[1] == 0)
+
+
+# ------------------------------------------------------------------------------------------------ VBx / assignment
+def _numpy_vbx(x, psi, init, S, Fa=0.07, Fb=0.8, iters=20, eps=1e-4):
+    T, D = x.shape
+    g = np.zeros((T, S)); g[np.arange(T), init] = 1
+    g = np.exp(7 * g - (7 * g).max(1, keepdims=True)); g /= g.sum(1, keepdims=True); g /= g.sum(1, keepdims=True)
+    pi = np.full(S, 1 / S)
+    phi = np.maximum(psi, 1e-12)
+    rho = x * np.sqrt(phi)
+    G = -0.5 * ((x ** 2).sum(1) + D * np.log(2 * np.pi))
+    prev, elbos = -np.inf, []
+    for it in range(iters):
+        invL = 1 / np.maximum(1 + (Fa / Fb) * g.sum(0)[:, None] * phi[None], 1e-12)
+        alpha = (Fa / Fb) * invL * (g.T @ rho)
+        phiT = ((alpha ** 2 + invL) * phi).sum(1)
+        logp = Fa * (rho @ alpha.T - 0.5 * phiT + G[:, None]) + np.log(np.maximum(pi, 1e-8))
+        mx = logp.max(1, keepdims=True)
+        e = np.exp(logp - mx); s = e.sum(1, keepdims=True)
+        g = e / s
+        ll = (mx + np.log(s)).sum()
+        pi = g.sum(0) / g.sum()
+        elbo = ll + Fb * 0.5 * (np.log(invL).sum() - invL.sum() - (alpha ** 2).sum() + invL.size)
+        elbos.append(elbo)
+        if it > 0 and abs(elbo - prev) < eps:
+            break
+        prev = elbo
+    return g, pi, np.array(elbos)
+
+
+def test_vbx_matches_independent_numpy_restatement(oracle):
+    emb, who = synth.speaker_embeddings(600, 256, 5, seed=5)
+    rho, psi = synth.synthetic_plda(emb)
+    init = oracle.ahc_cluster(emb.astype(np.float64), 0.6)
+    S = len(set(init.tolist()))
+    out = oracle.vbx_refine(rho, psi, init)
+    g, pi, elbos = _numpy_vbx(rho, psi, init, S)
+    assert out.num_clusters == S and len(out.elbos) == len(elbos)
+    assert np.abs(out.gamma - g).max() < 1e-9 and np.abs(out.pi - pi).max() < 1e-10
+    assert np.abs((out.elbos - elbos) / elbos).max() < 1e-12
+    assert np.allclose(out.gamma.sum(1), 1.0, atol=1e-12)
+    assert np.all(np.diff(out.elbos) > -1e-6)          # EM never decreases the bound
+    assert np.array_equal(out.hard, g.argmax(1))
+
+
+def test_pipeline_recovers_speakers_and_filters_nan(oracle):
+    emb, who = synth.speaker_embeddings(400, 256, 4, weights=(0.4, 0.3, 0.2, 0.1), seed=9)
+    emb[7, 100] = np.inf
+    emb[123, 0] = np.nan
+    rho, psi = synth.synthetic_plda(np.nan_to_num(emb, posinf=0.0))
+    r = oracle.diarize_cluster(emb, rho, psi)
+    assert r.training_indices.size == 398 and 7 not in r.training_indices
+    ok = np.isfinite(emb).all(1)
+    # AHC separates the four speakers exactly; VBx (with the synthetic PLDA and only 400 frames) may then merge
+    # some of them — every true speaker must still land in exactly one final cluster
+    init_pairs = set(zip(who[r.training_indices].tolist(), r.initial.tolist()))
+    assert len(init_pairs) == 4
+    pairs = set(zip(who[ok].tolist(), r.labels[ok].tolist()))
+    assert len(pairs) == 4
+    K = r.centroids.shape[0]
+    assert r.labels.shape == (400,) and 1 <= K <= 4 and r.labels.max() < K and r.centroids.shape[1] == 256
+
+
+def test_assign_first_maximum_wins(oracle):
+    cents = np.array([[1.0, 0.0], [2.0, 0.0], [0.0, 1.0]])     # centroids 0 and 1 are collinear: equal cosine
+    emb = np.array([[3.0, 0.0], [0.0, 5.0], [0.0, 0.0]])
+    labels, scores = oracle.assign_embeddings(emb, cents, want_scores=True)
+    assert labels.tolist() == [0, 2, 0]
+    assert scores[0, 0] == scores[0, 1] == 1.0
+
+
+# ------------------------------------------------------------------------------------------------ mel
+def test_mel_goldens_are_reproduced(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "mel_oracle.npz"))
+    a = g["audio"]
+    for nm in (80, 128):
+        m, ml, nf = oracle.mel_flat_transposed(oracle.mel_config(n_mels=nm), a)
+        assert np.array_equal(m, g[f"center_{nm}"])
+    assert np.array_equal(oracle.mel_legacy(oracle.mel_config(n_mels=128), a)[0], g["legacy_128"])
+    assert np.array_equal(oracle.hann_window(400, False), g["hann_400"])
+    assert np.array_equal(oracle.mel_filterbank(512, 80), g["filterbank_80"])
+
+
+def test_mel_matches_independent_float64_numpy_pipeline(oracle):
+    a = synth.tone_noise_audio(16000 + 137)
+    for nm in (80, 128):
+        w = oracle.hann_window().astype(np.float64)
+        fb = oracle.mel_filterbank(512, nm).astype(np.float64)
+        p = np.zeros(a.size + 512)
+        p[256] = a[0]
+        p[257:257 + a.size - 1] = a[1:].astype(np.float64) - float(np.float32(0.97)) * a[:-1].astype(np.float64)
+        T = 1 + (a.size + 512 - 400) // 160
+        fr = np.zeros((T, 512))
+        for f in range(T):
+            s = f * 160 + 56
+            av = min(400, p.size - s)
+            fr[f, 56:56 + av] = p[s:s + av] * w[:av]
+        ref = np.log(np.abs(np.fft.rfft(fr, axis=1)) ** 2 @ fb.T + float(np.float32(2.0 ** -24)))
+        m64, ml, _ = oracle.mel_flat_transposed(oracle.mel_config(n_mels=nm, precision=1), a)
+        assert ml == T and np.abs(m64 - ref).max() < 5e-6
+        m32, _, _ = oracle.mel_flat_transposed(oracle.mel_config(n_mels=nm), a)       # THE oracle
+        m32b, _, _ = oracle.mel_flat_transposed(oracle.mel_config(n_mels=nm, precision=2), a)   # float32 FFT variant
+        assert np.abs(m32 - ref).max() < 5e-5
+        assert np.abs(m32b - m32).max() < 1e-4
+
+
+def test_mel_reference_structure_tests(oracle):
+    """AudioMelSpectrogramTests.swift + EouChunkSizeFrameCountTests.swift."""
+    cfg = oracle.mel_config()
+    m, ml = oracle.mel_legacy(cfg, np.zeros(16000, np.float32))
+    assert ml == 98 and m.shape == (128, 98) and (m < 0).all()
+    assert oracle.mel_legacy(cfg, np.full(800, 0.1, np.float32))[1] > 0
+    flat, ml, nf = oracle.mel_flat(cfg, np.zeros(16000, np.float32))
+    assert nf > 0 and flat.size == 128 * nf
+    w = oracle.hann_window()
+    assert w.size == 400 and np.allclose(w, w[::-1], atol=1e-6) and abs(w[0]) < 1e-6 and abs(w[-1]) < 1e-6
+    assert abs(w[200] - 1.0) < 0.01
+    fb = oracle.mel_filterbank()
+    assert fb.shape == (128, 257) and (fb >= 0).all()
+    # StreamingChunkSize: chunkSamples = (melFrames - 1) * hop for 17 / 64(?) / 129 frames; formula check instead
+    for n in (1000, 2000, 5000, 8000, 10080, 12000, 15000, 20000, 25000, 30000, 2560, 20480):
+        assert oracle.mel_flat(cfg, np.full(n, 0.1, np.float32))[1] == 1 + (n + 512 - 400) // 160
+    assert oracle.mel_frame_count(cfg, 2560) == 17 and oracle.mel_frame_count(cfg, 20480) == 129
+
+
+def test_mel_modes_and_guards(oracle):
+    cfg = oracle.mel_config(n_mels=80, pad_to=16)
+    a = synth.tone_noise_audio(5000)
+    m, ml, nf = oracle.mel_flat_transposed(cfg, a)
+    assert ml == 32 and nf == 32 and m.shape == (32, 80)
+    m, ml, nf = oracle.mel_flat_transposed(cfg, a[:4000])
+    assert ml == 26 and nf == 32 and np.all(m[26:] == 0)              # padded rows are zero
+    # prePadded: (n - nFFT)/hop + 1 with truncating division; below 352 samples -> no frame
+    assert oracle.mel_frame_count(cfg, 400, 1) == 1 and oracle.mel_frame_count(cfg, 352, 1) == 0
+    out, ml, nf = oracle.mel_flat_transposed(cfg, np.zeros(0, np.float32))
+    assert ml == 0 and nf == 1 and out.size == 80 and np.all(out == 0)
+    # expectedFrameCount beyond the signal: all-zero frames -> log(floor)
+    m, ml, nf = oracle.mel_flat_transposed(oracle.mel_config(n_mels=80), a[:800], expected_frames=12)
+    assert ml == 12 and np.allclose(m[11], np.log(np.float32(2.0 ** -24)), atol=1e-6)
+    # streamed pre-padded == batch centre (SortformerStreamingMelTests.swift:84-132), within 1e-5
+    full, T, _ = oracle.mel_flat_transposed(oracle.mel_config(n_mels=128), a)
+    padded = np.concatenate([np.zeros(256, np.float32), a, np.zeros(256, np.float32)])
+    # pre-emphasis must see the true previous sample, so apply the same filter by passing preemph through the pad
+    pre, T2, _ = oracle.mel_flat_transposed(oracle.mel_config(n_mels=128), padded, padding_mode=1)
+    assert T2 == T
+    assert np.abs(pre[2:-2] - full[2:-2]).max() < 1e-5
+
+
+def test_adapters(oracle):
+    x = np.arange(24, dtype=np.float32).reshape(6, 4) ** 1.5
+    y = oracle.normalize_per_feature(x, 4)
+    assert np.all(y[4:] == 0) and np.allclose(y[:4].mean(0), 0, atol=1e-6)
+    assert np.allclose(y[:4].std(0, ddof=1), 1.0, atol=1e-3)
+    assert np.all(oracle.normalize_per_feature(x, 0) == 0)
+    planar = np.stack([np.arange(10, dtype=np.float32), np.arange(10, dtype=np.float32) * 3,
+                       np.zeros(10, np.float32)])
+    mono = planar.mean(0)
+    assert np.allclose(oracle.linear_resample(planar, 16000, 16000), mono)
+    half = oracle.linear_resample(planar, 32000, 16000)
+    assert half.size == 5 and np.allclose(half, mono[::2])
+    up = oracle.linear_resample(planar, 8000, 16000)
+    assert up.size == 20 and np.allclose(up[:19], np.interp(np.arange(19) / 2, np.arange(10), mono), atol=1e-5)
