@@ -53,7 +53,8 @@ EXPORTED_SYMBOLS = [
     "fa_kernel_launch_count", "fa_host_alloc", "fa_host_free", "fa_device_alloc", "fa_device_free", "fa_memcpy_h2d",
     "fa_memcpy_d2h", "fa_timer_start", "fa_timer_stop_ms", "fa_mel_default_config", "fa_mel_create",
     "fa_mel_destroy", "fa_mel_get_window", "fa_mel_get_filterbank", "fa_mel_frame_count", "fa_mel_compute",
-    "fa_mel_compute_device", "fa_mel_compute_batch", "fa_mel_compute_batch_device", "fa_mel_normalize_per_feature",
+    "fa_mel_compute_device", "fa_mel_compute_batch", "fa_mel_compute_batch_device", "fa_mel_timer_start",
+    "fa_mel_timer_stop_ms", "fa_mel_normalize_per_feature",
     "fa_linear_resample", "fa_l2_normalize_rows", "fa_ahc_cluster", "fa_dendrogram_cut", "fa_vbx_default_config",
     "fa_vbx_refine", "fa_compute_centroids", "fa_assign_embeddings", "fa_cluster_default_config",
     "fa_diarize_cluster", "fa_diarize_cluster_batch", "fa_ahc_last_stage_ms",
@@ -99,6 +100,8 @@ def load():
     L.fa_mel_compute_device.argtypes = L.fa_mel_compute.argtypes
     L.fa_mel_compute_batch.argtypes = [vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]
     L.fa_mel_compute_batch_device.argtypes = L.fa_mel_compute_batch.argtypes
+    L.fa_mel_timer_start.argtypes = [vp]
+    L.fa_mel_timer_stop_ms.argtypes = [vp, C.POINTER(f32)]
     L.fa_mel_normalize_per_feature.argtypes = [vp, i64, i32, i64]
     L.fa_linear_resample.argtypes = [vp, i64, i32, f64, f64, vp, i64, C.POINTER(i64)]
     L.fa_l2_normalize_rows.argtypes = [vp, sz, sz, vp]

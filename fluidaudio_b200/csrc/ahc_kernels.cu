@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -669,6 +670,10 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     if (N <= 65535)
         for (int l = 1; l <= 3; ++l)
             if (master_smem_bytes(N, l) <= smem_cap) level = l;
+    // test hooks: exercise the fall-back placements at small N (tests/test_gpu_parity.py)
+    const char *force_global = std::getenv("FA_AHC_FORCE_GLOBAL_MASTER");
+    const char *force_stream = std::getenv("FA_AHC_FORCE_STREAMED");
+    if (force_global && force_global[0] == '1') level = 0;
     const bool idx16 = level >= 1;
     // worker placement: resident (each CTA keeps <= 128 node vectors in shared memory) when the whole problem fits
     // into max_workers CTAs, else streamed from the k-major global copy
@@ -679,6 +684,7 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     }
     const int cap_slots = (int)std::min<size_t>(kMergeThreads, (smem_cap - worker_fixed) / (sizeof(double) * (size_t)D));
     bool resident = cap_slots >= 1 && (long long)cap_slots * max_workers >= N;
+    if (force_stream && force_stream[0] == '1') resident = false;
     int workers, slots_per_cta = 0;
     size_t worker_smem = worker_fixed;
     if (resident) {

@@ -633,6 +633,28 @@ FA_API fa_status fa_mel_compute_batch_device(fa_mel *mel, const float *d_audio, 
     FA_GUARD_END
 }
 
+// CUDA-event timing on the stream the mel kernels are launched on (device-resident entry points are asynchronous).
+FA_API fa_status fa_mel_timer_start(fa_mel *mel) {
+    if (!mel) return FA_STATUS_INVALID_ARGUMENT;
+    auto *h = reinterpret_cast<MelHandle *>(mel);
+    if (!h->plan.timer[0]) {
+        API_CUDA_TRY(cudaEventCreate(&h->plan.timer[0]));
+        API_CUDA_TRY(cudaEventCreate(&h->plan.timer[1]));
+    }
+    API_CUDA_TRY(cudaStreamSynchronize(h->plan.streams[1]));
+    API_CUDA_TRY(cudaEventRecord(h->plan.timer[0], h->plan.streams[1]));
+    return FA_STATUS_OK;
+}
+FA_API fa_status fa_mel_timer_stop_ms(fa_mel *mel, float *elapsed_ms) {
+    if (!mel || !elapsed_ms) return FA_STATUS_INVALID_ARGUMENT;
+    auto *h = reinterpret_cast<MelHandle *>(mel);
+    if (!h->plan.timer[0]) return FA_STATUS_INVALID_ARGUMENT;
+    API_CUDA_TRY(cudaEventRecord(h->plan.timer[1], h->plan.streams[1]));
+    API_CUDA_TRY(cudaEventSynchronize(h->plan.timer[1]));
+    API_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, h->plan.timer[0], h->plan.timer[1]));
+    return FA_STATUS_OK;
+}
+
 // UnifiedMelExtractor.normalizePerFeature (UnifiedMelExtractor.swift:88-113).  O(T*M) on a caller-owned host
 // buffer that is about to be handed to the encoder; not a GPU hot path.
 FA_API fa_status fa_mel_normalize_per_feature(float *x, int64_t frames, int32_t n_mels, int64_t valid) {

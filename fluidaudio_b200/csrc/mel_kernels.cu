@@ -315,6 +315,8 @@ void MelPlan::release() {
     for (auto &e : events)
         if (e) cudaEventDestroy(e);
     events.clear();
+    for (auto &e : timer)
+        if (e) cudaEventDestroy(e), e = nullptr;
 }
 
 int MelPlan::init(const MelConfig &c) {

@@ -85,6 +85,7 @@ struct MelPlan {
     size_t d_audio_cap = 0, d_out_cap = 0;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};   // h2d, compute, d2h
     std::vector<cudaEvent_t> events;
+    cudaEvent_t timer[2] = {nullptr, nullptr};   // fa_mel_timer_*: events on the compute stream
 
     ~MelPlan();
     void release();

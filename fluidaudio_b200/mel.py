@@ -145,6 +145,14 @@ class AudioMelSpectrogram:
                                                  C.byref(ml), C.byref(nf)), "fa_mel_compute_device")
         return int(ml.value), int(nf.value)
 
+    def timer_start(self):
+        _lib.check(self._L.fa_mel_timer_start(self._h), "fa_mel_timer_start")
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_float()
+        _lib.check(self._L.fa_mel_timer_stop_ms(self._h, C.byref(ms)), "fa_mel_timer_stop_ms")
+        return float(ms.value)
+
     def compute_batch_device(self, d_audio, offsets, d_out, out_offsets, padding_mode=PaddingMode.center,
                              time_major: bool = True):
         offsets = np.ascontiguousarray(offsets, np.int64)

@@ -106,6 +106,10 @@ fa_status fa_mel_compute_batch_device(fa_mel *mel, const float *d_audio, const i
                                       const float *last_samples, int32_t padding_mode, int32_t layout, float *d_out,
                                       const int64_t *out_offsets, int64_t *mel_lengths, int64_t *num_frames);
 
+/* CUDA-event timer on the stream the mel kernels run on: bracket any number of fa_mel_compute*_device calls. */
+fa_status fa_mel_timer_start(fa_mel *mel);
+fa_status fa_mel_timer_stop_ms(fa_mel *mel, float *elapsed_ms);
+
 /* NeMo per-feature normalisation of a time-major [frames x n_mels] buffer, in place (host buffer).
  * UnifiedMelExtractor.normalizePerFeature, Sources/FluidAudio/ASR/Parakeet/Unified/UnifiedMelExtractor.swift:88-113 */
 fa_status fa_mel_normalize_per_feature(float *x, int64_t frames, int32_t n_mels, int64_t valid_frames);

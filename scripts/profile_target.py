@@ -1,0 +1,26 @@
+"""Small, fixed workloads for ncu captures (never a bench value).  Usage: profile_target.py mel|cluster [reps]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from fluidaudio_b200 import _lib, synth
+what = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+if what == "mel":
+    from fluidaudio_b200.mel import AudioMelSpectrogram
+    n = 57_600_000
+    a = synth.tone_noise_audio(n)
+    m = AudioMelSpectrogram(n_mels=80)
+    d_a = _lib.DeviceBuffer(n * 4 + 64); d_a.upload(a)
+    d_o = _lib.DeviceBuffer(360001 * 80 * 4)
+    for _ in range(reps):
+        m.compute_device(d_a, n, d_o)
+    _lib.synchronize()
+else:
+    from fluidaudio_b200.clustering import OfflineClusterer
+    emb, _ = synth.speaker_embeddings(10000, 256, 8, seed=42)
+    rho, psi = synth.synthetic_plda(emb)
+    c = OfflineClusterer(psi=psi)
+    for _ in range(reps):
+        r = c.cluster(emb, rho)
+    print(r.info)
+print("profile target done")

@@ -59,7 +59,12 @@ def main():
         x = O.l2_normalize_rows(emb.astype(np.float64))
         z = ref_linkage(x)
         labels = O.dendrogram_cut(z, n, 0.6)
+        rho, psi = synth.synthetic_plda(emb)
+        pipe = O.diarize_cluster(emb, rho, psi, use_ref=True)
         large[name] = {"n": n, "speakers": k, "weights": w, "seed": seed,
+                       "final_labels_sha256": hashlib.sha256(pipe.labels.tobytes()).hexdigest(),
+                       "final_centroids": int(pipe.centroids.shape[0]), "vbx_iterations": int(len(pipe.vbx.elbos)),
+                       "vbx_last_elbo": float(pipe.vbx.elbos[-1]),
                        "z_sha256": hashlib.sha256(z.tobytes()).hexdigest(),
                        "labels_sha256": hashlib.sha256(labels.tobytes()).hexdigest(),
                        "clusters": int(labels.max() + 1), "last_merge_distance": float(z[-1, 2])}

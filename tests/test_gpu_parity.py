@@ -1,0 +1,375 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200 box).  Every call goes through the C ABI of
+libfluidaudio_b200.so (via the ctypes mirror in fluidaudio_b200/); the oracle is only the checker.
+
+Bars (BASELINE.json north_star): cluster labels and dendrograms BIT-EXACT; log-mel and float distances within 1e-4
+(tolerance spelled out as MEL_TOL below); frame counts, shapes and guards exact.
+"""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from fluidaudio_b200 import _lib, synth
+from fluidaudio_b200 import clustering as cl
+from fluidaudio_b200.mel import AudioMelSpectrogram, LogFloorMode, PaddingMode
+
+pytestmark = pytest.mark.gpu
+
+MEL_TOL = 1e-4          # |log-mel(GPU) - log-mel(oracle)| <= 1e-4, north_star's stated tolerance
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ================================================================================================ mel
+def test_mel_tables_are_bit_identical_to_the_oracle(gpu_lib, oracle):
+    for nm, periodic in ((128, False), (80, False), (80, True), (23, False)):
+        m = AudioMelSpectrogram(n_mels=nm, window_periodic=periodic)
+        assert np.array_equal(m.get_hann_window(), oracle.hann_window(400, periodic))
+        assert np.array_equal(m.get_filterbank(), oracle.mel_filterbank(512, nm))
+    # reference structural tests (AudioMelSpectrogramTests.swift:57-103)
+    w = AudioMelSpectrogram().get_hann_window()
+    assert w.size == 400 and abs(w[0]) < 1e-6 and abs(w[-1]) < 1e-6 and abs(w[200] - 1) < 0.01
+    fb = AudioMelSpectrogram().get_filterbank()
+    assert fb.shape == (128, 257) and (fb >= 0).all()
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_mel_center_mode_lengths_and_values(gpu_lib, oracle, n_mels):
+    m = AudioMelSpectrogram(n_mels=n_mels)
+    cfg = oracle.mel_config(n_mels=n_mels)
+    for n in (1, 2, 159, 160, 161, 399, 400, 401, 512, 4000, 5119, 5120, 16000 * 3 + 137, 16000 * 30):
+        a = synth.tone_noise_audio(n, seed=n % 11)
+        got, ml, nf = m.compute_flat_transposed(a)
+        ref, rml, rnf = oracle.mel_flat_transposed(cfg, a)
+        assert (ml, nf) == (rml, rnf) == (1 + (n + 112) // 160,) * 2
+        assert got.size == nf * n_mels
+        assert np.abs(got.reshape(nf, n_mels) - ref).max() <= MEL_TOL, n
+
+
+def test_mel_golden_fixture(gpu_lib, golden_dir):
+    g = np.load(os.path.join(golden_dir, "mel_oracle.npz"))
+    a = g["audio"]
+    for nm in (80, 128):
+        got, ml, nf = AudioMelSpectrogram(n_mels=nm).compute_flat_transposed(a)
+        assert np.abs(got.reshape(nf, nm) - g[f"center_{nm}"]).max() <= MEL_TOL
+    got, ml = AudioMelSpectrogram(n_mels=128).compute(a)
+    assert np.abs(got[0] - g["legacy_128"]).max() <= MEL_TOL
+    m = AudioMelSpectrogram(n_mels=80, preemph=0.0, log_floor=1e-10, log_floor_mode=LogFloorMode.clamped,
+                            window_periodic=True)
+    got, ml, nf = m.compute_flat_transposed(a, padding_mode=PaddingMode.pre_padded)
+    assert np.abs(got.reshape(nf, 80) - g["lseend_prepadded_80"]).max() <= MEL_TOL
+
+
+def test_mel_all_entry_points_and_modes(gpu_lib, oracle):
+    a = synth.tone_noise_audio(16000 * 5 + 77, seed=3)
+    sp = synth.speech_like_audio(16000 * 8)
+    for nm in (80, 128):
+        m = AudioMelSpectrogram(n_mels=nm)
+        cfg = oracle.mel_config(n_mels=nm)
+        # computeFlat: mel-major, carries lastAudioSample into the pre-emphasis
+        got, ml, nf = m.compute_flat(a, last_audio_sample=0.25)
+        ref, rml, rnf = oracle.mel_flat(cfg, a, last=0.25)
+        assert (ml, nf) == (rml, rnf) and np.abs(got.reshape(nm, nf) - ref).max() <= MEL_TOL
+        # compute(): legacy, [1, nMels, T]
+        got, ml = m.compute(a)
+        ref, rml = oracle.mel_legacy(cfg, a)
+        assert ml == rml and got.shape == (1, nm, ml) and np.abs(got[0] - ref).max() <= MEL_TOL
+        # prePadded with and without an expected frame count (streaming callers)
+        for exp in (None, 100, 600):
+            got, ml, nf = m.compute_flat_transposed(a, last_audio_sample=-0.1, padding_mode=PaddingMode.pre_padded,
+                                                    expected_frame_count=exp)
+            ref, rml, rnf = oracle.mel_flat_transposed(cfg, a, last=-0.1, padding_mode=1, expected_frames=exp)
+            assert (ml, nf) == (rml, rnf) and np.abs(got.reshape(nf, nm) - ref).max() <= MEL_TOL
+        got, ml, nf = m.compute_flat_transposed(sp)
+        ref, _, _ = oracle.mel_flat_transposed(cfg, sp)
+        assert np.abs(got.reshape(nf, nm) - ref).max() <= MEL_TOL
+    # padTo: padded rows are zero (AudioMelSpectrogram.swift:354,394)
+    m = AudioMelSpectrogram(n_mels=80, pad_to=16)
+    got, ml, nf = m.compute_flat_transposed(a[:4000])
+    assert (ml, nf) == (26, 32) and np.all(got.reshape(32, 80)[26:] == 0)
+    got, ml, nf = m.compute_flat(a[:4000])
+    assert (ml, nf) == (26, 32) and np.all(got.reshape(80, 32)[:, 26:] == 0)
+    ref, _, _ = oracle.mel_flat(oracle.mel_config(n_mels=80, pad_to=16), a[:4000])
+    assert np.abs(got.reshape(80, 32) - ref).max() <= MEL_TOL
+    # LS-EEND style configuration (LSEENDPreprocessor.swift:70-81)
+    m = AudioMelSpectrogram(n_mels=23, hop_length=80, win_length=200, preemph=0.0, log_floor=1e-10,
+                            log_floor_mode=LogFloorMode.clamped, window_periodic=True)
+    cfg = oracle.mel_config(n_mels=23, hop_length=80, win_length=200, preemph=0.0, log_floor=1e-10, log_floor_mode=1,
+                            window_periodic=True)
+    got, ml, nf = m.compute_flat_transposed(sp[:40000], padding_mode=PaddingMode.pre_padded)
+    ref, rml, rnf = oracle.mel_flat_transposed(cfg, sp[:40000], padding_mode=1)
+    assert (ml, nf) == (rml, rnf) and np.abs(got.reshape(nf, 23) - ref).max() <= MEL_TOL
+
+
+def test_mel_guards_silence_and_unsupported(gpu_lib):
+    m = AudioMelSpectrogram(n_mels=128)
+    out, ml, nf = m.compute_flat_transposed(np.zeros(0, np.float32))
+    assert (ml, nf) == (0, 1) and out.size == 128 and np.all(out == 0)           # :349-351
+    mel, ml = m.compute(np.zeros(300, np.float32))                              # fewer than one window
+    assert ml == 0
+    mel, ml = m.compute(np.zeros(16000, np.float32))                            # AudioMelSpectrogramTests.swift:32-45,107-122
+    assert ml == 98 and mel.shape == (1, 128, 98) and (mel < 0).all()
+    floor = np.log(np.float32(2.0 ** -24))
+    got, ml, nf = m.compute_flat_transposed(np.zeros(8000, np.float32))
+    assert np.all(got == floor)                                                 # silence is exactly log(floor)
+    assert m.compute(np.full(800, 0.1, np.float32))[1] > 0                      # :24-30
+    for n, frames in ((2560, 17), (20480, 129)):                                # EouChunkSizeFrameCountTests.swift
+        assert m.compute_flat(np.full(n, 0.1, np.float32))[1] == frames
+    with pytest.raises(_lib.FluidAudioError) as e:
+        AudioMelSpectrogram(n_fft=400)
+    assert e.value.status == 8
+
+
+def test_mel_batch_and_device_paths(gpu_lib, oracle):
+    m = AudioMelSpectrogram(n_mels=80)
+    cfg = oracle.mel_config(n_mels=80)
+    lens = [480000, 1000, 33333, 7, 480000, 161, 250001]
+    clips = [synth.tone_noise_audio(n, seed=i) for i, n in enumerate(lens)]
+    last = np.linspace(-0.2, 0.2, len(lens)).astype(np.float32)
+    out, offs, ml, nf = m.compute_batch(clips, last_samples=last)
+    for i, c in enumerate(clips):
+        ref, rml, rnf = oracle.mel_flat_transposed(cfg, c, last=float(last[i]))
+        assert (ml[i], nf[i]) == (rml, rnf)
+        assert np.abs(out[offs[i]:offs[i + 1]].reshape(-1, 80) - ref).max() <= MEL_TOL
+        single, _, _ = m.compute_flat_transposed(c, last_audio_sample=float(last[i]))
+        assert np.array_equal(single, out[offs[i]:offs[i + 1]])                  # batch == one-by-one, bitwise
+    # device-resident entry point == host entry point, bitwise; unaligned device pointers take the non-TMA path
+    a = clips[0]
+    T = m.frame_count(a.size)
+    host, _, _ = m.compute_flat_transposed(a)
+    d_a = _lib.DeviceBuffer(a.nbytes + 64)
+    d_o = _lib.DeviceBuffer(T * 80 * 4)
+    d_a.upload(a)
+    assert m.compute_device(d_a, a.size, d_o) == (T, T)
+    _lib.synchronize()
+    assert np.array_equal(d_o.download((T * 80,), np.float32), host)
+    shifted = np.concatenate([np.zeros(1, np.float32), a])
+    d_a.upload(shifted)
+
+    class Off:                                                                  # view of the buffer at +4 bytes
+        ptr = d_a.ptr.value + 4
+    ml2, nf2 = m.compute_device(Off, a.size, d_o)
+    _lib.synchronize()
+    assert np.array_equal(d_o.download((T * 80,), np.float32), host)
+
+
+def test_mel_one_hour_properties(gpu_lib, oracle):
+    """BASELINE config 2 at full size: 1 h of 16 kHz audio, 80 mels."""
+    n = 57_600_000
+    a = synth.tone_noise_audio(n)
+    m = AudioMelSpectrogram(n_mels=80)
+    T = m.frame_count(n)
+    assert T == 360001
+    host, ml, nf = m.compute_flat_transposed(a)                                 # chunked H2D / kernel / D2H pipeline
+    host = host.reshape(T, 80)
+    d_a = _lib.DeviceBuffer(n * 4 + 64)
+    d_o = _lib.DeviceBuffer(T * 80 * 4)
+    d_a.upload(a)
+    m.compute_device(d_a, n, d_o)                                               # one launch over all frames
+    _lib.synchronize()
+    assert np.array_equal(d_o.download((T, 80), np.float32), host)              # chunking is invisible, bitwise
+    assert np.isfinite(host).all()
+    # a frame depends only on its own 400 samples: excerpts starting on a hop boundary reproduce interior frames
+    for start_frame in (0, 1000, 123456, 359000):
+        s0 = start_frame * 160
+        ex = a[s0:s0 + 16000 * 5]
+        sub, sml, _ = m.compute_flat_transposed(ex, last_audio_sample=float(a[s0 - 1]) if s0 else 0.0)
+        sub = sub.reshape(sml, 80)
+        assert np.array_equal(sub[2:sml - 3], host[start_frame + 2:start_frame + sml - 3])
+    # against the oracle: the first minute and a window in the middle
+    cfg = oracle.mel_config(n_mels=80)
+    ref, rml, _ = oracle.mel_flat_transposed(cfg, a[:960000])
+    assert np.abs(host[:rml - 3] - ref[:rml - 3]).max() <= MEL_TOL
+    s0 = 200000 * 160
+    ref, rml, _ = oracle.mel_flat_transposed(cfg, a[s0:s0 + 960000], last=float(a[s0 - 1]))
+    assert np.abs(host[200000 + 2:200000 + rml - 3] - ref[2:rml - 3]).max() <= MEL_TOL
+
+
+# ================================================================================================ AHC
+def _ref_linkage(oracle, x):
+    return oracle.centroid_linkage(x, use_ref=oracle.ref_available())
+
+
+def test_linkage_reproduces_reference_goldens_bit_exact(gpu_lib, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ahc_reference.npz"))
+    for name in sorted({k.rsplit("__", 1)[0] for k in g.files}):
+        st, z = cl.centroid_linkage(g[name + "__x"])
+        assert st == 0 and np.array_equal(z, g[name + "__z"]), name
+
+
+def test_linkage_bit_exact_on_fresh_inputs_and_status_codes(gpu_lib, oracle):
+    rng = np.random.default_rng(99)
+    for n, d in ((2, 1), (3, 2), (33, 5), (129, 256), (1000, 64), (2049, 256), (777, 300), (64, 1023)):
+        x = rng.standard_normal((n, d))
+        st, z = cl.centroid_linkage(x)
+        st2, z2 = _ref_linkage(oracle, x)
+        assert st == st2 == 0 and np.array_equal(z, z2), (n, d)
+    x = np.round(rng.standard_normal((400, 4)), 1)                               # masses of exactly tied distances
+    assert np.array_equal(cl.centroid_linkage(x)[1], _ref_linkage(oracle, x)[1])
+    x = np.repeat(rng.standard_normal((40, 6)), 5, axis=0)[rng.permutation(200)]  # duplicates: zero distances
+    assert np.array_equal(cl.centroid_linkage(x)[1], _ref_linkage(oracle, x)[1])
+    bad = rng.standard_normal((50, 8)); bad[17, 3] = np.nan
+    assert cl.centroid_linkage(bad)[0] == 5                                      # nan_error -> RUNTIME_ERROR
+    inf = rng.standard_normal((20, 4)); inf[3, 0] = np.inf; inf[9, 0] = np.inf   # inf - inf = NaN
+    assert cl.centroid_linkage(inf)[0] == _ref_linkage(oracle, inf)[0] == 5
+    one_inf = rng.standard_normal((20, 4)); one_inf[3, 0] = np.inf               # infinite but never NaN
+    st, z = cl.centroid_linkage(one_inf)
+    st2, z2 = _ref_linkage(oracle, one_inf)
+    assert st == st2 and (st != 0 or np.array_equal(z, z2))
+    L = gpu_lib
+    zbuf = np.zeros(8)
+    assert L.fastcluster_compute_centroid_linkage(np.ones((3, 2)).ctypes.data, 3, 2, zbuf.ctypes.data, 7) == 3
+
+
+def test_linkage_fallback_placements_are_bit_exact(gpu_lib, oracle):
+    """Master state in global memory / node vectors streamed from L2 (the large-N code paths) at small N."""
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r);"
+        "from fluidaudio_b200 import clustering as cl; from oracle import oracle as O;"
+        "rng = np.random.default_rng(5);"
+        "ok = True\n"
+        "for n, d in ((3, 2), (300, 16), (1500, 256)):\n"
+        "    x = rng.standard_normal((n, d)); st, z = cl.centroid_linkage(x); st2, z2 = O.centroid_linkage(x)\n"
+        "    ok = ok and st == 0 and np.array_equal(z, z2)\n"
+        "print('FALLBACK_OK' if ok else 'FALLBACK_BAD')" % ROOT)
+    for env in ({"FA_AHC_FORCE_GLOBAL_MASTER": "1"}, {"FA_AHC_FORCE_STREAMED": "1"},
+                {"FA_AHC_FORCE_GLOBAL_MASTER": "1", "FA_AHC_FORCE_STREAMED": "1"}):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True,
+                             timeout=600)
+        assert "FALLBACK_OK" in out.stdout, (env, out.stdout[-500:], out.stderr[-1500:])
+
+
+def test_linkage_is_reentrant(gpu_lib, oracle):
+    rng = np.random.default_rng(4)
+    xs = [rng.standard_normal((400 + 50 * i, 32)) for i in range(6)]
+    want = [oracle.centroid_linkage(x)[1] for x in xs]
+    got = [None] * len(xs)
+
+    def run(i):
+        got[i] = cl.centroid_linkage(xs[i])
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(len(xs))]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for i in range(len(xs)):
+        assert got[i][0] == 0 and np.array_equal(got[i][1], want[i])
+
+
+def test_ahc_cluster_reference_unit_tests(gpu_lib, oracle):
+    """AHCClusteringTests.swift through the GPU path."""
+    ahc = cl.AHCClustering()
+    assert ahc.cluster([], 0.7).size == 0
+    assert ahc.cluster([[1.0, 0.0, 0.0]], 0.7).tolist() == [0]
+    assert len(set(ahc.cluster([[1.0, 2.0, 3.0]] * 5, 0.7).tolist())) == 1
+    g1 = [[1.0, 0, 0], [0.9, 0.1, 0], [0.95, 0.05, 0]]
+    g2 = [[0, 1.0, 0], [0, 0.9, 0.1], [0, 0.95, 0.05]]
+    r = ahc.cluster(g1 + g2, 0.8)
+    assert len(set(r[:3].tolist())) == 1 and len(set(r[3:].tolist())) == 1 and r[0] != r[3]
+    four = [[1.0, 0, 0], [0.9, 0.1, 0], [0, 1.0, 0], [0, 0.9, 0.1]]
+    assert len(set(ahc.cluster(four, 0.5).tolist())) == 2 and len(set(ahc.cluster(four, 1.5).tolist())) == 1
+    eye = np.eye(3)
+    ids = sorted(set(ahc.cluster(eye, 0.5).tolist()))
+    assert ids == list(range(len(ids)))
+    assert len(set(ahc.cluster(eye, 2.0).tolist())) == 1 and len(set(ahc.cluster(eye, 0.0).tolist())) == 3
+    assert ahc.cluster(np.zeros((3, 0)), 0.7).tolist() == [0, 0, 0]
+    nan_rows = np.array([[1.0, 0.0], [np.nan, 1.0], [0.0, 1.0]])
+    assert ahc.cluster(nan_rows, 0.7).tolist() == [0, 1, 2]                      # FFI failure -> identity (:52-55)
+    rng = np.random.default_rng(8)
+    for n in (5, 50, 700):
+        x = rng.standard_normal((n, 16)) + 3 * rng.integers(0, 3, (n, 1))
+        for thr in (0.0, 0.4, 0.9, 1.3, 2.0, 7.0, -2.0, float("nan")):
+            assert np.array_equal(ahc.cluster(x, thr), oracle.ahc_cluster(x, thr))
+    assert np.array_equal(cl.l2_normalize_rows(x), oracle.l2_normalize_rows(x))  # same operation order: bitwise
+
+
+def test_baseline_size_problems_match_reference_hashes(gpu_lib, golden_dir, oracle):
+    """C5 (5 000 x 256) and C3 (10 000 x 256): dendrogram bytes and labels hashed against the reference run."""
+    meta = json.load(open(os.path.join(golden_dir, "ahc_large.json")))
+    for name, m in meta.items():
+        emb, _ = synth.speaker_embeddings(m["n"], 256, m["speakers"], weights=m["weights"], seed=m["seed"])
+        x = oracle.l2_normalize_rows(emb.astype(np.float64))
+        st, z = cl.centroid_linkage(x)
+        assert st == 0
+        assert hashlib.sha256(z.tobytes()).hexdigest() == m["z_sha256"], name
+        labels = cl.dendrogram_cut(z, m["n"], 0.6)
+        assert hashlib.sha256(labels.tobytes()).hexdigest() == m["labels_sha256"]
+        assert np.array_equal(cl.AHCClustering().cluster(emb.astype(np.float64), 0.6), labels)
+        rho, psi = synth.synthetic_plda(emb)
+        res = cl.OfflineClusterer(psi=psi).cluster(emb, rho)
+        assert hashlib.sha256(res.labels.tobytes()).hexdigest() == m["final_labels_sha256"], name
+        assert res.info["centroid_count"] == m["final_centroids"]
+        assert res.info["vbx_iterations"] == m["vbx_iterations"]
+        # size-independent properties: sizes telescope to N, every node id appears exactly once as a child
+        assert z[-1, 3] == m["n"]
+        kids = np.concatenate([z[:, 0], z[:, 1]]).astype(np.int64)
+        assert np.array_equal(np.sort(kids), np.arange(2 * m["n"] - 2))
+
+
+# ================================================================================================ VBx / pipeline
+def test_vbx_centroids_assignment_against_oracle(gpu_lib, oracle):
+    for n, k, seed in ((300, 3, 1), (1500, 6, 2), (4000, 8, 3)):
+        emb, _ = synth.speaker_embeddings(n, 256, k, seed=seed)
+        rho, psi = synth.synthetic_plda(emb)
+        init = oracle.ahc_cluster(emb.astype(np.float64), 0.6)
+        o = oracle.vbx_refine(rho, psi, init)
+        v = cl.VBxClustering(psi=psi).refine(rho, init)
+        assert v.num_clusters == o.num_clusters and len(v.elbos) == len(o.elbos)
+        assert np.abs(v.gamma - o.gamma).max() <= 1e-9 and np.abs(v.pi - o.pi).max() <= 1e-9
+        assert np.abs((v.elbos - o.elbos) / o.elbos).max() <= 1e-10
+        assert np.array_equal(v.hard_clusters, o.hard)
+        cents = cl.compute_centroids(emb.astype(np.float64), v)
+        ocents = oracle.compute_centroids(emb.astype(np.float64), o, init)
+        assert cents.shape == ocents.shape and np.abs(cents - ocents).max() <= 1e-12
+        labels, scores = cl.assign_embeddings(emb.astype(np.float64), cents, want_scores=True)
+        olabels, oscores = oracle.assign_embeddings(emb.astype(np.float64), ocents, want_scores=True)
+        assert np.array_equal(labels, olabels) and np.abs(scores - oscores).max() <= 1e-4
+    # psi of the wrong length -> identity (VBxClustering.swift:71-76); no initial labels -> uniform gamma
+    v = cl.VBxClustering(psi=np.ones(7)).refine(rho[:200], init[:200])
+    o = oracle.vbx_refine(rho[:200], np.ones(7), init[:200])
+    assert np.array_equal(v.hard_clusters, o.hard) and np.abs(v.gamma - o.gamma).max() <= 1e-9
+    # run-to-run determinism (OfflineDiarizerTwoPhaseTests.swift:20-33: cluster phase bit-identical across repeats)
+    a = cl.VBxClustering(psi=psi).refine(rho, init)
+    b = cl.VBxClustering(psi=psi).refine(rho, init)
+    assert np.array_equal(a.gamma, b.gamma) and np.array_equal(a.elbos, b.elbos)
+
+
+def test_cluster_pipeline_labels_bit_exact(gpu_lib, oracle):
+    for n, k, seed in ((2, 1, 0), (9, 2, 1), (500, 4, 2), (2000, 8, 3)):
+        emb, _ = synth.speaker_embeddings(n, 256, k, seed=seed + 10)
+        if n >= 9:
+            emb[5, 3] = np.nan
+            emb[n - 1, 100] = np.inf
+        rho, psi = synth.synthetic_plda(np.nan_to_num(emb, posinf=0.0))
+        r = cl.OfflineClusterer(psi=psi).cluster(emb, rho)
+        o = oracle.diarize_cluster(emb, rho, psi, use_ref=oracle.ref_available())
+        assert np.array_equal(r.labels, o.labels), n
+        assert np.array_equal(r.initial[o.training_indices], o.initial)
+        assert r.info["training_count"] == o.training_indices.size
+        assert r.centroids.shape == o.centroids.shape and np.abs(r.centroids - o.centroids).max() <= 1e-9
+    # every row non-finite -> all rows are used (selectTrainingEmbeddings, OfflineDiarizerManager.swift:606-608):
+    # AHC then reports NaN and falls back to identity labels exactly like the Swift caller
+    emb = np.full((6, 256), np.nan, np.float32)
+    rho = np.zeros((6, 128))
+    r = cl.OfflineClusterer().cluster(emb, rho)
+    assert r.info["training_count"] == 6 and r.info["initial_clusters"] == 6
+
+
+def test_batch_of_sets_equals_one_by_one(gpu_lib, oracle):
+    sizes = [700, 1200, 300, 2, 950, 1500]
+    embs, rhos, offs = [], [], [0]
+    psi = None
+    for i, n in enumerate(sizes):
+        e, _ = synth.speaker_embeddings(n, 256, 4, weights=(0.4, 0.3, 0.2, 0.1), seed=100 + i)
+        r, psi = synth.synthetic_plda(e)
+        embs.append(e); rhos.append(r); offs.append(offs[-1] + n)
+    c = cl.OfflineClusterer(psi=psi)
+    labels, infos = c.cluster_batch(np.concatenate(embs), np.concatenate(rhos), offs)
+    for i, n in enumerate(sizes):
+        single = c.cluster(embs[i], rhos[i]).labels
+        assert np.array_equal(labels[offs[i]:offs[i + 1]], single)
+        assert np.array_equal(single, oracle.diarize_cluster(embs[i], rhos[i], psi).labels)
+        assert infos[i]["training_count"] == n
