@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -197,6 +198,16 @@ __device__ __forceinline__ void st_release_u64(u64 *p, u64 v) {
 __device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ u64 global_ns() {
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define FA_TRACE(slot)                                                                         \
+    do {                                                                                       \
+        if ((P.flags & 4) && trace_step >= 0 && trace_step < kTraceSteps) P.trace[trace_step * 8 + (slot)] = global_ns(); \
+    } while (0)
+
 __device__ __forceinline__ u64 pack_cmd(int type, unsigned counter, int a, int b) {
     return ((u64)type << 62) | ((u64)(counter & 0x3fffu) << 48) | ((u64)(unsigned)a << 24) | (u64)(unsigned)b;
 }
@@ -265,22 +276,44 @@ __device__ void ahc_master(const Problem &P, int W, unsigned char *sm) {
     LiveSet live{bits, 2 * N - 1, 0};
     unsigned counter = 0;
     bool failed = false;
+    __shared__ int path_pos[40], path_slot[40], path_depth;
+    __shared__ double path_key[40];
+    int sa_shared = 0;
 
     auto publish = [&](int type, int a, int b) {   // lane 0
         st_release_u64(P.cmd, pack_cmd(type, ++counter, a, b));
     };
-    auto collect = [&](unsigned tag, double &d, int &id) {   // whole warp; result valid in every lane
+    // Whole warp; result valid in every lane.  Each lane owns slots lane, lane+32, ... and keeps the loads of both
+    // words of all of them in flight; one L2 round trip after the last worker's store the warp has every candidate.
+    auto collect = [&](unsigned tag, double &d, int &id) {
+        constexpr int kMaxMine = 8;   // W <= 255 worker CTAs
+        u64 a0[kMaxMine], a1[kMaxMine];
+        bool pending = true;
+        while (pending) {
+            pending = false;
+#pragma unroll
+            for (int q = 0; q < kMaxMine; ++q) {
+                const int w = lane + 32 * q;
+                a0[q] = (w < W) ? ld_relaxed_u64(&P.results[w].w0) : (u64)(tag & 0xffu);
+                a1[q] = (w < W) ? ld_relaxed_u64(&P.results[w].w1) : (u64)tag;
+            }
+#pragma unroll
+            for (int q = 0; q < kMaxMine; ++q)
+                pending = pending || ((unsigned)(a0[q] & 0xffu) != (tag & 0xffu)) || ((unsigned)a1[q] != tag);
+            pending = __any_sync(full, pending);
+        }
         d = INFINITY;
         id = INT_MAX;
         bool bad = false;
-        for (int w = lane; w < W; w += 32) {
-            u64 it;
-            do {
-                it = ld_acquire_u64(&P.results[w].id_tag);
-            } while ((unsigned)it != tag);
-            const int oid = (int)(it >> 32);
-            const double od = __longlong_as_double((long long)ld_relaxed_u64(&P.results[w].d_bits));
-            if (oid == -2) bad = true; else cand_min(d, id, od, oid);
+#pragma unroll
+        for (int q = 0; q < kMaxMine; ++q) {
+            const int w = lane + 32 * q;
+            if (w < W) {
+                const unsigned oid = (unsigned)(a0[q] >> 8) & 0xffffffu;
+                const u64 bits = (a0[q] & 0xffffffff00000000ull) | (a1[q] >> 32);
+                if (oid == 0xfffffeu) bad = true;
+                else if (oid != 0xffffffu) cand_min(d, id, __longlong_as_double((long long)bits), (int)oid);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -293,6 +326,7 @@ __device__ void ahc_master(const Problem &P, int W, unsigned char *sm) {
 
     for (int step = 0; step < N - 1 && !failed; ++step) {
         const int fresh = N + step;
+        const int trace_step = step - N / 2;   // trace a window in the middle of the run
         int sa = 0;   // slot of the heap top
         for (;;) {    // lazy repair of a stale nearest neighbour (:1706-1734)
             int stale = 0;
@@ -320,6 +354,7 @@ __device__ void ahc_master(const Problem &P, int W, unsigned char *sm) {
             a = node_of[sa];
             b = nn[sa];
             if (step < N - 2) publish(CMD_MERGE, a, b);   // workers start while the bookkeeping below runs
+            FA_TRACE(0);
             live.drop(a);
             live.drop(b);
             P.merge_a[step] = a;
@@ -330,18 +365,66 @@ __device__ void ahc_master(const Problem &P, int W, unsigned char *sm) {
                 node_of[sa] = fresh;
                 node_of[sb] = -1;
                 P.slot_of[fresh] = sa;
+                if (P.flags & 1) {
+                // Heap maintenance that does not depend on the scan result is done NOW, in the reference's order
+                // (erase first, :1792-1796), hidden behind the workers' scan.  sa stays at the root: the element
+                // moved by erase() can only rise while strictly smaller than its parent, never past the minimum.
+                if (b < live.head) heap.erase(P.slot_of[live.head]); else heap.erase(sb);
+                // Descent path the root would take in replace_key (:1797 -> update_geq_): at every level the
+                // smaller child, the left one on ties.  sift_down(root, d) swaps along exactly this path while
+                // the child's key is < d, so once d is known the whole sift is one parallel rotation.
+                int pos = 0, depth = 0;
+                path_pos[0] = 0;
+                for (;;) {
+                    int child = 2 * pos + 1;
+                    if (child >= heap.size) break;
+                    if (child + 1 < heap.size && heap.val(child + 1) < heap.val(child)) ++child;
+                    ++depth;
+                    path_pos[depth] = child;
+                    path_slot[depth] = (int)at[child];
+                    path_key[depth] = heap.val(child);
+                    pos = child;
+                }
+                path_depth = depth;
+                }
             }
+            FA_TRACE(1);
         }
         if (step < N - 2) {
             counter = __shfl_sync(full, counter, 0);
             double d;
             int id;
             collect(counter, d, id);
+            if (lane == 0) FA_TRACE(2);
             if (failed) break;
+            if (!(P.flags & 1)) {
+                if (lane == 0) {
+                    nn[sa] = id;
+                    if (b < live.head) heap.erase(P.slot_of[live.head]); else heap.erase(sb);
+                    heap.replace_key(sa, d);
+                }
+                __syncwarp();
+                continue;
+            }
+            __syncwarp();
+            const int depth = path_depth;
+            const double old_key = key[sa_shared = __shfl_sync(full, sa, 0)];
+            // levels 1..m move up one position, the root element lands at level m
+            const bool goes_below = lane >= 1 && lane <= depth && path_key[lane] < d;
+            unsigned below = __ballot_sync(full, goes_below) | 1u;     // bit 0 set so that ffs(~below) = m + 1
+            const int m = (d <= old_key) ? 0 : (__ffs(~below) - 2);    // lower_key at the root never moves
+            if (lane >= 1 && lane <= m) {
+                const int slot = path_slot[lane], to = path_pos[lane - 1];
+                at[to] = (Idx)slot;
+                where[slot] = (Idx)to;
+            }
             if (lane == 0) {
+                const int to = path_pos[m];
+                at[to] = (Idx)sa;
+                where[sa] = (Idx)to;
+                key[sa] = d;
                 nn[sa] = id;
-                if (b < live.head) heap.erase(P.slot_of[live.head]); else heap.erase(sb);   // :1792-1796
-                heap.replace_key(sa, d);                                                    // :1797
+                FA_TRACE(3);
             }
             __syncwarp();
         }
@@ -409,6 +492,8 @@ __global__ void __launch_bounds__(kMergeThreads, 1) ahc_merge_kernel(const Probl
         const int a = (int)((c >> 24) & 0xffffffu), b = (int)(c & 0xffffffu);
         if (type == CMD_EXIT) break;
         int limit;
+        const int trace_step = (wb == 0 && t == 0 && type == CMD_MERGE) ? merges - N / 2 : -1;
+        FA_TRACE(4);
         if (type == CMD_MERGE) {
             const int fresh = N + merges;
             ++merges;
@@ -448,6 +533,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) ahc_merge_kernel(const Probl
             __syncthreads();
             limit = a;
         }
+        FA_TRACE(5);
         // ---- scan: one sequential chain per owned live node with id < limit ------------------------------
         double best = INFINITY;
         int best_id = INT_MAX;
@@ -457,15 +543,45 @@ __global__ void __launch_bounds__(kMergeThreads, 1) ahc_merge_kernel(const Probl
             if (id >= 0 && id < limit) {
                 const double *col = sv + t;
                 double sum = 0.0;
-                int k = 0;
-                for (; k + 8 <= D; k += 8) {
-                    double x[8];
+                if (!(P.flags & 2)) {
+                    int k = 0;
+                    for (; k + 8 <= D; k += 8) {
+                        double x[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) x[u] = col[(k + u) * SP];
+                        for (int u = 0; u < 8; ++u) x[u] = col[(k + u) * SP];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) sum = sq_step(sum, x[u], v[k + u]);
+                        for (int u = 0; u < 8; ++u) sum = sq_step(sum, x[u], v[k + u]);
+                    }
+                    for (; k < D; ++k) sum = sq_step(sum, col[k * SP], v[k]);
+                } else {
+                // the chain over k is strictly sequential; operands are fetched one batch ahead of it
+                double xa[8], va[8], xb[8], vb[8];
+                const int D16 = D & ~15;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    xa[u] = (u < D16) ? col[u * SP] : 0.0;
+                    va[u] = (u < D16) ? v[u] : 0.0;
                 }
-                for (; k < D; ++k) sum = sq_step(sum, col[k * SP], v[k]);
+                for (int k = 0; k < D16; k += 16) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        xb[u] = col[(k + 8 + u) * SP];
+                        vb[u] = v[k + 8 + u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) sum = sq_step(sum, xa[u], va[u]);
+                    if (k + 16 < D16) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            xa[u] = col[(k + 16 + u) * SP];
+                            va[u] = v[k + 16 + u];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) sum = sq_step(sum, xb[u], vb[u]);
+                }
+                for (int k = D16; k < D; ++k) sum = sq_step(sum, col[k * SP], v[k]);
+                }
                 if (sum != sum) bad = true;
                 best = sum;
                 best_id = id;
@@ -500,6 +616,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) ahc_merge_kernel(const Probl
             const int oid = __shfl_xor_sync(0xffffffffu, best_id, o);
             cand_min(best, best_id, od, oid);
         }
+        FA_TRACE(6);
         const bool warp_bad = __any_sync(0xffffffffu, bad);
         if (lane == 0) {
             red_d[warp] = best;
@@ -512,8 +629,11 @@ __global__ void __launch_bounds__(kMergeThreads, 1) ahc_merge_kernel(const Probl
             for (int w2 = 1; w2 < kMergeThreads / 32; ++w2) {
                 if (red_id[w2] == -2) any_bad = true; else cand_min(best, best_id, red_d[w2], red_id[w2]);
             }
-            st_relaxed_u64(&P.results[wb].d_bits, (u64)__double_as_longlong(best));
-            st_release_u64(&P.results[wb].id_tag, ((u64)(unsigned)(any_bad ? -2 : best_id) << 32) | (u64)expect);
+            const u64 bits = (u64)__double_as_longlong(best);
+            const unsigned oid = any_bad ? 0xfffffeu : (best_id == INT_MAX ? 0xffffffu : (unsigned)best_id);
+            st_relaxed_u64(&P.results[wb].w0, (bits & 0xffffffff00000000ull) | ((u64)oid << 8) | (u64)(expect & 0xffu));
+            st_release_u64(&P.results[wb].w1, (bits << 32) | (u64)expect);
+            FA_TRACE(7);
         }
         // s_cmd / red_* / s_owner are rewritten only after the next command's barrier
     }
@@ -601,7 +721,7 @@ struct Carver {
 };
 struct Layout {
     size_t rows, cols, node_weight, key, nn, heap_at, heap_where, node_of, slot_of, live_bits, merge_a, merge_b, merge_d,
-        cmd, results, error, init_partial, problem, total;
+        cmd, results, error, trace, init_partial, problem, total;
     int ranges;
 };
 Layout make_layout(int N, int D, int Ns, int workers) {
@@ -623,6 +743,7 @@ Layout make_layout(int N, int D, int Ns, int workers) {
     L.cmd = c.take<unsigned long long>(32);   // own 256-byte line
     L.results = c.take<ResultSlot>((size_t)workers + 1);
     L.error = c.take<int>(64);
+    L.trace = c.take<unsigned long long>((size_t)kTraceSteps * 8);
     L.ranges = (N + kJR - 1) / kJR;
     L.init_partial = c.take<Cand>((size_t)L.ranges * N);
     L.problem = c.take<Problem>(1);
@@ -665,7 +786,7 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     if (N < 2) return FA_OK;
     const int Ns = (N + 31) & ~31;
     // master placement: slot-indexed heap (+ nn, + node_of) in shared memory when it fits
-    const size_t smem_cap = 227 * 1024 - 512;
+    const size_t smem_cap = 227 * 1024 - 2048;   // leaves room for the kernel's static shared memory
     int level = 0;
     if (N <= 65535)
         for (int l = 1; l <= 3; ++l)
@@ -725,10 +846,15 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     P.cmd = reinterpret_cast<unsigned long long *>(base + L.cmd);
     P.results = reinterpret_cast<ResultSlot *>(base + L.results);
     P.error = reinterpret_cast<int *>(base + L.error);
+    P.trace = reinterpret_cast<unsigned long long *>(base + L.trace);
     P.resident = resident ? 1 : 0;
     P.slots_per_cta = slots_per_cta;
     P.idx16 = idx16 ? 1 : 0;
     P.smem_level = level;
+    {
+        const char *f = std::getenv("FA_AHC_FLAGS");   // tuning hook: bit 0 overlapped/parallel root sift, bit 1 pipelined scan
+        P.flags = f ? std::atoi(f) : 1;
+    }
     Cand *init_partial = reinterpret_cast<Cand *>(base + L.init_partial);
     Problem *d_prob = reinterpret_cast<Problem *>(base + L.problem);
 
@@ -751,6 +877,7 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     FA_CUDA_TRY(cudaMemsetAsync(base + L.cmd, 0, 256, stream));
     FA_CUDA_TRY(cudaMemsetAsync(base + L.results, 0, sizeof(ResultSlot) * (size_t)(max_workers + 1), stream));
     FA_CUDA_TRY(cudaMemsetAsync(base + L.error, 0, 256, stream));
+    FA_CUDA_TRY(cudaMemsetAsync(base + L.trace, 0, sizeof(unsigned long long) * kTraceSteps * 8, stream));
     FA_CUDA_TRY(cudaEventRecord(ev[0], stream));
     {
         dim3 grid((Ns + 31) / 32, (D + 31) / 32), block(32, 8);
@@ -793,7 +920,12 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     FA_CUDA_TRY(cudaMemcpyAsync(d_prob, &P, sizeof(Problem), cudaMemcpyHostToDevice, stream));
     FA_CUDA_TRY(cudaEventRecord(ev[2], stream));
     {
-        FA_CUDA_TRY(cudaFuncSetAttribute(ahc_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static std::once_flag once;   // a per-function attribute: set it once to the maximum, solvers run concurrently
+        static cudaError_t attr_err = cudaSuccess;
+        std::call_once(once, [&]() {
+            attr_err = cudaFuncSetAttribute(ahc_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+        });
+        FA_CUDA_TRY(attr_err);
         void *args[] = {&d_prob};
         FA_CUDA_TRY(cudaLaunchCooperativeKernel((void *)ahc_merge_kernel, dim3(workers + 1), dim3(kMergeThreads), args,
                                                 smem, stream));
@@ -810,6 +942,25 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     cudaEventElapsedTime(&last_ms[2], ev[2], ev[3]);
     cudaEventElapsedTime(&last_ms[3], ev[0], ev[3]);
     for (int q = 0; q < 4; ++q) g_last_ms[q] = last_ms[q];
+    if ((P.flags & 4) && N > 2 * kTraceSteps + 8) {
+        std::vector<unsigned long long> tr((size_t)kTraceSteps * 8);
+        cudaMemcpy(tr.data(), P.trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int used = 0;
+        for (int i = 1; i + 1 < kTraceSteps; ++i) {
+            const unsigned long long t0 = tr[(size_t)i * 8];
+            if (!t0) continue;
+            for (int q = 0; q < 8; ++q) acc[q] += (double)((long long)(tr[(size_t)i * 8 + q] - t0));
+            acc[0] += (double)((long long)(tr[(size_t)(i + 1) * 8] - t0));   // slot 0: step period
+            ++used;
+        }
+        for (int q = 0; q < 8; ++q) trace_avg_ns[q] = used ? acc[q] / used : 0.0;
+        std::fprintf(stderr,
+                     "[ahc trace] period %.0f ns | master: bookkeeping+erase+path done %.0f, results collected %.0f, heap "
+                     "rotated %.0f | worker0: command seen %.0f, centroid built %.0f, scan done %.0f, result released %.0f\n",
+                     trace_avg_ns[0], trace_avg_ns[1], trace_avg_ns[2], trace_avg_ns[3], trace_avg_ns[4], trace_avg_ns[5],
+                     trace_avg_ns[6], trace_avg_ns[7]);
+    }
     drop_events();
     if (*h_err != 0) {
         fa::set_error("NaN distance during merging");

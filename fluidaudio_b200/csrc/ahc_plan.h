@@ -14,11 +14,14 @@ namespace ahc {
 //   [47:24] node id a                                           [23:0]  node id b
 // The id of a freshly merged node is implicit (N + number of MERGE commands so far).  Workers find the slots of
 // a and b themselves (every thread knows which node its slot holds) and read member counts from node_weight[].
-// Workers -> master: one 16-byte slot per worker CTA, {distance bits, (node id << 32) | command counter},
-// second word written with st.release; the master warp polls the slots directly (no atomic counter).
+// Workers -> master: two self-validating 64-bit words per worker CTA (no atomic counter, no second round trip):
+//   w0 = [63:32] high half of the distance bits | [31:8] node id (0xFFFFFE = NaN seen, 0xFFFFFF = none) | [7:0] counter
+//   w1 = [63:32] low half of the distance bits  | [31:0] counter                       (written with st.release)
+// The master polls both words of all its slots with relaxed loads until every word carries the current command
+// counter; the fence inside its next st.release completes the acquire side of the workers' releases.
 struct ResultSlot {
-    unsigned long long d_bits;
-    unsigned long long id_tag;
+    unsigned long long w0;
+    unsigned long long w1;
 };
 
 // Everything the persistent kernel needs, resident in HBM.
@@ -44,9 +47,13 @@ struct Problem {
     int heap_size;           // after host heapify
     int idx16;               // heap index arrays are uint16_t and the master state lives in shared memory
     int smem_level;          // how much master state fits in smem: 1 = heap, 2 = + nn, 3 = + node_of
+    unsigned long long *trace;   // [kTraceSteps x 8] globaltimer stamps (flags bit 2), diagnostics only
+    int flags;               // bit 0: overlapped erase + parallel root sift; bit 1: software-pipelined scan
     int resident;            // 1: every worker keeps its nodes' vectors in shared memory; 0: streamed from `cols`
     int slots_per_cta;       // resident mode: slots [w*slots_per_cta, (w+1)*slots_per_cta) belong to worker w
 };
+
+constexpr int kTraceSteps = 256;
 
 struct Solver {
     int num_sms = 0;
@@ -62,7 +69,8 @@ struct Solver {
     // pinned host mirrors
     void *h_pool = nullptr;
     size_t h_pool_bytes = 0;
-    float last_ms[4] = {0, 0, 0, 0};   // init-nn, host heapify + copies, merge loop, total
+    float last_ms[4] = {0, 0, 0, 0};
+    double trace_avg_ns[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // mean offsets from "command published" (flags bit 2)   // init-nn, host heapify + copies, merge loop, total
 
     ~Solver();
     void release();

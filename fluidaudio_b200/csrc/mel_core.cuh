@@ -7,18 +7,26 @@
 // :459-481 (512-point DFT of a real frame, power of bins 0..256), :432-452 (filterbank mat-vec + log).
 //
 // Algorithm (one warp per frame):
-//   real frame x[0..512)  ->  z[m] = x[2m] + i x[2m+1], m < 256           (even/odd packing)
-//   Z = FFT256(z): radix 8 x 8 x 4 decimation in frequency, in shared memory, __syncwarp between passes
-//   X[b] = E[b] + W512^b O[b],  E = (Z[b] + conj Z[256-b]) / 2,  O = (Z[b] - conj Z[256-b]) / (2i)
-//   power[b] = |X[b]|^2, b = 0..256
+//   real frame x[0..512) (float32: window * pre-emphasised sample, exactly the reference's vDSP_vmul)
+//   z[m] = x[2m] + i x[2m+1], m < 256                                     (even/odd packing)
+//   Z = FFT256(z): radix 8 x 8 x 4 decimation in frequency in FP64, through shared memory, __syncwarp between passes
+//   X[b] = E[b] + W512^b O[b],  E = (Z[b] + conj Z[256-b]) / 2,  O = (Z[b] - conj Z[256-b]) / (2i)      (FP64)
+//   power[b] = fl32(Re X)^2 + fl32(Im X)^2 in float32, b = 0..256
 //
-// Shared-memory layout of the 256-point complex buffer (separate re/im arrays): element idx lives at
-// idx + 4*(idx >> 5)  (288 floats per array).  With it every pass is bank-conflict free:
-//   pass 1 stores  l + 32q            -> bank (l + 4q)      mod 32, distinct over lanes l
-//   pass 2 ld/st   32q + h + 4r       -> bank (4q+h + 4r)   mod 32, lane = 4q + h
-//   pass 3 loads   4C .. 4C+3 as one 128-bit access; stores natural order k = q + 8 q2 + 64 k2
-//                                      -> bank q + 4(q2>>2) + 8(q2&3) + 8 k2, distinct over C = 8q + q2
-//   post   loads   b = l + 32 j       -> bank (l + 4j)      mod 32
+// Why FP64 for the transform: the reference's DFT (vDSP_DFT_zop) is float32, and ANY float32 FFT carries rounding
+// noise of ~0.5 ulp of the frame's largest spectral line in every bin.  On input with 60 dB of dynamic range that
+// alone moves weak log-mel bins by up to ~1e-4, so two correct float32 implementations cannot be compared to
+// 1e-4.  Evaluating the transform in FP64 and rounding once reproduces the implementation-independent value (the
+// oracle's definition) to ~1e-6 in the log domain.  The kernel is instruction-issue bound, the FP64 pipe is not the
+// limiter (profiles/), so this costs little.
+//
+// Shared-memory layouts of the 256 complex doubles (16-byte elements; a warp-wide 16-byte access is 4 wavefronts
+// when every 8 consecutive lanes hit 8 distinct 16-byte banks):
+//   A  (pass 1 out / pass 2 in):  element idx            at idx + 4*(idx>>5)          = l + 36 q
+//   B  (pass 2 out / pass 3 in):  z_{q,q2}[h]            at 74 h + 9 q + q2
+//   N  (pass 3 out, natural):     Z[k]                   at k + (k>>3), plus a copy of Z[0] at 288
+// Twiddles are produced by recurrence in FP64 from one per-lane root per pass (W256^l, W32^(l&3), W512^l): 6 complex
+// multiplies cost less than 7 conflicted 16-byte table loads and their ~1e-16 error is irrelevant here.
 #pragma once
 
 #include "fa_common.cuh"
@@ -31,32 +39,36 @@ namespace mel {
 constexpr int kNfft = 512;
 constexpr int kHalf = 256;
 constexpr int kBins = 257;
-constexpr int kFftPad = 288;      // floats per re / im array
+constexpr int kFftPad = 304;      // complex doubles per warp buffer (max layout extent 296 + Z[0] mirror at 288)
 constexpr int kTileFrames = 32;   // frames per CTA tile == lanes of the mel stage
 constexpr int kPowStride = 257;   // odd: lane-per-frame reads of a fixed bin hit 32 distinct banks
 
 struct alignas(8) cpx {
     float x, y;
 };
-struct alignas(16) vec4 {
-    float a, b, c, d;
+struct alignas(16) cpxd {
+    double x, y;
 };
-
-FA_HD int pad_addr(int idx) { return idx + 4 * (idx >> 5); }
 
 // Constants a lane needs for every frame it processes; loaded once per kernel.
 struct LaneTables {
-    float win[16];     // window coefficient at buffer positions j = 2(l+32r) [even slot 2r] and j+1 [odd slot 2r+1]
+    float win[16];     // window coefficient at buffer positions j = 2(l+32r) [slot 2r] and j+1 [slot 2r+1]
     uint32_t in_win;   // bit s set  <=>  slot s lies inside [off, off+win)
-    float t1r[8], t1i[8];   // W256^(l q)
-    float t2r[8], t2i[8];   // W32^((l&3) q2)
-    float pwr[8], pwi[8];   // W512^(l + 32 j)
+    cpxd w256;         // W256^l        (pass 1 root)
+    cpxd w32;          // W32^(l & 3)   (pass 2 root)
+    cpxd w512;         // W512^l        (recombination root)
 };
 
+FA_HD cpxd unit_root(int k, int n) {   // exp(-2 pi i k / n) in FP64
+    const double a = -6.283185307179586476925286766559 * (double)k / (double)n;
+    cpxd r;
+    r.x = cos(a);
+    r.y = sin(a);
+    return r;
+}
+
 // win_tab[512]: window value per buffer position (0 outside the window), in_tab[512]: 1 inside the window.
-// tw256[k] = (cos 2 pi k/256, -sin 2 pi k/256), tw512[k] = (cos 2 pi k/512, -sin 2 pi k/512), k < 256.
-FA_HD void load_lane_tables(int l, const float *win_tab, const uint8_t *in_tab, const cpx *tw256, const cpx *tw512,
-                            LaneTables &T) {
+FA_HD void load_lane_tables(int l, const float *win_tab, const uint8_t *in_tab, LaneTables &T) {
     T.in_win = 0;
     for (int r = 0; r < 8; ++r) {
         const int j = 2 * (l + 32 * r);
@@ -65,25 +77,24 @@ FA_HD void load_lane_tables(int l, const float *win_tab, const uint8_t *in_tab, 
         if (in_tab[j]) T.in_win |= 1u << (2 * r);
         if (in_tab[j + 1]) T.in_win |= 1u << (2 * r + 1);
     }
-    for (int q = 0; q < 8; ++q) {
-        const cpx a = tw256[(l * q) & 255];
-        T.t1r[q] = a.x;
-        T.t1i[q] = a.y;
-        const cpx b = tw256[(8 * (l & 3) * q) & 255];
-        T.t2r[q] = b.x;
-        T.t2i[q] = b.y;
-        const cpx c = tw512[l + 32 * q];
-        T.pwr[q] = c.x;
-        T.pwi[q] = c.y;
-    }
+    T.w256 = unit_root(l, 256);
+    T.w32 = unit_root(l & 3, 32);
+    T.w512 = unit_root(l, 512);
+}
+
+FA_HD cpxd cmul(cpxd a, cpxd b) {
+    cpxd r;
+    r.x = a.x * b.x - a.y * b.y;
+    r.y = a.x * b.y + a.y * b.x;
+    return r;
 }
 
 // forward 4-point DFT, in place, natural order
-FA_HD void dft4(float &r0, float &i0, float &r1, float &i1, float &r2, float &i2, float &r3, float &i3) {
-    const float ar = r0 + r2, ai = i0 + i2;
-    const float br = r0 - r2, bi = i0 - i2;
-    const float cr = r1 + r3, ci = i1 + i3;
-    const float dr = r1 - r3, di = i1 - i3;
+FA_HD void dft4(double &r0, double &i0, double &r1, double &i1, double &r2, double &i2, double &r3, double &i3) {
+    const double ar = r0 + r2, ai = i0 + i2;
+    const double br = r0 - r2, bi = i0 - i2;
+    const double cr = r1 + r3, ci = i1 + i3;
+    const double dr = r1 - r3, di = i1 - i3;
     r0 = ar + cr;
     i0 = ai + ci;
     r2 = ar - cr;
@@ -95,19 +106,19 @@ FA_HD void dft4(float &r0, float &i0, float &r1, float &i1, float &r2, float &i2
 }
 
 // forward 8-point DFT, in place, natural order (decimation in frequency: 4 radix-2 + two 4-point DFTs)
-FA_HD void dft8(float (&re)[8], float (&im)[8]) {
-    const float kS = 0.70710678118654752440f;
-    float er0 = re[0] + re[4], ei0 = im[0] + im[4];
-    float er1 = re[1] + re[5], ei1 = im[1] + im[5];
-    float er2 = re[2] + re[6], ei2 = im[2] + im[6];
-    float er3 = re[3] + re[7], ei3 = im[3] + im[7];
-    float or0 = re[0] - re[4], oi0 = im[0] - im[4];
-    const float xr1 = re[1] - re[5], xi1 = im[1] - im[5];
-    const float xr2 = re[2] - re[6], xi2 = im[2] - im[6];
-    const float xr3 = re[3] - re[7], xi3 = im[3] - im[7];
-    float or1 = (xr1 + xi1) * kS, oi1 = (xi1 - xr1) * kS;     // * (1 - i)/sqrt2
-    float or2 = xi2, oi2 = -xr2;                              // * (-i)
-    float or3 = (xi3 - xr3) * kS, oi3 = -(xr3 + xi3) * kS;    // * (-1 - i)/sqrt2
+FA_HD void dft8(double (&re)[8], double (&im)[8]) {
+    const double kS = 0.70710678118654752440;
+    double er0 = re[0] + re[4], ei0 = im[0] + im[4];
+    double er1 = re[1] + re[5], ei1 = im[1] + im[5];
+    double er2 = re[2] + re[6], ei2 = im[2] + im[6];
+    double er3 = re[3] + re[7], ei3 = im[3] + im[7];
+    double or0 = re[0] - re[4], oi0 = im[0] - im[4];
+    const double xr1 = re[1] - re[5], xi1 = im[1] - im[5];
+    const double xr2 = re[2] - re[6], xi2 = im[2] - im[6];
+    const double xr3 = re[3] - re[7], xi3 = im[3] - im[7];
+    double or1 = (xr1 + xi1) * kS, oi1 = (xi1 - xr1) * kS;     // * (1 - i)/sqrt2
+    double or2 = xi2, oi2 = -xr2;                              // * (-i)
+    double or3 = (xi3 - xr3) * kS, oi3 = -(xr3 + xi3) * kS;    // * (-1 - i)/sqrt2
     dft4(er0, ei0, er1, ei1, er2, ei2, er3, ei3);
     dft4(or0, oi0, or1, oi1, or2, oi2, or3, oi3);
     re[0] = er0; im[0] = ei0;
@@ -120,92 +131,127 @@ FA_HD void dft8(float (&re)[8], float (&im)[8]) {
     re[7] = or3; im[7] = oi3;
 }
 
+// multiply element q by root^q, q = 1..7, and hand the product to `emit(q, value)`.  The powers are built as a
+// depth-3 tree (w2 = w*w, w3 = w2*w, w4 = w2*w2, w5 = w4*w, w6 = w4*w2, w7 = w4*w3) to keep the dependent chain short.
+template <typename Emit>
+FA_HD void twiddle_emit(double (&re)[8], double (&im)[8], cpxd root, Emit emit) {
+    cpxd p[8];
+    p[1] = root;
+    p[2] = cmul(root, root);
+    p[3] = cmul(p[2], root);
+    p[4] = cmul(p[2], p[2]);
+    p[5] = cmul(p[4], root);
+    p[6] = cmul(p[4], p[2]);
+    p[7] = cmul(p[4], p[3]);
+    cpxd v;
+    v.x = re[0];
+    v.y = im[0];
+    emit(0, v);
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+        v.x = re[q] * p[q].x - im[q] * p[q].y;
+        v.y = re[q] * p[q].y + im[q] * p[q].x;
+        emit(q, v);
+    }
+}
+
 // Pass 1.  pf -> pre-emphasised sample at buffer position j = 0 of this frame (8-byte aligned, hop even).
-FA_HD void pass1(int l, const float *pf, const LaneTables &T, float *sre, float *sim) {
-    float re[8], im[8];
+// Window product in float32 (the reference's vDSP_vmul), then widened.  Output layout A.
+FA_HD void pass1(int l, const float *pf, const LaneTables &T, cpxd *buf) {
+    double re[8], im[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int j = 2 * (l + 32 * r);
-        const cpx v = *reinterpret_cast<const cpx *>(pf + j);   // one 64-bit shared load
-        const float x0 = v.x, x1 = v.y;
-        re[r] = (T.in_win >> (2 * r)) & 1u ? T.win[2 * r] * x0 : 0.0f;
-        im[r] = (T.in_win >> (2 * r + 1)) & 1u ? T.win[2 * r + 1] * x1 : 0.0f;
+#if defined(__CUDA_ARCH__)
+        const float2 v = *reinterpret_cast<const float2 *>(pf + j);   // one 64-bit shared load (LDS.64)
+#else
+        const cpx v = *reinterpret_cast<const cpx *>(pf + j);
+#endif
+        const float a = (T.in_win >> (2 * r)) & 1u ? T.win[2 * r] * v.x : 0.0f;
+        const float b = (T.in_win >> (2 * r + 1)) & 1u ? T.win[2 * r + 1] * v.y : 0.0f;
+        re[r] = (double)a;
+        im[r] = (double)b;
     }
     dft8(re, im);
-    sre[l] = re[0];
-    sim[l] = im[0];
-#pragma unroll
-    for (int q = 1; q < 8; ++q) {
-        const float wr = T.t1r[q], wi = T.t1i[q];
-        sre[l + 36 * q] = re[q] * wr - im[q] * wi;
-        sim[l + 36 * q] = re[q] * wi + im[q] * wr;
-    }
+    twiddle_emit(re, im, T.w256, [&](int q, cpxd v) { buf[l + 36 * q] = v; });
 }
 
-FA_HD void pass2(int l, const LaneTables &T, float *sre, float *sim) {
+// Pass 2 is split: its output layout (B) differs from its input layout (A), every lane must finish loading first.
+FA_HD void pass2_load(int l, const cpxd *buf, double (&re)[8], double (&im)[8]) {
     const int base = 36 * (l >> 2) + (l & 3);
-    float re[8], im[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        re[r] = sre[base + 4 * r];
-        im[r] = sim[base + 4 * r];
-    }
-    dft8(re, im);
-    sre[base] = re[0];
-    sim[base] = im[0];
-#pragma unroll
-    for (int q = 1; q < 8; ++q) {
-        const float wr = T.t2r[q], wi = T.t2i[q];
-        sre[base + 4 * q] = re[q] * wr - im[q] * wi;
-        sim[base + 4 * q] = re[q] * wi + im[q] * wr;
+        const cpxd v = buf[base + 4 * r];
+        re[r] = v.x;
+        im[r] = v.y;
     }
 }
+FA_HD void pass2_store(int l, const LaneTables &T, double (&re)[8], double (&im)[8], cpxd *buf) {
+    dft8(re, im);
+    const int base = 74 * (l & 3) + 9 * (l >> 2);
+    twiddle_emit(re, im, T.w32, [&](int q2, cpxd v) { buf[base + q2] = v; });
+}
 
-// Pass 3 is split: every lane must finish loading before any lane stores (the store layout differs).
-FA_HD void pass3_load(int l, const float *sre, const float *sim, float (&re)[8], float (&im)[8]) {
+// Pass 3: two radix-4 butterflies per lane (C = l, l + 32), again split around the layout change B -> N.
+FA_HD void pass3_load(int l, const cpxd *buf, double (&re)[8], double (&im)[8]) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const int c = l + 32 * u;
-        const int a = 4 * c + 4 * (c >> 3);
-        const vec4 vr = *reinterpret_cast<const vec4 *>(sre + a);   // 128-bit shared loads
-        const vec4 vi = *reinterpret_cast<const vec4 *>(sim + a);
-        re[4 * u] = vr.a; re[4 * u + 1] = vr.b; re[4 * u + 2] = vr.c; re[4 * u + 3] = vr.d;
-        im[4 * u] = vi.a; im[4 * u + 1] = vi.b; im[4 * u + 2] = vi.c; im[4 * u + 3] = vi.d;
+        const int a = 9 * (c >> 3) + (c & 7);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const cpxd v = buf[a + 74 * h];
+            re[4 * u + h] = v.x;
+            im[4 * u + h] = v.y;
+        }
     }
 }
-
-FA_HD void pass3_store(int l, float (&re)[8], float (&im)[8], float *sre, float *sim) {
+FA_HD void pass3_store(int l, double (&re)[8], double (&im)[8], cpxd *buf) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const int c = l + 32 * u;
         dft4(re[4 * u], im[4 * u], re[4 * u + 1], im[4 * u + 1], re[4 * u + 2], im[4 * u + 2], re[4 * u + 3],
              im[4 * u + 3]);
-        const int k0 = (c >> 3) + 8 * (c & 7);
+        const int k0 = (c >> 3) + 8 * (c & 7);            // k = k0 + 64 k2,  address k + (k >> 3)
+        const int a0 = k0 + (k0 >> 3);
 #pragma unroll
         for (int k2 = 0; k2 < 4; ++k2) {
-            const int a = pad_addr(k0 + 64 * k2);
-            sre[a] = re[4 * u + k2];
-            sim[a] = im[4 * u + k2];
+            cpxd v;
+            v.x = re[4 * u + k2];
+            v.y = im[4 * u + k2];
+            buf[a0 + 72 * k2] = v;
+            if (c == 0 && k2 == 0) buf[288] = v;          // mirror of Z[0] for the "256 - b" access of lane 0
         }
     }
 }
 
 // Real-FFT recombination + power.  prow -> this frame's row of the power tile (257 floats).
-FA_HD void post_power(int l, const float *sre, const float *sim, const LaneTables &T, float *prow) {
+FA_HD void post_power(int l, const cpxd *buf, const LaneTables &T, float *prow) {
+    // W16^j = exp(-2 pi i j / 16): W512^(l + 32 j) = W512^l * W16^j
+    const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+    const double w16r[8] = {1.0, c1, h, s1, 0.0, -s1, -h, -c1};
+    const double w16i[8] = {0.0, -s1, -h, -c1, -1.0, -c1, -h, -s1};
+    const int fwd = l + (l >> 3);                               // address of Z[l + 32 j]   = fwd + 36 j
+    const int bwd = 252 + (32 - l) + ((32 - l) >> 3);           // address of Z[256-l-32 j] = bwd - 36 j
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int b = l + 32 * j;
-        const int kb = pad_addr(b), kc = pad_addr((kHalf - b) & (kHalf - 1));
-        const float ar = sre[kb], ai = sim[kb], cr = sre[kc], ci = sim[kc];
-        const float er = 0.5f * (ar + cr), ei = 0.5f * (ai - ci);
-        const float orr = 0.5f * (ai + ci), oi = 0.5f * (cr - ar);
-        const float wr = T.pwr[j], wi = T.pwi[j];
-        const float xr = er + (wr * orr - wi * oi);
-        const float xi = ei + (wr * oi + wi * orr);
-        prow[b] = xr * xr + xi * xi;
+        const cpxd zb = buf[fwd + 36 * j], zc = buf[bwd - 36 * j];
+        const double er = 0.5 * (zb.x + zc.x), ei = 0.5 * (zb.y - zc.y);
+        const double orr = 0.5 * (zb.y + zc.y), oi = 0.5 * (zc.x - zb.x);
+        const double wr = T.w512.x * w16r[j] - T.w512.y * w16i[j];
+        const double wi = T.w512.x * w16i[j] + T.w512.y * w16r[j];
+        const float xr = (float)(er + (wr * orr - wi * oi));    // single rounding of the exact-arithmetic DFT
+        const float xi = (float)(ei + (wr * oi + wi * orr));
+#if defined(__CUDA_ARCH__)
+        prow[l + 32 * j] = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi));
+#else
+        const float a = xr * xr, b = xi * xi;
+        prow[l + 32 * j] = a + b;
+#endif
     }
     if (l == 0) {
-        const float x = sre[0] - sim[0];   // X[256] = E[0] - O[0]
+        const cpxd z0 = buf[0];
+        const float x = (float)(z0.x - z0.y);                   // X[256] = E[0] - O[0], purely real
         prow[kHalf] = x * x;
     }
 }
@@ -213,14 +259,23 @@ FA_HD void post_power(int l, const float *sre, const float *sim, const LaneTable
 // float32 accumulate in bin order with separate multiply and add roundings (the oracle's mat-vec order).
 FA_HD float mel_dot(const float *prow, const float *w, int lo, int hi) {
     float acc = 0.0f;
-    for (int b = lo; b < hi; ++b) {
+    const float *p = prow + lo;
+    const int n = hi - lo;
+    int b = 0;
 #if defined(__CUDA_ARCH__)
-        acc = __fadd_rn(acc, __fmul_rn(w[b - lo], prow[b]));
-#else
-        const float t = w[b - lo] * prow[b];
-        acc = acc + t;
-#endif
+    for (; b + 4 <= n; b += 4) {   // same order, four products per trip
+        acc = __fadd_rn(acc, __fmul_rn(w[b], p[b]));
+        acc = __fadd_rn(acc, __fmul_rn(w[b + 1], p[b + 1]));
+        acc = __fadd_rn(acc, __fmul_rn(w[b + 2], p[b + 2]));
+        acc = __fadd_rn(acc, __fmul_rn(w[b + 3], p[b + 3]));
     }
+    for (; b < n; ++b) acc = __fadd_rn(acc, __fmul_rn(w[b], p[b]));
+#else
+    for (; b < n; ++b) {
+        const float t = w[b] * p[b];
+        acc = acc + t;
+    }
+#endif
     return acc;
 }
 

@@ -10,6 +10,7 @@
 //   raw --pre-emphasis--> ptile                                       all threads
 //   ptile --one warp per frame: FFT256 + recombination--> power[32][257]
 //   power --lane = frame, warp = mel: banded dot + log--> otile / HBM
+// The transform runs in FP64 (see mel_core.cuh for why), everything the reference does in float32 stays float32.
 // HBM traffic is the algorithmic minimum: every sample is read once (plus a 352-sample halo per tile) and
 // every log-mel value is written once, both fully coalesced.
 //
@@ -108,8 +109,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) mel512_kernel(const MelLaunch 
     float *raw0 = reinterpret_cast<float *>(smem);
     float *raw1 = raw0 + P.raw_cap;
     float *ptile = raw1 + P.raw_cap;
-    float *fftbuf = ptile + P.pt_cap;                       // kWarps * 2 * kFftPad
-    float *power = fftbuf + kWarps * 2 * kFftPad;           // 32 * 257
+    cpxd *fftbuf = reinterpret_cast<cpxd *>(ptile + P.pt_cap);   // kWarps * kFftPad complex doubles (16-byte aligned)
+    float *power = reinterpret_cast<float *>(fftbuf + kWarps * kFftPad);   // 32 * 257
     float *otile = power + kTileFrames * kPowStride;        // 32 * (n_mels + 1)
     float *fbw = otile + kTileFrames * (P.n_mels + 1);      // fb_nnz_cap
     int *fblo = reinterpret_cast<int *>(fbw + P.fb_cap);    // n_mels
@@ -131,11 +132,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) mel512_kernel(const MelLaunch 
         fboff[i] = P.fb_off[i];
     }
     LaneTables T;
-    load_lane_tables(lane, P.win_tab, P.in_tab, P.tw256, P.tw512, T);
+    load_lane_tables(lane, P.win_tab, P.in_tab, T);
     __syncthreads();
 
-    float *sre = fftbuf + warp * 2 * kFftPad;
-    float *sim = sre + kFftPad;
+    cpxd *buf = fftbuf + warp * kFftPad;
 
     auto issue = [&](int tile, int buf) {   // thread 0 only
         const TileGeom g = tile_geom(P, tile);
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) mel512_kernel(const MelLaunch 
     int it = 0;
     if (tid == 0 && (int)blockIdx.x < P.total_tiles) issue(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
+        const int buf_i = it & 1;
         const uint32_t parity = (uint32_t)(it >> 1) & 1u;
         const TileGeom g = tile_geom(P, tile);
         const MelUnit u = P.units[g.unit];
@@ -161,48 +161,61 @@ __global__ void __launch_bounds__(kWarps * 32, 1) mel512_kernel(const MelLaunch 
             const int next = tile + gridDim.x;
             if (next < P.total_tiles) {
                 fence_proxy_async();   // generic-proxy reads of raw[buf^1] (previous tile) precede this async write
-                issue(next, buf ^ 1);
+                issue(next, buf_i ^ 1);
             }
         }
-        mbar_wait(&bars[buf], parity);
+        mbar_wait(&bars[buf_i], parity);
 
         // ---- phase 1: pre-emphasis into ptile (zero outside [0, n)) -------------------------------------
         {
-            const float *raw = buf ? raw1 : raw0;
-            const float *gaudio = P.audio + u.audio_off;
-            auto sample = [&](long long i) -> float {   // x(i) for -1 <= i < n
-                if (i >= g.gs && i < g.ge) return raw[i - g.base];
-                if (i < 0) return u.last;
-                return __ldg(gaudio + i);
-            };
+            const float *raw = buf_i ? raw1 : raw0;
             const float a = P.preemph;
-            for (int t = tid; t < P.pt_len; t += kWarps * 32) {
-                const long long i = g.a0 + t;
-                float v = 0.0f;
-                if (i >= 0 && i < u.n) {
-                    const float x = sample(i);
-                    if (a == 0.0f) v = x;
-                    else if (i == 0) v = preemph_first(x, u.last, a);
-                    else v = preemph_rest(x, sample(i - 1), a);
+            const bool interior = g.a0 >= 1 && g.a0 - 1 >= g.gs && g.a0 + P.pt_len <= g.ge && g.a0 + P.pt_len <= u.n;
+            if (interior) {
+                // every sample of the tile and its predecessor came through the bulk copy (conflict-free, unit stride)
+                const float *src = raw + (g.a0 - g.base);   // src[t] = x(a0 + t), src[-1] valid
+                if (a == 0.0f) {
+                    for (int t = tid; t < P.pt_len; t += kWarps * 32) ptile[t] = src[t];
+                } else {
+                    for (int t = tid; t < P.pt_len; t += kWarps * 32) ptile[t] = preemph_rest(src[t], src[t - 1], a);
                 }
-                ptile[t] = v;
+            } else {
+                const float *gaudio = P.audio + u.audio_off;
+                auto sample = [&](long long i) -> float {   // x(i) for -1 <= i < n
+                    if (i >= g.gs && i < g.ge) return raw[i - g.base];
+                    if (i < 0) return u.last;
+                    return __ldg(gaudio + i);
+                };
+                for (int t = tid; t < P.pt_len; t += kWarps * 32) {
+                    const long long i = g.a0 + t;
+                    float v = 0.0f;
+                    if (i >= 0 && i < u.n) {
+                        const float x = sample(i);
+                        if (a == 0.0f) v = x;
+                        else if (i == 0) v = preemph_first(x, u.last, a);
+                        else v = preemph_rest(x, sample(i - 1), a);
+                    }
+                    ptile[t] = v;
+                }
             }
         }
         __syncthreads();
 
-        // ---- phase 2: one warp per frame: FFT + power ----------------------------------------------------
+        // ---- phase 2: one warp per frame: FP64 FFT256 + recombination + float32 power -------------------
         for (int fi = warp; fi < g.nf; fi += kWarps) {
             const float *pf = ptile + fi * P.hop;
-            pass1(lane, pf, T, sre, sim);
+            double re[8], im[8];
+            pass1(lane, pf, T, buf);
             __syncwarp();
-            pass2(lane, T, sre, sim);
+            pass2_load(lane, buf, re, im);
             __syncwarp();
-            float re[8], im[8];
-            pass3_load(lane, sre, sim, re, im);
+            pass2_store(lane, T, re, im, buf);
             __syncwarp();
-            pass3_store(lane, re, im, sre, sim);
+            pass3_load(lane, buf, re, im);
             __syncwarp();
-            post_power(lane, sre, sim, T, power + fi * kPowStride);
+            pass3_store(lane, re, im, buf);
+            __syncwarp();
+            post_power(lane, buf, T, power + fi * kPowStride);
             __syncwarp();
         }
         __syncthreads();
@@ -221,10 +234,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) mel512_kernel(const MelLaunch 
         }
         if (P.layout == 0) {
             __syncthreads();
-            // time-major tile is contiguous in HBM: rows f0..f0+nf, n_mels floats each
+            // time-major tile is contiguous in HBM: nf rows of n_mels floats; flat, fully coalesced copy
             float *dst = P.out + u.out_off + g.f0 * P.n_mels;
-            for (int fi = warp; fi < g.nf; fi += kWarps)
-                for (int m = lane; m < P.n_mels; m += 32) dst[fi * P.n_mels + m] = otile[fi * (P.n_mels + 1) + m];
+            const int total = g.nf * P.n_mels;
+            for (int idx = tid; idx < total; idx += kWarps * 32) {
+                const int fi = (int)__umulhi((unsigned)idx, P.inv_n_mels);   // idx / n_mels (exact for idx < 2^16)
+                dst[idx] = otile[idx + fi];                                  // padded row stride n_mels + 1
+            }
         }
         // next iteration's phase-1 barrier orders these reads against the next tile's writes
     }
@@ -297,8 +313,6 @@ void MelPlan::release() {
         fr(d_win_tab_mode[m]);
         fr(d_in_tab_mode[m]);
     }
-    fr(d_tw256);
-    fr(d_tw512);
     fr(d_fb_w);
     fr(d_fb_lo);
     fr(d_fb_hi);
@@ -379,15 +393,6 @@ int MelPlan::init(const MelConfig &c) {
         FA_CUDA_TRY(cudaMemcpy(d_win_tab_mode[mode], win_tab.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice));
         FA_CUDA_TRY(cudaMemcpy(d_in_tab_mode[mode], in_tab.data(), kNfft, cudaMemcpyHostToDevice));
     }
-    std::vector<cpx> tw256(256), tw512(256);
-    for (int k = 0; k < 256; ++k) {
-        tw256[k] = {(float)std::cos(2.0 * M_PI * k / 256.0), (float)-std::sin(2.0 * M_PI * k / 256.0)};
-        tw512[k] = {(float)std::cos(2.0 * M_PI * k / 512.0), (float)-std::sin(2.0 * M_PI * k / 512.0)};
-    }
-    FA_CUDA_TRY(cudaMalloc(&d_tw256, 256 * sizeof(cpx)));
-    FA_CUDA_TRY(cudaMalloc(&d_tw512, 256 * sizeof(cpx)));
-    FA_CUDA_TRY(cudaMemcpy(d_tw256, tw256.data(), 256 * sizeof(cpx), cudaMemcpyHostToDevice));
-    FA_CUDA_TRY(cudaMemcpy(d_tw512, tw512.data(), 256 * sizeof(cpx), cudaMemcpyHostToDevice));
     FA_CUDA_TRY(cudaMalloc(&d_fb_w, std::max<size_t>(1, w.size()) * sizeof(float)));
     FA_CUDA_TRY(cudaMalloc(&d_fb_lo, cfg.n_mels * sizeof(int)));
     FA_CUDA_TRY(cudaMalloc(&d_fb_hi, cfg.n_mels * sizeof(int)));
@@ -401,9 +406,10 @@ int MelPlan::init(const MelConfig &c) {
     pt_cap = (pt_len + 3) & ~3;
     raw_cap = (pt_len + 1 + 3 + 3 + 3) & ~3;
     fb_cap = (fb_nnz + 3) & ~3;
-    smem_bytes = sizeof(float) * ((size_t)2 * raw_cap + pt_cap + (size_t)kWarpsPerCta * 2 * kFftPad +
+    smem_bytes = sizeof(float) * ((size_t)2 * raw_cap + pt_cap + 0 +
                                   (size_t)kTileFrames * kPowStride + (size_t)kTileFrames * (cfg.n_mels + 1) + fb_cap) +
-                 sizeof(int) * 3 * (size_t)cfg.n_mels + 8 + 2 * sizeof(uint64_t);
+                 sizeof(cpxd) * (size_t)kWarpsPerCta * kFftPad + sizeof(int) * 3 * (size_t)cfg.n_mels + 8 +
+                 2 * sizeof(uint64_t);
     if (smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
         fa::set_error("mel config needs %zu bytes of shared memory per CTA, device allows %zu", smem_bytes,
                       (size_t)prop.sharedMemPerBlockOptin);
@@ -480,8 +486,6 @@ int MelPlan::launch(const float *d_audio_base, float *d_out_base, int first, int
     P.layout = layout;
     P.win_tab = d_win_tab_mode[mode == 2 ? 1 : 0];
     P.in_tab = d_in_tab_mode[mode == 2 ? 1 : 0];
-    P.tw256 = d_tw256;
-    P.tw512 = d_tw512;
     P.fb_w = d_fb_w;
     P.fb_lo = d_fb_lo;
     P.fb_hi = d_fb_hi;
@@ -492,6 +496,7 @@ int MelPlan::launch(const float *d_audio_base, float *d_out_base, int first, int
     P.pt_cap = pt_cap;
     P.raw_cap = raw_cap;
     P.use_tma = aligned16 ? 1 : 0;
+    P.inv_n_mels = (unsigned)((0x100000000ull + (unsigned)cfg.n_mels - 1) / (unsigned)cfg.n_mels);
     const int grid = std::min(total_tiles, num_sms);
     mel512_kernel<kWarpsPerCta><<<grid, kWarpsPerCta * 32, smem_bytes, stream>>>(P);
     FA_CUDA_TRY(cudaGetLastError());

@@ -52,8 +52,6 @@ struct MelLaunch {
     int layout;         // 0 time-major [T x nMels], 1 mel-major [nMels x stride]
     const float *win_tab;
     const uint8_t *in_tab;
-    const cpx *tw256;
-    const cpx *tw512;
     const float *fb_w;
     const int *fb_lo;
     const int *fb_hi;
@@ -61,6 +59,7 @@ struct MelLaunch {
     int fb_nnz, fb_cap;
     int pt_len, pt_cap, raw_cap;
     int use_tma;
+    unsigned inv_n_mels;   // ceil(2^32 / n_mels): idx / n_mels == umulhi(idx, inv) for idx < 2^16
 };
 
 struct MelPlan {
@@ -75,7 +74,6 @@ struct MelPlan {
 
     float *d_win_tab_mode[2] = {nullptr, nullptr};
     uint8_t *d_in_tab_mode[2] = {nullptr, nullptr};
-    cpx *d_tw256 = nullptr, *d_tw512 = nullptr;
     float *d_fb_w = nullptr;
     int *d_fb_lo = nullptr, *d_fb_hi = nullptr, *d_fb_off = nullptr;
 

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 namespace fa {
@@ -522,7 +523,14 @@ int refine_device(Workspace &ws, const double *d_x, int T, int D, const double *
         fa::set_error("VBx S x D = %d x %d does not fit the E-step's shared-memory alpha tile", S, D);
         return FA_UNSUPPORTED;
     }
-    FA_CUDA_TRY(cudaFuncSetAttribute(vbx_estep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+    {
+        static std::once_flag once;   // per-function attribute shared by concurrent callers: set once to the maximum
+        static cudaError_t attr_err = cudaSuccess;
+        std::call_once(once, [&]() {
+            attr_err = cudaFuncSetAttribute(vbx_estep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        });
+        FA_CUDA_TRY(attr_err);
+    }
     for (int it = 0; it < max_it; ++it) {
         vbx_accumulate_kernel<<<kChunks, 256, 0, stream>>>(d);
         vbx_update_kernel<<<1, 256, 0, stream>>>(d);

@@ -21,13 +21,8 @@ extern "C" int mel_emul(const float *audio, long long n, float last, int hop, in
             win_tab[j] = window[j - off];
             in_tab[j] = 1;
         }
-    std::vector<cpx> tw256(256), tw512(256);
-    for (int k = 0; k < 256; ++k) {
-        tw256[k] = {(float)std::cos(2.0 * M_PI * k / 256.0), (float)-std::sin(2.0 * M_PI * k / 256.0)};
-        tw512[k] = {(float)std::cos(2.0 * M_PI * k / 512.0), (float)-std::sin(2.0 * M_PI * k / 512.0)};
-    }
     std::vector<LaneTables> tabs(32);
-    for (int l = 0; l < 32; ++l) load_lane_tables(l, win_tab.data(), in_tab.data(), tw256.data(), tw512.data(), tabs[l]);
+    for (int l = 0; l < 32; ++l) load_lane_tables(l, win_tab.data(), in_tab.data(), tabs[l]);
     // sparse filterbank ranges
     std::vector<int> lo(n_mels), hi(n_mels);
     for (int m = 0; m < n_mels; ++m) {
@@ -41,7 +36,7 @@ extern "C" int mel_emul(const float *audio, long long n, float last, int hop, in
         lo[m] = a;
         hi[m] = b;
     }
-    alignas(16) float sre[kFftPad], sim[kFftPad];
+    alignas(16) cpxd buf[kFftPad];
     alignas(16) float pf[kNfft + 8];
     std::vector<float> prow(kBins);
     for (long long f = 0; f < T; ++f) {
@@ -55,14 +50,14 @@ extern "C" int mel_emul(const float *audio, long long n, float last, int hop, in
             }
             pf[j] = v;
         }
-        std::memset(sre, 0, sizeof(sre));
-        std::memset(sim, 0, sizeof(sim));
-        for (int l = 0; l < 32; ++l) pass1(l, pf, tabs[l], sre, sim);
-        for (int l = 0; l < 32; ++l) pass2(l, tabs[l], sre, sim);
-        float re[32][8], im[32][8];
-        for (int l = 0; l < 32; ++l) pass3_load(l, sre, sim, re[l], im[l]);
-        for (int l = 0; l < 32; ++l) pass3_store(l, re[l], im[l], sre, sim);
-        for (int l = 0; l < 32; ++l) post_power(l, sre, sim, tabs[l], prow.data());
+        std::memset(buf, 0, sizeof(buf));
+        double re[32][8], im[32][8];
+        for (int l = 0; l < 32; ++l) pass1(l, pf, tabs[l], buf);
+        for (int l = 0; l < 32; ++l) pass2_load(l, buf, re[l], im[l]);
+        for (int l = 0; l < 32; ++l) pass2_store(l, tabs[l], re[l], im[l], buf);
+        for (int l = 0; l < 32; ++l) pass3_load(l, buf, re[l], im[l]);
+        for (int l = 0; l < 32; ++l) pass3_store(l, re[l], im[l], buf);
+        for (int l = 0; l < 32; ++l) post_power(l, buf, tabs[l], prow.data());
         for (int m = 0; m < n_mels; ++m) {
             const float acc = mel_dot(prow.data(), fb + (size_t)m * kBins + lo[m], lo[m], hi[m]);
             out[f * n_mels + m] = log_value(acc, log_floor, clamped);

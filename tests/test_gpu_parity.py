@@ -109,8 +109,10 @@ def test_mel_guards_silence_and_unsupported(gpu_lib):
     m = AudioMelSpectrogram(n_mels=128)
     out, ml, nf = m.compute_flat_transposed(np.zeros(0, np.float32))
     assert (ml, nf) == (0, 1) and out.size == 128 and np.all(out == 0)           # :349-351
-    mel, ml = m.compute(np.zeros(300, np.float32))                              # fewer than one window
-    assert ml == 0
+    # legacy frame count 1 + (n - 400) / 160 uses Swift's truncating division: 300 samples still give one
+    # (partially filled) frame, 200 samples give none
+    assert m.compute(np.zeros(300, np.float32))[1] == 1
+    assert m.compute(np.zeros(200, np.float32))[1] == 0
     mel, ml = m.compute(np.zeros(16000, np.float32))                            # AudioMelSpectrogramTests.swift:32-45,107-122
     assert ml == 98 and mel.shape == (1, 128, 98) and (mel < 0).all()
     floor = np.log(np.float32(2.0 ** -24))
