@@ -1,0 +1,63 @@
+// Drop-in for the clustering phase of OfflineDiarizerManager.cluster(_:)
+// (Sources/FluidAudio/Diarizer/Offline/Core/OfflineDiarizerManager.swift:286-375): Float->Double, NaN filter, AHC,
+// VBx, centroids, argmax assignment — one call into libfluidaudio_b200.so.  AHCClustering / VBxClustering keep their
+// own Swift signatures (AHCClustering.swift:20-23, VBxClustering.swift:41-44) and forward to fa_ahc_cluster / fa_vbx_refine.
+// NOT compiled in this repository (no Swift toolchain in the build image) — see INTEGRATION.md.
+import CFluidAudioB200
+import Foundation
+
+struct AHCClustering {
+    func cluster(embeddingFeatures: [[Double]], threshold: Double) -> [Int] {
+        let count = embeddingFeatures.count
+        guard count > 0 else { return [] }
+        guard let dimension = embeddingFeatures.first?.count, dimension > 0 else { return Array(repeating: 0, count: count) }
+        if count == 1 { return [0] }
+        let flat = embeddingFeatures.flatMap { $0 }
+        var labels = [Int32](repeating: 0, count: count)
+        let status = fa_ahc_cluster(flat, count, dimension, threshold, &labels)
+        guard status == FA_STATUS_OK else { return Array(0..<count) }   // same fallback as AHCClustering.swift:52-55
+        return labels.map(Int.init)
+    }
+}
+
+struct OfflineClusteringBackend {
+    struct Output {
+        let assignments: [Int]          // one cluster per embedding (assignEmbeddings)
+        let initialClusters: [Int]      // AHC labels of the training rows, -1 for NaN-filtered rows
+        let centroids: [[Double]]
+        let info: fa_cluster_info
+    }
+
+    var threshold: Double = 0.6          // OfflineDiarizerConfig.clusteringThreshold
+    var warmStartFa: Double = 0.07
+    var warmStartFb: Double = 0.8
+    var maxIterations: Int = 20
+    var convergenceTolerance: Double = 1e-4
+
+    /// `embedding256`: N x dim row-major Float (TimedEmbedding.embedding256), `rho128`: N x rhoDim row-major Double,
+    /// `psi`: PLDATransform.phiParameters.
+    func cluster(embedding256: [Float], rho128: [Double], count: Int, dim: Int, rhoDim: Int, psi: [Double]) throws -> Output {
+        var cfg = fa_cluster_config()
+        fa_cluster_default_config(&cfg)
+        cfg.threshold = threshold
+        cfg.vbx.Fa = warmStartFa
+        cfg.vbx.Fb = warmStartFb
+        cfg.vbx.max_iterations = Int32(maxIterations)
+        cfg.vbx.epsilon = convergenceTolerance
+        var labels = [Int32](repeating: 0, count: count)
+        var initial = [Int32](repeating: 0, count: count)
+        let maxCentroids = 64
+        var centroids = [Double](repeating: 0, count: maxCentroids * dim)
+        var info = fa_cluster_info()
+        let status = fa_diarize_cluster(embedding256, rho128, count, dim, rhoDim, psi, &cfg, &labels, &initial,
+                                        &centroids, Int32(maxCentroids), &info)
+        guard status == FA_STATUS_OK else {
+            throw NSError(domain: "fluidaudio_b200", code: Int(status.rawValue),
+                          userInfo: [NSLocalizedDescriptionKey: String(cString: fa_last_error())])
+        }
+        let k = min(Int(info.centroid_count), maxCentroids)
+        return Output(
+            assignments: labels.map(Int.init), initialClusters: initial.map(Int.init),
+            centroids: (0..<k).map { Array(centroids[($0 * dim)..<(($0 + 1) * dim)]) }, info: info)
+    }
+}
