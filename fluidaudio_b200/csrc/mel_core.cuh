@@ -40,7 +40,7 @@ constexpr int kNfft = 512;
 constexpr int kHalf = 256;
 constexpr int kBins = 257;
 constexpr int kFftPad = 304;      // complex doubles per warp buffer (max layout extent 296 + Z[0] mirror at 288)
-constexpr int kTileFrames = 32;   // frames per CTA tile == lanes of the mel stage
+constexpr int kTileFrames = 16;   // frames per CTA tile; the mel stage maps 32 / kTileFrames mel bins onto one warp
 constexpr int kPowStride = 257;   // odd: lane-per-frame reads of a fixed bin hit 32 distinct banks
 
 struct alignas(8) cpx {
@@ -257,21 +257,20 @@ FA_HD void post_power(int l, const cpxd *buf, const LaneTables &T, float *prow) 
 }
 
 // float32 accumulate in bin order with separate multiply and add roundings (the oracle's mat-vec order).
+// [lo, hi) is a multiple of four bins wide on the device (the plan pads filters with explicit zero weights).
 FA_HD float mel_dot(const float *prow, const float *w, int lo, int hi) {
     float acc = 0.0f;
     const float *p = prow + lo;
     const int n = hi - lo;
-    int b = 0;
 #if defined(__CUDA_ARCH__)
-    for (; b + 4 <= n; b += 4) {   // same order, four products per trip
+    for (int b = 0; b < n; b += 4) {
         acc = __fadd_rn(acc, __fmul_rn(w[b], p[b]));
         acc = __fadd_rn(acc, __fmul_rn(w[b + 1], p[b + 1]));
         acc = __fadd_rn(acc, __fmul_rn(w[b + 2], p[b + 2]));
         acc = __fadd_rn(acc, __fmul_rn(w[b + 3], p[b + 3]));
     }
-    for (; b < n; ++b) acc = __fadd_rn(acc, __fmul_rn(w[b], p[b]));
 #else
-    for (; b < n; ++b) {
+    for (int b = 0; b < n; ++b) {
         const float t = w[b] * p[b];
         acc = acc + t;
     }

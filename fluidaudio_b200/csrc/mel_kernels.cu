@@ -5,7 +5,8 @@
 // :185-292 (computeFlat) and :132-178 (compute) — the three differ only in (pad, window offset, pre-emphasis,
 // output layout), which are kernel parameters here.
 //
-// Data flow per tile of 32 frames (kTileFrames):
+// Data flow per tile of kTileFrames (16) frames, two CTAs of 8 warps per SM so that one CTA's FP64 transform phase
+// overlaps the other's float32 mel/log phase and barrier waits:
 //   HBM --cp.async.bulk (TMA 1-D, mbarrier complete_tx)--> raw[2]   double-buffered, prefetched one tile ahead
 //   raw --pre-emphasis--> ptile                                       all threads
 //   ptile --one warp per frame: FFT256 + recombination--> power[32][257]
@@ -104,14 +105,14 @@ __device__ __forceinline__ TileGeom tile_geom(const MelLaunch &P, int tile) {
 }
 
 template <int kWarps>
-__global__ void __launch_bounds__(kWarps * 32, 1) mel512_kernel(const MelLaunch P) {
+__global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch P) {
     extern __shared__ __align__(128) unsigned char smem[];
     float *raw0 = reinterpret_cast<float *>(smem);
     float *raw1 = raw0 + P.raw_cap;
     float *ptile = raw1 + P.raw_cap;
     cpxd *fftbuf = reinterpret_cast<cpxd *>(ptile + P.pt_cap);   // kWarps * kFftPad complex doubles (16-byte aligned)
     float *power = reinterpret_cast<float *>(fftbuf + kWarps * kFftPad);   // 32 * 257
-    float *otile = power + kTileFrames * kPowStride;        // 32 * (n_mels + 1)
+    float *otile = power + kTileFrames * kPowStride;        // kTileFrames * (n_mels + 1)
     float *fbw = otile + kTileFrames * (P.n_mels + 1);      // fb_nnz_cap
     int *fblo = reinterpret_cast<int *>(fbw + P.fb_cap);    // n_mels
     int *fbhi = fblo + P.n_mels;
@@ -220,15 +221,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) mel512_kernel(const MelLaunch 
         }
         __syncthreads();
 
-        // ---- phase 3: mel filterbank + log; lane = frame, warp strides over mel bins --------------------
+        // ---- phase 3: mel filterbank + log; a warp covers kTileFrames frames x (32 / kTileFrames) mel bins -------
         {
-            const bool live = lane < g.nf;
-            const float *prow = power + lane * kPowStride;
-            const long long f = g.f0 + lane;
-            for (int m = warp; m < P.n_mels; m += kWarps) {
+            constexpr int kGroup = 32 / kTileFrames;               // mel bins handled concurrently by one warp
+            const int fl = lane % kTileFrames, mg = lane / kTileFrames;
+            const bool live = fl < g.nf;
+            const float *prow = power + fl * kPowStride;
+            const long long f = g.f0 + fl;
+            for (int m = warp * kGroup + mg; m < P.n_mels; m += kWarps * kGroup) {
                 float v = 0.0f;
                 if (live) v = log_value(mel_dot(prow, fbw + fboff[m], fblo[m], fbhi[m]), P.log_floor, P.log_clamped);
-                if (P.layout == 0) otile[lane * (P.n_mels + 1) + m] = v;
+                if (P.layout == 0) otile[fl * (P.n_mels + 1) + m] = v;
                 else if (live) P.out[u.out_off + (long long)m * u.out_stride + f] = v;
             }
         }
@@ -300,7 +303,8 @@ void build_filterbank(int n_fft, int n_mels, int sample_rate, std::vector<float>
         }                                                                                   \
     } while (0)
 
-static constexpr int kWarpsPerCta = 16;
+static constexpr int kWarpsPerCta = 8;
+static constexpr int kCtasPerSm = 2;
 
 MelPlan::~MelPlan() { release(); }
 
@@ -350,7 +354,9 @@ int MelPlan::init(const MelConfig &c) {
     build_window(cfg.win_length, cfg.window_periodic != 0, window);
     build_filterbank(cfg.n_fft, cfg.n_mels, cfg.sample_rate, filterbank);
 
-    // banded filterbank: per mel the contiguous range of non-zero bins
+    // banded filterbank: per mel the contiguous range of non-zero bins, widened with explicit zero weights to a
+    // multiple of four bins (adding fl32(0 * p) leaves a finite float32 sum unchanged, so the accumulation order and
+    // value are exactly the oracle's) so that the kernel's dot product is a branch-free 4-way unrolled loop
     std::vector<float> w;
     std::vector<int> lo(cfg.n_mels), hi(cfg.n_mels), off(cfg.n_mels);
     for (int m = 0; m < cfg.n_mels; ++m) {
@@ -361,6 +367,9 @@ int MelPlan::init(const MelConfig &c) {
                 b = k + 1;
             }
         if (b == 0) a = 0;
+        while ((b - a) % 4 != 0) {
+            if (b < kBins) ++b; else --a;
+        }
         lo[m] = a;
         hi[m] = b;
         off[m] = (int)w.size();
@@ -497,7 +506,7 @@ int MelPlan::launch(const float *d_audio_base, float *d_out_base, int first, int
     P.raw_cap = raw_cap;
     P.use_tma = aligned16 ? 1 : 0;
     P.inv_n_mels = (unsigned)((0x100000000ull + (unsigned)cfg.n_mels - 1) / (unsigned)cfg.n_mels);
-    const int grid = std::min(total_tiles, num_sms);
+    const int grid = std::min(total_tiles, num_sms * kCtasPerSm);
     mel512_kernel<kWarpsPerCta><<<grid, kWarpsPerCta * 32, smem_bytes, stream>>>(P);
     FA_CUDA_TRY(cudaGetLastError());
     ++launches;
