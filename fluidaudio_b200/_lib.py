@@ -57,7 +57,8 @@ EXPORTED_SYMBOLS = [
     "fa_mel_timer_stop_ms", "fa_mel_normalize_per_feature",
     "fa_linear_resample", "fa_l2_normalize_rows", "fa_ahc_cluster", "fa_dendrogram_cut", "fa_vbx_default_config",
     "fa_vbx_refine", "fa_compute_centroids", "fa_assign_embeddings", "fa_cluster_default_config",
-    "fa_diarize_cluster", "fa_diarize_cluster_batch", "fa_ahc_last_stage_ms",
+    "fa_diarize_cluster", "fa_diarize_cluster_batch", "fa_ahc_last_stage_ms", "fa_diarize_cluster_chunks",
+    "fa_hungarian_solve", "fa_max_score_assignment", "fa_constrained_assign", "fa_build_chunk_assignments",
     "fastcluster_compute_centroid_linkage",
 ]
 
@@ -117,6 +118,12 @@ def load():
     L.fa_diarize_cluster.argtypes = [vp, vp, sz, sz, sz, vp, C.POINTER(ClusterConfig), vp, vp, vp, i32,
                                      C.POINTER(ClusterInfo)]
     L.fa_diarize_cluster_batch.argtypes = [vp, vp, vp, i32, sz, sz, vp, C.POINTER(ClusterConfig), vp, vp]
+    L.fa_diarize_cluster_chunks.argtypes = [vp, vp, sz, sz, sz, vp, C.POINTER(ClusterConfig), vp, vp, vp, vp, i32,
+                                            C.POINTER(ClusterInfo)]
+    L.fa_hungarian_solve.argtypes = [vp, i32, vp]
+    L.fa_max_score_assignment.argtypes = [vp, i32, i32, vp]
+    L.fa_constrained_assign.argtypes = [vp, sz, i32, vp, vp]
+    L.fa_build_chunk_assignments.argtypes = [vp, vp, vp, sz, i32, i32, i32, vp]
     L.fa_ahc_last_stage_ms.argtypes = [vp]
     L.fa_ahc_last_stage_ms.restype = None
     L.fastcluster_compute_centroid_linkage.argtypes = [vp, sz, sz, vp, sz]

@@ -186,7 +186,10 @@ class OfflineClusterer:
         self.config = config or OfflineDiarizerConfig()
         self.psi = None if psi is None else np.ascontiguousarray(psi, np.float64)
 
-    def cluster(self, embedding256: np.ndarray, rho128: np.ndarray, max_centroids: int = 64) -> ClusterResult:
+    def cluster(self, embedding256: np.ndarray, rho128: np.ndarray, max_centroids: int = 64,
+                chunk_indices=None) -> ClusterResult:
+        """chunk_indices (TimedEmbedding.chunkIndex per embedding) switches on the reference's default constrained
+        assignment (labels -2 where a chunk has more local speakers than clusters)."""
         emb = np.ascontiguousarray(embedding256, np.float32)
         rho = np.ascontiguousarray(rho128, np.float64)
         N, E = emb.shape
@@ -196,10 +199,17 @@ class OfflineClusterer:
         cents = np.zeros((max_centroids, E), np.float64)
         info = _lib.ClusterInfo()
         cfg = self.config._c_cluster()
-        _lib.check(_lib.load().fa_diarize_cluster(emb.ctypes.data, rho.ctypes.data, N, E, R, _lib.ptr(self.psi),
-                                                  C.byref(cfg), labels.ctypes.data, initial.ctypes.data,
-                                                  cents.ctypes.data, max_centroids, C.byref(info)),
-                   "fa_diarize_cluster")
+        if chunk_indices is None:
+            _lib.check(_lib.load().fa_diarize_cluster(emb.ctypes.data, rho.ctypes.data, N, E, R, _lib.ptr(self.psi),
+                                                      C.byref(cfg), labels.ctypes.data, initial.ctypes.data,
+                                                      cents.ctypes.data, max_centroids, C.byref(info)),
+                       "fa_diarize_cluster")
+        else:
+            chunk = np.ascontiguousarray(chunk_indices, np.int32)
+            _lib.check(_lib.load().fa_diarize_cluster_chunks(emb.ctypes.data, rho.ctypes.data, N, E, R,
+                                                             _lib.ptr(self.psi), C.byref(cfg), chunk.ctypes.data,
+                                                             labels.ctypes.data, initial.ctypes.data, cents.ctypes.data,
+                                                             max_centroids, C.byref(info)), "fa_diarize_cluster_chunks")
         d = {f: getattr(info, f) for f, _ in _lib.ClusterInfo._fields_}
         return ClusterResult(labels, initial, cents[: min(info.centroid_count, max_centroids)].copy(), d)
 
@@ -216,3 +226,56 @@ class OfflineClusterer:
                                                         labels.ctypes.data, infos), "fa_diarize_cluster_batch")
         out = [{f: getattr(infos[i], f) for f, _ in _lib.ClusterInfo._fields_} for i in range(count)]
         return labels, out
+
+
+# ---- HungarianAssignment / ConstrainedClusterAssignment (Sources/FluidAudio/Diarizer/HungarianAssignment.swift,
+#      Diarizer/Offline/Clustering/ConstrainedClusterAssignment.swift) ---------------------------------------------
+class HungarianAssignment:
+    @staticmethod
+    def solve(cost_square, n: int) -> list[int]:
+        if n == 0:
+            return []
+        cost = np.ascontiguousarray(cost_square, np.int64).reshape(-1)
+        out = np.zeros(n, np.int32)
+        _lib.check(_lib.load().fa_hungarian_solve(cost.ctypes.data, n, out.ctypes.data), "fa_hungarian_solve")
+        return out.tolist()
+
+    @staticmethod
+    def max_score_assignment(scores) -> list[int]:
+        rows = len(scores)
+        if rows == 0:
+            return []
+        cols = len(scores[0])
+        s = np.ascontiguousarray(scores, np.float64).reshape(rows, cols) if cols else np.zeros((rows, 0))
+        out = np.zeros(rows, np.int32)
+        _lib.check(_lib.load().fa_max_score_assignment(s.ctypes.data if s.size else None, rows, cols, out.ctypes.data),
+                   "fa_max_score_assignment")
+        return out.tolist()
+
+
+class ConstrainedClusterAssignment:
+    @staticmethod
+    def assign(scores, chunk_indices) -> list[int]:
+        n = len(chunk_indices)
+        if n == 0:
+            return []
+        s = np.ascontiguousarray(scores, np.float64)
+        k = s.shape[1] if s.ndim == 2 else 0
+        chunk = np.ascontiguousarray(chunk_indices, np.int32)
+        out = np.zeros(n, np.int32)
+        _lib.check(_lib.load().fa_constrained_assign(s.ctypes.data if s.size else None, n, k, chunk.ctypes.data,
+                                                     out.ctypes.data), "fa_constrained_assign")
+        return out.tolist()
+
+
+def build_chunk_assignments(chunk_indices, speaker_indices, assignments, num_chunks: int, num_speakers: int,
+                            cluster_count: int) -> np.ndarray:
+    """OfflineDiarizerManager.buildChunkAssignments (:885-911): [numChunks x numSpeakers], -2 where unassigned."""
+    chunk = np.ascontiguousarray(chunk_indices, np.int32)
+    spk = np.ascontiguousarray(speaker_indices, np.int32)
+    asg = np.ascontiguousarray(assignments, np.int32)
+    m = np.zeros((num_chunks, num_speakers), np.int32)
+    _lib.check(_lib.load().fa_build_chunk_assignments(chunk.ctypes.data, spk.ctypes.data, asg.ctypes.data, chunk.size,
+                                                      num_chunks, num_speakers, cluster_count, m.ctypes.data),
+               "fa_build_chunk_assignments")
+    return m

@@ -4,6 +4,7 @@
 #include "../../include/fluidaudio_b200.h"
 
 #include "ahc_plan.h"
+#include "assign_host.h"
 #include "mel_plan.h"
 #include "vbx_plan.h"
 
@@ -180,7 +181,8 @@ static float ms_between(cudaEvent_t a, cudaEvent_t b) {
 // OfflineDiarizerManager.cluster(_:) :286-375 on one context.  All inputs are host pointers.
 static int cluster_pipeline(ClusterContext &C, const float *emb, const double *rho, size_t N, size_t E, size_t R,
                             const double *psi, const fa_cluster_config &cfg, int32_t *labels, int32_t *initial_out,
-                            double *centroids_out, int32_t max_centroids, fa_cluster_info *info) {
+                            double *centroids_out, int32_t max_centroids, fa_cluster_info *info,
+                            const int32_t *chunk_index = nullptr) {
     const auto wall0 = std::chrono::steady_clock::now();
     cudaStream_t s = C.stream;
     const int n = (int)N, e = (int)E, r = (int)R;
@@ -365,10 +367,25 @@ static int cluster_pipeline(ClusterContext &C, const float *emb, const double *r
         K = 1;
         lc += 2;
     }
-    st = vbx::assign_device(d_emb, n, e, d_cent_n, nullptr, K, d_labels, nullptr, s, &lc);
+    // constrained assignment (:357-369) needs the full N x K score matrix on the host; plain argmax (:371-374) does not
+    const bool constrained = chunk_index != nullptr && K > 1;
+    double *d_scores = nullptr;
+    if (constrained) {
+        st = C.vbx_ws.reserve(std::max(C.vbx_ws.pool_bytes, N * (size_t)K * sizeof(double) + 1024));
+        if (st != FA_OK) return st;
+        d_scores = static_cast<double *>(C.vbx_ws.pool);
+    }
+    st = vbx::assign_device(d_emb, n, e, d_cent_n, nullptr, K, d_labels, d_scores, s, &lc);
     if (st != FA_OK) return st;
     g_launches += lc;
-    FA_CUDA_TRY(cudaMemcpyAsync(labels, d_labels, N * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (constrained) {
+        std::vector<double> h_scores(N * (size_t)K);
+        FA_CUDA_TRY(cudaMemcpyAsync(h_scores.data(), d_scores, h_scores.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        FA_CUDA_TRY(cudaStreamSynchronize(s));
+        assign::constrained_assign(h_scores.data(), (long long)N, K, chunk_index, labels);
+    } else {
+        FA_CUDA_TRY(cudaMemcpyAsync(labels, d_labels, N * sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
     if (centroids_out && max_centroids > 0) {
         const int kc = std::min(K, max_centroids);
         FA_CUDA_TRY(cudaMemcpyAsync(centroids_out, d_cent, (size_t)kc * E * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1004,6 +1021,63 @@ FA_API fa_status fa_diarize_cluster(const float *emb256, const double *rho, size
                                     max_centroids, info);
     lease.status = st == FA_CUDA_ERROR ? FA_CUDA_ERROR : FA_OK;
     return (fa_status)st;
+    FA_GUARD_END
+}
+
+FA_API fa_status fa_diarize_cluster_chunks(const float *emb256, const double *rho, size_t N, size_t emb_dim,
+                                           size_t rho_dim, const double *psi, const fa_cluster_config *cfg,
+                                           const int32_t *chunk_index, int32_t *labels, int32_t *initial,
+                                           double *centroids, int32_t max_centroids, fa_cluster_info *info) {
+    if (!emb256 || !rho || !cfg || !labels || N == 0 || emb_dim == 0 || rho_dim == 0) return FA_STATUS_INVALID_ARGUMENT;
+    if (N > 0x7fffffffull / 4) return FA_STATUS_INDEX_OVERFLOW;
+    API_REQUIRE_DEVICE();
+    FA_GUARD_BEGIN
+    Lease lease;
+    if (lease.status != FA_OK) return (fa_status)lease.status;
+    const int st = cluster_pipeline(*lease.ctx, emb256, rho, N, emb_dim, rho_dim, psi, *cfg, labels, initial, centroids,
+                                    max_centroids, info, chunk_index);
+    lease.status = st == FA_CUDA_ERROR ? FA_CUDA_ERROR : FA_OK;
+    return (fa_status)st;
+    FA_GUARD_END
+}
+
+FA_API fa_status fa_hungarian_solve(const int64_t *cost, int32_t n, int32_t *assignment) {
+    if (n < 0 || (n > 0 && (!cost || !assignment))) return FA_STATUS_INVALID_ARGUMENT;
+    FA_GUARD_BEGIN
+    assign::min_cost_matching(cost, n, assignment);
+    return FA_STATUS_OK;
+    FA_GUARD_END
+}
+
+FA_API fa_status fa_max_score_assignment(const double *scores, int32_t rows, int32_t cols, int32_t *assignment) {
+    if (rows < 0 || cols < 0 || (rows > 0 && !assignment) || (rows > 0 && cols > 0 && !scores))
+        return FA_STATUS_INVALID_ARGUMENT;
+    FA_GUARD_BEGIN
+    assign::max_score_matching(scores, rows, cols, assignment);
+    return FA_STATUS_OK;
+    FA_GUARD_END
+}
+
+FA_API fa_status fa_constrained_assign(const double *scores, size_t N, int32_t K, const int32_t *chunk_index,
+                                       int32_t *labels) {
+    if (N == 0) return FA_STATUS_OK;
+    if (!chunk_index || !labels || K < 0 || (K > 0 && !scores)) return FA_STATUS_INVALID_ARGUMENT;
+    FA_GUARD_BEGIN
+    assign::constrained_assign(scores, (long long)N, K, chunk_index, labels);
+    return FA_STATUS_OK;
+    FA_GUARD_END
+}
+
+FA_API fa_status fa_build_chunk_assignments(const int32_t *chunk_index, const int32_t *speaker_index,
+                                            const int32_t *assignments, size_t N, int32_t num_chunks,
+                                            int32_t num_speakers, int32_t cluster_count, int32_t *matrix) {
+    if (num_chunks < 0 || num_speakers < 0 || (!matrix && (size_t)num_chunks * num_speakers > 0) ||
+        (N > 0 && (!chunk_index || !speaker_index || !assignments)))
+        return FA_STATUS_INVALID_ARGUMENT;
+    FA_GUARD_BEGIN
+    assign::build_chunk_assignments(chunk_index, speaker_index, assignments, (long long)N, num_chunks, num_speakers,
+                                    cluster_count, matrix);
+    return FA_STATUS_OK;
     FA_GUARD_END
 }
 

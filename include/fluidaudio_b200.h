@@ -17,6 +17,8 @@
  *   fa_compute_centroids Sources/FluidAudio/Diarizer/Offline/Core/OfflineDiarizerManager.swift:613-691
  *   fa_assign_embeddings OfflineDiarizerManager.swift:789-822
  *   fa_diarize_cluster   OfflineDiarizerManager.swift:270-384 (cluster(_:), clustering phase)
+ *   fa_constrained_assign / fa_hungarian_solve / fa_build_chunk_assignments
+ *                        ConstrainedClusterAssignment.swift:20-42, HungarianAssignment.swift:8-97, :885-911
  */
 #ifndef FLUIDAUDIO_B200_H
 #define FLUIDAUDIO_B200_H
@@ -178,6 +180,25 @@ typedef struct {
 fa_status fa_diarize_cluster(const float *emb256, const double *rho, size_t N, size_t emb_dim, size_t rho_dim,
                              const double *psi, const fa_cluster_config *cfg, int32_t *labels, int32_t *initial,
                              double *centroids, int32_t max_centroids, fa_cluster_info *info);
+
+/* Same with the reference's DEFAULT assignment (OfflineDiarizerConfig.Clustering.constrainedAssignment = true,
+ * OfflineDiarizerManager.swift:357-369): chunk_index[N] is TimedEmbedding.chunkIndex; local speakers that share a chunk
+ * are matched to distinct clusters (labels[i] = -2 when a chunk has more local speakers than clusters).
+ * chunk_index == NULL, or a single centroid, falls back to the plain argmax like the reference. */
+fa_status fa_diarize_cluster_chunks(const float *emb256, const double *rho, size_t N, size_t emb_dim, size_t rho_dim,
+                                    const double *psi, const fa_cluster_config *cfg, const int32_t *chunk_index,
+                                    int32_t *labels, int32_t *initial, double *centroids, int32_t max_centroids,
+                                    fa_cluster_info *info);
+
+/* HungarianAssignment.solve / maxScoreAssignment (HungarianAssignment.swift:8-61, :67-97),
+ * ConstrainedClusterAssignment.assign (ConstrainedClusterAssignment.swift:20-42) and
+ * OfflineDiarizerManager.buildChunkAssignments (:885-911).  Exact integer logic on tiny per-chunk matrices: host. */
+fa_status fa_hungarian_solve(const int64_t *cost_square, int32_t n, int32_t *assignment);
+fa_status fa_max_score_assignment(const double *scores, int32_t rows, int32_t cols, int32_t *assignment);
+fa_status fa_constrained_assign(const double *scores, size_t N, int32_t K, const int32_t *chunk_index, int32_t *labels);
+fa_status fa_build_chunk_assignments(const int32_t *chunk_index, const int32_t *speaker_index, const int32_t *assignments,
+                                     size_t N, int32_t num_chunks, int32_t num_speakers, int32_t cluster_count,
+                                     int32_t *matrix);
 
 /* Many independent embedding sets (meetings) on this GPU.  Set m is rows [set_offsets[m], set_offsets[m+1]).
  * Several sets are clustered concurrently on disjoint SM partitions. */

@@ -90,6 +90,10 @@ def lib():
         L.oracle_centroids_from_clusters.argtypes = [_f64p, C.c_int64, C.c_int64, _i32p, _f64p, C.c_int32]
         L.oracle_centroids_from_clusters.restype = C.c_int32
         L.oracle_assign_embeddings.argtypes = [_f64p, C.c_int64, C.c_int64, _f64p, C.c_int32, _i32p, C.c_void_p]
+        L.oracle_hungarian_solve.argtypes = [np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), C.c_int32, _i32p]
+        L.oracle_max_score_assignment.argtypes = [_f64p, C.c_int32, C.c_int32, _i32p]
+        L.oracle_constrained_assign.argtypes = [_f64p, C.c_int64, C.c_int32, _i32p, _i32p]
+        L.oracle_build_chunk_assignments.argtypes = [_i32p, _i32p, _i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _i32p]
         L.oracle_linear_resample.argtypes = [_f32p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_void_p]
         L.oracle_linear_resample.restype = C.c_int64
         L.oracle_normalize_per_feature.argtypes = [_f32p, C.c_int64, C.c_int32, C.c_int64]
@@ -303,6 +307,46 @@ def assign_embeddings(emb: np.ndarray, centroids: np.ndarray, want_scores=False)
     return (labels, scores) if want_scores else labels
 
 
+def hungarian_solve(cost: np.ndarray) -> np.ndarray:
+    cost = np.ascontiguousarray(cost, np.int64)
+    n = cost.shape[0] if cost.ndim == 2 else int(round(cost.size ** 0.5))
+    out = np.zeros(max(n, 1), np.int32)
+    if n:
+        lib().oracle_hungarian_solve(cost.reshape(-1), n, out)
+    return out[:n]
+
+
+def max_score_assignment(scores) -> np.ndarray:
+    scores = np.ascontiguousarray(scores, np.float64)
+    rows = scores.shape[0]
+    cols = scores.shape[1] if scores.ndim == 2 else 0
+    out = np.zeros(max(rows, 1), np.int32)
+    if rows:
+        lib().oracle_max_score_assignment(scores.reshape(-1) if scores.size else np.zeros(1), rows, cols, out)
+    return out[:rows]
+
+
+def constrained_assign(scores, chunk_indices) -> np.ndarray:
+    scores = np.ascontiguousarray(scores, np.float64)
+    chunk = np.ascontiguousarray(chunk_indices, np.int32)
+    N = chunk.size
+    K = scores.shape[1] if scores.ndim == 2 else 0
+    out = np.zeros(max(N, 1), np.int32)
+    if N:
+        lib().oracle_constrained_assign(scores.reshape(-1) if scores.size else np.zeros(1), N, K, chunk, out)
+    return out[:N]
+
+
+def build_chunk_assignments(chunk, speaker, assignments, num_chunks, num_speakers, cluster_count) -> np.ndarray:
+    chunk = np.ascontiguousarray(chunk, np.int32)
+    speaker = np.ascontiguousarray(speaker, np.int32)
+    assignments = np.ascontiguousarray(assignments, np.int32)
+    m = np.zeros((num_chunks, num_speakers), np.int32)
+    lib().oracle_build_chunk_assignments(chunk, speaker, assignments, chunk.size, num_chunks, num_speakers, cluster_count,
+                                         m.reshape(-1))
+    return m
+
+
 @dataclass
 class ClusterResult:
     labels: np.ndarray          # final assignment for all N embeddings (P3)
@@ -313,8 +357,9 @@ class ClusterResult:
 
 
 def diarize_cluster(emb256: np.ndarray, rho128: np.ndarray, psi: np.ndarray, threshold=0.6, Fa=0.07, Fb=0.8,
-                    max_iterations=20, epsilon=1e-4, use_ref: bool = False) -> ClusterResult:
-    """OfflineDiarizerManager.cluster(_:) lines 286-375, unconstrained argmax assignment."""
+                    max_iterations=20, epsilon=1e-4, use_ref: bool = False, chunk_indices=None) -> ClusterResult:
+    """OfflineDiarizerManager.cluster(_:) lines 286-375.  chunk_indices=None -> plain argmax (:371-374); otherwise
+    the reference's default constrained assignment (:357-369) whenever more than one centroid exists."""
     emb32 = np.ascontiguousarray(emb256, np.float32)
     feats = emb32.astype(np.float64)                      # :286  Float -> Double
     rho = np.ascontiguousarray(rho128, np.float64)
@@ -331,5 +376,9 @@ def diarize_cluster(emb256: np.ndarray, rho128: np.ndarray, psi: np.ndarray, thr
     cents = compute_centroids(train, vbx, initial)
     if cents.shape[0] == 0:
         cents = feats.mean(axis=0, keepdims=True)         # computeFallbackCentroids :748-786
-    labels = assign_embeddings(feats, cents)
+    if chunk_indices is not None and cents.shape[0] > 1:
+        _, scores = assign_embeddings(feats, cents, want_scores=True)
+        labels = constrained_assign(scores, chunk_indices)
+    else:
+        labels = assign_embeddings(feats, cents)
     return ClusterResult(labels, initial, vbx, cents, idx)

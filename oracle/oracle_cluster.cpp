@@ -555,3 +555,126 @@ void oracle_assign_embeddings(const double *emb, int64_t N, int64_t dim, const d
 }
 
 } // extern "C"
+
+// ---- "next" row: constrained assignment --------------------------------------------------
+// P4  Sources/FluidAudio/Diarizer/HungarianAssignment.swift:8-61 (solve), :67-97 (maxScoreAssignment)
+//     Sources/FluidAudio/Diarizer/Offline/Clustering/ConstrainedClusterAssignment.swift:20-42 (assign)
+//     OfflineDiarizerManager.swift:885-911 (buildChunkAssignments)
+// Pinned by the reference's own exact-integer unit tests (HungarianAssignmentTests.swift,
+// ConstrainedClusterAssignmentTests.swift), ported in tests/test_oracle_golden.py.
+extern "C" {
+
+// Kuhn-Munkres with row/column potentials on a square non-negative integer matrix; assign[row] = col.
+void oracle_hungarian_solve(const int64_t *cost, int32_t n, int32_t *assign) {
+    if (n <= 0) return;
+    const int64_t INF = std::numeric_limits<int64_t>::max() / 4;
+    std::vector<int64_t> u(n + 1, 0), v(n + 1, 0), minv(n + 1);
+    std::vector<int32_t> p(n + 1, 0), way(n + 1, 0);
+    std::vector<char> used(n + 1);
+    for (int32_t i = 1; i <= n; ++i) {
+        p[0] = i;
+        int32_t j0 = 0;
+        std::fill(minv.begin(), minv.end(), INF);
+        std::fill(used.begin(), used.end(), 0);
+        do {
+            used[j0] = 1;
+            const int32_t i0 = p[j0];
+            int64_t delta = INF;
+            int32_t j1 = 0;
+            for (int32_t j = 1; j <= n; ++j) {
+                if (used[j]) continue;
+                const int64_t cur = cost[(size_t)(i0 - 1) * n + (j - 1)] - u[i0] - v[j];
+                if (cur < minv[j]) {
+                    minv[j] = cur;
+                    way[j] = j0;
+                }
+                if (minv[j] < delta) {
+                    delta = minv[j];
+                    j1 = j;
+                }
+            }
+            for (int32_t j = 0; j <= n; ++j) {
+                if (used[j]) {
+                    u[p[j]] += delta;
+                    v[j] -= delta;
+                } else {
+                    minv[j] -= delta;
+                }
+            }
+            j0 = j1;
+        } while (p[j0] != 0);
+        do {
+            const int32_t j1 = way[j0];
+            p[j0] = p[j1];
+            j0 = j1;
+        } while (j0 != 0);
+    }
+    for (int32_t r = 0; r < n; ++r) assign[r] = -1;
+    for (int32_t j = 1; j <= n; ++j)
+        if (p[j] != 0) assign[p[j] - 1] = j - 1;
+}
+
+// scores: rows x cols row-major; assign[row] = col or -1
+void oracle_max_score_assignment(const double *scores, int32_t rows, int32_t cols, int32_t *assign) {
+    if (rows <= 0) return;
+    if (cols <= 0) {
+        for (int32_t r = 0; r < rows; ++r) assign[r] = -1;
+        return;
+    }
+    bool any = false;
+    double mx = 0, mn = 0;
+    for (int64_t i = 0; i < (int64_t)rows * cols; ++i)
+        if (std::isfinite(scores[i])) {
+            if (!any) mx = mn = scores[i];
+            mx = std::max(mx, scores[i]);
+            mn = std::min(mn, scores[i]);
+            any = true;
+        }
+    const double sentinel = mn - 1;
+    const int32_t n = std::max(rows, cols);
+    std::vector<int64_t> cost((size_t)n * n, 0);
+    for (int32_t r = 0; r < rows; ++r)
+        for (int32_t c = 0; c < cols; ++c) {
+            const double s = std::isfinite(scores[(size_t)r * cols + c]) ? scores[(size_t)r * cols + c] : sentinel;
+            cost[(size_t)r * n + c] = (int64_t)std::round((mx - s) * 1e6);
+        }
+    std::vector<int32_t> full(n);
+    oracle_hungarian_solve(cost.data(), n, full.data());
+    for (int32_t r = 0; r < rows; ++r) assign[r] = full[r] < cols ? full[r] : -1;
+}
+
+// scores: N x K; chunk[N]; out[N] = cluster or -2
+void oracle_constrained_assign(const double *scores, int64_t N, int32_t K, const int32_t *chunk, int32_t *out) {
+    for (int64_t i = 0; i < N; ++i) out[i] = -2;
+    std::vector<int64_t> order(N);
+    for (int64_t i = 0; i < N; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return chunk[a] < chunk[b]; });
+    int64_t i = 0;
+    std::vector<double> block;
+    std::vector<int32_t> assign;
+    while (i < N) {
+        int64_t j = i;
+        while (j < N && chunk[order[j]] == chunk[order[i]]) ++j;
+        const int32_t rows = (int32_t)(j - i);
+        block.resize((size_t)rows * std::max(K, 1));
+        for (int32_t r = 0; r < rows; ++r)
+            for (int32_t c = 0; c < K; ++c) block[(size_t)r * K + c] = scores[order[i + r] * K + c];
+        assign.assign(rows, -1);
+        oracle_max_score_assignment(block.data(), rows, K, assign.data());
+        for (int32_t r = 0; r < rows; ++r) out[order[i + r]] = assign[r] >= 0 ? assign[r] : -2;
+        i = j;
+    }
+}
+
+// matrix [num_chunks x num_speakers], -2 where nothing was assigned
+void oracle_build_chunk_assignments(const int32_t *chunk, const int32_t *speaker, const int32_t *assignments, int64_t N,
+                                    int32_t num_chunks, int32_t num_speakers, int32_t cluster_count, int32_t *matrix) {
+    for (int64_t i = 0; i < (int64_t)num_chunks * num_speakers; ++i) matrix[i] = -2;
+    for (int64_t i = 0; i < N; ++i) {
+        if (chunk[i] < 0 || chunk[i] >= num_chunks || speaker[i] < 0 || speaker[i] >= num_speakers) continue;
+        if (assignments[i] < 0 || assignments[i] >= cluster_count) continue;
+        matrix[(int64_t)chunk[i] * num_speakers + speaker[i]] = assignments[i];
+    }
+}
+
+} // extern "C"

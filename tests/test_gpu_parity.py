@@ -375,3 +375,24 @@ def test_batch_of_sets_equals_one_by_one(gpu_lib, oracle):
         assert np.array_equal(labels[offs[i]:offs[i + 1]], single)
         assert np.array_equal(single, oracle.diarize_cluster(embs[i], rhos[i], psi).labels)
         assert infos[i]["training_count"] == n
+
+
+def test_constrained_pipeline_matches_oracle(gpu_lib, oracle):
+    """The reference's DEFAULT configuration (constrainedAssignment = true): chunk-wise Hungarian on GPU scores."""
+    rng = np.random.default_rng(21)
+    for n, k, seed in ((600, 4, 5), (3000, 8, 6)):
+        emb, who = synth.speaker_embeddings(n, 256, k, seed=seed)
+        rho, psi = synth.synthetic_plda(emb)
+        chunk = np.sort(rng.integers(0, n // 2, n)).astype(np.int32)        # ~2 local speakers per chunk
+        r = cl.OfflineClusterer(psi=psi).cluster(emb, rho, chunk_indices=chunk)
+        o = oracle.diarize_cluster(emb, rho, psi, use_ref=oracle.ref_available(), chunk_indices=chunk)
+        assert np.array_equal(r.labels, o.labels)
+        plain = cl.OfflineClusterer(psi=psi).cluster(emb, rho).labels
+        assert (r.labels != plain).any() or r.info["centroid_count"] == 1       # the constraint changes something
+        for c in np.unique(chunk):
+            a = r.labels[chunk == c]
+            assert len(set(a[a >= 0].tolist())) == (a >= 0).sum()
+        spk = (np.arange(n) % 3).astype(np.int32)
+        m = cl.build_chunk_assignments(chunk, spk, r.labels, int(chunk.max()) + 1, 3, r.info["centroid_count"])
+        assert np.array_equal(m, oracle.build_chunk_assignments(chunk, spk, o.labels, int(chunk.max()) + 1, 3,
+                                                                o.centroids.shape[0]))

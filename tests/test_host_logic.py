@@ -122,6 +122,44 @@ def test_helpers_that_run_on_the_host(lib, oracle):
             assert np.array_equal(dendrogram_cut(z, n, thr), oracle.dendrogram_cut(z, n, thr))
 
 
+def test_constrained_assignment_host_functions(lib, oracle):
+    """The per-chunk Hungarian matching is host code inside the library (exact integer logic, O(chunks K^3)):
+    reference KATs (HungarianAssignmentTests.swift, ConstrainedClusterAssignmentTests.swift) and equality with the
+    oracle on tie-heavy random problems."""
+    from fluidaudio_b200.clustering import ConstrainedClusterAssignment as Cc, HungarianAssignment as H, \
+        build_chunk_assignments
+    assert H.solve([4, 1, 3, 2, 0, 5, 3, 2, 2], 3) == [1, 0, 2] and H.solve([1, 2, 0, 10], 2) == [1, 0]
+    assert H.solve([], 0) == []
+    assert H.max_score_assignment([[0.9, 0.1], [0.8, 0.2]]) == [0, 1]
+    assert H.max_score_assignment([[0.1, 0.9, 0.3]]) == [1]
+    assert H.max_score_assignment([[0.9], [0.5], [0.7]]) == [0, -1, -1]
+    assert H.max_score_assignment([[float("nan"), 0.2], [0.6, 0.5]]) == [1, 0]
+    assert H.max_score_assignment([]) == [] and H.max_score_assignment([[], []]) == [-1, -1]
+    assert Cc.assign([[0.9, 0.3], [0.8, 0.6]], [0, 0]) == [0, 1]
+    assert Cc.assign([[0.9, 0.3], [0.8, 0.6]], [0, 1]) == [0, 0]
+    assert Cc.assign([[0.9], [0.2]], [0, 0]) == [0, -2]
+    assert Cc.assign([[0.1, 0.7, 0.4], [0.5, 0.2, 0.9]], [3, 7]) == [1, 2]
+    assert Cc.assign([], []) == [] and Cc.assign([[0.50, 0.55], [0.10, 0.90]], [0, 0]) == [0, 1]
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        rows, cols = int(rng.integers(1, 5)), int(rng.integers(1, 7))
+        sc = np.round(rng.random((rows, cols)), 2)
+        if rng.random() < 0.2:
+            sc[rng.integers(rows), rng.integers(cols)] = np.inf if rng.random() < 0.5 else np.nan
+        assert H.max_score_assignment(sc.tolist()) == oracle.max_score_assignment(sc).tolist()
+    n, k = 700, 5
+    sc = np.round(rng.random((n, k)), 3)
+    chunk = rng.integers(0, 250, n)
+    spk = rng.integers(0, 3, n)
+    got = np.array(Cc.assign(sc, chunk), np.int32)
+    assert np.array_equal(got, oracle.constrained_assign(sc, chunk))
+    assert np.array_equal(build_chunk_assignments(chunk, spk, got, 250, 3, k),
+                          oracle.build_chunk_assignments(chunk, spk, got, 250, 3, k))
+    for c in np.unique(chunk):          # distinct clusters inside a chunk (or -2)
+        a = got[chunk == c]
+        assert len(set(a[a >= 0].tolist())) == (a >= 0).sum()
+
+
 # ------------------------------------------------------------------------------------------------ device code on the host
 def _compile(src, out):
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", out,

@@ -313,3 +313,31 @@ def test_adapters(oracle):
     assert half.size == 5 and np.allclose(half, mono[::2])
     up = oracle.linear_resample(planar, 8000, 16000)
     assert up.size == 20 and np.allclose(up[:19], np.interp(np.arange(19) / 2, np.arange(10), mono), atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ constrained assignment
+def test_hungarian_and_constrained_assignment_reference_kats(oracle):
+    """HungarianAssignmentTests.swift + ConstrainedClusterAssignmentTests.swift, exact integer outputs."""
+    assert oracle.hungarian_solve(np.array([[4, 1, 3], [2, 0, 5], [3, 2, 2]])).tolist() == [1, 0, 2]
+    assert oracle.hungarian_solve(np.array([[1, 2], [0, 10]])).tolist() == [1, 0]
+    assert oracle.hungarian_solve(np.zeros((0, 0))).size == 0
+    assert oracle.max_score_assignment([[0.9, 0.1], [0.8, 0.2]]).tolist() == [0, 1]
+    assert oracle.max_score_assignment([[0.1, 0.9, 0.3]]).tolist() == [1]
+    assert oracle.max_score_assignment([[0.9], [0.5], [0.7]]).tolist() == [0, -1, -1]
+    assert oracle.max_score_assignment([[np.nan, 0.2], [0.6, 0.5]]).tolist() == [1, 0]
+    assert oracle.max_score_assignment(np.zeros((2, 0))).tolist() == [-1, -1]
+    assert oracle.constrained_assign([[0.9, 0.3], [0.8, 0.6]], [0, 0]).tolist() == [0, 1]
+    assert oracle.constrained_assign([[0.9, 0.3], [0.8, 0.6]], [0, 1]).tolist() == [0, 0]
+    assert oracle.constrained_assign([[0.9], [0.2]], [0, 0]).tolist() == [0, -2]
+    assert oracle.constrained_assign([[0.1, 0.7, 0.4], [0.5, 0.2, 0.9]], [3, 7]).tolist() == [1, 2]
+    assert oracle.constrained_assign([[0.50, 0.55], [0.10, 0.90]], [0, 0]).tolist() == [0, 1]
+    assert oracle.constrained_assign(np.zeros((0, 2)), []).size == 0
+    # optimality against brute force on small random problems
+    import itertools
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        n = int(rng.integers(1, 6))
+        cost = rng.integers(0, 20, (n, n))
+        best = min(sum(cost[i, p[i]] for i in range(n)) for p in itertools.permutations(range(n)))
+        a = oracle.hungarian_solve(cost)
+        assert sorted(a.tolist()) == list(range(n)) and sum(cost[i, a[i]] for i in range(n)) == best
