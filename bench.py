@@ -171,7 +171,9 @@ def bench_mel(args, dist):
                 "host_buffers": "pinned (fa_host_alloc)", "api": "fa_mel_compute"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "mel512_kernel", "peak_source": peak_src,
+                     "traffic": 320.6e6, "traffic_source": "ncu --set full, profiles/r01b_summary.txt: dram read 231.3 MB + "
+                     "write 89.3 MB per launch (the tail of the output is still in L2 at kernel end)",
+                     "kernel": "mel512_kernel", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": MEL_BYTES_PER_HOUR},
         "config": {"workload": "log-mel STFT, 1 h synthetic 16 kHz mono, 25 ms/10 ms frames, nFFT 512, 80 mels, per GPU",
                    "samples": MEL_SAMPLES, "frames": MEL_FRAMES, "n_mels": N_MELS,
@@ -218,7 +220,9 @@ def bench_cluster(args, dist, steps=None):
                 "host_buffers": "pinned (fa_host_alloc)", "api": "fa_diarize_cluster"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "ahc_merge_kernel (+ ahc_init_nn_kernel)", "peak_source": peak_src,
+                     "traffic": 43.0e6, "traffic_source": "ncu --set full, profiles/r01b_summary.txt: ahc_merge_kernel dram "
+                     "read 41.3 MB + write 1.7 MB per launch (+ 20.6 MB read by ahc_init_nn_kernel)",
+                     "kernel": "ahc_merge_kernel (+ ahc_init_nn_kernel)", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": AHC_BYTES,
                      "note": "node vectors are resident in shared memory, so algorithmic bytes are served on-chip; "
                              "the loop is bound by N-1 dependent steps (latency), see DESIGN.md"},
