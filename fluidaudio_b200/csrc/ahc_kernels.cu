@@ -192,12 +192,16 @@ __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void ld_relaxed_v2(const u64 *p, u64 &x, u64 &y) {   // p 16-byte aligned
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void st_release_u64(u64 *p, u64 v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ u64 global_ns() {
     u64 t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -205,7 +209,7 @@ __device__ __forceinline__ u64 global_ns() {
 }
 #define FA_TRACE(slot)                                                                         \
     do {                                                                                       \
-        if ((P.flags & 4) && trace_step >= 0 && trace_step < kTraceSteps) P.trace[trace_step * 8 + (slot)] = global_ns(); \
+        if ((P.flags & 4) && trace_step >= 0 && trace_step < kTraceSteps) P.trace[trace_step * 16 + (slot)] = global_ns(); \
     } while (0)
 
 __device__ __forceinline__ u64 pack_cmd(int type, unsigned counter, int a, int b) {
@@ -219,10 +223,98 @@ __device__ __forceinline__ void cand_min(double &d, int &id, double od, int oid)
     }
 }
 
-// Master: one warp of CTA 0.  Lane 0 runs the reference's control flow (fastcluster_internal.hpp:1685-1799);
-// the other lanes poll and fold the per-CTA candidates.  Heap, nearest-neighbour table, slot->node table and
-// live bitmap sit in shared memory: every ld.acquire of a polling loop invalidates this SM's L1, and a sift
-// through L2-resident arrays would cost ~100 dependent 300-cycle loads per step.
+// One polling snapshot: both words of up to Q slots per lane plus (optionally) the threshold words.
+template <int Q> struct PollSnap {
+    u64 a0[Q], a1[Q], t0, t1;
+    __device__ __forceinline__ void issue(const ResultSlot *results, int shift, int W, int lane, unsigned tag,
+                                          const u64 *thr) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int w = lane + 32 * q;
+            a0[q] = (u64)(tag & 0xffu);
+            a1[q] = (u64)tag;
+            if (w < W) ld_relaxed_v2(&results[(size_t)w << shift].w0, a0[q], a1[q]);   // one 16-byte request per slot
+        }
+        t0 = t1 = (u64)tag;
+        if (thr) ld_relaxed_v2(thr, t0, t1);
+    }
+    __device__ __forceinline__ bool complete(unsigned tag) const {   // warp-uniform
+        bool pending = (unsigned)t0 != tag || (unsigned)t1 != tag;
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            pending = pending || ((unsigned)(a0[q] & 0xffu) != (tag & 0xffu)) || ((unsigned)a1[q] != tag);
+        return !__any_sync(0xffffffffu, pending);
+    }
+    __device__ __forceinline__ void reduce(int W, int lane, double &d, int &id, bool &bad, double *T) const {
+        if (T) *T = __longlong_as_double((long long)((t0 & 0xffffffff00000000ull) | (t1 >> 32)));
+        d = INFINITY;
+        id = INT_MAX;
+        bad = false;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int w = lane + 32 * q;
+            if (w < W) {
+                const unsigned oid = (unsigned)(a0[q] >> 8) & 0xffffffu;
+                const u64 bits = (a0[q] & 0xffffffff00000000ull) | (a1[q] >> 32);
+                if (oid == 0xfffffeu) bad = true;
+                else if (oid != 0xffffffu) cand_min(d, id, __longlong_as_double((long long)bits), (int)oid);
+            }
+        }
+    }
+};
+
+// One warp gathers the candidates of ALL worker CTAs for scan round `tag` (used by the master warp and by the
+// service warp of every worker CTA: the exchange is all-to-all) and, optionally, the round's threshold words in the
+// same polling loop.  Each lane owns slots lane, lane+32, ...; all words are self-validating, all loads relaxed.
+// ~90 CTAs poll the same few lines, so the polling traffic itself sets the latency of the exchange: one 16-byte
+// request per candidate, one snapshot in flight, and every candidate in its own 128-byte line (slot_shift = 3)
+// measured 1.1 us from the last candidate's store to the decision, against 1.9 us with two 8-byte loads per
+// packed slot, and three staggered snapshots in flight were slower than one (profiles/r01c_ahc_trace.md).
+// Returns the lexicographic (distance, id) minimum in every lane; `bad` = a NaN seen by any CTA.
+__device__ __forceinline__ void gather_candidates(const ResultSlot *results, int shift, int W, int lane, unsigned tag,
+                                                  double &d, int &id, bool &bad, const u64 *thr = nullptr,
+                                                  double *T = nullptr) {
+    const unsigned full = 0xffffffffu;
+    if (W <= 96) {
+        PollSnap<3> s0;
+        do {
+            s0.issue(results, shift, W, lane, tag, thr);
+        } while (!s0.complete(tag));
+        s0.reduce(W, lane, d, id, bad, T);
+    } else {
+        PollSnap<8> s0;   // W <= 255 worker CTAs
+        do {
+            s0.issue(results, shift, W, lane, tag, thr);
+        } while (!s0.complete(tag));
+        s0.reduce(W, lane, d, id, bad, T);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(full, d, o);
+        const int oid = __shfl_xor_sync(full, id, o);
+        cand_min(d, id, od, oid);
+    }
+    bad = __any_sync(full, bad);
+}
+
+// Threshold of a scan round: the key of the root's smaller child in the master's heap (after the round's erase).
+// If the new node's nearest-neighbour distance d satisfies d <= T the new node stays at the heap top and the next
+// merge is (new node, its nearest neighbour) — every CTA can conclude that by itself.  Two self-validating words.
+__device__ __forceinline__ void publish_threshold(u64 *thr, double T, unsigned tag) {
+    const u64 bits = (u64)__double_as_longlong(T);
+    st_relaxed_u64(&thr[0], (bits & 0xffffffff00000000ull) | (u64)tag);
+    st_release_u64(&thr[1], (bits << 32) | (u64)tag);
+}
+// Master: one warp of CTA 0.  Lane 0 runs the reference's control flow (fastcluster_internal.hpp:1685-1799); the
+// other lanes help gathering.  Heap, nearest-neighbour table, slot->node table and live bitmap sit in shared memory:
+// every acquire of a polling loop invalidates this SM's L1, and a sift through L2-resident arrays would cost ~100
+// dependent 300-cycle loads per step.
+//
+// The master is OFF the critical path in the common case.  Per scanned merge it (1) does the bookkeeping and the
+// reference's erase(), (2) pre-computes the root's descent path and publishes the round's threshold T, (3) gathers
+// the candidates like everybody else and finishes replace_key() as one parallel rotation.  If d <= T the workers
+// have already started the next merge on their own ("self-issued"); only otherwise (and for lazy nearest-neighbour
+// repairs, and for the very first merge) do they wait for an explicit command word.
 template <typename Idx>
 __device__ void ahc_master(const Problem &P, int W, unsigned char *sm) {
     const int lane = threadIdx.x;
@@ -274,86 +366,54 @@ __device__ void ahc_master(const Problem &P, int W, unsigned char *sm) {
 
     NnHeapT<Idx> heap{key, at, where, P.heap_size};
     LiveSet live{bits, 2 * N - 1, 0};
-    unsigned counter = 0;
+    unsigned cmd_counter = 0, round = 0;
     bool failed = false;
     __shared__ int path_pos[40], path_slot[40], path_depth;
     __shared__ double path_key[40];
-    int sa_shared = 0;
+    const bool allow_self = (P.flags & 8) == 0;
 
     auto publish = [&](int type, int a, int b) {   // lane 0
-        st_release_u64(P.cmd, pack_cmd(type, ++counter, a, b));
-    };
-    // Whole warp; result valid in every lane.  Each lane owns slots lane, lane+32, ... and keeps the loads of both
-    // words of all of them in flight; one L2 round trip after the last worker's store the warp has every candidate.
-    auto collect = [&](unsigned tag, double &d, int &id) {
-        constexpr int kMaxMine = 8;   // W <= 255 worker CTAs
-        u64 a0[kMaxMine], a1[kMaxMine];
-        bool pending = true;
-        while (pending) {
-            pending = false;
-#pragma unroll
-            for (int q = 0; q < kMaxMine; ++q) {
-                const int w = lane + 32 * q;
-                a0[q] = (w < W) ? ld_relaxed_u64(&P.results[w].w0) : (u64)(tag & 0xffu);
-                a1[q] = (w < W) ? ld_relaxed_u64(&P.results[w].w1) : (u64)tag;
-            }
-#pragma unroll
-            for (int q = 0; q < kMaxMine; ++q)
-                pending = pending || ((unsigned)(a0[q] & 0xffu) != (tag & 0xffu)) || ((unsigned)a1[q] != tag);
-            pending = __any_sync(full, pending);
-        }
-        d = INFINITY;
-        id = INT_MAX;
-        bool bad = false;
-#pragma unroll
-        for (int q = 0; q < kMaxMine; ++q) {
-            const int w = lane + 32 * q;
-            if (w < W) {
-                const unsigned oid = (unsigned)(a0[q] >> 8) & 0xffffffu;
-                const u64 bits = (a0[q] & 0xffffffff00000000ull) | (a1[q] >> 32);
-                if (oid == 0xfffffeu) bad = true;
-                else if (oid != 0xffffffu) cand_min(d, id, __longlong_as_double((long long)bits), (int)oid);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(full, d, o);
-            const int oid = __shfl_xor_sync(full, id, o);
-            cand_min(d, id, od, oid);
-        }
-        if (__any_sync(full, bad)) failed = true;
+        st_release_u64(P.cmd, pack_cmd(type, ++cmd_counter, a, b));
     };
 
+    int sa = 0;               // slot at the heap top (lane 0)
+    bool self_issued = false; // the workers already know the pair of this step
     for (int step = 0; step < N - 1 && !failed; ++step) {
         const int fresh = N + step;
         const int trace_step = step - N / 2;   // trace a window in the middle of the run
-        int sa = 0;   // slot of the heap top
-        for (;;) {    // lazy repair of a stale nearest neighbour (:1706-1734)
-            int stale = 0;
-            if (lane == 0) {
-                sa = heap.top();
-                stale = live.dead(nn[sa]) ? 1 : 0;
-                if (stale) publish(CMD_RESCAN, node_of[sa], 0);
+        if (!self_issued) {
+            for (;;) {    // lazy repair of a stale nearest neighbour (:1706-1734)
+                int stale = 0;
+                if (lane == 0) {
+                    sa = heap.top();
+                    stale = live.dead(nn[sa]) ? 1 : 0;
+                    if (stale) publish(CMD_RESCAN, node_of[sa], 0);
+                }
+                stale = __shfl_sync(full, stale, 0);
+                if (!stale) break;
+                ++round;
+                double d;
+                int id;
+                bool bad;
+                gather_candidates(P.results + (round & 1u) * P.result_stride, P.slot_shift, W, lane, round, d, id, bad);
+                if (bad) {
+                    failed = true;
+                    break;
+                }
+                if (lane == 0) {
+                    nn[sa] = id;
+                    heap.raise_key(sa, d);
+                }
+                __syncwarp();
             }
-            stale = __shfl_sync(full, stale, 0);
-            if (!stale) break;
-            counter = __shfl_sync(full, counter, 0);
-            double d;
-            int id;
-            collect(counter, d, id);
             if (failed) break;
-            if (lane == 0) {
-                nn[sa] = id;
-                heap.raise_key(sa, d);
-            }
-            __syncwarp();
         }
-        if (failed) break;
-        int a = 0, b = 0, sb = 0;
+        int a = 0, b = 0;
+        double T = INFINITY;
         if (lane == 0) {
             a = node_of[sa];
             b = nn[sa];
-            if (step < N - 2) publish(CMD_MERGE, a, b);   // workers start while the bookkeeping below runs
+            if (step < N - 2 && !self_issued) publish(CMD_MERGE, a, b);
             FA_TRACE(0);
             live.drop(a);
             live.drop(b);
@@ -361,18 +421,18 @@ __device__ void ahc_master(const Problem &P, int W, unsigned char *sm) {
             P.merge_b[step] = b;
             P.merge_d[step] = key[sa];
             if (step < N - 2) {
-                sb = P.slot_of[b];
+                const int sb = P.slot_of[b];
                 node_of[sa] = fresh;
                 node_of[sb] = -1;
                 P.slot_of[fresh] = sa;
-                if (P.flags & 1) {
-                // Heap maintenance that does not depend on the scan result is done NOW, in the reference's order
-                // (erase first, :1792-1796), hidden behind the workers' scan.  sa stays at the root: the element
-                // moved by erase() can only rise while strictly smaller than its parent, never past the minimum.
+                // Heap maintenance that does not depend on the scan result, in the reference's order (erase first,
+                // :1792-1796).  sa stays at the root: the element moved by erase() can only rise while strictly
+                // smaller than its parent, never past the minimum.
                 if (b < live.head) heap.erase(P.slot_of[live.head]); else heap.erase(sb);
-                // Descent path the root would take in replace_key (:1797 -> update_geq_): at every level the
-                // smaller child, the left one on ties.  sift_down(root, d) swaps along exactly this path while
-                // the child's key is < d, so once d is known the whole sift is one parallel rotation.
+                // Descent path the root would take in replace_key (:1797 -> update_geq_): at every level the smaller
+                // child, the left one on ties.  sift_down(root, d) swaps along exactly this path while the child's
+                // key is < d, so once d is known the whole sift is one parallel rotation, and d <= path_key[1]
+                // means the new node stays on top.
                 int pos = 0, depth = 0;
                 path_pos[0] = 0;
                 for (;;) {
@@ -386,33 +446,32 @@ __device__ void ahc_master(const Problem &P, int W, unsigned char *sm) {
                     pos = child;
                 }
                 path_depth = depth;
-                }
+                T = depth >= 1 ? path_key[1] : INFINITY;
+                if (!allow_self) T = -1.0;   // tuning hook: never self-issue
+                publish_threshold(P.threshold + 2 * ((round + 1) & 1u), T, round + 1);
             }
             FA_TRACE(1);
         }
         if (step < N - 2) {
-            counter = __shfl_sync(full, counter, 0);
+            ++round;
             double d;
             int id;
-            collect(counter, d, id);
+            bool bad;
+            gather_candidates(P.results + (round & 1u) * P.result_stride, P.slot_shift, W, lane, round, d, id, bad);
             if (lane == 0) FA_TRACE(2);
-            if (failed) break;
-            if (!(P.flags & 1)) {
-                if (lane == 0) {
-                    nn[sa] = id;
-                    if (b < live.head) heap.erase(P.slot_of[live.head]); else heap.erase(sb);
-                    heap.replace_key(sa, d);
-                }
-                __syncwarp();
-                continue;
+            if (bad) {
+                failed = true;
+                break;
             }
             __syncwarp();
             const int depth = path_depth;
-            const double old_key = key[sa_shared = __shfl_sync(full, sa, 0)];
+            const int sa_all = __shfl_sync(full, sa, 0);
+            T = __shfl_sync(full, T, 0);
+            const double old_key = key[sa_all];
             // levels 1..m move up one position, the root element lands at level m
             const bool goes_below = lane >= 1 && lane <= depth && path_key[lane] < d;
-            unsigned below = __ballot_sync(full, goes_below) | 1u;     // bit 0 set so that ffs(~below) = m + 1
-            const int m = (d <= old_key) ? 0 : (__ffs(~below) - 2);    // lower_key at the root never moves
+            const unsigned below = __ballot_sync(full, goes_below) | 1u;   // bit 0 set so that ffs(~below) = m + 2
+            const int m = (d <= old_key) ? 0 : (__ffs(~below) - 2);        // lower_key at the root never moves
             if (lane >= 1 && lane <= m) {
                 const int slot = path_slot[lane], to = path_pos[lane - 1];
                 at[to] = (Idx)slot;
@@ -427,6 +486,9 @@ __device__ void ahc_master(const Problem &P, int W, unsigned char *sm) {
                 FA_TRACE(3);
             }
             __syncwarp();
+            self_issued = d <= T;   // same doubles, same comparison as in every worker CTA
+        } else {
+            self_issued = false;
         }
     }
     if (lane == 0) {
@@ -435,7 +497,23 @@ __device__ void ahc_master(const Problem &P, int W, unsigned char *sm) {
     }
 }
 
-__global__ void __launch_bounds__(kMergeThreads, 1) ahc_merge_kernel(const Problem *pp) {
+// Worker CTAs: kMergeThreads scan threads (one resident node each) plus one SERVICE warp that owns all cross-CTA
+// traffic of the CTA: it waits for command words, publishes the CTA's candidate, gathers everybody's candidates and
+// the round's threshold, decides the next pair, and executes the CTA's only gpu-scope fence.
+//
+// Memory ordering without a fence on the critical path.  The only worker-written data other CTAs read are the node
+// store rows[fresh] / node_weight[fresh] of a merge.  Candidate slots and threshold words are self-validating and
+// relaxed.  At the END of every round the service warp executes one fence.acq_rel.gpu:
+//   * as a release it orders the CTA's row writes of round q (made visible to it by the round's block barriers)
+//     before its slot store of round q+1;
+//   * as an acquire it orders the slots it gathered in round q+1 before everything after the next block barrier it
+//     joins, i.e. before the row loads of round q+3 (a self-issued round q+2 starts its loads concurrently with it).
+// So rows[fresh_q] must not be read before round q+3 — and it is not: the vectors and weights of the two newest
+// nodes (fresh_{q+2}, fresh_{q+1}) are kept in shared memory by every CTA and used from there.  Explicit commands
+// are stronger still (release/acquire on the command word through the master, which gathered the same slots).
+constexpr int kWorkerThreads = kMergeThreads + 32;
+
+__global__ void __launch_bounds__(kWorkerThreads, 1) ahc_merge_kernel(const Problem *pp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Problem P = *pp;
     const int W = (int)gridDim.x - 1;
@@ -447,103 +525,151 @@ __global__ void __launch_bounds__(kMergeThreads, 1) ahc_merge_kernel(const Probl
     }
     const int wb = (int)blockIdx.x - 1;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool svc = warp == kMergeThreads / 32;   // the service warp
     const int N = P.N, D = P.D, Ns = P.Ns;
-    double *v = reinterpret_cast<double *>(smem_raw);       // [D] target vector
-    double *red_d = v + ((D + 1) & ~1);                     // [warps]
+    const int Dp = (D + 1) & ~1;
+    double *vbuf0 = reinterpret_cast<double *>(smem_raw);   // three vector buffers: the two newest nodes + scratch
+    double *vbuf1 = vbuf0 + Dp;
+    double *vbuf2 = vbuf1 + Dp;
+    double *red_d = vbuf2 + Dp;                             // [scan warps]
     int *red_id = reinterpret_cast<int *>(red_d + kMergeThreads / 32);
     double *sv = red_d + kMergeThreads / 32 + kMergeThreads / 32;   // resident node vectors [D x SP], k-major
     __shared__ u64 s_cmd;
-    __shared__ int s_owner;
+    __shared__ int s_owner, s_next_b, s_have_pair;
+    __shared__ double s_wnew, s_wprev;
 
     const bool resident = P.resident != 0;
     const int SP = P.slots_per_cta;
-    const int rounds = resident ? 1 : (Ns + W * kMergeThreads - 1) / (W * kMergeThreads);
+    const int rounds_per_thread = resident ? 1 : (Ns + W * kMergeThreads - 1) / (W * kMergeThreads);
     int ids[kMaxRounds];
 #pragma unroll
     for (int r = 0; r < kMaxRounds; ++r) ids[r] = -1;
-    if (resident) {
-        const int s = wb * SP + t;
-        if (t < SP && s < N) {
-            ids[0] = s;
-            for (int k = 0; k < D; ++k) sv[k * SP + t] = P.cols[(size_t)k * Ns + s];   // coalesced over t
-        }
-    } else {
+    if (!svc) {
+        if (resident) {
+            const int s = wb * SP + t;
+            if (t < SP && s < N) {
+                ids[0] = s;
+                for (int k = 0; k < D; ++k) sv[k * SP + t] = P.cols[(size_t)k * Ns + s];   // coalesced over t
+            }
+        } else {
 #pragma unroll
-        for (int r = 0; r < kMaxRounds; ++r) {
-            const int s = (r * W + wb) * kMergeThreads + t;
-            ids[r] = (r < rounds && s < N) ? s : -1;
+            for (int r = 0; r < kMaxRounds; ++r) {
+                const int s = (r * W + wb) * kMergeThreads + t;
+                ids[r] = (r < rounds_per_thread && s < N) ? s : -1;
+            }
         }
     }
-    unsigned expect = 0;
+    unsigned cmd_expect = 0, round = 0;
     int merges = 0;
+    int prev_fresh = -1, prev_prev = -1;   // nodes whose vectors vcur / vprev hold
+    double *vcur = vbuf0, *vprev = vbuf1, *valt = vbuf2;
+    bool have_pair = false;
+    int a = 0, b = 0;
+    if (t == kMergeThreads) s_owner = -1;
     for (;;) {
-        ++expect;
-        if (t == 0) {
-            u64 c;
-            do {
-                c = ld_acquire_u64(P.cmd);
-            } while ((unsigned)((c >> 48) & 0x3fffu) != (expect & 0x3fffu));
-            s_cmd = c;
-            s_owner = -1;
+        int type = CMD_MERGE;
+        if (!have_pair) {          // wait for an explicit command word
+            ++cmd_expect;
+            if (t == kMergeThreads) {
+                u64 c;
+                do {
+                    c = ld_acquire_u64(P.cmd);
+                } while ((unsigned)((c >> 48) & 0x3fffu) != (cmd_expect & 0x3fffu));
+                s_cmd = c;
+            }
+            __syncthreads();
+            const u64 c = s_cmd;
+            type = (int)(c >> 62);
+            a = (int)((c >> 24) & 0xffffffu);
+            b = (int)(c & 0xffffffu);
+            if (type == CMD_EXIT) break;
         }
-        __syncthreads();
-        const u64 c = s_cmd;
-        const int type = (int)(c >> 62);
-        const int a = (int)((c >> 24) & 0xffffffu), b = (int)(c & 0xffffffu);
-        if (type == CMD_EXIT) break;
+        ++round;
+        const int trace_step = (wb == 0 && lane == 0 && type == CMD_MERGE) ? merges - N / 2 : -1;
+        if (t == 0) FA_TRACE(4);
+        const int all_step = (lane == 0 && type == CMD_MERGE) ? merges - N / 2 : -1;   // any CTA (trace of the slowest)
+        if ((P.flags & 4) && t == 0 && all_step >= 0 && all_step < kTraceSteps) atomicMax(&P.trace[all_step * 16 + 12], global_ns());
         int limit;
-        const int trace_step = (wb == 0 && t == 0 && type == CMD_MERGE) ? merges - N / 2 : -1;
-        FA_TRACE(4);
+        const double *v;
         if (type == CMD_MERGE) {
             const int fresh = N + merges;
             ++merges;
-            const double wa = (double)__ldcg(P.node_weight + a), wbv = (double)__ldcg(P.node_weight + b);
-            const double *ra = P.rows + (size_t)a * D, *rb = P.rows + (size_t)b * D;
-            const double den = __dadd_rn(wa, wbv);
-            for (int k = t; k < D; k += kMergeThreads) {
-                const double xa = __ldcg(ra + k), xb = __ldcg(rb + k);
-                v[k] = __ddiv_rn(__dadd_rn(__dmul_rn(xa, wa), __dmul_rn(xb, wbv)), den);
-            }
-            // the thread holding a turns into `fresh`, the one holding b goes idle
+            // operands: the two newest nodes live on chip (see the ordering note above), older ones in the node store
+            const double *la = a == prev_fresh ? vcur : (a == prev_prev ? vprev : nullptr);
+            const double *lb = b == prev_fresh ? vcur : (b == prev_prev ? vprev : nullptr);
+            double wa = 0.0, wbv = 0.0;
+            if (!svc) {
+                wa = a == prev_fresh ? s_wnew : (a == prev_prev ? s_wprev : (double)__ldcg(P.node_weight + a));
+                wbv = b == prev_fresh ? s_wnew : (b == prev_prev ? s_wprev : (double)__ldcg(P.node_weight + b));
+                const double *ra = P.rows + (size_t)a * D, *rb = P.rows + (size_t)b * D;
+                const double den = __dadd_rn(wa, wbv);
+                for (int k = t; k < D; k += kMergeThreads) {
+                    const double xa = la ? la[k] : __ldcg(ra + k);
+                    const double xb = lb ? lb[k] : __ldcg(rb + k);
+                    valt[k] = __ddiv_rn(__dadd_rn(__dmul_rn(xa, wa), __dmul_rn(xb, wbv)), den);
+                }
+                // the thread holding a turns into `fresh`, the one holding b goes idle
 #pragma unroll
-            for (int r = 0; r < kMaxRounds; ++r) {
-                if (r < rounds) {
-                    if (ids[r] == a) {
-                        ids[r] = fresh;
-                        s_owner = resident ? t : (r * W + wb) * kMergeThreads + t;
-                    } else if (ids[r] == b) {
-                        ids[r] = -1;
+                for (int r = 0; r < kMaxRounds; ++r) {
+                    if (r < rounds_per_thread) {
+                        if (ids[r] == a) {
+                            ids[r] = fresh;
+                            s_owner = resident ? t : (r * W + wb) * kMergeThreads + t;
+                        } else if (ids[r] == b) {
+                            ids[r] = -1;
+                        }
                     }
                 }
             }
-            __syncthreads();
+            __syncthreads();   // valt complete, s_owner set; all reads of s_wnew / s_wprev / vcur / vprev done
+            {
+                double *tmp = vprev;
+                vprev = vcur;
+                vcur = valt;
+                valt = tmp;
+            }
+            if (t == 0) {
+                s_wprev = s_wnew;   // weight of the node vprev now holds
+                s_wnew = __dadd_rn(wa, wbv);
+            }
             const int os = s_owner;
-            if (os >= 0) {   // this CTA holds the slot: store the new node (scan copy + node-store row + weight)
+            if (os >= 0 && !svc) {   // this CTA holds the slot: store the new node (scan copy + node-store row + weight)
                 double *row = P.rows + (size_t)fresh * D;
                 for (int k = t; k < D; k += kMergeThreads) {
-                    if (resident) sv[k * SP + os] = v[k]; else P.cols[(size_t)k * Ns + os] = v[k];
-                    row[k] = v[k];
+                    if (resident) sv[k * SP + os] = vcur[k]; else P.cols[(size_t)k * Ns + os] = vcur[k];
+                    row[k] = vcur[k];
                 }
                 if (t == 0) P.node_weight[fresh] = (int)(wa + wbv);
             }
+            prev_prev = prev_fresh;
+            prev_fresh = fresh;
             limit = fresh;
+            v = vcur;
         } else {
-            const double *rt = P.rows + (size_t)a * D;
-            for (int k = t; k < D; k += kMergeThreads) v[k] = __ldcg(rt + k);
+            const double *lt = a == prev_fresh ? vcur : (a == prev_prev ? vprev : nullptr);
+            if (lt) {
+                v = lt;
+            } else {
+                const double *rt = P.rows + (size_t)a * D;
+                if (!svc)
+                    for (int k = t; k < D; k += kMergeThreads) valt[k] = __ldcg(rt + k);
+                v = valt;
+            }
             __syncthreads();
             limit = a;
         }
-        FA_TRACE(5);
+        if (t == 0) FA_TRACE(5);
+        __syncwarp();   // lane 0's single-thread work above must not leave the warp split across the scan chain
         // ---- scan: one sequential chain per owned live node with id < limit ------------------------------
-        double best = INFINITY;
-        int best_id = INT_MAX;
-        bool bad = false;
-        if (resident) {
-            const int id = ids[0];
-            if (id >= 0 && id < limit) {
-                const double *col = sv + t;
-                double sum = 0.0;
-                if (!(P.flags & 2)) {
+        if (!svc) {
+            double best = INFINITY;
+            int best_id = INT_MAX;
+            bool bad = false;
+            if (resident) {
+                const int id = ids[0];
+                if (id >= 0 && id < limit) {
+                    const double *col = sv + t;
+                    double sum = 0.0;
                     int k = 0;
                     for (; k + 8 <= D; k += 8) {
                         double x[8];
@@ -553,89 +679,101 @@ __global__ void __launch_bounds__(kMergeThreads, 1) ahc_merge_kernel(const Probl
                         for (int u = 0; u < 8; ++u) sum = sq_step(sum, x[u], v[k + u]);
                     }
                     for (; k < D; ++k) sum = sq_step(sum, col[k * SP], v[k]);
-                } else {
-                // the chain over k is strictly sequential; operands are fetched one batch ahead of it
-                double xa[8], va[8], xb[8], vb[8];
-                const int D16 = D & ~15;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    xa[u] = (u < D16) ? col[u * SP] : 0.0;
-                    va[u] = (u < D16) ? v[u] : 0.0;
+                    if (sum != sum) bad = true;
+                    best = sum;
+                    best_id = id;
                 }
-                for (int k = 0; k < D16; k += 16) {
+            } else {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        xb[u] = col[(k + 8 + u) * SP];
-                        vb[u] = v[k + 8 + u];
-                    }
+                for (int r = 0; r < kMaxRounds; ++r) {
+                    if (r < rounds_per_thread) {
+                        const int id = ids[r];
+                        if (id >= 0 && id < limit) {
+                            const int s = (r * W + wb) * kMergeThreads + t;
+                            const double *col = P.cols + s;
+                            double sum = 0.0;
+                            int k = 0;
+                            for (; k + 16 <= D; k += 16) {
+                                double x[16];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) sum = sq_step(sum, xa[u], va[u]);
-                    if (k + 16 < D16) {
+                                for (int u = 0; u < 16; ++u) x[u] = __ldcg(col + (size_t)(k + u) * Ns);
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            xa[u] = col[(k + 16 + u) * SP];
-                            va[u] = v[k + 16 + u];
+                                for (int u = 0; u < 16; ++u) sum = sq_step(sum, x[u], v[k + u]);
+                            }
+                            for (; k < D; ++k) sum = sq_step(sum, __ldcg(col + (size_t)k * Ns), v[k]);
+                            if (sum != sum) bad = true;
+                            cand_min(best, best_id, sum, id);
                         }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) sum = sq_step(sum, xb[u], vb[u]);
-                }
-                for (int k = D16; k < D; ++k) sum = sq_step(sum, col[k * SP], v[k]);
-                }
-                if (sum != sum) bad = true;
-                best = sum;
-                best_id = id;
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < kMaxRounds; ++r) {
-                if (r < rounds) {
-                    const int id = ids[r];
-                    if (id >= 0 && id < limit) {
-                        const int s = (r * W + wb) * kMergeThreads + t;
-                        const double *col = P.cols + s;
-                        double sum = 0.0;
-                        int k = 0;
-                        for (; k + 16 <= D; k += 16) {
-                            double x[16];
-#pragma unroll
-                            for (int u = 0; u < 16; ++u) x[u] = __ldcg(col + (size_t)(k + u) * Ns);
-#pragma unroll
-                            for (int u = 0; u < 16; ++u) sum = sq_step(sum, x[u], v[k + u]);
-                        }
-                        for (; k < D; ++k) sum = sq_step(sum, __ldcg(col + (size_t)k * Ns), v[k]);
-                        if (sum != sum) bad = true;
-                        cand_min(best, best_id, sum, id);
                     }
                 }
             }
-        }
+            if (t == 0) FA_TRACE(6);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oid = __shfl_xor_sync(0xffffffffu, best_id, o);
-            cand_min(best, best_id, od, oid);
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oid = __shfl_xor_sync(0xffffffffu, best_id, o);
+                cand_min(best, best_id, od, oid);
+            }
+            const bool warp_bad = __any_sync(0xffffffffu, bad);
+            if (lane == 0) {
+                red_d[warp] = best;
+                red_id[warp] = warp_bad ? -2 : best_id;
+            }
+            if (t == 0) FA_TRACE(11);
         }
-        FA_TRACE(6);
-        const bool warp_bad = __any_sync(0xffffffffu, bad);
-        if (lane == 0) {
-            red_d[warp] = best;
-            red_id[warp] = warp_bad ? -2 : best_id;
-        }
+        if (t == kMergeThreads) FA_TRACE(13);
         __syncthreads();
-        if (t == 0) {
-            bool any_bad = red_id[0] == -2;
-            if (any_bad) best_id = INT_MAX, best = INFINITY;
-            for (int w2 = 1; w2 < kMergeThreads / 32; ++w2) {
-                if (red_id[w2] == -2) any_bad = true; else cand_min(best, best_id, red_d[w2], red_id[w2]);
+        if (t == 0) FA_TRACE(15);
+        const bool last_scan = type == CMD_MERGE && merges >= N - 2;   // the master finishes the dendrogram alone
+        if (svc) {
+            if (lane == 0) {
+                FA_TRACE(8);
+                double best = INFINITY;
+                int best_id = INT_MAX;
+                bool any_bad = false;
+                for (int w2 = 0; w2 < kMergeThreads / 32; ++w2) {
+                    if (red_id[w2] == -2) any_bad = true; else cand_min(best, best_id, red_d[w2], red_id[w2]);
+                }
+                const u64 bits = (u64)__double_as_longlong(best);
+                const unsigned oid = any_bad ? 0xfffffeu : (best_id == INT_MAX ? 0xffffffu : (unsigned)best_id);
+                ResultSlot *slot = P.results + (round & 1u) * P.result_stride + ((size_t)wb << P.slot_shift);   // double-buffered by round parity:
+                // a CTA reuses a slot two rounds later, which it can only reach after every reader finished this round
+                st_relaxed_u64(&slot->w0, (bits & 0xffffffff00000000ull) | ((u64)oid << 8) | (u64)(round & 0xffu));
+                st_relaxed_u64(&slot->w1, (bits << 32) | (u64)round);
+                FA_TRACE(7);
+                if ((P.flags & 4) && all_step >= 0 && all_step < kTraceSteps) atomicMax(&P.trace[all_step * 16 + 14], global_ns());
+                s_owner = -1;
             }
-            const u64 bits = (u64)__double_as_longlong(best);
-            const unsigned oid = any_bad ? 0xfffffeu : (best_id == INT_MAX ? 0xffffffu : (unsigned)best_id);
-            st_relaxed_u64(&P.results[wb].w0, (bits & 0xffffffff00000000ull) | ((u64)oid << 8) | (u64)(expect & 0xffu));
-            st_release_u64(&P.results[wb].w1, (bits << 32) | (u64)expect);
-            FA_TRACE(7);
+            __syncwarp();   // lane 0 publishes before anybody starts polling
+            // all-to-all: every CTA learns the new node's nearest neighbour and decides what comes next
+            if (type == CMD_MERGE && !last_scan) {
+                double d;
+                int id;
+                bool any_bad;
+                double T;
+                gather_candidates(P.results + (round & 1u) * P.result_stride, P.slot_shift, W, lane, round, d, id, any_bad,
+                                  P.threshold + 2 * (round & 1u), &T);
+                if (lane == 0) {
+                    FA_TRACE(9);
+                    s_have_pair = (!any_bad && d <= T) ? 1 : 0;
+                    s_next_b = id;
+                }
+            }
         }
-        // s_cmd / red_* / s_owner are rewritten only after the next command's barrier
+        if (type != CMD_MERGE) {      // lazy repair round: the master alone consumes the result
+            have_pair = false;
+            if (svc) fence_acq_rel_gpu();
+            continue;
+        }
+        if (last_scan) break;
+        __syncthreads();
+        have_pair = s_have_pair != 0;
+        a = prev_fresh;
+        b = s_next_b;
+        if (svc) {
+            fence_acq_rel_gpu();   // the CTA's one fence per round, off the critical path (see above)
+            if (lane == 0) FA_TRACE(10);
+        }
     }
 }
 
@@ -721,7 +859,7 @@ struct Carver {
 };
 struct Layout {
     size_t rows, cols, node_weight, key, nn, heap_at, heap_where, node_of, slot_of, live_bits, merge_a, merge_b, merge_d,
-        cmd, results, error, trace, init_partial, problem, total;
+        cmd, threshold, results, error, trace, init_partial, problem, total;
     int ranges;
 };
 Layout make_layout(int N, int D, int Ns, int workers) {
@@ -740,10 +878,11 @@ Layout make_layout(int N, int D, int Ns, int workers) {
     L.merge_a = c.take<int>((size_t)N);
     L.merge_b = c.take<int>((size_t)N);
     L.merge_d = c.take<double>((size_t)N);
-    L.cmd = c.take<unsigned long long>(32);   // own 256-byte line
-    L.results = c.take<ResultSlot>((size_t)workers + 1);
+    L.cmd = c.take<unsigned long long>(32);         // own 256-byte line
+    L.threshold = c.take<unsigned long long>(32);   // own 256-byte line
+    L.results = c.take<ResultSlot>(2 * 8 * ((size_t)workers + 1));
     L.error = c.take<int>(64);
-    L.trace = c.take<unsigned long long>((size_t)kTraceSteps * 8);
+    L.trace = c.take<unsigned long long>((size_t)kTraceSteps * 16);
     L.ranges = (N + kJR - 1) / kJR;
     L.init_partial = c.take<Cand>((size_t)L.ranges * N);
     L.problem = c.take<Problem>(1);
@@ -798,7 +937,7 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     const bool idx16 = level >= 1;
     // worker placement: resident (each CTA keeps <= 128 node vectors in shared memory) when the whole problem fits
     // into max_workers CTAs, else streamed from the k-major global copy
-    const size_t worker_fixed = sizeof(double) * (size_t)((D + 1) & ~1) + 2 * sizeof(double) * (kMergeThreads / 32) + 64;
+    const size_t worker_fixed = 3 * sizeof(double) * (size_t)((D + 1) & ~1) + 2 * sizeof(double) * (kMergeThreads / 32) + 64;
     if (worker_fixed + sizeof(double) * D > smem_cap) {
         fa::set_error("dimension %d too large for the merge kernel's shared-memory target vector", D);
         return FA_RUNTIME_ERROR;
@@ -844,7 +983,13 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     P.merge_b = reinterpret_cast<int *>(base + L.merge_b);
     P.merge_d = reinterpret_cast<double *>(base + L.merge_d);
     P.cmd = reinterpret_cast<unsigned long long *>(base + L.cmd);
+    P.threshold = reinterpret_cast<unsigned long long *>(base + L.threshold);
     P.results = reinterpret_cast<ResultSlot *>(base + L.results);
+    {
+        const char *f = std::getenv("FA_AHC_SLOT_SHIFT");   // tuning hook: 0 = packed, 1 = 32 B, 3 = 128 B per candidate
+        P.slot_shift = f ? std::min(3, std::max(0, std::atoi(f))) : 3;
+    }
+    P.result_stride = (max_workers + 1) << P.slot_shift;
     P.error = reinterpret_cast<int *>(base + L.error);
     P.trace = reinterpret_cast<unsigned long long *>(base + L.trace);
     P.resident = resident ? 1 : 0;
@@ -852,8 +997,8 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     P.idx16 = idx16 ? 1 : 0;
     P.smem_level = level;
     {
-        const char *f = std::getenv("FA_AHC_FLAGS");   // tuning hook: bit 0 overlapped/parallel root sift, bit 1 pipelined scan
-        P.flags = f ? std::atoi(f) : 1;
+        const char *f = std::getenv("FA_AHC_FLAGS");   // tuning hooks: 4 = globaltimer trace, 8 = never self-issue
+        P.flags = f ? std::atoi(f) : 0;
     }
     Cand *init_partial = reinterpret_cast<Cand *>(base + L.init_partial);
     Problem *d_prob = reinterpret_cast<Problem *>(base + L.problem);
@@ -875,9 +1020,10 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     };
 
     FA_CUDA_TRY(cudaMemsetAsync(base + L.cmd, 0, 256, stream));
-    FA_CUDA_TRY(cudaMemsetAsync(base + L.results, 0, sizeof(ResultSlot) * (size_t)(max_workers + 1), stream));
+    FA_CUDA_TRY(cudaMemsetAsync(base + L.threshold, 0, 256, stream));
+    FA_CUDA_TRY(cudaMemsetAsync(base + L.results, 0, 2 * 8 * sizeof(ResultSlot) * (size_t)(max_workers + 1), stream));
     FA_CUDA_TRY(cudaMemsetAsync(base + L.error, 0, 256, stream));
-    FA_CUDA_TRY(cudaMemsetAsync(base + L.trace, 0, sizeof(unsigned long long) * kTraceSteps * 8, stream));
+    FA_CUDA_TRY(cudaMemsetAsync(base + L.trace, 0, sizeof(unsigned long long) * kTraceSteps * 16, stream));
     FA_CUDA_TRY(cudaEventRecord(ev[0], stream));
     {
         dim3 grid((Ns + 31) / 32, (D + 31) / 32), block(32, 8);
@@ -927,7 +1073,7 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
         });
         FA_CUDA_TRY(attr_err);
         void *args[] = {&d_prob};
-        FA_CUDA_TRY(cudaLaunchCooperativeKernel((void *)ahc_merge_kernel, dim3(workers + 1), dim3(kMergeThreads), args,
+        FA_CUDA_TRY(cudaLaunchCooperativeKernel((void *)ahc_merge_kernel, dim3(workers + 1), dim3(kWorkerThreads), args,
                                                 smem, stream));
         ++launches;
     }
@@ -943,23 +1089,27 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     cudaEventElapsedTime(&last_ms[3], ev[0], ev[3]);
     for (int q = 0; q < 4; ++q) g_last_ms[q] = last_ms[q];
     if ((P.flags & 4) && N > 2 * kTraceSteps + 8) {
-        std::vector<unsigned long long> tr((size_t)kTraceSteps * 8);
+        std::vector<unsigned long long> tr((size_t)kTraceSteps * 16);
         cudaMemcpy(tr.data(), P.trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double acc[16] = {0};
         int used = 0;
         for (int i = 1; i + 1 < kTraceSteps; ++i) {
-            const unsigned long long t0 = tr[(size_t)i * 8];
+            const unsigned long long t0 = tr[(size_t)i * 16];
             if (!t0) continue;
-            for (int q = 0; q < 8; ++q) acc[q] += (double)((long long)(tr[(size_t)i * 8 + q] - t0));
-            acc[0] += (double)((long long)(tr[(size_t)(i + 1) * 8] - t0));   // slot 0: step period
+            for (int q = 0; q < 16; ++q)
+                if (tr[(size_t)i * 16 + q]) acc[q] += (double)((long long)(tr[(size_t)i * 16 + q] - t0));
+            acc[0] += (double)((long long)(tr[(size_t)(i + 1) * 16] - t0));   // slot 0: step period
             ++used;
         }
         for (int q = 0; q < 8; ++q) trace_avg_ns[q] = used ? acc[q] / used : 0.0;
         std::fprintf(stderr,
                      "[ahc trace] period %.0f ns | master: bookkeeping+erase+path done %.0f, results collected %.0f, heap "
-                     "rotated %.0f | worker0: command seen %.0f, centroid built %.0f, scan done %.0f, result released %.0f\n",
+                     "rotated %.0f | worker0: command seen %.0f, centroid built %.0f, scan done %.0f, result released %.0f |"
+                     " extra",
                      trace_avg_ns[0], trace_avg_ns[1], trace_avg_ns[2], trace_avg_ns[3], trace_avg_ns[4], trace_avg_ns[5],
                      trace_avg_ns[6], trace_avg_ns[7]);
+        for (int q = 8; q < 16; ++q) std::fprintf(stderr, " %.0f", used ? acc[q] / used : 0.0);
+        std::fprintf(stderr, "\n");
     }
     drop_events();
     if (*h_err != 0) {

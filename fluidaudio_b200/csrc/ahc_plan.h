@@ -41,14 +41,17 @@ struct Problem {
     int *merge_a, *merge_b;  // [N-1] merge log
     double *merge_d;         // [N-1] squared distance of each merge
     // synchronisation
-    unsigned long long *cmd; // command word
-    ResultSlot *results;     // [workers]
+    unsigned long long *cmd;        // explicit command word (master -> workers)
+    unsigned long long *threshold;  // [2 parities][2 words] per-round self-issue threshold (master -> workers)
+    ResultSlot *results;     // [2][result_stride]: per-CTA candidates, double-buffered by scan-round parity
+    int result_stride;       // slots between the two parities
+    int slot_shift;          // log2 of the distance (in slots) between two CTAs' candidates
     int *error;              // 0 ok, 1 NaN distance (host-visible copy)
     int heap_size;           // after host heapify
     int idx16;               // heap index arrays are uint16_t and the master state lives in shared memory
     int smem_level;          // how much master state fits in smem: 1 = heap, 2 = + nn, 3 = + node_of
     unsigned long long *trace;   // [kTraceSteps x 8] globaltimer stamps (flags bit 2), diagnostics only
-    int flags;               // bit 0: overlapped erase + parallel root sift; bit 1: software-pipelined scan
+    int flags;               // bit 2: globaltimer trace; bit 3: never self-issue (every merge waits for the master)
     int resident;            // 1: every worker keeps its nodes' vectors in shared memory; 0: streamed from `cols`
     int slots_per_cta;       // resident mode: slots [w*slots_per_cta, (w+1)*slots_per_cta) belong to worker w
 };
