@@ -223,6 +223,19 @@ __device__ __forceinline__ void cand_min(double &d, int &id, double od, int oid)
     }
 }
 
+// Lexicographic (distance, id) minimum over a warp in three REDUX instructions instead of a five-step shuffle tree
+// (~0.2 us per use, twice per merge step).  Squared distances are sums of squares starting from +0, so they are
+// non-negative and their IEEE bit patterns order like unsigned integers; NaNs never get here (`bad` flags).
+__device__ __forceinline__ void warp_cand_min(double &d, int &id) {
+    const unsigned full = 0xffffffffu;
+    const unsigned hi = (unsigned)__double2hiint(d), lo = (unsigned)__double2loint(d);
+    const unsigned mh = __reduce_min_sync(full, hi);
+    const unsigned ml = __reduce_min_sync(full, hi == mh ? lo : 0xffffffffu);
+    const unsigned mi = __reduce_min_sync(full, (hi == mh && lo == ml) ? (unsigned)id : 0xffffffffu);
+    d = __hiloint2double((int)mh, (int)ml);
+    id = (int)mi;
+}
+
 // One polling snapshot: both words of up to Q slots per lane plus (optionally) the threshold words.
 template <int Q> struct PollSnap {
     u64 a0[Q], a1[Q], t0, t1;
@@ -288,12 +301,7 @@ __device__ __forceinline__ void gather_candidates(const ResultSlot *results, int
         } while (!s0.complete(tag));
         s0.reduce(W, lane, d, id, bad, T);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double od = __shfl_xor_sync(full, d, o);
-        const int oid = __shfl_xor_sync(full, id, o);
-        cand_min(d, id, od, oid);
-    }
+    warp_cand_min(d, id);
     bad = __any_sync(full, bad);
 }
 
@@ -708,12 +716,8 @@ __global__ void __launch_bounds__(kWorkerThreads, 1) ahc_merge_kernel(const Prob
                 }
             }
             if (t == 0) FA_TRACE(6);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double od = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oid = __shfl_xor_sync(0xffffffffu, best_id, o);
-                cand_min(best, best_id, od, oid);
-            }
+            if (bad) best = INFINITY, best_id = INT_MAX;   // keep NaN bit patterns out of the integer-ordered reduction
+            warp_cand_min(best, best_id);
             const bool warp_bad = __any_sync(0xffffffffu, bad);
             if (lane == 0) {
                 red_d[warp] = best;
