@@ -25,8 +25,14 @@
 //   A  (pass 1 out / pass 2 in):  element idx            at idx + 4*(idx>>5)          = l + 36 q
 //   B  (pass 2 out / pass 3 in):  z_{q,q2}[h]            at 74 h + 9 q + q2
 //   N  (pass 3 out, natural):     Z[k]                   at k + (k>>3), plus a copy of Z[0] at 288
-// Twiddles are produced by recurrence in FP64 from one per-lane root per pass (W256^l, W32^(l&3), W512^l): 6 complex
-// multiplies cost less than 7 conflicted 16-byte table loads and their ~1e-16 error is irrelevant here.
+// Twiddles are produced by recurrence in FP64 from one per-lane root per pass (W256^l, W32^(l&3), W512^l).  The
+// kernel is bound by shared-memory wavefronts (profiles/r01c_mel.md: the three transposes of 256 complex doubles cost
+// ~200 of ~330 wavefronts per frame), the FP64 pipe has headroom: twiddle tables in shared memory were measured and
+// bought nothing (80 fewer FP64 instructions, 67 more wavefronts per frame).
+// The recombination handles the bin pair (b, 256-b) together — both need only Z[b] and Z[256-b]:
+//   2 X[b] = S + T,  2 X[256-b] = conj(S - T),  S = Z[b] + conj Z[256-b],  T = W512^b * (D.y, -D.x),  D = Z[b] - conj Z[256-b]
+// — works on 2X (no multiplications by 1/2) and stores 4*|X|^2; the plan hands the kernel the filterbank weights
+// times 1/4, which gives bit-identical products (power-of-two scalings commute with rounding).
 #pragma once
 
 #include "fa_common.cuh"
@@ -41,7 +47,7 @@ constexpr int kHalf = 256;
 constexpr int kBins = 257;
 constexpr int kFftPad = 304;      // complex doubles per warp buffer (max layout extent 296 + Z[0] mirror at 288)
 constexpr int kTileFrames = 16;   // frames per CTA tile; the mel stage maps 32 / kTileFrames mel bins onto one warp
-constexpr int kPowStride = 257;   // odd: lane-per-frame reads of a fixed bin hit 32 distinct banks
+constexpr int kPowStride = 260;   // rows 16-byte aligned; stride = 4 (mod 32) floats: 8 lanes x 16 B of one bin quad hit distinct banks
 
 struct alignas(8) cpx {
     float x, y;
@@ -157,6 +163,9 @@ FA_HD void twiddle_emit(double (&re)[8], double (&im)[8], cpxd root, Emit emit) 
 
 // Pass 1.  pf -> pre-emphasised sample at buffer position j = 0 of this frame (8-byte aligned, hop even).
 // Window product in float32 (the reference's vDSP_vmul), then widened.  Output layout A.
+// kMidFull: the window covers buffer positions [64, 448), so slots r = 1..6 of every lane are inside it and only the
+// first and last slot need the in-window select (win 400 centred: positions 56..455).
+template <bool kMidFull>
 FA_HD void pass1(int l, const float *pf, const LaneTables &T, cpxd *buf) {
     double re[8], im[8];
 #pragma unroll
@@ -167,8 +176,11 @@ FA_HD void pass1(int l, const float *pf, const LaneTables &T, cpxd *buf) {
 #else
         const cpx v = *reinterpret_cast<const cpx *>(pf + j);
 #endif
-        const float a = (T.in_win >> (2 * r)) & 1u ? T.win[2 * r] * v.x : 0.0f;
-        const float b = (T.in_win >> (2 * r + 1)) & 1u ? T.win[2 * r + 1] * v.y : 0.0f;
+        float a = T.win[2 * r] * v.x, b = T.win[2 * r + 1] * v.y;
+        if (!kMidFull || r == 0 || r == 7) {   // outside the window the reference's buffer holds 0, whatever the sample
+            a = (T.in_win >> (2 * r)) & 1u ? a : 0.0f;
+            b = (T.in_win >> (2 * r + 1)) & 1u ? b : 0.0f;
+        }
         re[r] = (double)a;
         im[r] = (double)b;
     }
@@ -225,58 +237,84 @@ FA_HD void pass3_store(int l, double (&re)[8], double (&im)[8], cpxd *buf) {
     }
 }
 
-// Real-FFT recombination + power.  prow -> this frame's row of the power tile (257 floats).
+// Real-FFT recombination + power, one bin PAIR (b, 256 - b) per step (see the header).  prow -> this frame's row of
+// the power tile; receives 4 |X[b]|^2 for b = 0..256.
+FA_HD void pair_power(cpxd zb, cpxd zc, cpxd w, float &pb, float &pc) {
+    const double sr = zb.x + zc.x, si = zb.y - zc.y;             // S
+    const double dr = zb.y + zc.y, di = zc.x - zb.x;             // (D.y, -D.x)
+    const double tr = w.x * dr - w.y * di, ti = w.x * di + w.y * dr;
+    const float xr = (float)(sr + tr), xi = (float)(si + ti);    // single rounding of the exact-arithmetic DFT (x2)
+    const float yr = (float)(sr - tr), yi = (float)(si - ti);
+#if defined(__CUDA_ARCH__)
+    pb = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi));
+    pc = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
+#else
+    const float a = xr * xr, b = xi * xi, c = yr * yr, d = yi * yi;
+    pb = a + b;
+    pc = c + d;
+#endif
+}
 FA_HD void post_power(int l, const cpxd *buf, const LaneTables &T, float *prow) {
     // W16^j = exp(-2 pi i j / 16): W512^(l + 32 j) = W512^l * W16^j
     const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
-    const double w16r[8] = {1.0, c1, h, s1, 0.0, -s1, -h, -c1};
-    const double w16i[8] = {0.0, -s1, -h, -c1, -1.0, -c1, -h, -s1};
+    const double w16r[4] = {1.0, c1, h, s1};
+    const double w16i[4] = {0.0, -s1, -h, -c1};
     const int fwd = l + (l >> 3);                               // address of Z[l + 32 j]   = fwd + 36 j
     const int bwd = 252 + (32 - l) + ((32 - l) >> 3);           // address of Z[256-l-32 j] = bwd - 36 j
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
         const cpxd zb = buf[fwd + 36 * j], zc = buf[bwd - 36 * j];
-        const double er = 0.5 * (zb.x + zc.x), ei = 0.5 * (zb.y - zc.y);
-        const double orr = 0.5 * (zb.y + zc.y), oi = 0.5 * (zc.x - zb.x);
-        const double wr = T.w512.x * w16r[j] - T.w512.y * w16i[j];
-        const double wi = T.w512.x * w16i[j] + T.w512.y * w16r[j];
-        const float xr = (float)(er + (wr * orr - wi * oi));    // single rounding of the exact-arithmetic DFT
-        const float xi = (float)(ei + (wr * oi + wi * orr));
-#if defined(__CUDA_ARCH__)
-        prow[l + 32 * j] = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi));
-#else
-        const float a = xr * xr, b = xi * xi;
-        prow[l + 32 * j] = a + b;
-#endif
+        cpxd w = T.w512;
+        if (j > 0) {
+            w.x = T.w512.x * w16r[j] - T.w512.y * w16i[j];
+            w.y = T.w512.x * w16i[j] + T.w512.y * w16r[j];
+        }
+        float pb, pc;
+        pair_power(zb, zc, w, pb, pc);
+        prow[l + 32 * j] = pb;
+        prow[kHalf - l - 32 * j] = pc;                          // b = 0: bin 256 (Z[256] is the mirror of Z[0] at 288)
     }
-    if (l == 0) {
-        const cpxd z0 = buf[0];
-        const float x = (float)(z0.x - z0.y);                   // X[256] = E[0] - O[0], purely real
-        prow[kHalf] = x * x;
+    if (l == 0) {                                               // b = 128 pairs with itself, W512^128 = -i
+        const cpxd z = buf[128 + 16];
+        cpxd w;
+        w.x = 0.0;
+        w.y = -1.0;
+        float pb, pc;
+        pair_power(z, z, w, pb, pc);
+        prow[128] = pb;
     }
 }
 
-// float32 accumulate in bin order with separate multiply and add roundings (the oracle's mat-vec order).
-// [lo, hi) is a multiple of four bins wide on the device (the plan pads filters with explicit zero weights).
+// Filterbank dot product over the filter's non-zero band.  Host (emulator / oracle order): float32 accumulate in bin
+// order with separate multiply and add roundings.  Device: the plan aligns the band to bin quads (explicit zero
+// weights), rows of the power tile are 16-byte aligned, so one step is two 16-byte shared loads and four FMAs;
+// fusing the multiply-add moves the result by <= 1 ulp of the sum (the parity bar on log-mel is 1e-4).
 FA_HD float mel_dot(const float *prow, const float *w, int lo, int hi) {
     float acc = 0.0f;
     const float *p = prow + lo;
     const int n = hi - lo;
-#if defined(__CUDA_ARCH__)
-    for (int b = 0; b < n; b += 4) {
-        acc = __fadd_rn(acc, __fmul_rn(w[b], p[b]));
-        acc = __fadd_rn(acc, __fmul_rn(w[b + 1], p[b + 1]));
-        acc = __fadd_rn(acc, __fmul_rn(w[b + 2], p[b + 2]));
-        acc = __fadd_rn(acc, __fmul_rn(w[b + 3], p[b + 3]));
-    }
-#else
     for (int b = 0; b < n; ++b) {
         const float t = w[b] * p[b];
         acc = acc + t;
     }
-#endif
     return acc;
 }
+#if defined(__CUDACC__)
+// p4 / w4: first quad of the band in the power row / in the packed weights; nq quads.  Not unrolled: bands are 1..6
+// quads long and the unrolled remainder ladder cost ~100 instructions per dot product (profiles/r01c_mel.md).
+__device__ __forceinline__ float mel_dot_quads(const float4 *p4, const float4 *w4, int nq) {
+    float acc = 0.0f;
+#pragma unroll 1
+    for (int b = 0; b < nq; ++b) {
+        const float4 x = p4[b], c = w4[b];
+        acc = fmaf(c.x, x.x, acc);
+        acc = fmaf(c.y, x.y, acc);
+        acc = fmaf(c.z, x.z, acc);
+        acc = fmaf(c.w, x.w, acc);
+    }
+    return acc;
+}
+#endif
 
 FA_HD float log_value(float v, float floor_, int clamped) {
     return clamped ? logf(v > floor_ ? v : floor_) : logf(v + floor_);

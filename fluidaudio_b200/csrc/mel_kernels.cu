@@ -111,13 +111,11 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
     float *raw1 = raw0 + P.raw_cap;
     float *ptile = raw1 + P.raw_cap;
     cpxd *fftbuf = reinterpret_cast<cpxd *>(ptile + P.pt_cap);   // kWarps * kFftPad complex doubles (16-byte aligned)
-    float *power = reinterpret_cast<float *>(fftbuf + kWarps * kFftPad);   // 32 * 257
+    float *power = reinterpret_cast<float *>(fftbuf + kWarps * kFftPad);   // kTileFrames * kPowStride
     float *otile = power + kTileFrames * kPowStride;        // kTileFrames * (n_mels + 1)
     float *fbw = otile + kTileFrames * (P.n_mels + 1);      // fb_nnz_cap
-    int *fblo = reinterpret_cast<int *>(fbw + P.fb_cap);    // n_mels
-    int *fbhi = fblo + P.n_mels;
-    int *fboff = fbhi + P.n_mels;
-    uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(fboff + P.n_mels) + 7) & ~uintptr_t(7));
+    int4 *fbmeta = reinterpret_cast<int4 *>(fbw + P.fb_cap);   // n_mels x {first bin, quads, weight offset, -}
+    uint64_t *bars = reinterpret_cast<uint64_t *>(fbmeta + P.n_mels);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -127,11 +125,9 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P.fb_nnz; i += kWarps * 32) fbw[i] = P.fb_w[i];
-    for (int i = tid; i < P.n_mels; i += kWarps * 32) {
-        fblo[i] = P.fb_lo[i];
-        fbhi[i] = P.fb_hi[i];
-        fboff[i] = P.fb_off[i];
-    }
+    for (int i = tid; i < P.n_mels; i += kWarps * 32)
+        fbmeta[i] = make_int4(P.fb_lo[i], (P.fb_hi[i] - P.fb_lo[i]) >> 2, P.fb_off[i], 0);
+    for (int i = tid; i < kTileFrames * kPowStride; i += kWarps * 32) power[i] = 0.0f;   // rows of partial tiles, pad columns
     LaneTables T;
     load_lane_tables(lane, P.win_tab, P.in_tab, T);
     __syncthreads();
@@ -175,7 +171,21 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             if (interior) {
                 // every sample of the tile and its predecessor came through the bulk copy (conflict-free, unit stride)
                 const float *src = raw + (g.a0 - g.base);   // src[t] = x(a0 + t), src[-1] valid
-                if (a == 0.0f) {
+                if (((g.a0 - g.base) & 3) == 0 && (P.pt_len & 3) == 0) {   // 16-byte aligned rows: four samples per step
+                    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+                    float4 *d4 = reinterpret_cast<float4 *>(ptile);
+                    for (int q = tid; q < (P.pt_len >> 2); q += kWarps * 32) {
+                        const float4 x = s4[q];
+                        float4 y = x;
+                        if (a != 0.0f) {
+                            y.x = preemph_rest(x.x, src[4 * q - 1], a);
+                            y.y = preemph_rest(x.y, x.x, a);
+                            y.z = preemph_rest(x.z, x.y, a);
+                            y.w = preemph_rest(x.w, x.z, a);
+                        }
+                        d4[q] = y;
+                    }
+                } else if (a == 0.0f) {
                     for (int t = tid; t < P.pt_len; t += kWarps * 32) ptile[t] = src[t];
                 } else {
                     for (int t = tid; t < P.pt_len; t += kWarps * 32) ptile[t] = preemph_rest(src[t], src[t - 1], a);
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
         for (int fi = warp; fi < g.nf; fi += kWarps) {
             const float *pf = ptile + fi * P.hop;
             double re[8], im[8];
-            pass1(lane, pf, T, buf);
+            if (P.mid_full) pass1<true>(lane, pf, T, buf); else pass1<false>(lane, pf, T, buf);
             __syncwarp();
             pass2_load(lane, buf, re, im);
             __syncwarp();
@@ -229,8 +239,11 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             const float *prow = power + fl * kPowStride;
             const long long f = g.f0 + fl;
             for (int m = warp * kGroup + mg; m < P.n_mels; m += kWarps * kGroup) {
-                float v = 0.0f;
-                if (live) v = log_value(mel_dot(prow, fbw + fboff[m], fblo[m], fbhi[m]), P.log_floor, P.log_clamped);
+                const int4 md = fbmeta[m];
+                // rows beyond the tile's last frame hold finite leftovers: computed and dropped, no divergent branch
+                const float v = log_value(mel_dot_quads(reinterpret_cast<const float4 *>(prow + md.x),
+                                                        reinterpret_cast<const float4 *>(fbw + md.z), md.y),
+                                          P.log_floor, P.log_clamped);
                 if (P.layout == 0) otile[fl * (P.n_mels + 1) + m] = v;
                 else if (live) P.out[u.out_off + (long long)m * u.out_stride + f] = v;
             }
@@ -240,9 +253,18 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             // time-major tile is contiguous in HBM: nf rows of n_mels floats; flat, fully coalesced copy
             float *dst = P.out + u.out_off + g.f0 * P.n_mels;
             const int total = g.nf * P.n_mels;
-            for (int idx = tid; idx < total; idx += kWarps * 32) {
-                const int fi = (int)__umulhi((unsigned)idx, P.inv_n_mels);   // idx / n_mels (exact for idx < 2^16)
-                dst[idx] = otile[idx + fi];                                  // padded row stride n_mels + 1
+            if ((P.n_mels & 3) == 0) {   // rows are whole float4s and dst is 64-byte aligned (f0 is a multiple of 16)
+                float4 *d4 = reinterpret_cast<float4 *>(dst);
+                for (int q = tid; q < (total >> 2); q += kWarps * 32) {
+                    const int e = 4 * q;
+                    const float *src = otile + e + (int)__umulhi((unsigned)e, P.inv_n_mels);   // + row: stride n_mels + 1
+                    d4[q] = make_float4(src[0], src[1], src[2], src[3]);
+                }
+            } else {
+                for (int idx = tid; idx < total; idx += kWarps * 32) {
+                    const int fi = (int)__umulhi((unsigned)idx, P.inv_n_mels);   // idx / n_mels (exact for idx < 2^16)
+                    dst[idx] = otile[idx + fi];                                  // padded row stride n_mels + 1
+                }
             }
         }
         // next iteration's phase-1 barrier orders these reads against the next tile's writes
@@ -354,9 +376,8 @@ int MelPlan::init(const MelConfig &c) {
     build_window(cfg.win_length, cfg.window_periodic != 0, window);
     build_filterbank(cfg.n_fft, cfg.n_mels, cfg.sample_rate, filterbank);
 
-    // banded filterbank: per mel the contiguous range of non-zero bins, widened with explicit zero weights to a
-    // multiple of four bins (adding fl32(0 * p) leaves a finite float32 sum unchanged, so the accumulation order and
-    // value are exactly the oracle's) so that the kernel's dot product is a branch-free 4-way unrolled loop
+    // banded filterbank: per mel the contiguous range of non-zero bins, widened with explicit zero weights to whole
+    // bin quads.  Weights are stored times 1/4 because the kernel's power tile holds 4|X|^2 (mel_core.cuh).
     std::vector<float> w;
     std::vector<int> lo(cfg.n_mels), hi(cfg.n_mels), off(cfg.n_mels);
     for (int m = 0; m < cfg.n_mels; ++m) {
@@ -367,13 +388,12 @@ int MelPlan::init(const MelConfig &c) {
                 b = k + 1;
             }
         if (b == 0) a = 0;
-        while ((b - a) % 4 != 0) {
-            if (b < kBins) ++b; else --a;
-        }
+        a &= ~3;                       // whole bin quads: 16-byte aligned reads of the power row (stride kPowStride)
+        b = (b + 3) & ~3;              // may reach 260 > 257: the tile's pad columns are zero, so are these weights
         lo[m] = a;
         hi[m] = b;
-        off[m] = (int)w.size();
-        for (int k = a; k < b; ++k) w.push_back(filterbank[(size_t)m * kBins + k]);
+        off[m] = (int)w.size();        // a multiple of four: 16-byte aligned weight quads
+        for (int k = a; k < b; ++k) w.push_back(k < kBins ? 0.25f * filterbank[(size_t)m * kBins + k] : 0.0f);
     }
     fb_nnz = (int)w.size();
 
@@ -412,12 +432,12 @@ int MelPlan::init(const MelConfig &c) {
     FA_CUDA_TRY(cudaMemcpy(d_fb_off, off.data(), cfg.n_mels * sizeof(int), cudaMemcpyHostToDevice));
 
     pt_len = (kTileFrames - 1) * cfg.hop_length + kNfft;
-    pt_cap = (pt_len + 3) & ~3;
-    raw_cap = (pt_len + 1 + 3 + 3 + 3) & ~3;
+    pt_cap = (pt_len + 31) & ~31;
+    raw_cap = (pt_len + 1 + 3 + 3 + 31) & ~31;   // whole 128-byte lines: the pre-emphasised tile behind it stays line-aligned
     fb_cap = (fb_nnz + 3) & ~3;
     smem_bytes = sizeof(float) * ((size_t)2 * raw_cap + pt_cap + 0 +
                                   (size_t)kTileFrames * kPowStride + (size_t)kTileFrames * (cfg.n_mels + 1) + fb_cap) +
-                 sizeof(cpxd) * (size_t)kWarpsPerCta * kFftPad + sizeof(int) * 3 * (size_t)cfg.n_mels + 8 +
+                 sizeof(cpxd) * (size_t)kWarpsPerCta * kFftPad + sizeof(int) * 4 * (size_t)cfg.n_mels + 8 +
                  2 * sizeof(uint64_t);
     if (smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
         fa::set_error("mel config needs %zu bytes of shared memory per CTA, device allows %zu", smem_bytes,
@@ -505,6 +525,10 @@ int MelPlan::launch(const float *d_audio_base, float *d_out_base, int first, int
     P.pt_cap = pt_cap;
     P.raw_cap = raw_cap;
     P.use_tma = aligned16 ? 1 : 0;
+    {
+        const int off_w = mode == 2 ? 0 : (cfg.n_fft - cfg.win_length) / 2;
+        P.mid_full = (off_w <= 64 && off_w + cfg.win_length >= 448) ? 1 : 0;
+    }
     P.inv_n_mels = (unsigned)((0x100000000ull + (unsigned)cfg.n_mels - 1) / (unsigned)cfg.n_mels);
     const int grid = std::min(total_tiles, num_sms * kCtasPerSm);
     mel512_kernel<kWarpsPerCta><<<grid, kWarpsPerCta * 32, smem_bytes, stream>>>(P);

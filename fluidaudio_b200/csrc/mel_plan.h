@@ -59,6 +59,7 @@ struct MelLaunch {
     int fb_nnz, fb_cap;
     int pt_len, pt_cap, raw_cap;
     int use_tma;
+    int mid_full;          // window covers buffer positions [64, 448): pass 1 skips the in-window select for slots 1..6
     unsigned inv_n_mels;   // ceil(2^32 / n_mels): idx / n_mels == umulhi(idx, inv) for idx < 2^16
 };
 

@@ -23,6 +23,9 @@ extern "C" int mel_emul(const float *audio, long long n, float last, int hop, in
         }
     std::vector<LaneTables> tabs(32);
     for (int l = 0; l < 32; ++l) load_lane_tables(l, win_tab.data(), in_tab.data(), tabs[l]);
+    const bool mid_full = off <= 64 && off + win >= 448;
+    std::vector<float> fbq((size_t)n_mels * kBins);   // the kernel's weights: filterbank / 4 (its power tile holds 4|X|^2)
+    for (size_t i = 0; i < fbq.size(); ++i) fbq[i] = 0.25f * fb[i];
     // sparse filterbank ranges
     std::vector<int> lo(n_mels), hi(n_mels);
     for (int m = 0; m < n_mels; ++m) {
@@ -52,14 +55,16 @@ extern "C" int mel_emul(const float *audio, long long n, float last, int hop, in
         }
         std::memset(buf, 0, sizeof(buf));
         double re[32][8], im[32][8];
-        for (int l = 0; l < 32; ++l) pass1(l, pf, tabs[l], buf);
+        for (int l = 0; l < 32; ++l) {
+            if (mid_full) pass1<true>(l, pf, tabs[l], buf); else pass1<false>(l, pf, tabs[l], buf);
+        }
         for (int l = 0; l < 32; ++l) pass2_load(l, buf, re[l], im[l]);
         for (int l = 0; l < 32; ++l) pass2_store(l, tabs[l], re[l], im[l], buf);
         for (int l = 0; l < 32; ++l) pass3_load(l, buf, re[l], im[l]);
         for (int l = 0; l < 32; ++l) pass3_store(l, re[l], im[l], buf);
         for (int l = 0; l < 32; ++l) post_power(l, buf, tabs[l], prow.data());
         for (int m = 0; m < n_mels; ++m) {
-            const float acc = mel_dot(prow.data(), fb + (size_t)m * kBins + lo[m], lo[m], hi[m]);
+            const float acc = mel_dot(prow.data(), fbq.data() + (size_t)m * kBins + lo[m], lo[m], hi[m]);
             out[f * n_mels + m] = log_value(acc, log_floor, clamped);
         }
     }
