@@ -12,6 +12,8 @@
 //   Z = FFT256(z): radix 8 x 8 x 4 decimation in frequency in FP64, through shared memory, __syncwarp between passes
 //   X[b] = E[b] + W512^b O[b],  E = (Z[b] + conj Z[256-b]) / 2,  O = (Z[b] - conj Z[256-b]) / (2i)      (FP64)
 //   power[b] = fl32(Re X)^2 + fl32(Im X)^2 in float32, b = 0..256
+//   The last radix-4 pass and the recombination are ONE register-resident step: a lane computes the two radix-4
+//   butterflies whose outputs are each other's mirror images (k and 256-k), so Z never goes back to shared memory.
 //
 // Why FP64 for the transform: the reference's DFT (vDSP_DFT_zop) is float32, and ANY float32 FFT carries rounding
 // noise of ~0.5 ulp of the frame's largest spectral line in every bin.  On input with 60 dB of dynamic range that
@@ -24,7 +26,6 @@
 // when every 8 consecutive lanes hit 8 distinct 16-byte banks):
 //   A  (pass 1 out / pass 2 in):  element idx            at idx + 4*(idx>>5)          = l + 36 q
 //   B  (pass 2 out / pass 3 in):  z_{q,q2}[h]            at 74 h + 9 q + q2
-//   N  (pass 3 out, natural):     Z[k]                   at k + (k>>3), plus a copy of Z[0] at 288
 // Twiddles are produced by recurrence in FP64 from one per-lane root per pass (W256^l, W32^(l&3), W512^l).  The
 // kernel is bound by shared-memory wavefronts (profiles/r01c_mel.md: the three transposes of 256 complex doubles cost
 // ~200 of ~330 wavefronts per frame), the FP64 pipe has headroom: twiddle tables in shared memory were measured and
@@ -62,8 +63,30 @@ struct LaneTables {
     uint32_t in_win;   // bit s set  <=>  slot s lies inside [off, off+win)
     cpxd w256;         // W256^l        (pass 1 root)
     cpxd w32;          // W32^(l & 3)   (pass 2 root)
-    cpxd w512;         // W512^l        (recombination root)
+    cpxd wk0;          // W512^k0       (recombination root of this lane's first butterfly)
+    int a1, a2, k0;    // layout-B addresses of the lane's two mirror-image radix-4 butterflies; first output index
 };
+
+// Pass 3 + recombination: which two of the 64 radix-4 butterflies a lane owns.  Butterfly c = 8a + b reads
+// z_{c}[h] (layout B) and produces Z[k0 + 64 k2], k0 = a + 8b.  The mirror bins 256 - k come out of the butterfly
+// with k0' = 64 - k0: c' = 8(8-a) + (7-b) for a >= 1, c' = (8-b) mod 8 for a = 0.  Lanes 8..31 own (l, mirror(l)),
+// lanes 1..3 own (1,7) (2,6) (3,5), lanes 4..7 own (32,39) .. (35,36), lane 0 owns the two self-mirrored butterflies
+// 0 and 4.  Both 16-byte loads of a quarter-warp hit eight distinct banks ((a + b + 2h) mod 8).
+FA_HD void lane_butterflies(int l, int &c1, int &c2) {
+    if (l >= 8) {
+        c1 = l;
+        c2 = 8 * (8 - (l >> 3)) + (7 - (l & 7));
+    } else if (l >= 4) {
+        c1 = 32 + (l - 4);
+        c2 = 39 - (l - 4);
+    } else if (l >= 1) {
+        c1 = l;
+        c2 = 8 - l;
+    } else {
+        c1 = 0;
+        c2 = 4;
+    }
+}
 
 FA_HD cpxd unit_root(int k, int n) {   // exp(-2 pi i k / n) in FP64
     const double a = -6.283185307179586476925286766559 * (double)k / (double)n;
@@ -85,7 +108,12 @@ FA_HD void load_lane_tables(int l, const float *win_tab, const uint8_t *in_tab, 
     }
     T.w256 = unit_root(l, 256);
     T.w32 = unit_root(l & 3, 32);
-    T.w512 = unit_root(l, 512);
+    int c1, c2;
+    lane_butterflies(l, c1, c2);
+    T.a1 = 9 * (c1 >> 3) + (c1 & 7);
+    T.a2 = 9 * (c2 >> 3) + (c2 & 7);
+    T.k0 = (c1 >> 3) + 8 * (c1 & 7);
+    T.wk0 = unit_root(T.k0, 512);
 }
 
 FA_HD cpxd cmul(cpxd a, cpxd b) {
@@ -204,39 +232,6 @@ FA_HD void pass2_store(int l, const LaneTables &T, double (&re)[8], double (&im)
     twiddle_emit(re, im, T.w32, [&](int q2, cpxd v) { buf[base + q2] = v; });
 }
 
-// Pass 3: two radix-4 butterflies per lane (C = l, l + 32), again split around the layout change B -> N.
-FA_HD void pass3_load(int l, const cpxd *buf, double (&re)[8], double (&im)[8]) {
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int c = l + 32 * u;
-        const int a = 9 * (c >> 3) + (c & 7);
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const cpxd v = buf[a + 74 * h];
-            re[4 * u + h] = v.x;
-            im[4 * u + h] = v.y;
-        }
-    }
-}
-FA_HD void pass3_store(int l, double (&re)[8], double (&im)[8], cpxd *buf) {
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int c = l + 32 * u;
-        dft4(re[4 * u], im[4 * u], re[4 * u + 1], im[4 * u + 1], re[4 * u + 2], im[4 * u + 2], re[4 * u + 3],
-             im[4 * u + 3]);
-        const int k0 = (c >> 3) + 8 * (c & 7);            // k = k0 + 64 k2,  address k + (k >> 3)
-        const int a0 = k0 + (k0 >> 3);
-#pragma unroll
-        for (int k2 = 0; k2 < 4; ++k2) {
-            cpxd v;
-            v.x = re[4 * u + k2];
-            v.y = im[4 * u + k2];
-            buf[a0 + 72 * k2] = v;
-            if (c == 0 && k2 == 0) buf[288] = v;          // mirror of Z[0] for the "256 - b" access of lane 0
-        }
-    }
-}
-
 // Real-FFT recombination + power, one bin PAIR (b, 256 - b) per step (see the header).  prow -> this frame's row of
 // the power tile; receives 4 |X[b]|^2 for b = 0..256.
 FA_HD void pair_power(cpxd zb, cpxd zc, cpxd w, float &pb, float &pc) {
@@ -254,34 +249,69 @@ FA_HD void pair_power(cpxd zb, cpxd zc, cpxd w, float &pb, float &pc) {
     pc = c + d;
 #endif
 }
-FA_HD void post_power(int l, const cpxd *buf, const LaneTables &T, float *prow) {
-    // W16^j = exp(-2 pi i j / 16): W512^(l + 32 j) = W512^l * W16^j
-    const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
-    const double w16r[4] = {1.0, c1, h, s1};
-    const double w16i[4] = {0.0, -s1, -h, -c1};
-    const int fwd = l + (l >> 3);                               // address of Z[l + 32 j]   = fwd + 36 j
-    const int bwd = 252 + (32 - l) + ((32 - l) >> 3);           // address of Z[256-l-32 j] = bwd - 36 j
+// Pass 3 fused with the recombination (see lane_butterflies): A = butterfly c1 -> Z[k0 + 64 k2], B = butterfly c2 ->
+// Z[(64 - k0) + 64 k2], so bin b = k0 + 64 k2 pairs A[k2] with B[3 - k2] and W512^b = W512^k0 * W8^k2.
+// Lane 0 (k0 = 0; A = Z[0], Z[64], Z[128], Z[192]; B = Z[32], Z[96], Z[160], Z[224]) pairs inside its butterflies:
+// (0,256 = Z[0]) (64,192) (128,128) in slots 0..2, (32,224) in slot 3 and (96,160) in one extra step.
+FA_HD void pass3_post(int l, const cpxd *buf, const LaneTables &T, float *prow) {
+    double ar[4], ai[4], br[4], bi[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const cpxd zb = buf[fwd + 36 * j], zc = buf[bwd - 36 * j];
-        cpxd w = T.w512;
-        if (j > 0) {
-            w.x = T.w512.x * w16r[j] - T.w512.y * w16i[j];
-            w.y = T.w512.x * w16i[j] + T.w512.y * w16r[j];
-        }
-        float pb, pc;
-        pair_power(zb, zc, w, pb, pc);
-        prow[l + 32 * j] = pb;
-        prow[kHalf - l - 32 * j] = pc;                          // b = 0: bin 256 (Z[256] is the mirror of Z[0] at 288)
+    for (int h = 0; h < 4; ++h) {
+        const cpxd u = buf[T.a1 + 74 * h], v = buf[T.a2 + 74 * h];
+        ar[h] = u.x;
+        ai[h] = u.y;
+        br[h] = v.x;
+        bi[h] = v.y;
     }
-    if (l == 0) {                                               // b = 128 pairs with itself, W512^128 = -i
-        const cpxd z = buf[128 + 16];
-        cpxd w;
-        w.x = 0.0;
-        w.y = -1.0;
-        float pb, pc;
-        pair_power(z, z, w, pb, pc);
-        prow[128] = pb;
+    dft4(ar[0], ai[0], ar[1], ai[1], ar[2], ai[2], ar[3], ai[3]);
+    dft4(br[0], bi[0], br[1], bi[1], br[2], bi[2], br[3], bi[3]);
+    const bool z = l == 0;
+    const double hh = 0.70710678118654752440, c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;
+    const cpxd w0 = T.wk0;
+    cpxd w1, w2, w3;
+    w1.x = hh * (w0.x + w0.y);   // * W8   = (1 - i)/sqrt2
+    w1.y = hh * (w0.y - w0.x);
+    w2.x = w0.y;                 // * W8^2 = -i
+    w2.y = -w0.x;
+    w3.x = w1.y;                 // * W8^3 = W8 * (-i)
+    w3.y = -w1.x;
+    cpxd zb, zc, w;
+    float pb, pc;
+    // slot 0
+    zb.x = ar[0]; zb.y = ai[0];
+    zc.x = z ? ar[0] : br[3]; zc.y = z ? ai[0] : bi[3];
+    pair_power(zb, zc, w0, pb, pc);
+    prow[T.k0] = pb;
+    prow[kHalf - T.k0] = pc;
+    // slot 1
+    zb.x = ar[1]; zb.y = ai[1];
+    zc.x = z ? ar[3] : br[2]; zc.y = z ? ai[3] : bi[2];
+    pair_power(zb, zc, w1, pb, pc);
+    prow[T.k0 + 64] = pb;
+    prow[kHalf - 64 - T.k0] = pc;
+    // slot 2
+    zb.x = ar[2]; zb.y = ai[2];
+    zc.x = z ? ar[2] : br[1]; zc.y = z ? ai[2] : bi[1];
+    pair_power(zb, zc, w2, pb, pc);
+    prow[T.k0 + 128] = pb;
+    prow[kHalf - 128 - T.k0] = pc;
+    // slot 3 (lane 0: bins 32 / 224, W512^32 = W16)
+    zb.x = z ? br[0] : ar[3]; zb.y = z ? bi[0] : ai[3];
+    zc.x = z ? br[3] : br[0]; zc.y = z ? bi[3] : bi[0];
+    w.x = z ? c1 : w3.x;
+    w.y = z ? -s1 : w3.y;
+    pair_power(zb, zc, w, pb, pc);
+    const int b3 = z ? 32 : T.k0 + 192;
+    prow[b3] = pb;
+    prow[kHalf - b3] = pc;
+    if (z) {                     // bins 96 / 160, W512^96 = W16^3
+        zb.x = br[1]; zb.y = bi[1];
+        zc.x = br[2]; zc.y = bi[2];
+        w.x = s1;
+        w.y = -c1;
+        pair_power(zb, zc, w, pb, pc);
+        prow[96] = pb;
+        prow[160] = pc;
     }
 }
 

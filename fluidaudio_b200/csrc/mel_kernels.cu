@@ -222,11 +222,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             __syncwarp();
             pass2_store(lane, T, re, im, buf);
             __syncwarp();
-            pass3_load(lane, buf, re, im);
-            __syncwarp();
-            pass3_store(lane, re, im, buf);
-            __syncwarp();
-            post_power(lane, buf, T, power + fi * kPowStride);
+            pass3_post(lane, buf, T, power + fi * kPowStride);
             __syncwarp();
         }
         __syncthreads();

@@ -60,9 +60,7 @@ extern "C" int mel_emul(const float *audio, long long n, float last, int hop, in
         }
         for (int l = 0; l < 32; ++l) pass2_load(l, buf, re[l], im[l]);
         for (int l = 0; l < 32; ++l) pass2_store(l, tabs[l], re[l], im[l], buf);
-        for (int l = 0; l < 32; ++l) pass3_load(l, buf, re[l], im[l]);
-        for (int l = 0; l < 32; ++l) pass3_store(l, re[l], im[l], buf);
-        for (int l = 0; l < 32; ++l) post_power(l, buf, tabs[l], prow.data());
+        for (int l = 0; l < 32; ++l) pass3_post(l, buf, tabs[l], prow.data());
         for (int m = 0; m < n_mels; ++m) {
             const float acc = mel_dot(prow.data(), fbq.data() + (size_t)m * kBins + lo[m], lo[m], hi[m]);
             out[f * n_mels + m] = log_value(acc, log_floor, clamped);
