@@ -91,18 +91,25 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
-def cpu_mel(audio: np.ndarray, threads: int):
-    """Oracle port of AudioMelSpectrogram on `threads` host threads (30 s clips, one instance per thread)."""
+def cpu_mel(audio: np.ndarray, threads: int, repeats: int = 1):
+    """Oracle port of AudioMelSpectrogram on `threads` host threads: the audio cut into 30 s clips, every clip
+    processed `repeats` times, each thread working through its own share of the clips (one task per thread)."""
     from oracle import oracle as O
     cfg = O.mel_config(n_mels=N_MELS)
     clip = 480_000
-    pieces = [audio[i:i + clip] for i in range(0, audio.size, clip)]
+    pieces = [audio[i:i + clip] for i in range(0, audio.size, clip)] * repeats
+    shares = [pieces[t::threads] for t in range(threads)]
+    shares = [s for s in shares if s]
     O.mel_flat_transposed(cfg, pieces[0][:16000])
+
+    def work(share):
+        return sum(O.mel_flat_transposed(cfg, p)[1] for p in share)
+
     t0 = time.perf_counter()
-    with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(lambda p: O.mel_flat_transposed(cfg, p)[1], pieces))
+    with ThreadPoolExecutor(len(shares)) as ex:
+        list(ex.map(work, shares))
     dt = time.perf_counter() - t0
-    return (audio.size / 16000.0 / 3600.0) / dt, dt
+    return (repeats * audio.size / 16000.0 / 3600.0) / dt, dt
 
 
 def cpu_cluster(emb, rho, psi):
@@ -171,7 +178,7 @@ def bench_mel(args, dist):
                 "host_buffers": "pinned (fa_host_alloc)", "api": "fa_mel_compute"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 320.6e6, "traffic_source": "ncu --set full, profiles/r01b_summary.txt: dram read 231.3 MB + "
+                     "traffic": 319.9e6, "traffic_source": "ncu --set full, profiles/r01c_summary.txt: dram read 230.6 MB + "
                      "write 89.3 MB per launch (the tail of the output is still in L2 at kernel end)",
                      "kernel": "mel512_kernel", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": MEL_BYTES_PER_HOUR},
@@ -220,8 +227,8 @@ def bench_cluster(args, dist, steps=None):
                 "host_buffers": "pinned (fa_host_alloc)", "api": "fa_diarize_cluster"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 43.0e6, "traffic_source": "ncu --set full, profiles/r01b_summary.txt: ahc_merge_kernel dram "
-                     "read 41.3 MB + write 1.7 MB per launch (+ 20.6 MB read by ahc_init_nn_kernel)",
+                     "traffic": 42.3e6, "traffic_source": "ncu --set full, profiles/r01c_summary.txt: ahc_merge_kernel dram "
+                     "read 41.3 MB + write 1.0 MB per launch (+ 20.5 MB read by ahc_init_nn_kernel)",
                      "kernel": "ahc_merge_kernel (+ ahc_init_nn_kernel)", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": AHC_BYTES,
                      "note": "node vectors are resident in shared memory, so algorithmic bytes are served on-chip; "
@@ -256,16 +263,16 @@ def main():
         threads = host_threads()
         steps = max(1, min(args.steps, 3))
         if args.workload == "mel":
-            sample_s = 1800                                                      # 30 min of audio per step
+            sample_s, repeats = 3600, 4                                          # 4 audio-hours (~20 s of CPU work) per step
             audio = synth.tone_noise_audio(16000 * sample_s)
             for _ in range(min(args.warmup, 1)):
                 cpu_mel(audio[: 16000 * 120], threads)
-            vals = [cpu_mel(audio, threads) for _ in range(steps)]
+            vals = [cpu_mel(audio, threads, repeats) for _ in range(steps)]
             v = float(np.mean([x[0] for x in vals])); dt = float(np.mean([x[1] for x in vals]))
             line = {"impl": "reference", "metric": "audio-hours/s", "value": v, "unit": "audio-hours/s", "dtype": "f32",
                     "config": {"workload": "log-mel STFT, 1 h synthetic 16 kHz mono, 25 ms/10 ms frames, nFFT 512, 80 mels"},
                     "cpu_baseline": {"value": v, "unit": "audio-hours/s", "cores": threads, "kind": "port",
-                                     "sample": f"{sample_s} s of the workload's audio per step, 30 s clips over {threads} threads "
+                                     "sample": f"the workload's {sample_s} s of audio x {repeats} per step, 30 s clips over {threads} threads "
                                                "(oracle port of AudioMelSpectrogram.swift; no Swift toolchain)"}}
         else:
             emb, _ = synth.speaker_embeddings(CLUSTER_N, CLUSTER_D, CLUSTER_K, seed=42)
@@ -302,11 +309,11 @@ def main():
     if dist.is_root and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         if args.workload == "mel":
-            sample_s = 1800
-            v, dt = cpu_mel(audio[: 16000 * sample_s], threads)
+            repeats = 4
+            v, dt = cpu_mel(audio, threads, repeats)
             line["cpu_baseline"] = {"value": v, "unit": "audio-hours/s", "cores": threads, "kind": "port",
-                                    "sample": f"first {sample_s} s of the workload, 30 s clips over {threads} host threads, "
-                                              f"{dt:.1f} s wall (oracle port of AudioMelSpectrogram.swift)"}
+                                    "sample": f"the workload's hour of audio x {repeats}, 30 s clips over {threads} host threads, "
+                                              f"{dt:.2f} s wall (oracle port of AudioMelSpectrogram.swift)"}
             v1, dt1 = cpu_mel(audio[: 16000 * 300], 1)
             line["cpu_baseline"]["single_thread_value"] = v1
             emb, rho, psi, res = cluster_data
