@@ -59,6 +59,7 @@ EXPORTED_SYMBOLS = [
     "fa_vbx_refine", "fa_compute_centroids", "fa_assign_embeddings", "fa_cluster_default_config",
     "fa_diarize_cluster", "fa_diarize_cluster_batch", "fa_ahc_last_stage_ms", "fa_diarize_cluster_chunks",
     "fa_hungarian_solve", "fa_max_score_assignment", "fa_constrained_assign", "fa_build_chunk_assignments",
+    "fa_export_shape", "fa_export_read", "fa_export_write",
     "fastcluster_compute_centroid_linkage",
 ]
 
@@ -124,6 +125,9 @@ def load():
     L.fa_max_score_assignment.argtypes = [vp, i32, i32, vp]
     L.fa_constrained_assign.argtypes = [vp, sz, i32, vp, vp]
     L.fa_build_chunk_assignments.argtypes = [vp, vp, vp, sz, i32, i32, i32, vp]
+    L.fa_export_shape.argtypes = [C.c_char_p, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+    L.fa_export_read.argtypes = [C.c_char_p, sz, sz, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.fa_export_write.argtypes = [C.c_char_p, sz, sz, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.fa_ahc_last_stage_ms.argtypes = [vp]
     L.fa_ahc_last_stage_ms.restype = None
     L.fastcluster_compute_centroid_linkage.argtypes = [vp, sz, sz, vp, sz]

@@ -19,6 +19,8 @@
  *   fa_diarize_cluster   OfflineDiarizerManager.swift:270-384 (cluster(_:), clustering phase)
  *   fa_constrained_assign / fa_hungarian_solve / fa_build_chunk_assignments
  *                        ConstrainedClusterAssignment.swift:20-42, HungarianAssignment.swift:8-97, :885-911
+ *   fa_export_*          OfflineDiarizerManager.swift:913-955 (exportEmbeddings: the JSON dump of TimedEmbedding +
+ *                        cluster, OfflineDiarizerTypes.swift:706-716) — the backend's on-disk input format
  */
 #ifndef FLUIDAUDIO_B200_H
 #define FLUIDAUDIO_B200_H
@@ -199,6 +201,20 @@ fa_status fa_constrained_assign(const double *scores, size_t N, int32_t K, const
 fa_status fa_build_chunk_assignments(const int32_t *chunk_index, const int32_t *speaker_index, const int32_t *assignments,
                                      size_t N, int32_t num_chunks, int32_t num_speakers, int32_t cluster_count,
                                      int32_t *matrix);
+
+/* Embedding-export files (JSON array written by the reference when OfflineDiarizerConfig.embeddingExportPath is set):
+ * {chunkIndex, speakerIndex, startFrame, endFrame, startTime, endTime, embedding256[], rho128[], cluster} per entry.
+ * fa_export_shape parses the file and reports the entry count and vector lengths; fa_export_read fills caller-owned
+ * arrays (any output pointer may be NULL); fa_export_write produces a file the reference's Codable struct decodes.
+ * float32 values round-trip bit-exactly (shortest-form decimal <-> strtof). */
+fa_status fa_export_shape(const char *path, size_t *count, size_t *emb_dim, size_t *rho_dim);
+fa_status fa_export_read(const char *path, size_t count, size_t emb_dim, size_t rho_dim, int32_t *chunk_index,
+                         int32_t *speaker_index, int32_t *start_frame, int32_t *end_frame, double *start_time,
+                         double *end_time, float *emb, double *rho, int32_t *cluster);
+fa_status fa_export_write(const char *path, size_t count, size_t emb_dim, size_t rho_dim, const int32_t *chunk_index,
+                          const int32_t *speaker_index, const int32_t *start_frame, const int32_t *end_frame,
+                          const double *start_time, const double *end_time, const float *emb, const double *rho,
+                          const int32_t *cluster);
 
 /* Many independent embedding sets (meetings) on this GPU.  Set m is rows [set_offsets[m], set_offsets[m+1]).
  * Several sets are clustered concurrently on disjoint SM partitions. */

@@ -396,3 +396,35 @@ def test_constrained_pipeline_matches_oracle(gpu_lib, oracle):
         m = cl.build_chunk_assignments(chunk, spk, r.labels, int(chunk.max()) + 1, 3, r.info["centroid_count"])
         assert np.array_equal(m, oracle.build_chunk_assignments(chunk, spk, o.labels, int(chunk.max()) + 1, 3,
                                                                 o.centroids.shape[0]))
+
+
+def test_export_replay_matches_oracle_and_file_labels(gpu_lib, oracle, tmp_path):
+    """an embedding-export file (as the reference writes it) replayed through the B200 backend gives
+    the oracle's labels, and the partition stored in the file's `cluster` column is recognised."""
+    from fluidaudio_b200.export_io import EmbeddingExport, PreparedDiarization, cluster_prepared
+    rng = np.random.default_rng(3)
+    n, k = 900, 5
+    emb, _ = synth.speaker_embeddings(n, 256, k, seed=11)
+    rho, psi = synth.synthetic_plda(emb)
+    chunk = np.sort(rng.integers(0, n // 2, n)).astype(np.int32)
+    spk = np.zeros(n, np.int32)
+    for c in np.unique(chunk):                                                    # local speaker slots 0, 1, 2 ... per chunk
+        idx = np.nonzero(chunk == c)[0]
+        spk[idx] = np.arange(idx.size) % 3
+    o = oracle.diarize_cluster(emb, rho, psi, use_ref=oracle.ref_available(), chunk_indices=chunk)
+    stored = np.where(o.labels >= 0, (o.labels + 3) % (o.labels.max() + 1), o.labels).astype(np.int32)   # renamed ids
+    ex = EmbeddingExport(chunk, spk, (chunk * 10).astype(np.int32), (chunk * 10 + 9).astype(np.int32),
+                         chunk * 0.17, chunk * 0.17 + 0.16, emb, rho, stored)
+    path = tmp_path / "meeting.json"
+    ex.write(path)
+    prep = PreparedDiarization.load(path)
+    assert prep.embedding_count == n and prep.segmentation_chunk_count == int(chunk.max()) + 1
+    rep = cluster_prepared(prep, psi)
+    assert np.array_equal(rep.result.labels, o.labels)
+    assert rep.matches_export is True
+    assert np.array_equal(rep.chunk_assignments,
+                          oracle.build_chunk_assignments(chunk, spk, o.labels, prep.num_chunks, prep.num_local_speakers,
+                                                         max(int(o.labels.max()) + 1, 1)))
+    plain = cluster_prepared(prep, psi, constrained=False)
+    assert np.array_equal(plain.result.labels,
+                          oracle.diarize_cluster(emb, rho, psi, use_ref=oracle.ref_available()).labels)

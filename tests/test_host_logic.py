@@ -255,3 +255,85 @@ def test_two_rank_gloo_plumbing(tmp_path):
                          env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+# ---- embedding-export files (OfflineDiarizerManager.exportEmbeddings, :913-955): host-only code of the library ----
+def _random_export(n, seed=0, e=256, r=128):
+    from fluidaudio_b200.export_io import EmbeddingExport
+    rng = np.random.default_rng(seed)
+    return EmbeddingExport(
+        chunk_index=np.sort(rng.integers(0, max(1, n // 2), n)).astype(np.int32),
+        speaker_index=rng.integers(0, 3, n).astype(np.int32),
+        start_frame=rng.integers(0, 500, n).astype(np.int32), end_frame=rng.integers(500, 1000, n).astype(np.int32),
+        start_time=rng.random(n) * 1e3, end_time=rng.random(n) * 1e3 + 1e3,
+        embedding256=(rng.standard_normal((n, e)) * 10.0 ** rng.integers(-6, 3, (n, e))).astype(np.float32),
+        rho128=rng.standard_normal((n, r)) * 10.0 ** rng.integers(-12, 6, (n, r)),
+        cluster=rng.integers(-1, 5, n).astype(np.int32))
+
+
+def test_embedding_export_round_trip_is_bit_exact(lib, tmp_path):
+    from fluidaudio_b200.export_io import EmbeddingExport, PreparedDiarization
+    for n in (0, 1, 37):
+        ex = _random_export(n, seed=n)
+        p = tmp_path / f"export_{n}.json"
+        ex.write(p)
+        back = EmbeddingExport.read(p)
+        assert back.count == n
+        for f in ("chunk_index", "speaker_index", "start_frame", "end_frame", "cluster"):
+            assert np.array_equal(getattr(back, f), getattr(ex, f))
+        for f in ("start_time", "end_time", "embedding256", "rho128"):            # bit patterns, not just values
+            a, b = getattr(back, f), getattr(ex, f)
+            assert a.dtype == b.dtype and a.tobytes() == b.tobytes()
+        if n:
+            import json                                                              # the file is plain JSON
+            doc = json.load(open(p))
+            assert len(doc) == n and set(doc[0]) == {"chunkIndex", "speakerIndex", "startFrame", "endFrame", "startTime",
+                                                      "endTime", "embedding256", "rho128", "cluster"}
+            prep = PreparedDiarization.load(p)
+            assert prep.embedding_count == n and prep.segmentation_chunk_count == int(ex.chunk_index.max()) + 1
+
+
+def test_embedding_export_reads_foundation_style_json(lib, tmp_path):
+    """Key order, whitespace, exponents and unknown keys as Foundation's JSONEncoder / other tools may produce."""
+    from fluidaudio_b200.export_io import EmbeddingExport
+    text = """ [ {"rho128":[1e-05, -3.5E+2 ,0.1], "cluster" : 2, "embedding256":[0.100000001,-7,1.17549435e-38],
+                  "endTime":12.5,"startTime":2,"endFrame":40,"startFrame":4,"speakerIndex":1,"chunkIndex":3,
+                  "frameWeights":[0.5,{"nested":[1,2,{"x":null}]},"s\\"tr"], "extra": true },
+                 {"chunkIndex":4,"speakerIndex":0,"startFrame":5,"endFrame":6,"startTime":0.25,"endTime":0.5,
+                  "embedding256":[1,2,3],"rho128":[4,5,6]} ]\n"""
+    p = tmp_path / "swift.json"
+    p.write_text(text)
+    ex = EmbeddingExport.read(p)
+    assert ex.count == 2 and ex.embedding256.shape == (2, 3) and ex.rho128.shape == (2, 3)
+    assert ex.chunk_index.tolist() == [3, 4] and ex.speaker_index.tolist() == [1, 0]
+    assert ex.start_frame.tolist() == [4, 5] and ex.end_frame.tolist() == [40, 6]
+    assert ex.start_time.tolist() == [2.0, 0.25] and ex.end_time.tolist() == [12.5, 0.5]
+    assert ex.cluster.tolist() == [2, -1]                                           # absent -> -1, as the writer's default
+    assert ex.embedding256[0].tolist() == [np.float32(0.1), -7.0, np.float32(1.17549435e-38)]
+    assert ex.rho128[0].tolist() == [1e-05, -350.0, 0.1]
+
+
+def test_embedding_export_errors_are_reported(lib, tmp_path):
+    from fluidaudio_b200.export_io import EmbeddingExport
+    with pytest.raises(_lib.FluidAudioError) as e:
+        EmbeddingExport.read(tmp_path / "missing.json")
+    assert e.value.status == 1 and "cannot open" in str(e.value)
+    for name, text, what in (("trunc", '[{"chunkIndex":1,"embedding256":[1,2', "expected"),
+                             ("ragged", '[{"embedding256":[1,2],"rho128":[1]},{"embedding256":[1],"rho128":[1]}]', "different"),
+                             ("notarray", '{"chunkIndex":1}', "expected '['"),
+                             ("frac", '[{"chunkIndex":1.5,"embedding256":[],"rho128":[]}]', "integer"),
+                             ("tail", '[] x', "trailing")):
+        p = tmp_path / f"{name}.json"
+        p.write_text(text)
+        with pytest.raises(_lib.FluidAudioError) as e:
+            EmbeddingExport.read(p)
+        assert e.value.status == 1 and what in str(e.value), (name, str(e.value))
+
+
+def test_same_partition_helper():
+    from fluidaudio_b200.export_io import same_partition
+    assert same_partition([0, 0, 1, 2, -2], [5, 5, 3, 9, -1])
+    assert not same_partition([0, 0, 1], [1, 2, 2])
+    assert not same_partition([0, 1], [0, 0])
+    assert not same_partition([0, -2], [0, 1])
+    assert not same_partition([0, 1], [0, 1, 2])
