@@ -54,7 +54,7 @@ EXPORTED_SYMBOLS = [
     "fa_memcpy_d2h", "fa_timer_start", "fa_timer_stop_ms", "fa_mel_default_config", "fa_mel_create",
     "fa_mel_destroy", "fa_mel_get_window", "fa_mel_get_filterbank", "fa_mel_frame_count", "fa_mel_compute",
     "fa_mel_compute_device", "fa_mel_compute_batch", "fa_mel_compute_batch_device", "fa_mel_timer_start",
-    "fa_mel_timer_stop_ms", "fa_mel_normalize_per_feature",
+    "fa_mel_timer_stop_ms", "fa_mel_normalize_per_feature", "fa_mel_unified_features", "fa_mel_lseend_features",
     "fa_linear_resample", "fa_l2_normalize_rows", "fa_ahc_cluster", "fa_dendrogram_cut", "fa_vbx_default_config",
     "fa_vbx_refine", "fa_compute_centroids", "fa_assign_embeddings", "fa_cluster_default_config",
     "fa_diarize_cluster", "fa_diarize_cluster_batch", "fa_ahc_last_stage_ms", "fa_diarize_cluster_chunks",
@@ -105,6 +105,8 @@ def load():
     L.fa_mel_timer_start.argtypes = [vp]
     L.fa_mel_timer_stop_ms.argtypes = [vp, C.POINTER(f32)]
     L.fa_mel_normalize_per_feature.argtypes = [vp, i64, i32, i64]
+    L.fa_mel_unified_features.argtypes = [vp, vp, sz, sz, vp, sz, C.POINTER(i64), C.POINTER(i32)]
+    L.fa_mel_lseend_features.argtypes = [vp, vp, sz, vp, C.POINTER(i64), vp, sz, C.POINTER(i64)]
     L.fa_linear_resample.argtypes = [vp, i64, i32, f64, f64, vp, i64, C.POINTER(i64)]
     L.fa_l2_normalize_rows.argtypes = [vp, sz, sz, vp]
     L.fa_ahc_cluster.argtypes = [vp, sz, sz, f64, vp]

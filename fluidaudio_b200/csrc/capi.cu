@@ -672,6 +672,43 @@ FA_API fa_status fa_mel_timer_stop_ms(fa_mel *mel, float *elapsed_ms) {
     return FA_STATUS_OK;
 }
 
+// UnifiedMelExtractor.features(window:validCount:) (UnifiedMelExtractor.swift:52-86): log-mel + per-feature
+// normalisation + [1, nMels, T] packing, normalisation and packing as a device epilogue of the mel kernel.
+FA_API fa_status fa_mel_unified_features(fa_mel *mel, const float *window, size_t window_samples, size_t valid_count,
+                                         float *out, size_t out_len, int64_t *total_frames, int32_t *valid_frames) {
+    if (!mel || !out || (!window && window_samples)) return FA_STATUS_INVALID_ARGUMENT;
+    FA_GUARD_BEGIN
+    auto *h = reinterpret_cast<MelHandle *>(mel);
+    const long long before = h->plan.launches;
+    long long T = 0;
+    int valid = 0;
+    const int st = fa::mel::unified_features(h->plan, window, (long long)window_samples, (long long)valid_count, out,
+                                             (long long)out_len, &T, &valid);
+    g_launches += h->plan.launches - before;
+    if (total_frames) *total_frames = T;
+    if (valid_frames) *valid_frames = valid;
+    return (fa_status)st;
+    FA_GUARD_END
+}
+
+// LSEENDPreprocessor.processAudioQueue (LSEENDPreprocessor.swift:249-283): .prePadded log-mel of one audio chunk,
+// log10 scaling and cumulative mean normalisation; (cmn_mean, cmn_count) is the preprocessor's running state.
+FA_API fa_status fa_mel_lseend_features(fa_mel *mel, const float *chunk, size_t n, float *cmn_mean, int64_t *cmn_count,
+                                        float *out, size_t out_len, int64_t *frames) {
+    if (!mel || !cmn_mean || !cmn_count || *cmn_count < 0 || (!chunk && n) || (!out && out_len))
+        return FA_STATUS_INVALID_ARGUMENT;
+    FA_GUARD_BEGIN
+    auto *h = reinterpret_cast<MelHandle *>(mel);
+    const long long before = h->plan.launches;
+    long long T = 0, count = *cmn_count;
+    const int st = fa::mel::lseend_features(h->plan, chunk, (long long)n, cmn_mean, &count, out, (long long)out_len, &T);
+    g_launches += h->plan.launches - before;
+    *cmn_count = count;
+    if (frames) *frames = T;
+    return (fa_status)st;
+    FA_GUARD_END
+}
+
 // UnifiedMelExtractor.normalizePerFeature (UnifiedMelExtractor.swift:88-113).  O(T*M) on a caller-owned host
 // buffer that is about to be handed to the encoder; not a GPU hot path.
 FA_API fa_status fa_mel_normalize_per_feature(float *x, int64_t frames, int32_t n_mels, int64_t valid) {

@@ -111,6 +111,12 @@ struct MelPlan {
                              long long *num_frames, cudaStream_t stream);
 };
 
+// mel_adapters.cu: device epilogues for the callers directly behind AudioMelSpectrogram (host buffers in and out)
+int unified_features(MelPlan &p, const float *window, long long n, long long valid_count, float *out, long long out_len,
+                     long long *total_frames, int *valid_frames);
+int lseend_features(MelPlan &p, const float *chunk, long long n, float *cmn_mean, long long *cmn_count, float *out,
+                    long long out_len, long long *frames);
+
 void build_window(int length, bool periodic, std::vector<float> &w);
 void build_filterbank(int n_fft, int n_mels, int sample_rate, std::vector<float> &fb);
 

@@ -178,3 +178,60 @@ def normalize_per_feature(mel_time_major: np.ndarray, valid_frames: int) -> np.n
 def to_channel_major(mel_time_major: np.ndarray) -> np.ndarray:
     """NemotronMelExtractor.melSpectrogram's [T x M] → [1, M, T] re-layout (NemotronMelExtractor.swift:44-67)."""
     return np.ascontiguousarray(mel_time_major.T)[None]
+
+
+class UnifiedMelExtractor:
+    """ASR/Parakeet/Unified/UnifiedMelExtractor.swift:15-113: NeMo `AudioToMelSpectrogramPreprocessor` features with
+    `normalize: per_feature`, packed for the encoder.  The normalisation and the [1, nMels, T] packing run on the GPU
+    behind the mel kernel (`fa_mel_unified_features`)."""
+
+    def __init__(self, window_samples: int, n_mels: int = 128):
+        self.window_samples = int(window_samples)
+        self.n_mels = n_mels
+        self.hop_length = 160
+        self.total_frames = self.window_samples // self.hop_length + 1
+        self._mel = AudioMelSpectrogram(sample_rate=16000, n_mels=n_mels, n_fft=512, hop_length=160, win_length=400,
+                                        preemph=0.97, pad_to=0, window_periodic=False)
+
+    def features(self, window: np.ndarray, valid_count: int) -> tuple[np.ndarray, np.ndarray]:
+        """Returns (mel [1, nMels, totalFrames] float32, length [1] int32) — the CoreML preprocessor's contract."""
+        window = np.ascontiguousarray(window, np.float32)
+        if window.size != self.window_samples:
+            raise ValueError(f"window must hold {self.window_samples} samples, got {window.size}")
+        out = np.zeros((1, self.n_mels, self.total_frames), np.float32)
+        T, valid = C.c_int64(), C.c_int32()
+        _lib.check(self._mel._L.fa_mel_unified_features(self._mel._h, window.ctypes.data, window.size, int(valid_count),
+                                                        out.ctypes.data, out.size, C.byref(T), C.byref(valid)),
+                   "fa_mel_unified_features")
+        assert T.value == self.total_frames
+        return out, np.array([valid.value], np.int32)
+
+
+class LSEENDMelFrontend:
+    """The mel half of LSEENDPreprocessor (Diarizer/LS-EEND/LSEENDPreprocessor.swift:70-81, 249-283): `.prePadded`
+    log-mel with preemph 0 / periodic Hann / clamped floor 1e-10, log10 scaling, cumulative mean normalisation whose
+    state (`cmn_mean`, `cmn_count`) lives here exactly as in the preprocessor; `reset()` as :236-245."""
+
+    def __init__(self, n_mels: int = 23, n_fft: int = 512, hop_length: int = 160, win_length: int = 400,
+                 sample_rate: int = 16000):
+        self.n_mels = n_mels
+        self._mel = AudioMelSpectrogram(sample_rate=sample_rate, n_mels=n_mels, n_fft=n_fft, hop_length=hop_length,
+                                        win_length=win_length, preemph=0.0, pad_to=0, log_floor=1e-10,
+                                        log_floor_mode=LogFloorMode.clamped, window_periodic=True)
+        self.reset()
+
+    def reset(self):
+        self.cmn_mean = np.zeros(self.n_mels, np.float32)
+        self.cmn_count = 0
+
+    def process(self, audio_chunk: np.ndarray) -> np.ndarray:
+        """One popped audio chunk (already carrying its left / right context) -> [frames x nMels] features."""
+        chunk = np.ascontiguousarray(audio_chunk, np.float32)
+        T = self._mel.frame_count(chunk.size, PaddingMode.pre_padded)
+        out = np.zeros((max(T, 0), self.n_mels), np.float32)
+        cnt, frames = C.c_int64(self.cmn_count), C.c_int64()
+        _lib.check(self._mel._L.fa_mel_lseend_features(self._mel._h, chunk.ctypes.data, chunk.size,
+                                                       self.cmn_mean.ctypes.data, C.byref(cnt), out.ctypes.data,
+                                                       out.size, C.byref(frames)), "fa_mel_lseend_features")
+        self.cmn_count = cnt.value
+        return out[: frames.value]

@@ -114,6 +114,20 @@ fa_status fa_mel_compute_batch_device(fa_mel *mel, const float *d_audio, const i
 fa_status fa_mel_timer_start(fa_mel *mel);
 fa_status fa_mel_timer_stop_ms(fa_mel *mel, float *elapsed_ms);
 
+/* Callers directly behind AudioMelSpectrogram, with their post-processing as device epilogues of the mel kernel.
+ * fa_mel_unified_features = UnifiedMelExtractor.features(window:validCount:) (ASR/Parakeet/Unified/
+ *   UnifiedMelExtractor.swift:52-113): the handle must be configured like its AudioMelSpectrogram (:31-40);
+ *   total_frames = window_samples / hop + 1, valid_frames = min(valid_count / hop, total_frames); out receives the
+ *   per-feature-normalised log-mel packed [n_mels x total_frames] (the MLMultiArray [1, nMels, T]).
+ * fa_mel_lseend_features = LSEENDPreprocessor.processAudioQueue (Diarizer/LS-EEND/LSEENDPreprocessor.swift:249-283):
+ *   the handle configured as :70-81 (preemph 0, periodic Hann, clamped floor 1e-10); out receives [frames x n_mels]
+ *   log10-scaled, cumulative-mean-normalised features; cmn_mean[n_mels] / cmn_count are the running state, updated. */
+fa_status fa_mel_unified_features(fa_mel *mel, const float *window, size_t window_samples, size_t valid_count,
+                                  float *out, size_t out_len, int64_t *total_frames, int32_t *valid_frames);
+fa_status fa_mel_lseend_features(fa_mel *mel, const float *chunk, size_t n, float *cmn_mean, int64_t *cmn_count,
+                                 float *out, size_t out_len, int64_t *frames);
+
+
 /* NeMo per-feature normalisation of a time-major [frames x n_mels] buffer, in place (host buffer).
  * UnifiedMelExtractor.normalizePerFeature, Sources/FluidAudio/ASR/Parakeet/Unified/UnifiedMelExtractor.swift:88-113 */
 fa_status fa_mel_normalize_per_feature(float *x, int64_t frames, int32_t n_mels, int64_t valid_frames);

@@ -97,6 +97,8 @@ def lib():
         L.oracle_linear_resample.argtypes = [_f32p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_void_p]
         L.oracle_linear_resample.restype = C.c_int64
         L.oracle_normalize_per_feature.argtypes = [_f32p, C.c_int64, C.c_int32, C.c_int64]
+        L.oracle_lseend_scale_cmn.argtypes = [_f32p, C.c_int64, C.c_int32, _f32p, C.POINTER(C.c_int64)]
+        L.oracle_lseend_scale_cmn.restype = None
         L.oracle_transpose_tm.argtypes = [_f32p, C.c_int64, C.c_int32, _f32p]
         _lib = L
     return _lib
@@ -185,6 +187,36 @@ def normalize_per_feature(x: np.ndarray, valid_frames: int) -> np.ndarray:
     y = np.ascontiguousarray(x, np.float32).copy()
     lib().oracle_normalize_per_feature(y, y.shape[0], y.shape[1], valid_frames)
     return y
+
+
+def unified_mel_features(window: np.ndarray, valid_count: int, n_mels: int = 128, hop: int = 160):
+    """UnifiedMelExtractor.features(window:validCount:) (UnifiedMelExtractor.swift:52-86): center-padded log-mel with
+    expectedFrameCount = windowSamples / hop + 1, NeMo per-feature normalisation over validCount / hop frames, packed as
+    [nMels x totalFrames].  Returns (mel [n_mels x T], valid_frames)."""
+    window = np.ascontiguousarray(window, np.float32)
+    total = window.size // hop + 1
+    cfg = mel_config(n_mels=n_mels)
+    flat, _, _ = mel_flat_transposed(cfg, window, 0.0, 0, expected_frames=total)
+    valid = min(int(valid_count) // hop, total)
+    norm = normalize_per_feature(flat[:total], valid)
+    return np.ascontiguousarray(norm.T), valid
+
+
+def lseend_config(n_mels: int = 23, n_fft: int = 512, hop_length: int = 160, win_length: int = 400, sample_rate: int = 16000):
+    """The AudioMelSpectrogram LSEENDPreprocessor builds (LSEENDPreprocessor.swift:70-81)."""
+    return mel_config(sample_rate=sample_rate, n_mels=n_mels, n_fft=n_fft, hop_length=hop_length, win_length=win_length,
+                      preemph=0.0, pad_to=0, log_floor=1e-10, log_floor_mode=1, window_periodic=True)
+
+
+def lseend_features(cfg: MelConfig, chunk: np.ndarray, cmn_mean: np.ndarray, cmn_count: int):
+    """LSEENDPreprocessor.processAudioQueue (:249-283): .prePadded log-mel, log10 scaling, cumulative mean
+    normalisation.  Returns (features [T x nMels], cmn_mean', cmn_count')."""
+    flat, ml, _ = mel_flat_transposed(cfg, np.ascontiguousarray(chunk, np.float32), 0.0, 1, None)
+    x = np.ascontiguousarray(flat[:ml], np.float32).copy()
+    mean = np.ascontiguousarray(cmn_mean, np.float32).copy()
+    cnt = C.c_int64(int(cmn_count))
+    lib().oracle_lseend_scale_cmn(x, x.shape[0], x.shape[1], mean, C.byref(cnt))
+    return x, mean, cnt.value
 
 
 def linear_resample(planar: np.ndarray, in_rate: float, out_rate: float) -> np.ndarray:

@@ -69,6 +69,30 @@ void oracle_normalize_per_feature(float *x, int64_t frames, int32_t n_mels, int6
     }
 }
 
+// LS-EEND feature scaling + cumulative mean normalisation (LSEENDPreprocessor.swift:259-279), in place on a time-major
+// [frames x n_mels] log-mel buffer, carrying (cmn_mean[n_mels], cmn_count) across calls exactly like the preprocessor's
+// state.  Per frame k: count += 1; alpha = 1 / Float(count); mean = mean + alpha * (x - mean)  (vDSP_vintb: one
+// subtract, one multiply, one add, each rounded to float32); x = x - mean  (vDSP_vsub).  The scale is
+// Float(1) / logf(10) (:36) applied with vDSP_vsmul first.
+void oracle_lseend_scale_cmn(float *x, int64_t frames, int32_t n_mels, float *cmn_mean, int64_t *cmn_count) {
+    const float scale = 1.0f / logf(10.0f);
+    int64_t count = *cmn_count;
+    for (int64_t t = 0; t < frames; ++t) {
+        count += 1;
+        const float alpha = 1.0f / (float)count;
+        float *row = x + t * n_mels;
+        for (int32_t m = 0; m < n_mels; ++m) {
+            const float v = row[m] * scale;
+            const float d = v - cmn_mean[m];
+            const float ad = alpha * d;
+            const float mu = cmn_mean[m] + ad;
+            cmn_mean[m] = mu;
+            row[m] = v - mu;
+        }
+    }
+    *cmn_count = count;
+}
+
 // time-major [T x M] -> mel-major [M x T]
 void oracle_transpose_tm(const float *in, int64_t T, int32_t M, float *out) {
     for (int64_t t = 0; t < T; ++t)

@@ -428,3 +428,37 @@ def test_export_replay_matches_oracle_and_file_labels(gpu_lib, oracle, tmp_path)
     plain = cluster_prepared(prep, psi, constrained=False)
     assert np.array_equal(plain.result.labels,
                           oracle.diarize_cluster(emb, rho, psi, use_ref=oracle.ref_available()).labels)
+
+
+def test_mel_adapters_match_oracle(gpu_lib, oracle):
+    """UnifiedMelExtractor.features and the LS-EEND mel front end, post-processing on the GPU."""
+    from fluidaudio_b200.mel import LSEENDMelFrontend, UnifiedMelExtractor
+    a = synth.tone_noise_audio(16000 * 6)
+    for window_samples, valid_count, n_mels in ((64000, 40000, 128), (24000, 24000, 80), (16000, 100, 128), (4800, 4000, 128)):
+        window = np.zeros(window_samples, np.float32)
+        window[:valid_count] = a[:valid_count]
+        ex = UnifiedMelExtractor(window_samples, n_mels)
+        mel, length = ex.features(window, valid_count)
+        ref, valid = oracle.unified_mel_features(window, valid_count, n_mels)
+        assert mel.shape == (1, n_mels, window_samples // 160 + 1) and length.tolist() == [valid]
+        # the normalised value divides a log-mel difference (accurate to ~1e-6) by a std of order 1
+        assert np.abs(mel[0] - ref).max() < 1e-4, (window_samples, np.abs(mel[0] - ref).max())
+        assert not mel[0][:, valid:].any()
+    fe = LSEENDMelFrontend()
+    cfg = oracle.lseend_config()
+    mean, count = np.zeros(23, np.float32), 0
+    pos = 0
+    # 511 samples still give one (partial) frame — Swift's (n - nFFT) / hop truncates toward zero (:345); 300 give none
+    for n in (16000, 8000 + 352, 511, 300, 24000):
+        chunk = a[pos:pos + n]
+        pos += max(n - 352, 0)
+        got = fe.process(chunk)
+        if n == 300:
+            assert got.shape == (0, 23) and fe.cmn_count == count
+            continue
+        ref, mean, count = oracle.lseend_features(cfg, chunk, mean, count)
+        assert got.shape == ref.shape and fe.cmn_count == count
+        assert np.abs(got - ref).max() < 1e-4
+        assert np.abs(fe.cmn_mean - mean).max() < 1e-4
+    fe.reset()
+    assert fe.cmn_count == 0 and not fe.cmn_mean.any()

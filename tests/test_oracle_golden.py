@@ -341,3 +341,34 @@ def test_hungarian_and_constrained_assignment_reference_kats(oracle):
         best = min(sum(cost[i, p[i]] for i in range(n)) for p in itertools.permutations(range(n)))
         a = oracle.hungarian_solve(cost)
         assert sorted(a.tolist()) == list(range(n)) and sum(cost[i, a[i]] for i in range(n)) == best
+
+
+def test_adapter_restatements_against_numpy(oracle):
+    """UnifiedMelExtractor per-feature normalisation and LS-EEND cumulative mean normalisation:
+    the C restatements against straightforward numpy float64 formulas."""
+    from fluidaudio_b200 import synth
+    a = synth.tone_noise_audio(16000 * 4)
+    window = np.concatenate([a[:40000], np.zeros(24000, np.float32)])
+    mel, valid = oracle.unified_mel_features(window, 40000)
+    total = window.size // 160 + 1
+    assert mel.shape == (128, total) and valid == 40000 // 160
+    raw, _, _ = oracle.mel_flat_transposed(oracle.mel_config(n_mels=128), window, 0.0, 0, expected_frames=total)
+    x = raw[:valid].astype(np.float64)
+    ref = (x - x.mean(axis=0)) / (x.std(axis=0, ddof=1) + 1e-5)
+    assert np.abs(mel[:, :valid].T - ref).max() < 2e-4
+    assert not mel[:, valid:].any()
+    m0, v0 = oracle.unified_mel_features(window, 100)                  # fewer samples than one hop: everything zero
+    assert v0 == 0 and not m0.any()
+
+    cfg = oracle.lseend_config()
+    f1, mean1, c1 = oracle.lseend_features(cfg, a[:16000], np.zeros(23, np.float32), 0)
+    f2, mean2, c2 = oracle.lseend_features(cfg, a[16000 - 352:40000], mean1, c1)
+    assert c1 == f1.shape[0] == (16000 - 512) // 160 + 1 and c2 == c1 + f2.shape[0]
+    raw1, ml1, _ = oracle.mel_flat_transposed(cfg, a[:16000], 0.0, 1, None)
+    raw2, ml2, _ = oracle.mel_flat_transposed(cfg, a[16000 - 352:40000], 0.0, 1, None)
+    y = np.concatenate([raw1[:ml1], raw2[:ml2]]).astype(np.float64) / np.log(10.0)
+    cum = np.cumsum(y, axis=0) / np.arange(1, y.shape[0] + 1)[:, None]
+    got = np.concatenate([f1, f2])
+    assert np.abs(got - (y - cum)).max() < 1e-4
+    assert np.abs(mean2 - cum[-1]).max() < 1e-4
+    assert not got[0].any()                                            # first frame minus its own mean
