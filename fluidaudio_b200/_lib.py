@@ -26,6 +26,9 @@ class FluidAudioError(RuntimeError):
         super().__init__(f"{where}: {STATUS_NAMES.get(status, status)}" + (f" — {detail}" if detail else ""))
 
 
+NO_VALUE = -2 ** 31   # FA_NO_VALUE: an absent optional count (Swift nil)
+
+
 class MelConfig(C.Structure):
     _fields_ = [("sample_rate", C.c_int32), ("n_mels", C.c_int32), ("n_fft", C.c_int32), ("hop_length", C.c_int32),
                 ("win_length", C.c_int32), ("preemph", C.c_float), ("pad_to", C.c_int32), ("log_floor", C.c_float),
@@ -38,13 +41,15 @@ class VbxConfig(C.Structure):
 
 
 class ClusterConfig(C.Structure):
-    _fields_ = [("threshold", C.c_double), ("vbx", VbxConfig)]
+    _fields_ = [("threshold", C.c_double), ("vbx", VbxConfig), ("num_speakers", C.c_int32),
+                ("min_speakers", C.c_int32), ("max_speakers", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ClusterInfo(C.Structure):
     _fields_ = [("training_count", C.c_int32), ("initial_clusters", C.c_int32), ("vbx_iterations", C.c_int32),
                 ("centroid_count", C.c_int32), ("ms_normalize", C.c_float), ("ms_ahc", C.c_float),
-                ("ms_cut", C.c_float), ("ms_vbx", C.c_float), ("ms_assign", C.c_float), ("ms_total", C.c_float)]
+                ("ms_cut", C.c_float), ("ms_vbx", C.c_float), ("ms_assign", C.c_float), ("ms_total", C.c_float),
+                ("was_adjusted", C.c_int32), ("detected_clusters", C.c_int32)]
 
 
 # every symbol include/fluidaudio_b200.h and include/FastClusterWrapper.h declare (tests check the export table)
@@ -59,7 +64,7 @@ EXPORTED_SYMBOLS = [
     "fa_vbx_refine", "fa_compute_centroids", "fa_assign_embeddings", "fa_cluster_default_config",
     "fa_diarize_cluster", "fa_diarize_cluster_batch", "fa_ahc_last_stage_ms", "fa_diarize_cluster_chunks",
     "fa_hungarian_solve", "fa_max_score_assignment", "fa_constrained_assign", "fa_build_chunk_assignments",
-    "fa_export_shape", "fa_export_read", "fa_export_write",
+    "fa_export_shape", "fa_export_read", "fa_export_write", "fa_kmeans_cluster", "fa_speaker_constraints_resolve",
     "fastcluster_compute_centroid_linkage",
 ]
 
@@ -127,6 +132,8 @@ def load():
     L.fa_max_score_assignment.argtypes = [vp, i32, i32, vp]
     L.fa_constrained_assign.argtypes = [vp, sz, i32, vp, vp]
     L.fa_build_chunk_assignments.argtypes = [vp, vp, vp, sz, i32, i32, i32, vp]
+    L.fa_kmeans_cluster.argtypes = [vp, sz, sz, i32, i32, i32, C.c_uint64, vp, vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.fa_speaker_constraints_resolve.argtypes = [i64, i64, i64, i64, C.POINTER(i64), C.POINTER(i64)]
     L.fa_export_shape.argtypes = [C.c_char_p, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
     L.fa_export_read.argtypes = [C.c_char_p, sz, sz, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.fa_export_write.argtypes = [C.c_char_p, sz, sz, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]

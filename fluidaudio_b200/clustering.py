@@ -26,6 +26,9 @@ class ClusteringConfig:           # OfflineDiarizerConfig.Clustering.community
     threshold: float = 0.6
     warm_start_fa: float = 0.07
     warm_start_fb: float = 0.8
+    num_speakers: int | None = None      # exact count, overrides min / max (OfflineDiarizerTypes.swift)
+    min_speakers: int | None = None
+    max_speakers: int | None = None
 
 
 @dataclass
@@ -48,7 +51,21 @@ class OfflineDiarizerConfig:
                               self.vbx.convergence_tolerance, 7.0)
 
     def _c_cluster(self) -> _lib.ClusterConfig:
-        return _lib.ClusterConfig(self.clustering.threshold, self._c_vbx())
+        opt = lambda v: _lib.NO_VALUE if v is None else int(v)
+        c = self.clustering
+        return _lib.ClusterConfig(c.threshold, self._c_vbx(), opt(c.num_speakers), opt(c.min_speakers),
+                                  opt(c.max_speakers), 0)
+
+    def with_speakers(self, min: int | None = None, max: int | None = None, exactly: int | None = None):
+        """OfflineDiarizerConfig.withSpeakers(min:max:) / withSpeakers(exactly:) (OfflineDiarizerTypes.swift:731-):
+        a copy with the constraints applied; `exactly` takes precedence, min/max clear a previous exact count."""
+        import copy
+        out = copy.deepcopy(self)
+        if exactly is not None:
+            out.clustering.num_speakers, out.clustering.min_speakers, out.clustering.max_speakers = exactly, None, None
+        else:
+            out.clustering.num_speakers, out.clustering.min_speakers, out.clustering.max_speakers = None, min, max
+        return out
 
 
 def centroid_linkage(normalized_rows: np.ndarray):
@@ -279,3 +296,57 @@ def build_chunk_assignments(chunk_indices, speaker_indices, assignments, num_chu
                                                       num_chunks, num_speakers, cluster_count, m.ctypes.data),
                "fa_build_chunk_assignments")
     return m
+
+
+# ---- speaker-count constraints + K-Means re-clustering (SpeakerCountConstraints.swift, KMeansClustering.swift) -----
+@dataclass
+class SpeakerCountConstraints:
+    num_speakers: int | None
+    min_speakers: int
+    max_speakers: int
+
+    @staticmethod
+    def resolve(num_embeddings: int, num_speakers=None, min_speakers=None, max_speakers=None) -> "SpeakerCountConstraints":
+        opt = lambda v: _lib.NO_VALUE if v is None else int(v)
+        lo, hi = C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().fa_speaker_constraints_resolve(int(num_embeddings), opt(num_speakers), opt(min_speakers),
+                                                              opt(max_speakers), C.byref(lo), C.byref(hi)),
+                   "fa_speaker_constraints_resolve")
+        num = lo.value if lo.value == hi.value else num_speakers
+        return SpeakerCountConstraints(num, lo.value, hi.value)
+
+    def needs_adjustment(self, detected_count: int) -> bool:
+        return detected_count < self.min_speakers or detected_count > self.max_speakers
+
+    def target_count(self, detected_count: int) -> int:
+        return min(max(detected_count, self.min_speakers), self.max_speakers)
+
+
+class KMeansClustering:
+    """KMeansClustering.swift:39-130; all arithmetic on the GPU (`fa_kmeans_cluster`)."""
+
+    @staticmethod
+    def cluster_with_centroids_n_init(embeddings, num_clusters: int, max_iterations: int = 300, n_init: int = 10,
+                                      base_seed: int = 0):
+        emb = np.ascontiguousarray(embeddings, np.float64)
+        if emb.ndim != 2 or emb.shape[0] == 0:
+            return np.zeros(0, np.int32), np.zeros((0, 0), np.float64), 0
+        n, d = emb.shape
+        cap = max(1, min(int(num_clusters), n))
+        labels = np.zeros(n, np.int32)
+        cents = np.zeros((cap, d), np.float64)
+        rows, best = C.c_int32(), C.c_int32()
+        _lib.check(_lib.load().fa_kmeans_cluster(emb.ctypes.data, n, d, int(num_clusters), int(max_iterations),
+                                                 int(n_init), int(base_seed), labels.ctypes.data, cents.ctypes.data, cap,
+                                                 C.byref(rows), C.byref(best)), "fa_kmeans_cluster")
+        return labels, cents[: rows.value].copy(), best.value
+
+    @staticmethod
+    def cluster_with_centroids(embeddings, num_clusters: int, max_iterations: int = 300, seed: int | None = None):
+        labels, cents, _ = KMeansClustering.cluster_with_centroids_n_init(embeddings, num_clusters, max_iterations, 1,
+                                                                          seed or 0)
+        return labels, cents
+
+    @staticmethod
+    def cluster(embeddings, num_clusters: int, max_iterations: int = 300, seed: int | None = None):
+        return KMeansClustering.cluster_with_centroids(embeddings, num_clusters, max_iterations, seed)[0]

@@ -784,13 +784,16 @@ __global__ void __launch_bounds__(kWorkerThreads, 1) ahc_merge_kernel(const Prob
 // ------------------------------------------------------------------------------------------------ small kernels
 // Row-wise L2 normalisation with the oracle's (= AHCClustering.normalizeFeatures') operation order:
 // s = sum_k x*x sequentially, scale = s > 0 ? 1/sqrt(s) : 0, out = x*scale.
-__global__ void ahc_normalize_rows_kernel(const double *__restrict__ in, double *__restrict__ out, int rows, int dim) {
+// zero_scale: what a zero-norm row is multiplied by — 0 for AHCClustering.normalizeFeatures (:70-105), 1 for
+// OfflineDiarizerManager.normalize (:824-860, the row is kept).
+__global__ void ahc_normalize_rows_kernel(const double *__restrict__ in, double *__restrict__ out, int rows, int dim,
+                                          double zero_scale) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const double *x = in + (size_t)r * dim;
     double s = 0.0;
     for (int k = 0; k < dim; ++k) s = __dadd_rn(s, __dmul_rn(x[k], x[k]));
-    const double scale = s > 0.0 ? __ddiv_rn(1.0, __dsqrt_rn(s)) : 0.0;
+    const double scale = s > 0.0 ? __ddiv_rn(1.0, __dsqrt_rn(s)) : zero_scale;
     double *o = out + (size_t)r * dim;
     for (int k = 0; k < dim; ++k) o[k] = __dmul_rn(x[k], scale);
 }
@@ -802,7 +805,14 @@ __global__ void ahc_widen_kernel(const float *__restrict__ in, double *__restric
 
 int launch_normalize_rows(const double *d_in, double *d_out, int rows, int dim, cudaStream_t s) {
     if (rows <= 0) return FA_OK;
-    ahc_normalize_rows_kernel<<<(rows + 127) / 128, 128, 0, s>>>(d_in, d_out, rows, dim);
+    ahc_normalize_rows_kernel<<<(rows + 127) / 128, 128, 0, s>>>(d_in, d_out, rows, dim, 0.0);
+    FA_CUDA_TRY(cudaGetLastError());
+    return FA_OK;
+}
+
+int launch_normalize_rows_keep(const double *d_in, double *d_out, int rows, int dim, cudaStream_t s) {
+    if (rows <= 0) return FA_OK;
+    ahc_normalize_rows_kernel<<<(rows + 127) / 128, 128, 0, s>>>(d_in, d_out, rows, dim, 1.0);
     FA_CUDA_TRY(cudaGetLastError());
     return FA_OK;
 }

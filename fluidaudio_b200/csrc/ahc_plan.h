@@ -91,6 +91,7 @@ const float *last_stage_ms();
 
 // Standalone kernels used by the clustering pipeline
 int launch_normalize_rows(const double *d_in, double *d_out, int rows, int dim, cudaStream_t s);
+int launch_normalize_rows_keep(const double *d_in, double *d_out, int rows, int dim, cudaStream_t s);   // zero rows kept
 int launch_widen_rows(const float *d_in, double *d_out, long long count, cudaStream_t s);
 
 // Swift-side dendrogram cut + first-appearance relabel (AHCClustering.swift:112-121,124-210), host, O(N).

@@ -7,6 +7,7 @@
 #include "assign_host.h"
 #include "mel_plan.h"
 #include "vbx_plan.h"
+#include "kmeans_plan.h"
 
 #include <atomic>
 #include <chrono>
@@ -326,10 +327,44 @@ static int cluster_pipeline(ClusterContext &C, const float *emb, const double *r
             used_vbx = true;
         }
     }
+    // ---- speaker-count constraints (:311-336, VBxClustering.swift:685-733) ----------------------------------
+    bool adjusted = false;
+    int detected = S, K = 0;
+    if (used_vbx && (cfg.num_speakers != FA_NO_VALUE || cfg.min_speakers != FA_NO_VALUE || cfg.max_speakers != FA_NO_VALUE)) {
+        std::vector<int> hard(Tn);
+        FA_CUDA_TRY(cudaMemcpyAsync(hard.data(), d_hard, sizeof(int) * Tn, cudaMemcpyDeviceToHost, s));
+        FA_CUDA_TRY(cudaStreamSynchronize(s));
+        std::vector<char> seen(S, 0);
+        detected = 0;                                       // VBxOutput.assignedClusterCount: row-argmax winners
+        for (int i = 0; i < Tn; ++i)
+            if (hard[i] >= 0 && hard[i] < S && !seen[hard[i]]) {
+                seen[hard[i]] = 1;
+                ++detected;
+            }
+        long long lo = 1, hi = Tn;
+        kmeans::resolve_constraints(Tn, cfg.num_speakers, cfg.min_speakers, cfg.max_speakers, &lo, &hi);
+        if (detected < lo || detected > hi) {
+            const int target = (int)(detected < lo ? lo : hi);
+            st = C.cent_ws.reserve(std::max(C.cent_ws.pool_bytes, gbytes + 2 * (size_t)target * E * sizeof(double)));
+            if (st != FA_OK) return st;
+            // the arena may have moved: re-carve (gamma / pi are not needed any more on this path)
+            Carver kc{static_cast<char *>(C.cent_ws.pool)};
+            d_cent = kc.take<double>((size_t)target * E + E);
+            d_cent_n = kc.take<double>((size_t)target * E + E);
+            int rows = 0;
+            st = kmeans::cluster_ninit_device(C.vbx_ws, d_tr, Tn, e, target, 100, 10, 0ull, d_hard, d_cent, &rows, nullptr,
+                                              s, &lc);
+            if (st != FA_OK) return st;
+            st = ahc::launch_normalize_rows_keep(d_cent, d_cent_n, rows, e, s);   // normalize (:824-860) for the cosine
+            if (st != FA_OK) return st;
+            lc += 1;
+            K = rows;
+            adjusted = true;
+        }
+    }
     FA_CUDA_TRY(cudaEventRecord(C.ev[5], s));
     // ---- centroids (:345-353) + assignment (:371-374) -----------------------------------------------------
-    int K = 0;
-    if (S <= 1024) {
+    if (!adjusted && S <= 1024) {
         st = vbx::centroids_device(C.vbx_ws, d_tr, Tn, e, d_gamma, d_pi, S, d_cent, d_cent_n, d_count, s, &lc);
         if (st != FA_OK) return st;
         FA_CUDA_TRY(cudaMemcpyAsync(h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -368,7 +403,7 @@ static int cluster_pipeline(ClusterContext &C, const float *emb, const double *r
         lc += 2;
     }
     // constrained assignment (:357-369) needs the full N x K score matrix on the host; plain argmax (:371-374) does not
-    const bool constrained = chunk_index != nullptr && K > 1;
+    const bool constrained = chunk_index != nullptr && K > 1 && !adjusted;   // :357-360
     double *d_scores = nullptr;
     if (constrained) {
         st = C.vbx_ws.reserve(std::max(C.vbx_ws.pool_bytes, N * (size_t)K * sizeof(double) + 1024));
@@ -404,6 +439,8 @@ static int cluster_pipeline(ClusterContext &C, const float *emb, const double *r
         info->ms_assign = ms_between(C.ev[5], C.ev[6]);
         info->ms_total =
             std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+        info->was_adjusted = adjusted ? 1 : 0;
+        info->detected_clusters = detected;
     }
     return FA_OK;
 }
@@ -897,6 +934,62 @@ FA_API void fa_cluster_default_config(fa_cluster_config *cfg) {
     if (!cfg) return;
     cfg->threshold = 0.6;
     fa_vbx_default_config(&cfg->vbx);
+    cfg->num_speakers = cfg->min_speakers = cfg->max_speakers = FA_NO_VALUE;
+    cfg->reserved = 0;
+}
+
+FA_API fa_status fa_speaker_constraints_resolve(int64_t num_embeddings, int64_t num_speakers, int64_t min_speakers,
+                                                int64_t max_speakers, int64_t *resolved_min, int64_t *resolved_max) {
+    if (!resolved_min || !resolved_max) return FA_STATUS_INVALID_ARGUMENT;
+    long long lo = 0, hi = 0;
+    kmeans::resolve_constraints(num_embeddings, num_speakers, min_speakers, max_speakers, &lo, &hi);
+    *resolved_min = lo;
+    *resolved_max = hi;
+    return FA_STATUS_OK;
+}
+
+FA_API fa_status fa_kmeans_cluster(const double *emb, size_t N, size_t D, int32_t num_clusters, int32_t max_iterations,
+                                   int32_t n_init, uint64_t base_seed, int32_t *labels, double *centroids,
+                                   int32_t centroid_cap, int32_t *centroid_rows, int32_t *best_init) {
+    if (centroid_rows) *centroid_rows = 0;
+    if (best_init) *best_init = 0;
+    if (N == 0) return FA_STATUS_OK;                                  // :50-52
+    if (!emb || !labels || max_iterations < 0) return FA_STATUS_INVALID_ARGUMENT;
+    const long long rows_needed = D == 0 || num_clusters <= 0 ? 0 : std::min<long long>(num_clusters, (long long)N);
+    if (rows_needed > 0 && (!centroids || centroid_cap < rows_needed)) return FA_STATUS_OUTPUT_TOO_SMALL;
+    if (rows_needed == 0) {                                           // :53-58: dimension 0 or k <= 0 -> all zeros
+        for (size_t i = 0; i < N; ++i) labels[i] = 0;
+        return FA_STATUS_OK;
+    }
+    API_REQUIRE_DEVICE();
+    FA_GUARD_BEGIN
+    Lease lease;
+    if (lease.status != FA_OK) return (fa_status)lease.status;
+    ClusterContext &C = *lease.ctx;
+    Carver sz{nullptr};
+    sz.take<double>(N * D);
+    sz.take<double>((size_t)rows_needed * D);
+    sz.take<int>(N);
+    int st = C.reserve(sz.off + 1024, 64);
+    if (st != FA_OK) return (fa_status)st;
+    Carver c{static_cast<char *>(C.d_buf)};
+    double *d_emb = c.take<double>(N * D);
+    double *d_cent = c.take<double>((size_t)rows_needed * D);
+    int *d_labels = c.take<int>(N);
+    API_CUDA_TRY(cudaMemcpyAsync(d_emb, emb, N * D * sizeof(double), cudaMemcpyHostToDevice, C.stream));
+    long long lc = 0;
+    int rows = 0, best = 0;
+    st = kmeans::cluster_ninit_device(C.vbx_ws, d_emb, (int)N, (int)D, num_clusters, max_iterations, n_init, base_seed,
+                                      d_labels, d_cent, &rows, &best, C.stream, &lc);
+    g_launches += lc;
+    if (st != FA_OK) return (fa_status)st;
+    API_CUDA_TRY(cudaMemcpyAsync(labels, d_labels, N * sizeof(int), cudaMemcpyDeviceToHost, C.stream));
+    API_CUDA_TRY(cudaMemcpyAsync(centroids, d_cent, (size_t)rows * D * sizeof(double), cudaMemcpyDeviceToHost, C.stream));
+    API_CUDA_TRY(cudaStreamSynchronize(C.stream));
+    if (centroid_rows) *centroid_rows = rows;
+    if (best_init) *best_init = best;
+    return FA_STATUS_OK;
+    FA_GUARD_END
 }
 
 FA_API fa_status fa_vbx_refine(const double *rho, size_t T, size_t D, const double *psi, size_t psi_len,

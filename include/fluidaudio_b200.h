@@ -19,6 +19,9 @@
  *   fa_diarize_cluster   OfflineDiarizerManager.swift:270-384 (cluster(_:), clustering phase)
  *   fa_constrained_assign / fa_hungarian_solve / fa_build_chunk_assignments
  *                        ConstrainedClusterAssignment.swift:20-42, HungarianAssignment.swift:8-97, :885-911
+ *   fa_kmeans_cluster / fa_speaker_constraints_resolve
+ *                        KMeansClustering.swift:39-130,212-223, SpeakerCountConstraints.swift:27-85,
+ *                        VBxClustering.swift:685-733 (refineWithConstraints)
  *   fa_export_*          OfflineDiarizerManager.swift:913-955 (exportEmbeddings: the JSON dump of TimedEmbedding +
  *                        cluster, OfflineDiarizerTypes.swift:706-716) — the backend's on-disk input format
  */
@@ -175,9 +178,17 @@ fa_status fa_compute_centroids(const double *embeddings, size_t T, size_t dim, c
 fa_status fa_assign_embeddings(const double *embeddings, size_t N, size_t dim, const double *centroids, int32_t K,
                                int32_t *labels, double *scores);
 
+#define FA_NO_VALUE INT32_MIN   /* an absent optional count (Swift nil) in fa_cluster_config / fa_speaker_constraints_resolve */
+
 typedef struct {
     double threshold;        /* 0.6  OfflineDiarizerConfig.clusteringThreshold */
     fa_vbx_config vbx;       /* warmStartFa/Fb, VBx.maxIterations, convergenceTolerance */
+    /* OfflineDiarizerConfig.Clustering.numSpeakers / minSpeakers / maxSpeakers (OfflineDiarizerTypes.swift);
+     * FA_NO_VALUE = nil (zero and negative counts are legal inputs, the reference clamps them to 1).
+     * When the count VBx arrives at violates them the embeddings are re-clustered with K-Means (n_init 10, seeds 0..9,
+     * 100 iterations) and assigned by plain argmax (VBxClustering.swift:685-733, OfflineDiarizerManager.swift:354-375). */
+    int32_t num_speakers, min_speakers, max_speakers;
+    int32_t reserved;
 } fa_cluster_config;
 void fa_cluster_default_config(fa_cluster_config *cfg);
 
@@ -187,6 +198,8 @@ typedef struct {
     int32_t vbx_iterations;
     int32_t centroid_count;    /* K */
     float ms_normalize, ms_ahc, ms_cut, ms_vbx, ms_assign, ms_total;   /* device/host stage times */
+    int32_t was_adjusted;      /* VBxOutput.wasAdjusted: K-Means replaced the VBx clusters */
+    int32_t detected_clusters; /* VBxOutput.assignedClusterCount before the adjustment */
 } fa_cluster_info;
 
 /* OfflineDiarizerManager.cluster(_:) lines 286-375 (unconstrained argmax assignment):
@@ -215,6 +228,17 @@ fa_status fa_constrained_assign(const double *scores, size_t N, int32_t K, const
 fa_status fa_build_chunk_assignments(const int32_t *chunk_index, const int32_t *speaker_index, const int32_t *assignments,
                                      size_t N, int32_t num_chunks, int32_t num_speakers, int32_t cluster_count,
                                      int32_t *matrix);
+
+/* KMeansClustering.clusterWithCentroidsNInit (Diarizer/Offline/Clustering/KMeansClustering.swift:39-130) on raw
+ * embeddings [N x D]: labels [N], centroids (normalised space) [min(num_clusters, N) x D] -> *centroid_rows rows;
+ * *best_init = index of the winning seed.  n_init <= 1 runs the single seeded clustering (:39-92).
+ * fa_speaker_constraints_resolve = SpeakerCountConstraints.resolve (SpeakerCountConstraints.swift:27-71);
+ * FA_NO_VALUE = nil. */
+fa_status fa_kmeans_cluster(const double *embeddings, size_t N, size_t D, int32_t num_clusters, int32_t max_iterations,
+                            int32_t n_init, uint64_t base_seed, int32_t *labels, double *centroids,
+                            int32_t centroid_cap, int32_t *centroid_rows, int32_t *best_init);
+fa_status fa_speaker_constraints_resolve(int64_t num_embeddings, int64_t num_speakers, int64_t min_speakers,
+                                         int64_t max_speakers, int64_t *resolved_min, int64_t *resolved_max);
 
 /* Embedding-export files (JSON array written by the reference when OfflineDiarizerConfig.embeddingExportPath is set):
  * {chunkIndex, speakerIndex, startFrame, endFrame, startTime, endTime, embedding256[], rho128[], cluster} per entry.

@@ -97,6 +97,14 @@ def lib():
         L.oracle_linear_resample.argtypes = [_f32p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_void_p]
         L.oracle_linear_resample.restype = C.c_int64
         L.oracle_normalize_per_feature.argtypes = [_f32p, C.c_int64, C.c_int32, C.c_int64]
+        L.oracle_kmeans.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _i32p, _f64p,
+                                    C.POINTER(C.c_int32)]
+        L.oracle_kmeans.restype = C.c_int32
+        L.oracle_kmeans_ninit.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _i32p,
+                                          _f64p, C.POINTER(C.c_int32)]
+        L.oracle_kmeans_ninit.restype = C.c_int32
+        L.oracle_speaker_constraints.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
+        L.oracle_speaker_constraints.restype = None
         L.oracle_lseend_scale_cmn.argtypes = [_f32p, C.c_int64, C.c_int32, _f32p, C.POINTER(C.c_int64)]
         L.oracle_lseend_scale_cmn.restype = None
         L.oracle_transpose_tm.argtypes = [_f32p, C.c_int64, C.c_int32, _f32p]
@@ -386,12 +394,47 @@ class ClusterResult:
     vbx: VBxOutput
     centroids: np.ndarray
     training_indices: np.ndarray
+    was_adjusted: bool = False  # VBxOutput.wasAdjusted (K-Means replaced the VBx clusters)
+    detected_clusters: int = 0  # VBxOutput.assignedClusterCount
+
+
+def kmeans(emb: np.ndarray, num_clusters: int, max_iterations: int = 300, seed: int = 0):
+    """KMeansClustering.clusterWithCentroids (:39-92): (labels, centroids, loop iterations)."""
+    emb = np.ascontiguousarray(emb, np.float64)
+    n, d = emb.shape
+    labels = np.zeros(n, np.int32)
+    cents = np.zeros((max(1, min(num_clusters, n)), d), np.float64)
+    it = C.c_int32()
+    rows = lib().oracle_kmeans(emb, n, d, num_clusters, max_iterations, seed, labels, cents, C.byref(it))
+    return labels, cents[:rows].copy(), it.value
+
+
+def kmeans_ninit(emb: np.ndarray, num_clusters: int, max_iterations: int = 300, n_init: int = 10, base_seed: int = 0):
+    """KMeansClustering.clusterWithCentroidsNInit (:99-130): (labels, centroids, winning init)."""
+    emb = np.ascontiguousarray(emb, np.float64)
+    n, d = emb.shape
+    labels = np.zeros(n, np.int32)
+    cents = np.zeros((max(1, min(num_clusters, n)), d), np.float64)
+    best = C.c_int32()
+    rows = lib().oracle_kmeans_ninit(emb, n, d, num_clusters, max_iterations, n_init, base_seed, labels, cents,
+                                     C.byref(best))
+    return labels, cents[:rows].copy(), best.value
+
+
+def speaker_constraints(num_embeddings: int, num_speakers=None, min_speakers=None, max_speakers=None):
+    """SpeakerCountConstraints.resolve (:27-71): (min, max)."""
+    opt = lambda v: -2 ** 63 if v is None else int(v)
+    out = (C.c_int64 * 2)()
+    lib().oracle_speaker_constraints(num_embeddings, opt(num_speakers), opt(min_speakers), opt(max_speakers), out)
+    return int(out[0]), int(out[1])
 
 
 def diarize_cluster(emb256: np.ndarray, rho128: np.ndarray, psi: np.ndarray, threshold=0.6, Fa=0.07, Fb=0.8,
-                    max_iterations=20, epsilon=1e-4, use_ref: bool = False, chunk_indices=None) -> ClusterResult:
+                    max_iterations=20, epsilon=1e-4, use_ref: bool = False, chunk_indices=None, num_speakers=None,
+                    min_speakers=None, max_speakers=None) -> ClusterResult:
     """OfflineDiarizerManager.cluster(_:) lines 286-375.  chunk_indices=None -> plain argmax (:371-374); otherwise
-    the reference's default constrained assignment (:357-369) whenever more than one centroid exists."""
+    the reference's default constrained assignment (:357-369) whenever more than one centroid exists and the speaker
+    count was not forced.  num/min/max_speakers: VBxClustering.refineWithConstraints (:685-733)."""
     emb32 = np.ascontiguousarray(emb256, np.float32)
     feats = emb32.astype(np.float64)                      # :286  Float -> Double
     rho = np.ascontiguousarray(rho128, np.float64)
@@ -405,12 +448,22 @@ def diarize_cluster(emb256: np.ndarray, rho128: np.ndarray, psi: np.ndarray, thr
     else:
         initial = np.zeros(train.shape[0], np.int32)
     vbx = vbx_refine(train_rho, psi, initial, Fa, Fb, max_iterations, epsilon)
-    cents = compute_centroids(train, vbx, initial)
+    adjusted, detected = False, len(set(vbx.hard.tolist())) if vbx.hard.size else 0      # assignedClusterCount
+    cents = None
+    if (num_speakers is not None or min_speakers is not None or max_speakers is not None) and train_rho.size and initial.size:
+        lo, hi = speaker_constraints(train.shape[0], num_speakers, min_speakers, max_speakers)
+        if detected < lo or detected > hi:
+            target = lo if detected < lo else hi
+            km_labels, cents, _ = kmeans_ninit(train, target, 100, 10, 0)               # :715-721
+            vbx = VBxOutput(vbx.gamma, vbx.pi, km_labels, target, vbx.elbos)
+            adjusted = True                                                              # centroids used directly (:622-629)
+    if cents is None:
+        cents = compute_centroids(train, vbx, initial)
     if cents.shape[0] == 0:
         cents = feats.mean(axis=0, keepdims=True)         # computeFallbackCentroids :748-786
-    if chunk_indices is not None and cents.shape[0] > 1:
+    if chunk_indices is not None and cents.shape[0] > 1 and not adjusted:
         _, scores = assign_embeddings(feats, cents, want_scores=True)
         labels = constrained_assign(scores, chunk_indices)
     else:
         labels = assign_embeddings(feats, cents)
-    return ClusterResult(labels, initial, vbx, cents, idx)
+    return ClusterResult(labels, initial, vbx, cents, idx, adjusted, detected)

@@ -677,4 +677,182 @@ void oracle_build_chunk_assignments(const int32_t *chunk, const int32_t *speaker
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Speaker-count-constrained re-clustering.
+//   KMeansClustering.clusterWithCentroids / clusterWithCentroidsNInit   Diarizer/Offline/Clustering/KMeansClustering.swift:39-130
+//   SeededRNG (LCG)                                                     KMeansClustering.swift:212-223
+//   SpeakerCountConstraints.resolve / needsAdjustment / targetCount     SpeakerCountConstraints.swift:27-85
+// Third-party semantics this depends on and that are NOT in /root/reference: the Swift standard library's
+// `MutableCollection.shuffle(using:)`, `Collection.randomElement(using:)`, `Int.random(in:using:)` and
+// `RandomNumberGenerator.next(upperBound:)` (swift/stdlib/public/core/{CollectionAlgorithms,Random,Integers}.swift,
+// Swift 5.9+/6.x as required by the package's tools version).  Published algorithm, restated here:
+//   next(upperBound: u)  -- Lemire's nearly-divisionless method on the full-width product random * u, rejecting while
+//                           low < (0 &- u) % u, result = high word;
+//   Int.random(in: 0..<n) -- next(upperBound: UInt(n));
+//   shuffle               -- for amount = count, count-1, .. 2: swap(current, current + random(0..<amount)), advance;
+//   randomElement         -- self[random(0..<count)].
+// No Swift toolchain here: this part of the oracle is "parity unpinned" beyond the reference's own seeded
+// determinism tests (KMeansClusteringTests.swift), which it satisfies by construction.
+struct oracle_lcg {
+    uint64_t state;
+    uint64_t next() {
+        state = state * 6364136223846793005ull + 1442695040888963407ull;
+        return state;
+    }
+    uint64_t next_below(uint64_t upper) {
+        unsigned __int128 m = (unsigned __int128)next() * upper;
+        if ((uint64_t)m < upper) {
+            const uint64_t t = (0 - upper) % upper;
+            while ((uint64_t)m < t) m = (unsigned __int128)next() * upper;
+        }
+        return (uint64_t)(m >> 64);
+    }
+};
+
+static double oracle_sqdist(const double *a, const double *b, int64_t d) {   // vDSP_vsubD + vDSP_svesqD (:178-185)
+    double s = 0.0;
+    for (int64_t k = 0; k < d; ++k) {
+        const double t = a[k] - b[k];
+        s += t * t;
+    }
+    return s;
+}
+
+// normalizeEmbeddings (:133-145): rows with norm <= 1e-10 are kept as they are
+void oracle_kmeans_normalize(const double *x, int64_t n, int64_t d, double *out) {
+    for (int64_t i = 0; i < n; ++i) {
+        double s = 0.0;
+        for (int64_t k = 0; k < d; ++k) s += x[i * d + k] * x[i * d + k];
+        const double norm = std::sqrt(s);
+        if (norm > 1e-10) {
+            const double inv = 1.0 / norm;
+            for (int64_t k = 0; k < d; ++k) out[i * d + k] = x[i * d + k] * inv;
+        } else {
+            for (int64_t k = 0; k < d; ++k) out[i * d + k] = x[i * d + k];
+        }
+    }
+}
+
+// clusterWithCentroids (:39-92).  Returns the number of centroid rows written (k, or n when n <= k, or 0).
+int32_t oracle_kmeans(const double *emb, int64_t n, int64_t d, int32_t num_clusters, int32_t max_iterations, uint64_t seed,
+                      int32_t *labels, double *centroids, int32_t *iterations_out) {
+    if (iterations_out) *iterations_out = 0;
+    if (n <= 0) return 0;
+    if (d <= 0) {
+        for (int64_t i = 0; i < n; ++i) labels[i] = 0;
+        return 0;
+    }
+    const int64_t k = std::min<int64_t>(num_clusters, n);
+    if (k <= 0) {
+        for (int64_t i = 0; i < n; ++i) labels[i] = 0;
+        return 0;
+    }
+    if (n <= k) {                                            // :60-62: identity labels, centroids = raw embeddings
+        for (int64_t i = 0; i < n; ++i) labels[i] = (int32_t)i;
+        std::memcpy(centroids, emb, sizeof(double) * n * d);
+        return (int32_t)n;
+    }
+    oracle_lcg rng{seed};
+    std::vector<double> x((size_t)n * d);
+    oracle_kmeans_normalize(emb, n, d, x.data());
+    std::vector<int64_t> idx(n);
+    for (int64_t i = 0; i < n; ++i) idx[i] = i;
+    {   // indices.shuffle(using:)
+        int64_t amount = n, cur = 0;
+        while (amount > 1) {
+            const int64_t r = (int64_t)rng.next_below((uint64_t)amount);
+            amount -= 1;
+            std::swap(idx[cur], idx[cur + r]);
+            cur += 1;
+        }
+    }
+    std::vector<double> c((size_t)k * d);
+    for (int64_t j = 0; j < k; ++j) std::memcpy(&c[j * d], &x[idx[j] * d], sizeof(double) * d);
+    std::vector<int32_t> assign(n, 0), fresh(n);
+    std::vector<double> sums((size_t)k * d);
+    std::vector<int64_t> counts(k);
+    int it = 0;
+    for (; it < max_iterations; ++it) {
+        for (int64_t i = 0; i < n; ++i) {                    // assignToCentroids (:161-176): strict <, first minimum wins
+            int32_t best = 0;
+            double bd = std::numeric_limits<double>::max();
+            for (int64_t j = 0; j < k; ++j) {
+                const double dist = oracle_sqdist(&x[i * d], &c[j * d], d);
+                if (dist < bd) {
+                    bd = dist;
+                    best = (int32_t)j;
+                }
+            }
+            fresh[i] = best;
+        }
+        if (fresh == assign) break;
+        assign = fresh;
+        std::fill(sums.begin(), sums.end(), 0.0);            // updateCentroids (:187-210): sums in index order
+        std::fill(counts.begin(), counts.end(), 0);
+        for (int64_t i = 0; i < n; ++i) {
+            const int32_t cl = assign[i];
+            counts[cl] += 1;
+            for (int64_t q = 0; q < d; ++q) sums[cl * d + q] += x[i * d + q];
+        }
+        for (int64_t j = 0; j < k; ++j) {
+            if (counts[j] > 0) {
+                const double inv = 1.0 / (double)counts[j];
+                for (int64_t q = 0; q < d; ++q) c[j * d + q] = sums[j * d + q] * inv;
+            } else {                                          // empty cluster: embeddings.randomElement(using:)
+                const int64_t r = (int64_t)rng.next_below((uint64_t)n);
+                std::memcpy(&c[j * d], &x[r * d], sizeof(double) * d);
+            }
+        }
+    }
+    if (iterations_out) *iterations_out = it;
+    for (int64_t i = 0; i < n; ++i) labels[i] = assign[i];
+    std::memcpy(centroids, c.data(), sizeof(double) * k * d);
+    return (int32_t)k;
+}
+
+// clusterWithCentroidsNInit (:99-130): seeds base, base+1, ...; the lowest inertia wins, the first on ties
+int32_t oracle_kmeans_ninit(const double *emb, int64_t n, int64_t d, int32_t num_clusters, int32_t max_iterations,
+                            int32_t n_init, uint64_t base_seed, int32_t *labels, double *centroids, int32_t *best_init) {
+    if (best_init) *best_init = 0;
+    if (!(n > num_clusters && n_init > 1))
+        return oracle_kmeans(emb, n, d, num_clusters, max_iterations, base_seed, labels, centroids, nullptr);
+    std::vector<double> x((size_t)n * d);
+    oracle_kmeans_normalize(emb, n, d, x.data());
+    const int64_t kmax = std::max<int64_t>(1, std::min<int64_t>(num_clusters, n));
+    std::vector<int32_t> lab(n);
+    std::vector<double> cen((size_t)kmax * d);
+    double best = std::numeric_limits<double>::max();
+    int32_t best_k = -1;
+    for (int32_t i = 0; i < n_init; ++i) {
+        const int32_t k = oracle_kmeans(emb, n, d, num_clusters, max_iterations, base_seed + (uint64_t)i, lab.data(),
+                                        cen.data(), nullptr);
+        double inertia = 0.0;
+        for (int64_t q = 0; q < n; ++q)
+            if (lab[q] >= 0 && lab[q] < k) inertia += oracle_sqdist(&x[q * d], &cen[(int64_t)lab[q] * d], d);
+        if (inertia < best) {
+            best = inertia;
+            best_k = k;
+            std::memcpy(labels, lab.data(), sizeof(int32_t) * n);
+            std::memcpy(centroids, cen.data(), sizeof(double) * (size_t)k * d);
+            if (best_init) *best_init = i;
+        }
+    }
+    if (best_k < 0) return oracle_kmeans(emb, n, d, num_clusters, max_iterations, base_seed, labels, centroids, nullptr);
+    return best_k;
+}
+
+// SpeakerCountConstraints.resolve (:27-71); absent options (nil) are passed as INT64_MIN.  out = {min, max}.
+void oracle_speaker_constraints(int64_t num_embeddings, int64_t num_speakers, int64_t min_speakers, int64_t max_speakers,
+                                int64_t *out) {
+    auto opt = [](int64_t v) { return v != INT64_MIN; };
+    int64_t lo = opt(num_speakers) ? num_speakers : (opt(min_speakers) ? min_speakers : 1);
+    lo = std::max<int64_t>(1, std::min(num_embeddings, lo));
+    int64_t hi = opt(num_speakers) ? num_speakers : (opt(max_speakers) ? max_speakers : num_embeddings);
+    hi = std::max<int64_t>(1, std::min(num_embeddings, hi));
+    if (lo > hi) lo = hi;
+    out[0] = lo;
+    out[1] = hi;
+}
+
 } // extern "C"

@@ -462,3 +462,46 @@ def test_mel_adapters_match_oracle(gpu_lib, oracle):
         assert np.abs(fe.cmn_mean - mean).max() < 1e-4
     fe.reset()
     assert fe.cmn_count == 0 and not fe.cmn_mean.any()
+
+
+def test_kmeans_matches_oracle(gpu_lib, oracle):
+    """KMeansClustering on the GPU — labels and the winning seed exact, centroids bit-identical
+    (same summation order as the oracle's restatement)."""
+    six = np.array([[1.0, 0.0], [1.1, 0.1], [0.0, 1.0], [0.1, 1.1], [-1.0, 0.0], [-0.9, 0.1]])
+    for emb, k, iters, seed in ((six, 3, 100, 42), (six, 1, 100, 42), (six[:2], 5, 100, 42), (six, 3, 300, 12345),
+                                (np.repeat(np.eye(3), 4, axis=0), 3, 50, 1)):
+        lab, cen = cl.KMeansClustering.cluster_with_centroids(emb, k, iters, seed)
+        ol, oc, _ = oracle.kmeans(emb, k, iters, seed)
+        assert np.array_equal(lab, ol) and cen.tobytes() == oc.tobytes()
+    for n, d, k, seed in ((500, 64, 5, 9), (2000, 256, 8, 4), (300, 256, 12, 2)):
+        emb, _ = synth.speaker_embeddings(n, d, min(k, 8), seed=seed)
+        x = emb.astype(np.float64)
+        lab, cen, best = cl.KMeansClustering.cluster_with_centroids_n_init(x, k, 100, 10, 0)
+        ol, oc, ob = oracle.kmeans_ninit(x, k, 100, 10, 0)
+        assert best == ob and np.array_equal(lab, ol) and cen.tobytes() == oc.tobytes()
+        lab1, cen1 = cl.KMeansClustering.cluster_with_centroids(x, k, 3, 7)           # stopped by max_iterations
+        ol1, oc1, _ = oracle.kmeans(x, k, 3, 7)
+        assert np.array_equal(lab1, ol1) and cen1.tobytes() == oc1.tobytes()
+
+
+def test_speaker_count_constraints_pipeline_matches_oracle(gpu_lib, oracle):
+    """refineWithConstraints inside the pipeline: forced counts re-cluster with K-Means and skip the constrained
+    assignment; satisfied constraints change nothing."""
+    rng = np.random.default_rng(5)
+    emb, _ = synth.speaker_embeddings(1200, 256, 5, seed=13)
+    rho, psi = synth.synthetic_plda(emb)
+    chunk = np.sort(rng.integers(0, 600, 1200)).astype(np.int32)
+    base = cl.OfflineClusterer(psi=psi).cluster(emb, rho)
+    detected = base.info["detected_clusters"]
+    assert base.info["was_adjusted"] == 0 and detected >= 1
+    for kw in ({"exactly": detected + 2}, {"min": detected + 1, "max": detected + 4}, {"max": max(1, detected - 1)},
+               {"min": 1, "max": detected + 3}, {"exactly": -5}):
+        cfg = cl.OfflineDiarizerConfig().with_speakers(**kw)
+        c = cfg.clustering
+        for chunks in (None, chunk):
+            r = cl.OfflineClusterer(cfg, psi=psi).cluster(emb, rho, chunk_indices=chunks)
+            o = oracle.diarize_cluster(emb, rho, psi, use_ref=oracle.ref_available(), chunk_indices=chunks,
+                                       num_speakers=c.num_speakers, min_speakers=c.min_speakers, max_speakers=c.max_speakers)
+            assert bool(r.info["was_adjusted"]) == o.was_adjusted and r.info["detected_clusters"] == o.detected_clusters
+            assert np.array_equal(r.labels, o.labels), kw
+            assert r.centroids.shape == o.centroids.shape and np.abs(r.centroids - o.centroids).max() < 1e-12

@@ -337,3 +337,24 @@ def test_same_partition_helper():
     assert not same_partition([0, 1], [0, 0])
     assert not same_partition([0, -2], [0, 1])
     assert not same_partition([0, 1], [0, 1, 2])
+
+
+def test_speaker_constraints_host_function(lib, oracle):
+    """fa_speaker_constraints_resolve needs no device; same table as SpeakerCountConstraintsTests.swift."""
+    from fluidaudio_b200.clustering import OfflineDiarizerConfig, SpeakerCountConstraints
+    cases = [(100, None, None, None), (100, 3, 1, 10), (5, None, 2, 20), (100, None, 10, 5), (100, 0, None, None),
+             (100, -5, None, None), (100, None, 0, 5), (100, None, -3, 5), (1, None, None, None), (7, -1, None, None)]
+    for n, num, lo, hi in cases:
+        got = SpeakerCountConstraints.resolve(n, num, lo, hi)
+        assert (got.min_speakers, got.max_speakers) == oracle.speaker_constraints(n, num, lo, hi)
+    c = SpeakerCountConstraints.resolve(100, None, 5, 10)
+    assert c.needs_adjustment(3) and c.target_count(3) == 5 and c.num_speakers is None    # :104-113
+    c = SpeakerCountConstraints.resolve(100, None, 2, 5)
+    assert c.needs_adjustment(8) and c.target_count(8) == 5                               # :115-124
+    assert not c.needs_adjustment(3) and c.target_count(3) == 3                           # :126-135
+    assert SpeakerCountConstraints.resolve(100, 3, 1, 10).num_speakers == 3
+    cfg = OfflineDiarizerConfig().with_speakers(min=2, max=4)
+    cc = cfg._c_cluster()
+    assert (cc.num_speakers, cc.min_speakers, cc.max_speakers) == (_lib.NO_VALUE, 2, 4)
+    cc = cfg.with_speakers(exactly=3)._c_cluster()
+    assert (cc.num_speakers, cc.min_speakers, cc.max_speakers) == (3, _lib.NO_VALUE, _lib.NO_VALUE)

@@ -372,3 +372,82 @@ def test_adapter_restatements_against_numpy(oracle):
     assert np.abs(got - (y - cum)).max() < 1e-4
     assert np.abs(mean2 - cum[-1]).max() < 1e-4
     assert not got[0].any()                                            # first frame minus its own mean
+
+
+# ---- K-Means re-clustering + speaker-count constraints ---------------------------------------------
+class _SwiftLCG:
+    """KMeansClustering.SeededRNG (:212-223) + the Swift stdlib's next(upperBound:) / Double.random(in: a...b),
+    restated independently of the oracle to generate the reference test's inputs."""
+    def __init__(self, seed):
+        self.state = seed & (2 ** 64 - 1)
+
+    def next(self):
+        self.state = (self.state * 6364136223846793005 + 1442695040888963407) & (2 ** 64 - 1)
+        return self.state
+
+    def next_below(self, upper):
+        m = self.next() * upper
+        if (m & (2 ** 64 - 1)) < upper:
+            t = (2 ** 64 - upper) % upper
+            while (m & (2 ** 64 - 1)) < t:
+                m = self.next() * upper
+        return m >> 64
+
+    def double_closed(self, lo, hi):
+        rand = self.next_below((1 << 53) + 1)
+        if rand == (1 << 53):
+            return hi
+        return (hi - lo) * (rand * 2.0 ** -53) + lo
+
+
+def test_kmeans_reference_tests(oracle):
+    """Tests/FluidAudioTests/Diarizer/Clustering/KMeansClusteringTests.swift, case by case."""
+    six = np.array([[1.0, 0.0], [1.1, 0.1], [0.0, 1.0], [0.1, 1.1], [-1.0, 0.0], [-0.9, 0.1]])
+    lab, cen, _ = oracle.kmeans(six, 3, 100, 42)                                     # :10-31
+    assert lab.size == 6 and len(set(lab.tolist())) == 3
+    lab, _, _ = oracle.kmeans(np.array([[1.0, 0.0], [1.1, 0.1], [0.9, 0.2]]), 1, 100, 42)   # :33-49
+    assert lab.tolist() == [0, 0, 0]
+    lab, cen, _ = oracle.kmeans(np.array([[1.0, 0.0], [0.0, 1.0]]), 5, 100, 42)      # :51-67
+    assert lab.tolist() == [0, 1] and np.array_equal(cen, [[1.0, 0.0], [0.0, 1.0]])
+    lab, cen, _ = oracle.kmeans(np.array([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0], [0.0, 1.0]]), 2, 100, 42)   # :69-86
+    assert cen.shape[0] == 2 and lab.size == 4
+    a = oracle.kmeans(six, 3, 300, 12345)[0]                                         # :90-109
+    assert np.array_equal(a, oracle.kmeans(six, 3, 300, 12345)[0])
+    rng = _SwiftLCG(42)                                                              # :113-131
+    emb = np.array([[rng.double_closed(-1.0, 1.0) for _ in range(192)] for _ in range(20)])
+    lab, _, _ = oracle.kmeans(emb, 3, 100, 42)
+    assert lab.size == 20 and len(set(lab.tolist())) == 3
+
+
+def test_kmeans_restatement_properties(oracle):
+    from fluidaudio_b200 import synth
+    emb, who = synth.speaker_embeddings(500, 64, 5, seed=9)
+    x = emb.astype(np.float64)
+    lab, cen, it = oracle.kmeans(x, 5, 100, 3)
+    xn = x / np.linalg.norm(x, axis=1, keepdims=True)
+    d = ((xn[:, None, :] - cen[None]) ** 2).sum(-1)
+    assert np.array_equal(lab, d.argmin(1))                                          # fixed point of the assignment step
+    for j in range(5):                                                               # centroids = means of their members
+        if (lab == j).any():
+            assert np.abs(cen[j] - xn[lab == j].mean(0)).max() < 1e-12
+    best_lab, best_cen, best = oracle.kmeans_ninit(x, 5, 100, 10, 0)
+    inertias = []
+    for s in range(10):
+        l, c, _ = oracle.kmeans(x, 5, 100, s)
+        inertias.append(((xn - c[l]) ** 2).sum())
+    assert best == int(np.argmin(inertias)) and np.array_equal(best_lab, oracle.kmeans(x, 5, 100, best)[0])
+    # an empty cluster is re-seeded from a data point: duplicates force it
+    dup = np.repeat(np.eye(3), 4, axis=0)
+    l, c, _ = oracle.kmeans(dup, 3, 50, 1)
+    assert len(set(l.tolist())) == 3
+
+
+def test_speaker_constraints_reference_tests(oracle):
+    """Tests/FluidAudioTests/Diarizer/Offline/SpeakerCountConstraintsTests.swift (resolve; -> (min, max))."""
+    r = oracle.speaker_constraints
+    assert r(100) == (1, 100)                            # :10-20
+    assert r(100, 3, 1, 10) == (3, 3)                    # :22-32
+    assert r(5, None, 2, 20) == (2, 5)                   # :34-43
+    assert r(100, None, 10, 5) == (5, 5)                 # :47-56
+    assert r(100, 0) == (1, 1) and r(100, -5) == (1, 1)  # :60-80
+    assert r(100, None, 0, 5)[0] == 1 and r(100, None, -3, 5)[0] == 1   # :82-100
