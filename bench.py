@@ -242,6 +242,46 @@ def bench_cluster(args, dist, steps=None):
     return out, (emb, rho, psi, res)
 
 
+def bench_batched_shares():
+    """Per-GPU shares of BASELINE configs[3] and configs[4] (secondary numbers, N = 1 only): 64 clips x 30 s through
+    fa_mel_compute_batch from pinned host memory, and 8 meetings x 5 000 x 256 through fa_diarize_cluster_batch
+    (three meetings side by side on disjoint SM partitions)."""
+    from fluidaudio_b200 import _lib, synth
+    from fluidaudio_b200.clustering import OfflineClusterer
+    from fluidaudio_b200.mel import AudioMelSpectrogram
+    out = {}
+    mel = AudioMelSpectrogram(n_mels=N_MELS)
+    n_clip, count = 480_000, 64
+    pin_in = _lib.PinnedArray((count * n_clip,), np.float32)
+    for i in range(count):
+        pin_in.array[i * n_clip:(i + 1) * n_clip] = synth.tone_noise_audio(n_clip, seed=i)
+    offsets = np.arange(count + 1, dtype=np.int64) * n_clip
+    T = mel.frame_count(n_clip)
+    pin_out = _lib.PinnedArray((count * T * N_MELS,), np.float32)
+    for _ in range(2):
+        mel.compute_batch(None, packed_audio=pin_in.array, offsets=offsets, out=pin_out.array)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        mel.compute_batch(None, packed_audio=pin_in.array, offsets=offsets, out=pin_out.array)
+    dt = (time.perf_counter() - t0) / reps
+    out["mel_c4_share"] = {"workload": "64 clips x 30 s (configs[3] / 8 GPUs), pinned host buffers, fa_mel_compute_batch",
+                           "e2e_ms": dt * 1e3, "e2e_audio_hours_per_s": count * 30 / 3600 / dt}
+    sets = [synth.speaker_embeddings(5000, CLUSTER_D, 4, weights=(0.4, 0.3, 0.2, 0.1), sigma=0.02, seed=m)[0] for m in range(8)]
+    emb = np.concatenate(sets)
+    rho, psi = synth.synthetic_plda(emb, CLUSTER_R)
+    offs = np.arange(9, dtype=np.int64) * 5000
+    c = OfflineClusterer(psi=psi)
+    c.cluster_batch(emb, rho, offs)
+    t0 = time.perf_counter()
+    labels, infos = c.cluster_batch(emb, rho, offs)
+    dt = time.perf_counter() - t0
+    out["cluster_c5_share"] = {"workload": "8 meetings x 5 000 x 256 (configs[4] / 8 GPUs), fa_diarize_cluster_batch",
+                               "e2e_ms": dt * 1e3, "e2e_embeddings_per_s": emb.shape[0] / dt,
+                               "ahc_ms_per_meeting": [round(i["ms_ahc"], 2) for i in infos]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -306,6 +346,8 @@ def main():
         line, cluster_data = bench_cluster(args, dist)
         audio = None
 
+    if dist.is_root and world == 1 and args.workload == "mel" and not args.no_cpu_baseline:
+        line["batched_shares"] = bench_batched_shares()
     if dist.is_root and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         if args.workload == "mel":

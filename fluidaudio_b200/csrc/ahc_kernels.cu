@@ -473,9 +473,9 @@ __device__ void ahc_master(const Problem &P, int W, unsigned char *sm) {
             }
             __syncwarp();
             const int depth = path_depth;
-            const int sa_all = __shfl_sync(full, sa, 0);
             T = __shfl_sync(full, T, 0);
-            const double old_key = key[sa_all];
+            // lane 0 alone touches the root's key (it rewrites it below): read once, broadcast
+            const double old_key = __shfl_sync(full, lane == 0 ? key[sa] : 0.0, 0);
             // levels 1..m move up one position, the root element lands at level m
             const bool goes_below = lane >= 1 && lane <= depth && path_key[lane] < d;
             const unsigned below = __ballot_sync(full, goes_below) | 1u;   // bit 0 set so that ffs(~below) = m + 2
@@ -913,6 +913,17 @@ size_t master_smem_bytes(int N, int level) {
     return b;
 }
 } // namespace
+
+// Worker CTAs a problem needs to keep every node vector in shared memory (the fast placement), or 0 if a single CTA
+// cannot hold even one vector.  Mirrors the sizing in linkage_device.
+int resident_workers_needed(int N, int D) {
+    const size_t smem_cap = 227 * 1024 - 2048;
+    const size_t worker_fixed = 3 * sizeof(double) * (size_t)((D + 1) & ~1) + 2 * sizeof(double) * (kMergeThreads / 32) + 64;
+    if (worker_fixed + sizeof(double) * D > smem_cap) return 0;
+    const int cap_slots = (int)std::min<size_t>(kMergeThreads, (smem_cap - worker_fixed) / (sizeof(double) * (size_t)D));
+    if (cap_slots < 1) return 0;
+    return (N + cap_slots - 1) / cap_slots;
+}
 
 int Solver::ensure_pool(int N, int D) {
     const int Ns = (N + 31) & ~31;

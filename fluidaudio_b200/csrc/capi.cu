@@ -1225,7 +1225,15 @@ FA_API fa_status fa_diarize_cluster_batch(const float *emb256, const double *rho
     API_CUDA_TRY(cudaGetDevice(&dev));
     cudaDeviceProp prop;
     API_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-    const int lanes = std::max(1, std::min(set_count, 4));
+    // Concurrency: as many sets at a time as still leaves each of them enough SMs to keep its node vectors in shared
+    // memory (the merge loop is ~3x slower when they are streamed from L2): 5 000 x 256 needs 46 workers + 1 master,
+    // so three sets run side by side on 148 SMs; small sets run four at a time.
+    long long n_max = 0;
+    for (int m = 0; m < set_count; ++m) n_max = std::max<long long>(n_max, set_offsets[m + 1] - set_offsets[m]);
+    int lanes = std::max(1, std::min(set_count, 4));
+    const int need = ahc::resident_workers_needed((int)std::min<long long>(n_max, INT32_MAX), (int)emb_dim);
+    if (need > 0 && need + 1 <= prop.multiProcessorCount)
+        lanes = std::max(1, std::min(lanes, prop.multiProcessorCount / (need + 1)));
     const int worker_limit = lanes == 1 ? 0 : std::max(1, prop.multiProcessorCount / lanes - 1);
     std::atomic<int> next{0};
     std::vector<int> status(lanes, FA_OK);
