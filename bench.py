@@ -334,6 +334,8 @@ def main():
     if _lib.device_count() < 1:
         raise SystemExit("bench.py needs a B200: " + "no sm_100a device visible (there is no CPU fallback)")
     _lib.set_device(dist.local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = sharding.bind_to_gpu_numa(dist.local_rank)
 
     if args.workload == "mel":
         line, audio = bench_mel(args, dist)
@@ -348,6 +350,7 @@ def main():
 
     if dist.is_root and world == 1 and args.workload == "mel" and not args.no_cpu_baseline:
         line["batched_shares"] = bench_batched_shares()
+    os.sched_setaffinity(0, all_cpus)      # the CPU baseline may use every host core again
     if dist.is_root and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         if args.workload == "mel":
@@ -371,6 +374,7 @@ def main():
                                     "sample": f"the full 10 000 x 256 problem once, {cdt:.1f} s"}
             line["labels_equal_cpu"] = bool(np.array_equal(res.labels, ores.labels))
 
+    line["host_binding"] = numa
     line.update({"n_gpus": dist.world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
                  "scaling": "weak", "vs_baseline": None, "data": "synthetic"})
     if dist.is_root:
