@@ -93,17 +93,31 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ CPU arms
 def cpu_mel(audio: np.ndarray, threads: int, repeats: int = 1):
     """Oracle port of AudioMelSpectrogram on `threads` host threads: the audio cut into 30 s clips, every clip
-    processed `repeats` times, each thread working through its own share of the clips (one task per thread)."""
+    processed `repeats` times, each thread working through its own share of the clips with its own output buffer
+    (one AudioMelSpectrogram-like instance per thread; ctypes releases the GIL inside the C++ call)."""
+    import ctypes as C
     from oracle import oracle as O
+    L = O.lib()
+    L.oracle_tune_allocator()
     cfg = O.mel_config(n_mels=N_MELS)
     clip = 480_000
-    pieces = [audio[i:i + clip] for i in range(0, audio.size, clip)] * repeats
+    pieces = [np.ascontiguousarray(audio[i:i + clip]) for i in range(0, audio.size, clip)] * repeats
     shares = [pieces[t::threads] for t in range(threads)]
     shares = [s for s in shares if s]
     O.mel_flat_transposed(cfg, pieces[0][:16000])
+    ml0, nf0 = C.c_int64(), C.c_int64()
+    cap = max(int(L.oracle_mel_compute_flat_transposed(C.byref(cfg), p.ctypes.data, p.size, 0.0, 0, -1, None, 0,
+                                                       C.byref(ml0), C.byref(nf0))) for p in {p.size: p for p in pieces}.values())
 
     def work(share):
-        return sum(O.mel_flat_transposed(cfg, p)[1] for p in share)
+        out = np.empty(cap, np.float32)
+        ml, nf = C.c_int64(), C.c_int64()
+        frames = 0
+        for p in share:
+            L.oracle_mel_compute_flat_transposed(C.byref(cfg), p.ctypes.data, p.size, 0.0, 0, -1, out.ctypes.data, cap,
+                                                 C.byref(ml), C.byref(nf))
+            frames += ml.value
+        return frames
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(len(shares)) as ex:

@@ -8,6 +8,7 @@
 //       Sources/FluidAudio/ASR/Parakeet/Streaming/Nemotron/NemotronMelExtractor.swift:44-67  [T x M] -> [1,M,T]
 
 #include <cmath>
+#include <malloc.h>
 #include <cstdint>
 
 extern "C" {
@@ -91,6 +92,15 @@ void oracle_lseend_scale_cmn(float *x, int64_t frames, int32_t n_mels, float *cm
         }
     }
     *cmn_count = count;
+}
+
+// Benchmark hygiene for the multi-threaded CPU baseline (bench.py): keep multi-megabyte scratch vectors on the
+// per-thread heaps instead of mmap/munmap-ing them on every call, which serialises 64 threads on the process's
+// address-space lock and on page faults.  Has no effect on results.
+void oracle_tune_allocator(void) {
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_TOP_PAD, 64 << 20);
 }
 
 // time-major [T x M] -> mel-major [M x T]
