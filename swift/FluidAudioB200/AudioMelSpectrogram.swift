@@ -87,3 +87,35 @@ public final class AudioMelSpectrogram {
         return (0..<nMels).map { Array(flat[($0 * bins)..<(($0 + 1) * bins)]) }
     }
 }
+
+
+// MARK: - Callers directly behind AudioMelSpectrogram, post-processing on the GPU
+
+/// Body of UnifiedMelExtractor.features(window:validCount:) (ASR/Parakeet/Unified/UnifiedMelExtractor.swift:52-86):
+/// returns the packed [nMels x totalFrames] floats and the valid frame count; the caller wraps them in MLMultiArrays.
+func unifiedMelFeatures(handle: OpaquePointer, window: [Float], validCount: Int, nMels: Int) throws -> (mel: [Float], validFrames: Int32) {
+    let totalFrames = window.count / 160 + 1
+    var out = [Float](repeating: 0, count: nMels * totalFrames)
+    var frames: Int64 = 0
+    var valid: Int32 = 0
+    let status = fa_mel_unified_features(handle, window, window.count, validCount, &out, out.count, &frames, &valid)
+    guard status == FA_STATUS_OK else {
+        throw NSError(domain: "fluidaudio_b200", code: Int(status.rawValue),
+                      userInfo: [NSLocalizedDescriptionKey: String(cString: fa_last_error())])
+    }
+    return (out, valid)
+}
+
+/// Replacement for the arithmetic of LSEENDPreprocessor.processAudioQueue (Diarizer/LS-EEND/LSEENDPreprocessor.swift:
+/// 249-283); `cmnMean` / `cmnCount` are the preprocessor's own stored properties.
+func lseendMelFeatures(handle: OpaquePointer, audioChunk: [Float], nMels: Int, cmnMean: inout [Float], cmnCount: inout Int64) throws -> [Float] {
+    let frames = max(0, (audioChunk.count - 512) / 160 + 1)
+    var out = [Float](repeating: 0, count: max(frames, 1) * nMels)
+    var produced: Int64 = 0
+    let status = fa_mel_lseend_features(handle, audioChunk, audioChunk.count, &cmnMean, &cmnCount, &out, out.count, &produced)
+    guard status == FA_STATUS_OK else {
+        throw NSError(domain: "fluidaudio_b200", code: Int(status.rawValue),
+                      userInfo: [NSLocalizedDescriptionKey: String(cString: fa_last_error())])
+    }
+    return Array(out.prefix(Int(produced) * nMels))
+}
