@@ -147,72 +147,95 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
         }
     };
 
+    // pre-emphasis of one tile from its raw buffer into ptile (zero outside [0, n))
+    auto preemphasize = [&](const TileGeom &g, const MelUnit &u, const float *raw) {
+        const float a = P.preemph;
+        const bool interior = g.a0 >= 1 && g.a0 - 1 >= g.gs && g.a0 + P.pt_len <= g.ge && g.a0 + P.pt_len <= u.n;
+        if (interior) {
+            // every sample of the tile and its predecessor came through the bulk copy (conflict-free, unit stride)
+            const float *src = raw + (g.a0 - g.base);   // src[t] = x(a0 + t), src[-1] valid
+            if (((g.a0 - g.base) & 3) == 0 && (P.pt_len & 3) == 0) {   // 16-byte aligned rows: four samples per step
+                const float4 *s4 = reinterpret_cast<const float4 *>(src);
+                float4 *d4 = reinterpret_cast<float4 *>(ptile);
+                for (int q = tid; q < (P.pt_len >> 2); q += kWarps * 32) {
+                    const float4 x = s4[q];
+                    float4 y = x;
+                    if (a != 0.0f) {
+                        y.x = preemph_rest(x.x, src[4 * q - 1], a);
+                        y.y = preemph_rest(x.y, x.x, a);
+                        y.z = preemph_rest(x.z, x.y, a);
+                        y.w = preemph_rest(x.w, x.z, a);
+                    }
+                    d4[q] = y;
+                }
+            } else if (a == 0.0f) {
+                for (int t = tid; t < P.pt_len; t += kWarps * 32) ptile[t] = src[t];
+            } else {
+                for (int t = tid; t < P.pt_len; t += kWarps * 32) ptile[t] = preemph_rest(src[t], src[t - 1], a);
+            }
+        } else {
+            const float *gaudio = P.audio + u.audio_off;
+            auto sample = [&](long long i) -> float {   // x(i) for -1 <= i < n
+                if (i >= g.gs && i < g.ge) return raw[i - g.base];
+                if (i < 0) return u.last;
+                return __ldg(gaudio + i);
+            };
+            for (int t = tid; t < P.pt_len; t += kWarps * 32) {
+                const long long i = g.a0 + t;
+                float v = 0.0f;
+                if (i >= 0 && i < u.n) {
+                    const float x = sample(i);
+                    if (a == 0.0f) v = x;
+                    else if (i == 0) v = preemph_first(x, u.last, a);
+                    else v = preemph_rest(x, sample(i - 1), a);
+                }
+                ptile[t] = v;
+            }
+        }
+    };
+    // time-major tile is contiguous in HBM: nf rows of n_mels floats; flat, fully coalesced copy out of otile
+    auto copy_out = [&](float *dst, int total) {
+        if ((P.n_mels & 3) == 0) {   // rows are whole float4s and dst is 64-byte aligned (f0 is a multiple of 16)
+            float4 *d4 = reinterpret_cast<float4 *>(dst);
+            for (int q = tid; q < (total >> 2); q += kWarps * 32) {
+                const int e = 4 * q;
+                const float *src = otile + e + (int)__umulhi((unsigned)e, P.inv_n_mels);   // + row: stride n_mels + 1
+                d4[q] = make_float4(src[0], src[1], src[2], src[3]);
+            }
+        } else {
+            for (int idx = tid; idx < total; idx += kWarps * 32) {
+                const int fi = (int)__umulhi((unsigned)idx, P.inv_n_mels);   // idx / n_mels (exact for idx < 2^16)
+                dst[idx] = otile[idx + fi];                                  // padded row stride n_mels + 1
+            }
+        }
+    };
+
+    // Software pipeline over the CTA's tiles, two block barriers per tile:
+    //   phase A(i): copy-out of tile i-1 (otile -> HBM)  +  FFT of tile i (ptile -> power)
+    //   phase B(i): mel + log of tile i (power -> otile)  +  pre-emphasis of tile i+1 (raw -> ptile), TMA for tile i+2
+    // The bulk copy of a tile is issued two phases B ahead of its use, its raw buffer was last read one phase B earlier.
+    const int first = blockIdx.x, stride = gridDim.x;
+    if (first >= P.total_tiles) return;
+    if (tid == 0) {
+        issue(first, 0);
+        if (first + stride < P.total_tiles) issue(first + stride, 1);
+    }
+    {
+        const TileGeom g0 = tile_geom(P, first);
+        const MelUnit u0 = P.units[g0.unit];
+        mbar_wait(&bars[0], 0);
+        preemphasize(g0, u0, raw0);
+    }
+    __syncthreads();
+    float *pending_dst = nullptr;
+    int pending_total = 0;
     int it = 0;
-    if (tid == 0 && (int)blockIdx.x < P.total_tiles) issue(blockIdx.x, 0);
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-        const int buf_i = it & 1;
-        const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+    for (int tile = first; tile < P.total_tiles; tile += stride, ++it) {
         const TileGeom g = tile_geom(P, tile);
         const MelUnit u = P.units[g.unit];
-        if (tid == 0) {
-            const int next = tile + gridDim.x;
-            if (next < P.total_tiles) {
-                fence_proxy_async();   // generic-proxy reads of raw[buf^1] (previous tile) precede this async write
-                issue(next, buf_i ^ 1);
-            }
-        }
-        mbar_wait(&bars[buf_i], parity);
 
-        // ---- phase 1: pre-emphasis into ptile (zero outside [0, n)) -------------------------------------
-        {
-            const float *raw = buf_i ? raw1 : raw0;
-            const float a = P.preemph;
-            const bool interior = g.a0 >= 1 && g.a0 - 1 >= g.gs && g.a0 + P.pt_len <= g.ge && g.a0 + P.pt_len <= u.n;
-            if (interior) {
-                // every sample of the tile and its predecessor came through the bulk copy (conflict-free, unit stride)
-                const float *src = raw + (g.a0 - g.base);   // src[t] = x(a0 + t), src[-1] valid
-                if (((g.a0 - g.base) & 3) == 0 && (P.pt_len & 3) == 0) {   // 16-byte aligned rows: four samples per step
-                    const float4 *s4 = reinterpret_cast<const float4 *>(src);
-                    float4 *d4 = reinterpret_cast<float4 *>(ptile);
-                    for (int q = tid; q < (P.pt_len >> 2); q += kWarps * 32) {
-                        const float4 x = s4[q];
-                        float4 y = x;
-                        if (a != 0.0f) {
-                            y.x = preemph_rest(x.x, src[4 * q - 1], a);
-                            y.y = preemph_rest(x.y, x.x, a);
-                            y.z = preemph_rest(x.z, x.y, a);
-                            y.w = preemph_rest(x.w, x.z, a);
-                        }
-                        d4[q] = y;
-                    }
-                } else if (a == 0.0f) {
-                    for (int t = tid; t < P.pt_len; t += kWarps * 32) ptile[t] = src[t];
-                } else {
-                    for (int t = tid; t < P.pt_len; t += kWarps * 32) ptile[t] = preemph_rest(src[t], src[t - 1], a);
-                }
-            } else {
-                const float *gaudio = P.audio + u.audio_off;
-                auto sample = [&](long long i) -> float {   // x(i) for -1 <= i < n
-                    if (i >= g.gs && i < g.ge) return raw[i - g.base];
-                    if (i < 0) return u.last;
-                    return __ldg(gaudio + i);
-                };
-                for (int t = tid; t < P.pt_len; t += kWarps * 32) {
-                    const long long i = g.a0 + t;
-                    float v = 0.0f;
-                    if (i >= 0 && i < u.n) {
-                        const float x = sample(i);
-                        if (a == 0.0f) v = x;
-                        else if (i == 0) v = preemph_first(x, u.last, a);
-                        else v = preemph_rest(x, sample(i - 1), a);
-                    }
-                    ptile[t] = v;
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- phase 2: one warp per frame: FP64 FFT256 + recombination + float32 power -------------------
+        // ---- phase A: previous tile's copy-out, then one warp per frame: FP64 FFT256 + recombination + power ----
+        if (pending_dst) copy_out(pending_dst, pending_total);
         for (int fi = warp; fi < g.nf; fi += kWarps) {
             const float *pf = ptile + fi * P.hop;
             double re[8], im[8];
@@ -227,7 +250,12 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
         }
         __syncthreads();
 
-        // ---- phase 3: mel filterbank + log; a warp covers kTileFrames frames x (32 / kTileFrames) mel bins -------
+        // ---- phase B: mel filterbank + log; a warp covers kTileFrames frames x (32 / kTileFrames) mel bins -------
+        const int next = tile + stride;
+        if (tid == 0 && next + stride < P.total_tiles) {
+            fence_proxy_async();   // generic-proxy reads of this raw buffer (pre-emphasis, previous phase B) precede the async write
+            issue(next + stride, it & 1);
+        }
         {
             constexpr int kGroup = 32 / kTileFrames;               // mel bins handled concurrently by one warp
             const int fl = lane % kTileFrames, mg = lane / kTileFrames;
@@ -245,26 +273,19 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             }
         }
         if (P.layout == 0) {
-            __syncthreads();
-            // time-major tile is contiguous in HBM: nf rows of n_mels floats; flat, fully coalesced copy
-            float *dst = P.out + u.out_off + g.f0 * P.n_mels;
-            const int total = g.nf * P.n_mels;
-            if ((P.n_mels & 3) == 0) {   // rows are whole float4s and dst is 64-byte aligned (f0 is a multiple of 16)
-                float4 *d4 = reinterpret_cast<float4 *>(dst);
-                for (int q = tid; q < (total >> 2); q += kWarps * 32) {
-                    const int e = 4 * q;
-                    const float *src = otile + e + (int)__umulhi((unsigned)e, P.inv_n_mels);   // + row: stride n_mels + 1
-                    d4[q] = make_float4(src[0], src[1], src[2], src[3]);
-                }
-            } else {
-                for (int idx = tid; idx < total; idx += kWarps * 32) {
-                    const int fi = (int)__umulhi((unsigned)idx, P.inv_n_mels);   // idx / n_mels (exact for idx < 2^16)
-                    dst[idx] = otile[idx + fi];                                  // padded row stride n_mels + 1
-                }
-            }
+            pending_dst = P.out + u.out_off + g.f0 * P.n_mels;
+            pending_total = g.nf * P.n_mels;
         }
-        // next iteration's phase-1 barrier orders these reads against the next tile's writes
+        if (next < P.total_tiles) {
+            const int nb = (it + 1) & 1;
+            const TileGeom gn = tile_geom(P, next);
+            const MelUnit un = P.units[gn.unit];
+            mbar_wait(&bars[nb], (uint32_t)((it + 1) >> 1) & 1u);
+            preemphasize(gn, un, nb ? raw1 : raw0);
+        }
+        __syncthreads();
     }
+    if (pending_dst) copy_out(pending_dst, pending_total);
 }
 
 // ------------------------------------------------------------------------------------------------ host plan
