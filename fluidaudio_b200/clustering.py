@@ -211,20 +211,21 @@ class OfflineClusterer:
         rho = np.ascontiguousarray(rho128, np.float64)
         N, E = emb.shape
         R = rho.shape[1]
+        psi = self.psi if self.psi is not None and self.psi.size == R else None   # VBxClustering.swift:71-76: identity
         labels = np.zeros(N, np.int32)
         initial = np.zeros(N, np.int32)
         cents = np.zeros((max_centroids, E), np.float64)
         info = _lib.ClusterInfo()
         cfg = self.config._c_cluster()
         if chunk_indices is None:
-            _lib.check(_lib.load().fa_diarize_cluster(emb.ctypes.data, rho.ctypes.data, N, E, R, _lib.ptr(self.psi),
+            _lib.check(_lib.load().fa_diarize_cluster(emb.ctypes.data, rho.ctypes.data, N, E, R, _lib.ptr(psi),
                                                       C.byref(cfg), labels.ctypes.data, initial.ctypes.data,
                                                       cents.ctypes.data, max_centroids, C.byref(info)),
                        "fa_diarize_cluster")
         else:
             chunk = np.ascontiguousarray(chunk_indices, np.int32)
             _lib.check(_lib.load().fa_diarize_cluster_chunks(emb.ctypes.data, rho.ctypes.data, N, E, R,
-                                                             _lib.ptr(self.psi), C.byref(cfg), chunk.ctypes.data,
+                                                             _lib.ptr(psi), C.byref(cfg), chunk.ctypes.data,
                                                              labels.ctypes.data, initial.ctypes.data, cents.ctypes.data,
                                                              max_centroids, C.byref(info)), "fa_diarize_cluster_chunks")
         d = {f: getattr(info, f) for f, _ in _lib.ClusterInfo._fields_}
@@ -238,8 +239,9 @@ class OfflineClusterer:
         labels = np.zeros(emb.shape[0], np.int32)
         infos = (_lib.ClusterInfo * max(count, 1))()
         cfg = self.config._c_cluster()
+        psi = self.psi if self.psi is not None and self.psi.size == rho.shape[1] else None
         _lib.check(_lib.load().fa_diarize_cluster_batch(emb.ctypes.data, rho.ctypes.data, offs.ctypes.data, count,
-                                                        emb.shape[1], rho.shape[1], _lib.ptr(self.psi), C.byref(cfg),
+                                                        emb.shape[1], rho.shape[1], _lib.ptr(psi), C.byref(cfg),
                                                         labels.ctypes.data, infos), "fa_diarize_cluster_batch")
         out = [{f: getattr(infos[i], f) for f, _ in _lib.ClusterInfo._fields_} for i in range(count)]
         return labels, out

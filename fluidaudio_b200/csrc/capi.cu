@@ -315,17 +315,10 @@ static int cluster_pipeline(ClusterContext &C, const float *emb, const double *r
     bool used_vbx = false;
     long long lc = 0;
     if (Tn > 0) {
-        if (S > 1024) {
-            // degenerate input (AHC found >1024 clusters): skip VBx, fall back to cluster means below
-            st = vbx::onehot_device(d_init, Tn, S, d_gamma, d_pi, s);
-            if (st != FA_OK) return st;
-            lc += 1;
-        } else {
-            st = vbx::refine_device(C.vbx_ws, d_tr_rho, Tn, r, psi_eff.data(), d_init, S, vc, d_gamma, d_pi, d_elbos,
-                                    d_hard, &iterations, s, &lc);
-            if (st != FA_OK) return st;
-            used_vbx = true;
-        }
+        st = vbx::refine_device(C.vbx_ws, d_tr_rho, Tn, r, psi_eff.data(), d_init, S, vc, d_gamma, d_pi, d_elbos, d_hard,
+                                &iterations, s, &lc);
+        if (st != FA_OK) return st;
+        used_vbx = true;
     }
     // ---- speaker-count constraints (:311-336, VBxClustering.swift:685-733) ----------------------------------
     bool adjusted = false;
@@ -364,7 +357,7 @@ static int cluster_pipeline(ClusterContext &C, const float *emb, const double *r
     }
     FA_CUDA_TRY(cudaEventRecord(C.ev[5], s));
     // ---- centroids (:345-353) + assignment (:371-374) -----------------------------------------------------
-    if (!adjusted && S <= 1024) {
+    if (!adjusted) {
         st = vbx::centroids_device(C.vbx_ws, d_tr, Tn, e, d_gamma, d_pi, S, d_cent, d_cent_n, d_count, s, &lc);
         if (st != FA_OK) return st;
         FA_CUDA_TRY(cudaMemcpyAsync(h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -383,7 +376,7 @@ static int cluster_pipeline(ClusterContext &C, const float *emb, const double *r
         }
     }
     if (K == 0) {
-        // computeFallbackCentroids: mean of all embeddings (:748-786); also the >1024-cluster escape hatch
+        // computeFallbackCentroids: mean of all embeddings (:748-786)
         st = vbx::mean_rows_device(d_emb, n, e, d_cent, s);
         if (st != FA_OK) return st;
         st = vbx::onehot_device(d_init, 0, 1, d_gamma, d_pi, s);   // pi[0] = 1

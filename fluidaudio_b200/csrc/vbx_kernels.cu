@@ -30,11 +30,15 @@ namespace vbx {
         }                                                                                               \
     } while (0)
 
-constexpr int kChunks = 128;      // frame chunks for the two-level reductions
+constexpr int kChunks = 128;      // frame chunks for the two-level reductions (fewer when there are > 1024 speakers)
 constexpr int kEThreads = 128;    // threads per CTA in the E-step
 
+// Partial sums are [chunks x S x D]: keep them bounded when AHC hands over thousands of clusters (degenerate input:
+// every embedding its own speaker).  The chunk count only changes the (fixed) summation order.
+static int chunks_for(int S) { return S <= 1024 ? kChunks : std::max(1, (kChunks * 1024) / S); }
+
 struct Dev {
-    int T, D, S, Tp;
+    int T, D, S, Tp, chunks;
     const double *x;      // [T x D] features
     const double *phi_c;  // [D] clamped psi
     double *rho;          // [T x D]
@@ -104,7 +108,7 @@ __global__ void vbx_init_kernel(Dev d, const int *__restrict__ init, double smoo
 __global__ void vbx_accumulate_kernel(Dev d) {
     if (d.state[0]) return;
     const int c = blockIdx.x;
-    const int per = (d.T + kChunks - 1) / kChunks;
+    const int per = (d.T + d.chunks - 1) / d.chunks;
     const int t0 = c * per, t1 = min(d.T, t0 + per);
     const int SD = d.S * d.D;
     for (int o = threadIdx.x; o < SD; o += blockDim.x) {
@@ -127,7 +131,7 @@ __global__ void vbx_update_kernel(Dev d) {
     const double ratio = d.Fa / d.Fb;
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
         double acc = 0.0;
-        for (int c = 0; c < kChunks; ++c) acc += d.pG[(size_t)c * S + s];
+        for (int c = 0; c < d.chunks; ++c) acc += d.pG[(size_t)c * S + s];
         d.gsum[s] = acc;
         d.logPi[s] = log(fmax(d.pi[s], 1e-8));
     }
@@ -135,7 +139,7 @@ __global__ void vbx_update_kernel(Dev d) {
     for (int o = threadIdx.x; o < SD; o += blockDim.x) {
         const int s = o / D, k = o % D;
         double acc = 0.0;
-        for (int c = 0; c < kChunks; ++c) acc += d.pA[(size_t)c * SD + o];
+        for (int c = 0; c < d.chunks; ++c) acc += d.pA[(size_t)c * SD + o];
         const double il = 1.0 / fmax(1.0 + (ratio * d.gsum[s]) * d.phi_c[k], 1e-12);
         d.invL[o] = il;
         d.alpha[o] = (acc * il) * ratio;
@@ -176,20 +180,29 @@ __global__ void vbx_update_kernel(Dev d) {
 }
 
 // thread per frame: log-likelihood row, soft-max -> gamma, per-CTA partial LL and partial pi   (:438-602)
+// kAlphaSmem: alpha [S x D], -phiTerm/2 and log pi staged in shared memory (the normal case, S x D x 8 <= 200 KB);
+// otherwise read through L2 (hundreds of speakers: same arithmetic, every warp reads the same addresses).
+template <bool kAlphaSmem>
 __global__ void __launch_bounds__(kEThreads) vbx_estep_kernel(Dev d) {
     if (d.state[0]) return;
     extern __shared__ double sm[];
     const int S = d.S, D = d.D;
-    double *alpha = sm;                 // [S x D]
-    double *off = alpha + (size_t)S * D; // [S]  -0.5 phiTerm
-    double *lpi = off + S;              // [S]
-    double *red = lpi + S;              // [kEThreads]
-    for (int o = threadIdx.x; o < S * D; o += kEThreads) alpha[o] = d.alpha[o];
-    for (int s = threadIdx.x; s < S; s += kEThreads) {
-        off[s] = d.phiTerm[s] * -0.5;
-        lpi[s] = d.logPi[s];
+    double *red = sm;                                        // [kEThreads]
+    const double *alpha = d.alpha;
+    if (kAlphaSmem) {
+        double *a_s = sm + kEThreads;                        // [S x D]
+        double *off_s = a_s + (size_t)S * D;                 // [S]  -0.5 phiTerm
+        double *lpi_s = off_s + S;                           // [S]
+        for (int o = threadIdx.x; o < S * D; o += kEThreads) a_s[o] = d.alpha[o];
+        for (int s = threadIdx.x; s < S; s += kEThreads) {
+            off_s[s] = d.phiTerm[s] * -0.5;
+            lpi_s[s] = d.logPi[s];
+        }
+        __syncthreads();
+        alpha = a_s;
     }
-    __syncthreads();
+    const double *off = kAlphaSmem ? sm + kEThreads + (size_t)S * D : nullptr;
+    const double *lpi = kAlphaSmem ? off + S : nullptr;
     const int t = blockIdx.x * kEThreads + threadIdx.x;
     double ll = 0.0;
     if (t < d.T) {
@@ -200,7 +213,9 @@ __global__ void __launch_bounds__(kEThreads) vbx_estep_kernel(Dev d) {
             double acc = 0.0;
             const double *a = alpha + (size_t)s * D;
             for (int k = 0; k < D; ++k) acc += d.rhoT[(size_t)k * d.Tp + t] * a[k];
-            const double v = ((acc + off[s]) + Gt) * d.Fa + lpi[s];
+            const double o_s = kAlphaSmem ? off[s] : d.phiTerm[s] * -0.5;
+            const double l_s = kAlphaSmem ? lpi[s] : d.logPi[s];
+            const double v = ((acc + o_s) + Gt) * d.Fa + l_s;
             g[s] = v;
             mx = fmax(mx, v);
         }
@@ -284,9 +299,10 @@ __global__ void vbx_hard_kernel(const double *__restrict__ gamma, int T, int S, 
 // ---- centroids ----------------------------------------------------------------------------------------
 // per chunk: num[c][s][k] = sum_t (gamma>0) gamma[t][s] e[t][k], den[c][s] = sum_t gamma   (:642-674)
 __global__ void centroid_accumulate_kernel(const double *__restrict__ emb, const double *__restrict__ gamma, int T,
-                                           int E, int S, double *__restrict__ pnum, double *__restrict__ pden) {
+                                           int E, int S, int chunks, double *__restrict__ pnum,
+                                           double *__restrict__ pden) {
     const int c = blockIdx.x;
-    const int per = (T + kChunks - 1) / kChunks;
+    const int per = (T + chunks - 1) / chunks;
     const int t0 = c * per, t1 = min(T, t0 + per);
     const int SE = S * E;
     for (int o = threadIdx.x; o < SE; o += blockDim.x) {
@@ -310,9 +326,8 @@ __global__ void centroid_accumulate_kernel(const double *__restrict__ emb, const
 
 // single CTA: speakers with pi > 1e-7 in ascending order become centroids 0..K-1; also L2-normalised copies
 __global__ void centroid_finish_kernel(const double *__restrict__ pnum, const double *__restrict__ pden,
-                                       const double *__restrict__ pi, int E, int S, double *__restrict__ cent,
-                                       double *__restrict__ cent_n, int *__restrict__ count) {
-    __shared__ int map[1024];
+                                       const double *__restrict__ pi, int E, int S, int chunks, int *__restrict__ map,
+                                       double *__restrict__ cent, double *__restrict__ cent_n, int *__restrict__ count) {
     __shared__ int K;
     if (threadIdx.x == 0) {
         int k = 0;
@@ -325,7 +340,7 @@ __global__ void centroid_finish_kernel(const double *__restrict__ pnum, const do
         const int s = o / E, k = o % E;
         if (map[s] < 0) continue;
         double num = 0.0, den = 0.0;
-        for (int c = 0; c < kChunks; ++c) {
+        for (int c = 0; c < chunks; ++c) {
             num += pnum[(size_t)c * S * E + o];
             den += pden[(size_t)c * S + s];
         }
@@ -334,10 +349,10 @@ __global__ void centroid_finish_kernel(const double *__restrict__ pnum, const do
     __syncthreads();
     for (int c = threadIdx.x; c < K; c += blockDim.x) {   // normalize (:824-860): unchanged if |c|^2 <= 0
         const double *v = cent + (size_t)c * E;
-        double ss = 0.0;
-        for (int k = 0; k < E; ++k) ss += v[k] * v[k];
-        const double sc = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
-        for (int k = 0; k < E; ++k) cent_n[(size_t)c * E + k] = v[k] * sc;
+        double ss = 0.0;   // individually rounded operations, like the reference's scalar loops (no FMA contraction)
+        for (int k = 0; k < E; ++k) ss = __dadd_rn(ss, __dmul_rn(v[k], v[k]));
+        const double sc = ss > 0.0 ? __ddiv_rn(1.0, __dsqrt_rn(ss)) : 1.0;
+        for (int k = 0; k < E; ++k) cent_n[(size_t)c * E + k] = __dmul_rn(v[k], sc);
     }
 }
 
@@ -353,15 +368,15 @@ __global__ void assign_kernel(const double *__restrict__ emb, int N, int E, cons
         return;
     }
     const double *e = emb + (size_t)n * E;
-    double ss = 0.0;
-    for (int k = 0; k < E; ++k) ss += e[k] * e[k];
-    const double sc = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
+    double ss = 0.0;   // individually rounded operations in the reference's order: exact ties resolve the same way
+    for (int k = 0; k < E; ++k) ss = __dadd_rn(ss, __dmul_rn(e[k], e[k]));
+    const double sc = ss > 0.0 ? __ddiv_rn(1.0, __dsqrt_rn(ss)) : 1.0;
     int best = 0;
     double best_score = -INFINITY;
     for (int c = 0; c < K; ++c) {
         const double *v = cent_n + (size_t)c * E;
         double dot = 0.0;
-        for (int k = 0; k < E; ++k) dot += (e[k] * sc) * v[k];
+        for (int k = 0; k < E; ++k) dot = __dadd_rn(dot, __dmul_rn(__dmul_rn(e[k], sc), v[k]));
         if (scores) scores[(size_t)n * K + c] = dot;
         if (dot > best_score) {
             best_score = dot;
@@ -447,8 +462,8 @@ size_t refine_bytes(int T, int D, int S, int max_it) {
     c.take<double>(S);
     c.take<double>(S);
     c.take<double>(S);
-    c.take<double>((size_t)kChunks * S * D);
-    c.take<double>((size_t)kChunks * S);
+    c.take<double>((size_t)chunks_for(S) * S * D);
+    c.take<double>((size_t)chunks_for(S) * S);
     c.take<double>(eblocks);
     c.take<double>((size_t)eblocks * S);
     c.take<double>(std::max(max_it, 1));
@@ -463,10 +478,6 @@ int refine_device(Workspace &ws, const double *d_x, int T, int D, const double *
                   const Config &cfg, double *d_gamma, double *d_pi, double *d_elbos, int *d_hard, int *iterations_host,
                   cudaStream_t stream, long long *launches) {
     if (T <= 0 || D <= 0 || S <= 0) return FA_INVALID_ARGUMENT;
-    if (S > 1024) {
-        fa::set_error("VBx speaker count %d exceeds the supported maximum of 1024", S);
-        return FA_UNSUPPORTED;
-    }
     const int max_it = cfg.max_iterations;
     int st = ws.reserve(refine_bytes(T, D, S, max_it));
     if (st != FA_OK) return st;
@@ -476,6 +487,7 @@ int refine_device(Workspace &ws, const double *d_x, int T, int D, const double *
     d.D = D;
     d.S = S;
     d.Tp = (T + 31) & ~31;
+    d.chunks = chunks_for(S);
     d.eblocks = (T + kEThreads - 1) / kEThreads;
     d.x = d_x;
     d.rho = c.take<double>((size_t)T * D);
@@ -488,8 +500,8 @@ int refine_device(Workspace &ws, const double *d_x, int T, int D, const double *
     d.phiTerm = c.take<double>(S);
     d.logPi = c.take<double>(S);
     d.gsum = c.take<double>(S);
-    d.pA = c.take<double>((size_t)kChunks * S * D);
-    d.pG = c.take<double>((size_t)kChunks * S);
+    d.pA = c.take<double>((size_t)d.chunks * S * D);
+    d.pG = c.take<double>((size_t)d.chunks * S);
     d.pLL = c.take<double>(d.eblocks);
     d.pPi = c.take<double>((size_t)d.eblocks * S);
     (void)c.take<double>(std::max(max_it, 1));
@@ -518,23 +530,22 @@ int refine_device(Workspace &ws, const double *d_x, int T, int D, const double *
     vbx_init_kernel<<<(T + 127) / 128, 128, 0, stream>>>(d, d_init, cfg.init_smoothing);
     FA_CUDA_TRY(cudaGetLastError());
     long long n_launch = 1;
-    const size_t esmem = sizeof(double) * ((size_t)S * D + 2 * S + kEThreads);
-    if (esmem > 200 * 1024) {
-        fa::set_error("VBx S x D = %d x %d does not fit the E-step's shared-memory alpha tile", S, D);
-        return FA_UNSUPPORTED;
-    }
+    const size_t esmem_full = sizeof(double) * ((size_t)S * D + 2 * S + kEThreads);
+    const bool alpha_smem = esmem_full <= 200 * 1024;
+    const size_t esmem = alpha_smem ? esmem_full : sizeof(double) * kEThreads;
     {
         static std::once_flag once;   // per-function attribute shared by concurrent callers: set once to the maximum
         static cudaError_t attr_err = cudaSuccess;
         std::call_once(once, [&]() {
-            attr_err = cudaFuncSetAttribute(vbx_estep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_err = cudaFuncSetAttribute(vbx_estep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         });
         FA_CUDA_TRY(attr_err);
     }
     for (int it = 0; it < max_it; ++it) {
-        vbx_accumulate_kernel<<<kChunks, 256, 0, stream>>>(d);
+        vbx_accumulate_kernel<<<d.chunks, 256, 0, stream>>>(d);
         vbx_update_kernel<<<1, 256, 0, stream>>>(d);
-        vbx_estep_kernel<<<d.eblocks, kEThreads, esmem, stream>>>(d);
+        if (alpha_smem) vbx_estep_kernel<true><<<d.eblocks, kEThreads, esmem, stream>>>(d);
+        else vbx_estep_kernel<false><<<d.eblocks, kEThreads, esmem, stream>>>(d);
         vbx_finish_kernel<<<1, 256, 0, stream>>>(d, it);
         n_launch += 4;
     }
@@ -552,18 +563,21 @@ int refine_device(Workspace &ws, const double *d_x, int T, int D, const double *
     return FA_OK;
 }
 
-size_t centroid_bytes(int E, int S) { return ((size_t)kChunks * S * E + (size_t)kChunks * S) * sizeof(double) + 1024; }
+size_t centroid_bytes(int E, int S) {
+    return ((size_t)chunks_for(S) * S * E + (size_t)chunks_for(S) * S) * sizeof(double) + (size_t)S * sizeof(int) + 2048;
+}
 
 int centroids_device(Workspace &ws, const double *d_emb, int T, int E, const double *d_gamma, const double *d_pi, int S,
                      double *d_cent, double *d_cent_n, int *d_count, cudaStream_t stream, long long *launches) {
-    if (S > 1024) return FA_UNSUPPORTED;
+    const int chunks = chunks_for(S);
     int st = ws.reserve(centroid_bytes(E, S));
     if (st != FA_OK) return st;
     Carver c{static_cast<char *>(ws.pool)};
-    double *pnum = c.take<double>((size_t)kChunks * S * E);
-    double *pden = c.take<double>((size_t)kChunks * S);
-    centroid_accumulate_kernel<<<kChunks, 256, 0, stream>>>(d_emb, d_gamma, T, E, S, pnum, pden);
-    centroid_finish_kernel<<<1, 256, 0, stream>>>(pnum, pden, d_pi, E, S, d_cent, d_cent_n, d_count);
+    double *pnum = c.take<double>((size_t)chunks * S * E);
+    double *pden = c.take<double>((size_t)chunks * S);
+    int *map = c.take<int>(S);
+    centroid_accumulate_kernel<<<chunks, 256, 0, stream>>>(d_emb, d_gamma, T, E, S, chunks, pnum, pden);
+    centroid_finish_kernel<<<1, 256, 0, stream>>>(pnum, pden, d_pi, E, S, chunks, map, d_cent, d_cent_n, d_count);
     FA_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 2;
     return FA_OK;

@@ -203,7 +203,8 @@ typedef struct {
 } fa_cluster_info;
 
 /* OfflineDiarizerManager.cluster(_:) lines 286-375 (unconstrained argmax assignment):
- *   emb256: N x emb_dim float32; rho: N x rho_dim float64; psi: rho_dim.  labels: N final assignments.
+ *   emb256: N x emb_dim float32; rho: N x rho_dim float64; psi: rho_dim doubles, or NULL for the identity (pass NULL
+ *   when the PLDA parameters have another length: VBxClustering.swift:71-76).  labels: N final assignments.
  * Optional outputs (may be NULL): initial [N] AHC labels of the training rows (-1 for filtered rows),
  * centroids [max_centroids x emb_dim], info. */
 fa_status fa_diarize_cluster(const float *emb256, const double *rho, size_t N, size_t emb_dim, size_t rho_dim,
