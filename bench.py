@@ -192,8 +192,8 @@ def bench_mel(args, dist):
                 "host_buffers": "pinned (fa_host_alloc)", "api": "fa_mel_compute"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 319.9e6, "traffic_source": "ncu --set full, profiles/r01c_summary.txt: dram read 230.6 MB + "
-                     "write 89.3 MB per launch (the tail of the output is still in L2 at kernel end)",
+                     "traffic": 317.5e6, "traffic_source": "ncu --set full, profiles/r01c_summary.txt: dram read 230.5 MB + "
+                     "write 87.0 MB per launch (the tail of the output is still in L2 at kernel end)",
                      "kernel": "mel512_kernel", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": MEL_BYTES_PER_HOUR},
         "config": {"workload": "log-mel STFT, 1 h synthetic 16 kHz mono, 25 ms/10 ms frames, nFFT 512, 80 mels, per GPU",

@@ -505,3 +505,31 @@ def test_speaker_count_constraints_pipeline_matches_oracle(gpu_lib, oracle):
             assert bool(r.info["was_adjusted"]) == o.was_adjusted and r.info["detected_clusters"] == o.detected_clusters
             assert np.array_equal(r.labels, o.labels), kw
             assert r.centroids.shape == o.centroids.shape and np.abs(r.centroids - o.centroids).max() < 1e-12
+
+
+def test_vbx_with_hundreds_and_thousands_of_speakers(gpu_lib, oracle):
+    """Degenerate AHC output (every embedding nearly its own cluster) must still run: the E-step reads alpha through L2
+    when S x D x 8 exceeds shared memory, and beyond 1 024 speakers the partial sums use fewer frame chunks."""
+    for T, S, D in ((600, 260, 128), (1300, 1100, 64)):
+        rng = np.random.default_rng(S)
+        emb, _ = synth.speaker_embeddings(T, 256, 6, seed=S)
+        rho, psi = synth.synthetic_plda(emb, D)
+        init = np.concatenate([np.arange(S), rng.integers(0, S, T - S)]).astype(np.int32)   # every label occurs
+        g = cl.VBxClustering(psi=psi).refine(rho, init)
+        o = oracle.vbx_refine(rho, psi, init)
+        assert g.gamma.shape == (T, S) and g.elbos.size == o.elbos.size
+        assert np.abs(g.elbos - o.elbos).max() <= 1e-9 * np.abs(o.elbos).max()
+        assert np.abs(g.gamma - o.gamma).max() < 1e-8 and np.abs(g.pi - o.pi).max() < 1e-10
+        cents = cl.compute_centroids(emb.astype(np.float64), g)
+        ocents = oracle.compute_centroids(emb.astype(np.float64), o, init)
+        assert cents.shape == ocents.shape and np.abs(cents - ocents).max() < 1e-9
+    # the whole phase with a threshold that leaves ~hundreds of clusters to VBx
+    emb, _ = synth.speaker_embeddings(500, 256, 4, seed=77)
+    rho, psi = synth.synthetic_plda(emb)
+    cfg = cl.OfflineDiarizerConfig()
+    cfg.clustering.threshold = 0.2
+    r = cl.OfflineClusterer(cfg, psi=psi).cluster(emb, rho)
+    o = oracle.diarize_cluster(emb, rho, psi, threshold=0.2, use_ref=oracle.ref_available())
+    assert r.info["initial_clusters"] == len(set(o.initial.tolist())) and r.info["initial_clusters"] > 200
+    assert r.info["vbx_iterations"] == o.vbx.elbos.size and r.centroids.shape == o.centroids.shape
+    assert np.abs(r.centroids - o.centroids).max() < 1e-9
