@@ -7,6 +7,8 @@
               restatement (CPU tests) and the CUDA path (GPU tests).
 * ahc_large.json  SHA-256 of the reference dendrogram bytes for the BASELINE-size problems (N = 5 000 / 10 000),
               whose inputs are regenerated from seeds (fluidaudio_b200/synth.py) instead of being stored.
+* next_rows.npz  the rows either side of the hot path: seeded K-Means runs, UnifiedMelExtractor and LS-EEND
+              features from the oracle restatement (`python tests/golden/make_golden.py next` regenerates only these).
 * mel_*.npz   log-mel of the reference's own test signal (SortformerStreamingMelTests.swift:17-25 shape) from the
               oracle restatement: the reference has no golden mel values and no Swift toolchain exists here, so
               these pin the oracle against silent drift, not against Apple's vDSP.
@@ -31,8 +33,32 @@ def ref_linkage(x):
     return z
 
 
+def next_rows():
+    out = {}
+    six = np.array([[1.0, 0.0], [1.1, 0.1], [0.0, 1.0], [0.1, 1.1], [-1.0, 0.0], [-0.9, 0.1]])
+    for name, (x, k, iters, seed) in {"six_k3_seed42": (six, 3, 100, 42), "six_k3_seed12345": (six, 3, 300, 12345)}.items():
+        lab, cen, it = O.kmeans(x, k, iters, seed)
+        out[f"kmeans_{name}__labels"], out[f"kmeans_{name}__centroids"] = lab, cen
+    emb, _ = synth.speaker_embeddings(300, 64, 5, seed=9)
+    lab, cen, best = O.kmeans_ninit(emb.astype(np.float64), 5, 100, 10, 0)
+    out["kmeans_ninit_300x64__labels"], out["kmeans_ninit_300x64__centroids"] = lab, cen
+    out["kmeans_ninit_300x64__best"] = np.array([best])
+    a = synth.tone_noise_audio(16000)
+    window = np.concatenate([a[:6000], np.zeros(2000, np.float32)])
+    mel, valid = O.unified_mel_features(window, 6000)
+    out["unified_8000_valid6000__mel"], out["unified_8000_valid6000__valid"] = mel, np.array([valid])
+    cfg = O.lseend_config()
+    f1, mean, cnt = O.lseend_features(cfg, a[:4000], np.zeros(23, np.float32), 0)
+    f2, mean, cnt = O.lseend_features(cfg, a[4000 - 352:9000], mean, cnt)
+    out["lseend__f1"], out["lseend__f2"], out["lseend__mean"], out["lseend__count"] = f1, f2, mean, np.array([cnt])
+    np.savez_compressed(os.path.join(HERE, "next_rows.npz"), **out)
+    print("next_rows.npz written:", sorted(out))
+
+
 def main():
     O.build()
+    if len(sys.argv) > 1 and sys.argv[1] == "next":
+        return next_rows()
     assert O.ref_available(), "oracle/_ref/liboracle_fc.so missing: run `make -C oracle ref` where /root/reference exists"
     rng = np.random.default_rng(2024)
     cases = {}
@@ -86,6 +112,7 @@ def main():
     mel["hann_400"] = O.hann_window(400, False)
     mel["filterbank_80"] = O.mel_filterbank(512, 80)
     np.savez_compressed(os.path.join(HERE, "mel_oracle.npz"), **mel)
+    next_rows()
     print("golden fixtures written to", HERE)
 
 

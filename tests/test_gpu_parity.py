@@ -533,3 +533,27 @@ def test_vbx_with_hundreds_and_thousands_of_speakers(gpu_lib, oracle):
     assert r.info["initial_clusters"] == len(set(o.initial.tolist())) and r.info["initial_clusters"] > 200
     assert r.info["vbx_iterations"] == o.vbx.elbos.size and r.centroids.shape == o.centroids.shape
     assert np.abs(r.centroids - o.centroids).max() < 1e-9
+
+
+def test_next_rows_against_committed_goldens(gpu_lib, golden_dir):
+    """CUDA path vs tests/golden/next_rows.npz (made by tests/golden/make_golden.py): nothing of the oracle runs here."""
+    import os
+    from fluidaudio_b200.mel import LSEENDMelFrontend, UnifiedMelExtractor
+    g = np.load(os.path.join(golden_dir, "next_rows.npz"))
+    six = np.array([[1.0, 0.0], [1.1, 0.1], [0.0, 1.0], [0.1, 1.1], [-1.0, 0.0], [-0.9, 0.1]])
+    for name, (k, iters, seed) in {"six_k3_seed42": (3, 100, 42), "six_k3_seed12345": (3, 300, 12345)}.items():
+        lab, cen = cl.KMeansClustering.cluster_with_centroids(six, k, iters, seed)
+        assert np.array_equal(lab, g[f"kmeans_{name}__labels"]) and cen.tobytes() == g[f"kmeans_{name}__centroids"].tobytes()
+    emb, _ = synth.speaker_embeddings(300, 64, 5, seed=9)
+    lab, cen, best = cl.KMeansClustering.cluster_with_centroids_n_init(emb.astype(np.float64), 5, 100, 10, 0)
+    assert best == int(g["kmeans_ninit_300x64__best"][0]) and np.array_equal(lab, g["kmeans_ninit_300x64__labels"])
+    assert cen.tobytes() == g["kmeans_ninit_300x64__centroids"].tobytes()
+    a = synth.tone_noise_audio(16000)
+    mel, length = UnifiedMelExtractor(8000).features(np.concatenate([a[:6000], np.zeros(2000, np.float32)]), 6000)
+    assert length.tolist() == g["unified_8000_valid6000__valid"].tolist()
+    assert np.abs(mel[0] - g["unified_8000_valid6000__mel"]).max() < 1e-4
+    fe = LSEENDMelFrontend()
+    f1 = fe.process(a[:4000])
+    f2 = fe.process(a[4000 - 352:9000])
+    assert np.abs(f1 - g["lseend__f1"]).max() < 1e-4 and np.abs(f2 - g["lseend__f2"]).max() < 1e-4
+    assert np.abs(fe.cmn_mean - g["lseend__mean"]).max() < 1e-4 and fe.cmn_count == int(g["lseend__count"][0])

@@ -451,3 +451,26 @@ def test_speaker_constraints_reference_tests(oracle):
     assert r(100, None, 10, 5) == (5, 5)                 # :47-56
     assert r(100, 0) == (1, 1) and r(100, -5) == (1, 1)  # :60-80
     assert r(100, None, 0, 5)[0] == 1 and r(100, None, -3, 5)[0] == 1   # :82-100
+
+
+def test_next_row_goldens(oracle, golden_dir):
+    """The committed fixtures of the 8f rows (K-Means, UnifiedMelExtractor, LS-EEND) are reproduced bit for bit."""
+    import os
+    from fluidaudio_b200 import synth
+    g = np.load(os.path.join(golden_dir, "next_rows.npz"))
+    six = np.array([[1.0, 0.0], [1.1, 0.1], [0.0, 1.0], [0.1, 1.1], [-1.0, 0.0], [-0.9, 0.1]])
+    for name, (k, iters, seed) in {"six_k3_seed42": (3, 100, 42), "six_k3_seed12345": (3, 300, 12345)}.items():
+        lab, cen, _ = oracle.kmeans(six, k, iters, seed)
+        assert np.array_equal(lab, g[f"kmeans_{name}__labels"]) and cen.tobytes() == g[f"kmeans_{name}__centroids"].tobytes()
+    emb, _ = synth.speaker_embeddings(300, 64, 5, seed=9)
+    lab, cen, best = oracle.kmeans_ninit(emb.astype(np.float64), 5, 100, 10, 0)
+    assert best == int(g["kmeans_ninit_300x64__best"][0]) and np.array_equal(lab, g["kmeans_ninit_300x64__labels"])
+    assert cen.tobytes() == g["kmeans_ninit_300x64__centroids"].tobytes()
+    a = synth.tone_noise_audio(16000)
+    mel, valid = oracle.unified_mel_features(np.concatenate([a[:6000], np.zeros(2000, np.float32)]), 6000)
+    assert valid == int(g["unified_8000_valid6000__valid"][0]) and mel.tobytes() == g["unified_8000_valid6000__mel"].tobytes()
+    cfg = oracle.lseend_config()
+    f1, mean, cnt = oracle.lseend_features(cfg, a[:4000], np.zeros(23, np.float32), 0)
+    f2, mean, cnt = oracle.lseend_features(cfg, a[4000 - 352:9000], mean, cnt)
+    assert f1.tobytes() == g["lseend__f1"].tobytes() and f2.tobytes() == g["lseend__f2"].tobytes()
+    assert mean.tobytes() == g["lseend__mean"].tobytes() and cnt == int(g["lseend__count"][0])
