@@ -1127,13 +1127,14 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
             ++used;
         }
         for (int q = 0; q < 8; ++q) trace_avg_ns[q] = used ? acc[q] / used : 0.0;
+        const auto avg = [&](int q) { return used ? acc[q] / used : 0.0; };
         std::fprintf(stderr,
-                     "[ahc trace] period %.0f ns | master: bookkeeping+erase+path done %.0f, results collected %.0f, heap "
-                     "rotated %.0f | worker0: command seen %.0f, centroid built %.0f, scan done %.0f, result released %.0f |"
-                     " extra",
-                     trace_avg_ns[0], trace_avg_ns[1], trace_avg_ns[2], trace_avg_ns[3], trace_avg_ns[4], trace_avg_ns[5],
-                     trace_avg_ns[6], trace_avg_ns[7]);
-        for (int q = 8; q < 16; ++q) std::fprintf(stderr, " %.0f", used ? acc[q] / used : 0.0);
+                     "[ahc trace] ns from the master's step start, mean of %d steps | period %.0f | master: bookkeeping+erase+"
+                     "path %.0f, candidates gathered %.0f, heap rotated %.0f | worker 0: round start %.0f, centroid built %.0f, "
+                     "scan done %.0f, warp reduce done %.0f, service warp at barrier %.0f / released %.0f, candidate published "
+                     "%.0f, all gathered %.0f, fence retired %.0f | slowest CTA: round start %.0f, candidate published %.0f",
+                     used, avg(0), avg(1), avg(2), avg(3), avg(4), avg(5), avg(6), avg(11), avg(13), avg(8), avg(7), avg(9),
+                     avg(10), avg(12), avg(14));
         std::fprintf(stderr, "\n");
     }
     drop_events();

@@ -1,5 +1,5 @@
 #!/bin/bash
-for f in ${FLAGS:-4 12}; do
+for f in ${FLAGS:-4 8}; do
   echo "FA_AHC_FLAGS=$f"
   FA_AHC_FLAGS=$f timeout 120 python - <<'PY' 2>&1 | grep -E "trace|N=|Error|error" 
 import sys; sys.path.insert(0,'.')
