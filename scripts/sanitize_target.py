@@ -22,4 +22,15 @@ for n in (2, 3, 50, 400):
     cl.OfflineClusterer(psi=psi).cluster(emb, rho, chunk_indices=chunk)
     if n >= 50:
         cl.OfflineClusterer(cl.OfflineDiarizerConfig().with_speakers(exactly=6), psi=psi).cluster(emb, rho)
+# hundreds of speakers: E-step reads alpha through L2; batch entry point: several sets side by side
+rng = np.random.default_rng(0)
+emb, _ = synth.speaker_embeddings(320, 256, 4, seed=5)
+rho, psi = synth.synthetic_plda(emb)
+init = np.concatenate([np.arange(260), rng.integers(0, 260, 60)]).astype(np.int32)
+cl.VBxClustering(psi=psi).refine(rho, init)
+emb, _ = synth.speaker_embeddings(900, 256, 4, seed=6)
+rho, psi = synth.synthetic_plda(emb)
+cl.OfflineClusterer(psi=psi).cluster_batch(emb, rho, np.array([0, 300, 600, 900], np.int64))
+m = AudioMelSpectrogram(n_mels=80)
+m.compute_batch([a[:30000], a[:1000], a[:48077]])
 print("sanitize target done")
