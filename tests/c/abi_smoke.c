@@ -1,0 +1,37 @@
+/* Plain-C consumer of the drop-in boundary: proves that the headers under include/ are valid C (not only C++) and that the shared
+ * library links and runs from C without a GPU for everything that is host-only.  Built and run by
+ * tests/test_host_logic.py::test_headers_are_plain_c_and_link. */
+#include "FastClusterWrapper.h"
+#include "fluidaudio_b200.h"
+
+#include <stdio.h>
+#include <string.h>
+
+int main(void) {
+    const char *v = fa_version();
+    if (!v || !strstr(v, "sm_100a")) return 1;
+
+    /* the reference's argument contract needs no device (FastClusterWrapper.cpp:203-216) */
+    double x[4] = {1.0, 0.0, 0.0, 1.0}, z[4];
+    if (fastcluster_compute_centroid_linkage(NULL, 2, 2, z, 4) != FASTCLUSTER_WRAPPER_INVALID_ARGUMENT) return 2;
+    if (fastcluster_compute_centroid_linkage(x, 0, 2, z, 4) != FASTCLUSTER_WRAPPER_SUCCESS) return 3;
+    if (fastcluster_compute_centroid_linkage(x, 2, 2, z, 3) != FASTCLUSTER_WRAPPER_OUTPUT_TOO_SMALL) return 4;
+
+    /* host-only entry points */
+    int64_t lo = 0, hi = 0;
+    if (fa_speaker_constraints_resolve(5, FA_NO_VALUE, 2, 20, &lo, &hi) != FA_STATUS_OK || lo != 2 || hi != 5) return 5;
+    int64_t cost[9] = {4, 1, 3, 2, 0, 5, 3, 2, 2};
+    int32_t assign[3] = {-1, -1, -1};
+    if (fa_hungarian_solve(cost, 3, assign) != FA_STATUS_OK) return 6;
+    if (assign[0] != 1 || assign[1] != 0 || assign[2] != 2) return 7;   /* 1 + 2 + 2 = 5 is the optimum */
+
+    fa_cluster_config cfg;
+    fa_cluster_default_config(&cfg);
+    if (cfg.threshold != 0.6 || cfg.num_speakers != FA_NO_VALUE) return 8;
+    fa_mel_config mc;
+    fa_mel_default_config(&mc);
+    if (mc.n_fft != 512 || mc.hop_length != 160) return 9;
+
+    printf("abi ok: %s, devices visible: %d\n", v, fa_device_count());
+    return 0;
+}

@@ -358,3 +358,15 @@ def test_speaker_constraints_host_function(lib, oracle):
     assert (cc.num_speakers, cc.min_speakers, cc.max_speakers) == (_lib.NO_VALUE, 2, 4)
     cc = cfg.with_speakers(exactly=3)._c_cluster()
     assert (cc.num_speakers, cc.min_speakers, cc.max_speakers) == (3, _lib.NO_VALUE, _lib.NO_VALUE)
+
+
+def test_headers_are_plain_c_and_link(lib, tmp_path):
+    """include/*.h compile as C11 with -Wall -Wextra -pedantic -Werror, and a C program linked against the shared
+    library runs the host-only part of the ABI (no GPU needed)."""
+    exe = tmp_path / "abi_smoke"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", str(exe), "-L", libdir,
+                           "-lfluidaudio_b200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.check_output([str(exe)], text=True)
+    assert out.startswith("abi ok:")
