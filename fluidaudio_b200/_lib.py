@@ -52,6 +52,12 @@ class ClusterInfo(C.Structure):
                 ("was_adjusted", C.c_int32), ("detected_clusters", C.c_int32)]
 
 
+class ReconstructConfig(C.Structure):
+    _fields_ = [("frame_duration", C.c_double), ("window_duration", C.c_double), ("min_gap_duration", C.c_double),
+                ("seg_min_duration_off", C.c_double), ("seg_min_duration_on", C.c_double),
+                ("min_segment_duration", C.c_double), ("exclusive_segments", C.c_int32), ("reserved", C.c_int32)]
+
+
 # every symbol include/fluidaudio_b200.h and include/FastClusterWrapper.h declare (tests check the export table)
 EXPORTED_SYMBOLS = [
     "fa_version", "fa_last_error", "fa_device_count", "fa_set_device", "fa_device_synchronize",
@@ -65,6 +71,7 @@ EXPORTED_SYMBOLS = [
     "fa_diarize_cluster", "fa_diarize_cluster_batch", "fa_ahc_last_stage_ms", "fa_diarize_cluster_chunks",
     "fa_hungarian_solve", "fa_max_score_assignment", "fa_constrained_assign", "fa_build_chunk_assignments",
     "fa_export_shape", "fa_export_read", "fa_export_write", "fa_kmeans_cluster", "fa_speaker_constraints_resolve",
+    "fa_reconstruct_default_config", "fa_build_segments",
     "fastcluster_compute_centroid_linkage",
 ]
 
@@ -134,6 +141,10 @@ def load():
     L.fa_build_chunk_assignments.argtypes = [vp, vp, vp, sz, i32, i32, i32, vp]
     L.fa_kmeans_cluster.argtypes = [vp, sz, sz, i32, i32, i32, C.c_uint64, vp, vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.fa_speaker_constraints_resolve.argtypes = [i64, i64, i64, i64, C.POINTER(i64), C.POINTER(i64)]
+    L.fa_reconstruct_default_config.argtypes = [C.POINTER(ReconstructConfig)]
+    L.fa_reconstruct_default_config.restype = None
+    L.fa_build_segments.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, i32, C.POINTER(ReconstructConfig), vp, vp, vp, vp,
+                                    i32, C.POINTER(i32)]
     L.fa_export_shape.argtypes = [C.c_char_p, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
     L.fa_export_read.argtypes = [C.c_char_p, sz, sz, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.fa_export_write.argtypes = [C.c_char_p, sz, sz, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -352,3 +352,47 @@ class KMeansClustering:
     @staticmethod
     def cluster(embeddings, num_clusters: int, max_iterations: int = 300, seed: int | None = None):
         return KMeansClustering.cluster_with_centroids(embeddings, num_clusters, max_iterations, seed)[0]
+
+
+# ---- timeline reconstruction (Diarizer/Offline/Utils/OfflineReconstruction.swift) -----------------------------------
+@dataclass
+class TimedSpeakerSegment:            # Diarizer/Core/DiarizerTypes.swift:191-213 (embedding = centroid of `cluster`)
+    speaker_id: str
+    cluster: int
+    start_time_seconds: float
+    end_time_seconds: float
+    quality_score: float
+
+
+class OfflineReconstruction:
+    """buildSegments (:24-253) without the optional zero-vote re-embed pass; host code inside the library."""
+
+    def __init__(self, frame_duration: float, window_duration: float = 10.0, min_gap_duration: float = 0.1,
+                 segmentation_min_duration_off: float = 0.0, segmentation_min_duration_on: float = 0.0,
+                 min_segment_duration: float = 1.0, exclusive_segments: bool = True):
+        self.cfg = _lib.ReconstructConfig(frame_duration, window_duration, min_gap_duration, segmentation_min_duration_off,
+                                          segmentation_min_duration_on, min_segment_duration, int(exclusive_segments), 0)
+
+    def build_segments(self, speaker_weights, hard_clusters, centroid_count: int, chunk_offsets=None) -> list:
+        w = np.ascontiguousarray(speaker_weights, np.float32)
+        chunks, frames, speakers = (w.shape if w.ndim == 3 else (0, 0, 0))
+        hard = np.ascontiguousarray(hard_clusters, np.int32).reshape(-1, max(speakers, 1)) if np.size(hard_clusters) else \
+            np.zeros((0, max(speakers, 1)), np.int32)
+        offs = np.ascontiguousarray(chunk_offsets if chunk_offsets is not None else [], np.float64)
+        cap = max(16, chunks * max(speakers, 1) * 4)
+        while True:
+            cl, st, en, q = (np.zeros(cap, np.int32), np.zeros(cap, np.float32), np.zeros(cap, np.float32),
+                             np.zeros(cap, np.float32))
+            n = C.c_int32()
+            status = _lib.load().fa_build_segments(w.ctypes.data if w.size else None, chunks, frames, speakers,
+                                                   offs.ctypes.data if offs.size else None, offs.size,
+                                                   hard.ctypes.data if hard.size else None, hard.shape[0], int(centroid_count),
+                                                   C.byref(self.cfg), cl.ctypes.data, st.ctypes.data, en.ctypes.data,
+                                                   q.ctypes.data, cap, C.byref(n))
+            if status == 3 and n.value > cap:      # FA_STATUS_OUTPUT_TOO_SMALL: retry with the reported size
+                cap = n.value
+                continue
+            _lib.check(status, "fa_build_segments")
+            break
+        return [TimedSpeakerSegment(f"S{int(cl[i]) + 1}", int(cl[i]), float(st[i]), float(en[i]), float(q[i]))
+                for i in range(n.value)]

@@ -8,6 +8,7 @@
 #include "mel_plan.h"
 #include "vbx_plan.h"
 #include "kmeans_plan.h"
+#include "reconstruct_host.h"
 
 #include <atomic>
 #include <chrono>
@@ -929,6 +930,52 @@ FA_API void fa_cluster_default_config(fa_cluster_config *cfg) {
     fa_vbx_default_config(&cfg->vbx);
     cfg->num_speakers = cfg->min_speakers = cfg->max_speakers = FA_NO_VALUE;
     cfg->reserved = 0;
+}
+
+FA_API void fa_reconstruct_default_config(fa_reconstruct_config *cfg) {
+    if (!cfg) return;
+    const reconstruct::Config d;
+    cfg->frame_duration = d.frame_duration;
+    cfg->window_duration = d.window_duration;
+    cfg->min_gap_duration = d.min_gap_duration;
+    cfg->seg_min_duration_off = d.seg_min_duration_off;
+    cfg->seg_min_duration_on = d.seg_min_duration_on;
+    cfg->min_segment_duration = d.min_segment_duration;
+    cfg->exclusive_segments = d.exclusive_segments ? 1 : 0;
+    cfg->reserved = 0;
+}
+
+FA_API fa_status fa_build_segments(const float *weights, int32_t num_chunks, int32_t num_frames, int32_t num_speakers,
+                                   const double *chunk_offsets, int32_t offsets_count, const int32_t *hard_clusters,
+                                   int32_t hard_rows, int32_t centroid_count, const fa_reconstruct_config *cfg,
+                                   int32_t *seg_cluster, float *seg_start, float *seg_end, float *seg_quality,
+                                   int32_t segment_cap, int32_t *segment_count) {
+    if (!cfg || !segment_count || num_speakers < 0 || offsets_count < 0 || hard_rows < 0 || segment_cap < 0 ||
+        (num_chunks > 0 && num_frames > 0 && num_speakers > 0 && !weights) || (offsets_count > 0 && !chunk_offsets) ||
+        (hard_rows > 0 && !hard_clusters))
+        return FA_STATUS_INVALID_ARGUMENT;
+    FA_GUARD_BEGIN
+    reconstruct::Config c;
+    c.frame_duration = cfg->frame_duration;
+    c.window_duration = cfg->window_duration;
+    c.min_gap_duration = cfg->min_gap_duration;
+    c.seg_min_duration_off = cfg->seg_min_duration_off;
+    c.seg_min_duration_on = cfg->seg_min_duration_on;
+    c.min_segment_duration = cfg->min_segment_duration;
+    c.exclusive_segments = cfg->exclusive_segments != 0;
+    std::vector<reconstruct::Segment> segs;
+    reconstruct::build_segments(weights, num_chunks, num_frames, num_speakers, chunk_offsets, offsets_count, hard_clusters,
+                                hard_rows, centroid_count, c, segs);
+    *segment_count = (int32_t)segs.size();
+    const int32_t n = std::min<int32_t>((int32_t)segs.size(), segment_cap);
+    for (int32_t i = 0; i < n; ++i) {
+        if (seg_cluster) seg_cluster[i] = segs[i].cluster;
+        if (seg_start) seg_start[i] = segs[i].start;
+        if (seg_end) seg_end[i] = segs[i].end;
+        if (seg_quality) seg_quality[i] = segs[i].quality;
+    }
+    return (int32_t)segs.size() > segment_cap ? FA_STATUS_OUTPUT_TOO_SMALL : FA_STATUS_OK;
+    FA_GUARD_END
 }
 
 FA_API fa_status fa_speaker_constraints_resolve(int64_t num_embeddings, int64_t num_speakers, int64_t min_speakers,

@@ -22,6 +22,7 @@
  *   fa_kmeans_cluster / fa_speaker_constraints_resolve
  *                        KMeansClustering.swift:39-130,212-223, SpeakerCountConstraints.swift:27-85,
  *                        VBxClustering.swift:685-733 (refineWithConstraints)
+ *   fa_build_segments    Diarizer/Offline/Utils/OfflineReconstruction.swift:24-253, 359-505
  *   fa_export_*          OfflineDiarizerManager.swift:913-955 (exportEmbeddings: the JSON dump of TimedEmbedding +
  *                        cluster, OfflineDiarizerTypes.swift:706-716) — the backend's on-disk input format
  */
@@ -229,6 +230,26 @@ fa_status fa_constrained_assign(const double *scores, size_t N, int32_t K, const
 fa_status fa_build_chunk_assignments(const int32_t *chunk_index, const int32_t *speaker_index, const int32_t *assignments,
                                      size_t N, int32_t num_chunks, int32_t num_speakers, int32_t cluster_count,
                                      int32_t *matrix);
+
+/* OfflineReconstruction.buildSegments (Diarizer/Offline/Utils/OfflineReconstruction.swift:24-253): the step after
+ * fa_build_chunk_assignments in OfflineDiarizerManager.cluster(_:).  speaker_weights: SegmentationOutput.speakerWeights
+ * flattened [num_chunks x num_frames x num_speakers]; chunk_offsets: SegmentationOutput.chunkOffsets (offsets_count may
+ * be smaller than num_chunks: missing chunks start at chunk * window_duration); hard_clusters: the matrix returned by
+ * fa_build_chunk_assignments [hard_rows x num_speakers] (-2 = inactive); centroid_count: centroids.count.
+ * Output: *segment_count segments sorted by start (speakerId = "S<cluster+1>", embedding = centroid[cluster]); when
+ * segment_cap is too small the first segment_cap are written and FA_STATUS_OUTPUT_TOO_SMALL is returned.  Host code; the
+ * zero-vote re-embed pass (off by default, needs the embedding model) is not part of it. */
+typedef struct {
+    double frame_duration, window_duration, min_gap_duration, seg_min_duration_off, seg_min_duration_on, min_segment_duration;
+    int32_t exclusive_segments;
+    int32_t reserved;
+} fa_reconstruct_config;
+void fa_reconstruct_default_config(fa_reconstruct_config *cfg);   /* OfflineDiarizerConfig defaults, frame_duration = 0 */
+fa_status fa_build_segments(const float *speaker_weights, int32_t num_chunks, int32_t num_frames, int32_t num_speakers,
+                            const double *chunk_offsets, int32_t offsets_count, const int32_t *hard_clusters,
+                            int32_t hard_rows, int32_t centroid_count, const fa_reconstruct_config *cfg,
+                            int32_t *seg_cluster, float *seg_start, float *seg_end, float *seg_quality,
+                            int32_t segment_cap, int32_t *segment_count);
 
 /* KMeansClustering.clusterWithCentroidsNInit (Diarizer/Offline/Clustering/KMeansClustering.swift:39-130) on raw
  * embeddings [N x D]: labels [N], centroids (normalised space) [min(num_clusters, N) x D] -> *centroid_rows rows;

@@ -398,6 +398,42 @@ class ClusterResult:
     detected_clusters: int = 0  # VBxOutput.assignedClusterCount
 
 
+class _OracleSegment(C.Structure):
+    _fields_ = [("cluster", C.c_int32), ("start", C.c_float), ("end", C.c_float), ("quality", C.c_float)]
+
+
+class _OracleReconstructConfig(C.Structure):
+    _fields_ = [("frame_duration", C.c_double), ("window_duration", C.c_double), ("min_gap_duration", C.c_double),
+                ("seg_min_duration_off", C.c_double), ("seg_min_duration_on", C.c_double),
+                ("min_segment_duration", C.c_double), ("exclusive_segments", C.c_int32)]
+
+
+def build_segments(speaker_weights, hard_clusters, centroid_count, frame_duration, chunk_offsets=None, window_duration=10.0,
+                   min_gap_duration=0.1, seg_min_duration_off=0.0, seg_min_duration_on=0.0, min_segment_duration=1.0,
+                   exclusive_segments=True):
+    """OfflineReconstruction.buildSegments (:24-253) -> list of (cluster, start, end, quality)."""
+    w = np.ascontiguousarray(speaker_weights, np.float32)
+    chunks, frames, speakers = w.shape if w.ndim == 3 else (0, 0, 0)
+    hard = np.ascontiguousarray(hard_clusters, np.int32).reshape(-1, max(speakers, 1)) if np.size(hard_clusters) else \
+        np.zeros((0, max(speakers, 1)), np.int32)
+    offs = np.ascontiguousarray(chunk_offsets if chunk_offsets is not None else [], np.float64)
+    cfg = _OracleReconstructConfig(frame_duration, window_duration, min_gap_duration, seg_min_duration_off,
+                                   seg_min_duration_on, min_segment_duration, int(exclusive_segments))
+    L = lib()
+    L.oracle_build_segments.restype = C.c_int32
+    L.oracle_build_segments.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                        C.c_int32, C.c_int32, C.POINTER(_OracleReconstructConfig), C.c_void_p, C.c_int32]
+    cap = max(16, chunks * max(speakers, 1) * 4 + 16)
+    while True:
+        buf = (_OracleSegment * cap)()
+        n = L.oracle_build_segments(w.ctypes.data if w.size else None, chunks, frames, speakers,
+                                    offs.ctypes.data if offs.size else None, offs.size,
+                                    hard.ctypes.data if hard.size else None, hard.shape[0], centroid_count, C.byref(cfg), buf, cap)
+        if n <= cap:
+            return [(buf[i].cluster, buf[i].start, buf[i].end, buf[i].quality) for i in range(n)]
+        cap = n
+
+
 def kmeans(emb: np.ndarray, num_clusters: int, max_iterations: int = 300, seed: int = 0):
     """KMeansClustering.clusterWithCentroids (:39-92): (labels, centroids, loop iterations)."""
     emb = np.ascontiguousarray(emb, np.float64)

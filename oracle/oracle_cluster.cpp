@@ -855,4 +855,169 @@ void oracle_speaker_constraints(int64_t num_embeddings, int64_t num_speakers, in
     out[1] = hi;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Timeline reconstruction (second half): OfflineReconstruction.buildSegments
+//   Sources/FluidAudio/Diarizer/Offline/Utils/OfflineReconstruction.swift:24-253 (aggregation, per-frame speaker count,
+//   ranking, segment accumulation), :399-425 appendSegment, :427-460 mergeSegments, :462-476 blendedQuality,
+//   :478-493 sanitize, :359-397 excludeOverlaps, :495-505 chunkStartTime.
+// Inputs are what the (not re-implemented) segmentation model produced: per chunk / frame / local-speaker weights.
+// The optional zero-vote re-embed pass (:177-186) needs a span-embedding closure, i.e. model inference, and is disabled
+// by default (OfflineDiarizerTypes.swift:279): not restated.
+// "parity unpinned" in one respect: the reference closes and opens segments by iterating a Swift Dictionary / Set,
+// whose order is randomised per process; only segments with EXACTLY equal start times can be reordered by that, and
+// here they are taken in ascending cluster order (Swift's sort is stable, the later steps are order-preserving).
+struct oracle_segment {
+    int32_t cluster;
+    float start, end, quality;
+};
+struct oracle_reconstruct_config {
+    double frame_duration, window_duration, min_gap_duration, seg_min_duration_off, seg_min_duration_on, min_segment_duration;
+    int32_t exclusive_segments;
+};
+
+static float oracle_blended_quality(const oracle_segment &l, const oracle_segment &r) {   // :462-476
+    const double ld = (double)(l.end - l.start), rd = (double)(r.end - r.start), total = ld + rd;
+    if (!(total > 0)) return std::min(std::max((l.quality + r.quality) / 2, 0.0f), 1.0f);
+    const double weighted = (double)l.quality * ld + (double)r.quality * rd;
+    return (float)std::min(std::max(weighted / total, 0.0), 1.0);
+}
+
+int32_t oracle_build_segments(const float *weights, int32_t num_chunks, int32_t num_frames, int32_t num_speakers,
+                              const double *chunk_offsets, int32_t offsets_count, const int32_t *hard_clusters,
+                              int32_t hard_rows, int32_t centroid_count, const oracle_reconstruct_config *cfg,
+                              oracle_segment *out, int32_t cap) {
+    if (num_chunks <= 0 || num_frames <= 0) return 0;
+    const double dur = cfg->frame_duration;
+    if (!(dur > 0)) return 0;
+    const int K = std::max(centroid_count, 1);
+    const double gap_threshold = std::max(cfg->min_gap_duration, cfg->seg_min_duration_off);
+    auto chunk_start = [&](int c) { return c < offsets_count ? chunk_offsets[c] : (double)c * cfg->window_duration; };
+    double max_time = 0.0;
+    for (int c = 0; c < num_chunks; ++c) max_time = std::max(max_time, chunk_start(c) + (double)num_frames * dur);
+    const int total = std::max(1, (int)std::ceil(max_time / dur));
+    std::vector<std::vector<double>> sums(total, std::vector<double>(K, 0.0)), counts(total, std::vector<double>(K, 0.0));
+    std::vector<double> exp_sum(total, 0.0), exp_w(total, 0.0);
+    for (int c = 0; c < num_chunks; ++c) {
+        const double off = chunk_start(c);
+        for (int f = 0; f < num_frames; ++f) {
+            const double fs = off + (double)f * dur;
+            int g = (int)std::round(fs / dur);                       // .rounded(): to nearest, ties away from zero
+            g = std::min(std::max(g, 0), total - 1);
+            const float *w = weights + ((size_t)c * num_frames + f) * num_speakers;
+            std::vector<double> act(K, 0.0);
+            for (int s = 0; s < num_speakers; ++s) {
+                const int cl = c < hard_rows ? hard_clusters[(size_t)c * num_speakers + s] : -2;
+                if (cl < 0 || cl >= K) continue;
+                if ((double)w[s] > act[cl]) act[cl] = (double)w[s];
+            }
+            double expected = 0.0;
+            for (int s = 0; s < num_speakers; ++s) expected += (double)w[s];
+            exp_sum[g] += expected;
+            exp_w[g] += 1;
+            for (int k = 0; k < K; ++k)
+                if (act[k] > 0) {
+                    sums[g][k] += act[k];
+                    counts[g][k] += 1;
+                }
+        }
+    }
+    std::vector<std::vector<double>> avg(total, std::vector<double>(K, 0.0));
+    for (int g = 0; g < total; ++g)
+        for (int k = 0; k < K; ++k) avg[g][k] = counts[g][k] == 0 ? 0.0 : sums[g][k] / counts[g][k];
+    const int max_allowed = std::min(K, num_speakers);
+    std::vector<std::vector<int>> per_frame(total);
+    for (int g = 0; g < total; ++g) {
+        if (!(exp_w[g] > 0)) continue;
+        int required = (int)std::nearbyint(exp_sum[g] / exp_w[g]);   // .toNearestOrEven (default FE_TONEAREST)
+        required = std::min(std::max(required, 0), max_allowed);
+        if (required <= 0) continue;
+        std::vector<int> order(K);
+        for (int k = 0; k < K; ++k) order[k] = k;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return sums[g][a] > sums[g][b]; });
+        per_frame[g].assign(order.begin(), order.begin() + required);
+    }
+    struct Acc {
+        bool on = false;
+        double start = 0, end = 0, score = 0;
+        int frames = 0;
+    };
+    std::vector<Acc> active(K);
+    std::vector<oracle_segment> raw;
+    auto append = [&](int k, const Acc &a, double end_time) {        // appendSegment (:399-425)
+        if (!(end_time > a.start)) return;
+        const double mean = a.frames > 0 ? a.score / (double)a.frames : a.score;
+        raw.push_back({k, (float)a.start, (float)end_time, (float)std::min(std::max(mean, 0.0), 1.0)});
+    };
+    for (int g = 0; g < total; ++g) {
+        const double fs = (double)g * dur, fe = fs + dur;
+        std::vector<char> now(K, 0);
+        for (int k : per_frame[g]) now[k] = 1;
+        for (int k = 0; k < K; ++k)
+            if (active[k].on && !now[k]) {
+                append(k, active[k], fs);
+                active[k] = Acc{};
+            }
+        for (int k = 0; k < K; ++k) {
+            if (!now[k]) continue;
+            if (active[k].on) {
+                active[k].end = fe;
+                active[k].score += avg[g][k];
+                active[k].frames += 1;
+            } else {
+                active[k].on = true;
+                active[k].start = fs;
+                active[k].end = fe;
+                active[k].score = avg[g][k];
+                active[k].frames = 1;
+            }
+        }
+    }
+    for (int k = 0; k < K; ++k)
+        if (active[k].on) append(k, active[k], active[k].end);
+    // mergeSegments (:427-460)
+    std::vector<oracle_segment> merged;
+    if (!raw.empty()) {
+        std::stable_sort(raw.begin(), raw.end(), [](const oracle_segment &a, const oracle_segment &b) { return a.start < b.start; });
+        oracle_segment cur = raw[0];
+        for (size_t i = 1; i < raw.size(); ++i) {
+            const oracle_segment &sg = raw[i];
+            if (sg.cluster == cur.cluster && (double)sg.start - (double)cur.end <= gap_threshold) {
+                const float q = oracle_blended_quality(cur, sg);
+                cur.end = std::max(cur.end, sg.end);
+                cur.quality = q;
+                continue;
+            }
+            merged.push_back(cur);
+            cur = sg;
+        }
+        merged.push_back(cur);
+    }
+    // sanitize (:478-493)
+    std::stable_sort(merged.begin(), merged.end(), [](const oracle_segment &a, const oracle_segment &b) { return a.start < b.start; });
+    const float min_dur = std::max((float)cfg->min_segment_duration, (float)cfg->seg_min_duration_on);
+    std::vector<oracle_segment> kept;
+    for (const auto &sg : merged)
+        if (sg.end - sg.start >= min_dur) kept.push_back(sg);
+    std::vector<oracle_segment> result;
+    if (cfg->exclusive_segments) {                                    // excludeOverlaps (:359-397)
+        for (const auto &sg : kept) {
+            float st = sg.start;
+            const float en = sg.end;
+            if (!result.empty() && st < result.back().end) st = result.back().end;
+            if (st >= en) continue;
+            const float d = en - st;
+            if (d < (float)cfg->min_segment_duration) continue;
+            const float orig = sg.end - sg.start;
+            const float scale = orig > 0 ? d / orig : 1.0f;
+            result.push_back({sg.cluster, st, en, std::max(0.0f, std::min(1.0f, sg.quality * scale))});
+        }
+    } else {
+        result = kept;
+    }
+    const int32_t n = (int32_t)result.size();
+    for (int32_t i = 0; i < n && i < cap; ++i) out[i] = result[i];
+    return n;
+}
+
 } // extern "C"

@@ -370,3 +370,64 @@ def test_headers_are_plain_c_and_link(lib, tmp_path):
                            "-lfluidaudio_b200", f"-Wl,-rpath,{libdir}"])
     out = subprocess.check_output([str(exe)], text=True)
     assert out.startswith("abi ok:")
+
+
+# ---- timeline reconstruction (OfflineReconstruction.buildSegments): host code of the library vs the oracle -----------
+def _synthetic_segmentation(rng, chunks, frames=60, speakers=3, step=20, dur=0.05, k=3):
+    """Sliding windows over a piecewise-constant speaker timeline: weights in {~0, ~1}, local slots permuted per chunk."""
+    total = step * (chunks - 1) + frames
+    truth = np.zeros((total, k), np.float32)
+    t = 0
+    while t < total:
+        length = int(rng.integers(5, 40))
+        who = rng.choice(k, size=int(rng.integers(0, 3)), replace=False)
+        truth[t:t + length, who] = 1.0
+        t += length
+    w = np.zeros((chunks, frames, speakers), np.float32)
+    hard = np.full((chunks, speakers), -2, np.int32)
+    for c in range(chunks):
+        perm = rng.permutation(k)[:speakers]
+        seg = truth[c * step:c * step + frames]
+        for s, cl in enumerate(perm):
+            if seg[:, cl].any():
+                hard[c, s] = cl
+                w[c, :, s] = np.clip(seg[:, cl] * rng.uniform(0.7, 1.0) + rng.uniform(0, 0.05, frames), 0, 1)
+    offsets = np.arange(chunks) * step * dur
+    return w, hard, offsets, dur, truth
+
+
+def test_timeline_reconstruction_matches_oracle(lib, oracle):
+    from fluidaudio_b200.clustering import OfflineReconstruction
+    rng = np.random.default_rng(4)
+    for case in range(12):
+        chunks = int(rng.integers(1, 30))
+        w, hard, offsets, dur, truth = _synthetic_segmentation(rng, chunks)
+        kw = dict(min_gap_duration=float(rng.choice([0.0, 0.1, 0.5])), min_segment_duration=float(rng.choice([0.0, 0.2, 1.0])),
+                  exclusive_segments=bool(rng.integers(0, 2)))
+        use_off = offsets if case % 3 else offsets[: max(1, chunks // 2)]        # missing offsets -> chunk * windowDuration
+        got = OfflineReconstruction(dur, window_duration=1.0, **kw).build_segments(w, hard, 3, use_off)
+        ref = oracle.build_segments(w, hard, 3, dur, use_off, window_duration=1.0, **kw)
+        assert [(s.cluster, s.start_time_seconds, s.end_time_seconds, s.quality_score) for s in got] == \
+            [(c, float(a), float(b), float(q)) for c, a, b, q in ref], case
+        starts = [s.start_time_seconds for s in got]
+        assert starts == sorted(starts) and all(s.speaker_id == f"S{s.cluster + 1}" for s in got)
+        if kw["exclusive_segments"]:
+            assert all(a.end_time_seconds <= b.start_time_seconds for a, b in zip(got, got[1:]))
+        assert all(s.end_time_seconds - s.start_time_seconds >= np.float32(kw["min_segment_duration"]) for s in got)
+    # hand-checked cases: two chunks of 4 frames (0.5 s each), one local speaker each, both mapped to cluster 1
+    w = np.zeros((2, 4, 2), np.float32)
+    w[0, :, 0] = 0.9
+    w[1, 2:, 1] = 0.8
+    hard = np.array([[1, -2], [-2, 1]], np.int32)
+    r = OfflineReconstruction(0.5, window_duration=2.0, min_segment_duration=0.0)
+    segs = r.build_segments(w, hard, 2, [0.0, 2.0])
+    assert [(s.cluster, s.start_time_seconds, s.end_time_seconds) for s in segs] == [(1, 0.0, 2.0), (1, 3.0, 4.0)]
+    assert abs(segs[0].quality_score - 0.9) < 1e-6 and abs(segs[1].quality_score - 0.8) < 1e-6
+    merged = OfflineReconstruction(0.5, window_duration=2.0, min_segment_duration=0.0, min_gap_duration=1.0) \
+        .build_segments(w, hard, 2, [0.0, 2.0])
+    assert [(s.cluster, s.start_time_seconds, s.end_time_seconds) for s in merged] == [(1, 0.0, 4.0)]
+    assert abs(merged[0].quality_score - (0.9 * 2 + 0.8 * 1) / 3) < 1e-6          # duration-weighted blend
+    assert OfflineReconstruction(0.0).build_segments(w, hard, 2) == []            # frameDuration <= 0 -> []
+    assert OfflineReconstruction(0.5).build_segments(np.zeros((0, 0, 0), np.float32), [], 2) == []
+    none = r.build_segments(w, np.full((2, 2), -2, np.int32), 2, [0.0, 2.0])
+    assert all(s.cluster == 0 for s in none)     # zero votes everywhere: the ranking's tie-break picks cluster 0 (:177-186)
