@@ -32,6 +32,21 @@ int main(void) {
     fa_mel_default_config(&mc);
     if (mc.n_fft != 512 || mc.hop_length != 160) return 9;
 
+    /* timeline reconstruction: one chunk, four frames of 0.5 s, local speaker 0 -> cluster 1 */
+    {
+        fa_reconstruct_config rc;
+        fa_reconstruct_default_config(&rc);
+        rc.frame_duration = 0.5;
+        rc.min_segment_duration = 0.0;
+        const float weights[8] = {0.9f, 0.0f, 0.9f, 0.0f, 0.9f, 0.0f, 0.9f, 0.0f};
+        const int32_t hard[2] = {1, -2};
+        const double offsets[1] = {0.0};
+        int32_t cl[4], count = 0;
+        float st[4], en[4], q[4];
+        if (fa_build_segments(weights, 1, 4, 2, offsets, 1, hard, 1, 2, &rc, cl, st, en, q, 4, &count) != FA_STATUS_OK) return 10;
+        if (count != 1 || cl[0] != 1 || st[0] != 0.0f || en[0] != 2.0f) return 11;
+    }
+
     printf("abi ok: %s, devices visible: %d\n", v, fa_device_count());
     return 0;
 }
