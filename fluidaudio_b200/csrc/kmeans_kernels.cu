@@ -298,7 +298,6 @@ int cluster_ninit_device(vbx::Workspace &ws, const double *d_emb, int N, int D, 
     lc += 2;
 
     double best = DBL_MAX;
-    bool have = false;
     RunState h{};
     std::vector<int> perm(N);
     for (int run = 0; run < runs; ++run) {
@@ -343,13 +342,11 @@ int cluster_ninit_device(vbx::Workspace &ws, const double *d_emb, int N, int D, 
         FA_CUDA_TRY(cudaStreamSynchronize(s));
         if (runs == 1 || h.inertia < best) {                  // :122-125: strictly lower inertia wins
             best = h.inertia;
-            have = true;
             FA_CUDA_TRY(cudaMemcpyAsync(d_labels, final_labels, sizeof(int) * N, cudaMemcpyDeviceToDevice, s));
             FA_CUDA_TRY(cudaMemcpyAsync(d_centroids, d_cent, sizeof(double) * (size_t)k * D, cudaMemcpyDeviceToDevice, s));
             if (best_init) *best_init = run;
         }
     }
-    (void)have;
     FA_CUDA_TRY(cudaStreamSynchronize(s));
     if (rows) *rows = k;
     if (launches) *launches += lc;
