@@ -557,3 +557,30 @@ def test_next_rows_against_committed_goldens(gpu_lib, golden_dir):
     f2 = fe.process(a[4000 - 352:9000])
     assert np.abs(f1 - g["lseend__f1"]).max() < 1e-4 and np.abs(f2 - g["lseend__f2"]).max() < 1e-4
     assert np.abs(fe.cmn_mean - g["lseend__mean"]).max() < 1e-4 and fe.cmn_count == int(g["lseend__count"][0])
+
+
+def test_pipeline_odd_shapes_and_tiny_inputs(gpu_lib, oracle):
+    """Shapes the fuzz sweep (scripts/gpu_fuzz.py) covers, pinned as a test: embedding widths that are not 256, one to five
+    embeddings, filtered (NaN / Inf) rows, a PLDA vector of the wrong length (-> identity, VBxClustering.swift:71-76).
+    Labels must agree wherever the decision is not a rounding-level tie (two identical centroids can come out of VBx)."""
+    rng = np.random.default_rng(12)
+    cases = [(1, 256, 1), (2, 256, 2), (3, 64, 2), (5, 192, 2), (17, 64, 2), (100, 255, 3), (333, 257, 3), (400, 192, 4)]
+    for n, d, k in cases:
+        emb, _ = synth.speaker_embeddings(n, d, k, seed=n + d)
+        if n >= 100:
+            emb[rng.integers(0, n)] = np.nan
+            emb[rng.integers(0, n)] = np.inf
+        rho, psi = synth.synthetic_plda(np.nan_to_num(emb, nan=0.0, posinf=0.0, neginf=0.0), min(128, d))
+        for p in (psi, psi[:-1]):                                   # second pass: wrong length -> identity on both sides
+            got = cl.OfflineClusterer(psi=p).cluster(emb, rho)
+            ref = oracle.diarize_cluster(emb, rho, p, use_ref=oracle.ref_available())
+            assert got.info["training_count"] == ref.training_indices.size
+            assert np.array_equal(got.initial[got.initial >= 0], ref.initial)
+            assert got.centroids.shape == ref.centroids.shape and np.abs(got.centroids - ref.centroids).max() < 1e-9
+            ok = np.isfinite(emb).all(axis=1)
+            cn = ref.centroids / np.maximum(np.linalg.norm(ref.centroids, axis=1, keepdims=True), 1e-300)
+            e = np.where(ok[:, None], emb, 0.0).astype(np.float64)
+            sc = (e / np.maximum(np.linalg.norm(e, axis=1, keepdims=True), 1e-300)) @ cn.T
+            srt = np.sort(sc, axis=1)
+            decided = ok & ((srt[:, -1] - srt[:, -2] > 1e-9) if sc.shape[1] > 1 else np.ones(n, bool))
+            assert np.array_equal(got.labels[decided], ref.labels[decided]), (n, d, k)
