@@ -71,7 +71,7 @@ EXPORTED_SYMBOLS = [
     "fa_diarize_cluster", "fa_diarize_cluster_batch", "fa_ahc_last_stage_ms", "fa_diarize_cluster_chunks",
     "fa_hungarian_solve", "fa_max_score_assignment", "fa_constrained_assign", "fa_build_chunk_assignments",
     "fa_export_shape", "fa_export_read", "fa_export_write", "fa_kmeans_cluster", "fa_speaker_constraints_resolve",
-    "fa_reconstruct_default_config", "fa_build_segments",
+    "fa_reconstruct_default_config", "fa_build_segments", "fa_build_speaker_database",
     "fastcluster_compute_centroid_linkage",
 ]
 
@@ -145,6 +145,7 @@ def load():
     L.fa_reconstruct_default_config.restype = None
     L.fa_build_segments.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, i32, C.POINTER(ReconstructConfig), vp, vp, vp, vp,
                                     i32, C.POINTER(i32)]
+    L.fa_build_speaker_database.argtypes = [vp, i32, vp, i32, i32, vp, vp]
     L.fa_export_shape.argtypes = [C.c_char_p, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
     L.fa_export_read.argtypes = [C.c_char_p, sz, sz, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.fa_export_write.argtypes = [C.c_char_p, sz, sz, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -396,3 +396,17 @@ class OfflineReconstruction:
             break
         return [TimedSpeakerSegment(f"S{int(cl[i]) + 1}", int(cl[i]), float(st[i]), float(en[i]), float(q[i]))
                 for i in range(n.value)]
+
+    @staticmethod
+    def build_speaker_database(segments, centroids) -> dict:
+        """buildSpeakerDatabase (:296-357): {"S<k+1>": float32 mean embedding} for the speakers that own a segment."""
+        cen = np.ascontiguousarray(centroids, np.float64)
+        K, dim = cen.shape if cen.ndim == 2 else (0, 0)
+        cl = np.ascontiguousarray([s.cluster for s in segments], np.int32)
+        db = np.zeros((K, dim), np.float32)
+        counts = np.zeros(max(K, 1), np.int32)
+        _lib.check(_lib.load().fa_build_speaker_database(cl.ctypes.data if cl.size else None, cl.size,
+                                                         cen.ctypes.data if cen.size else None, K, dim,
+                                                         db.ctypes.data if db.size else None, counts.ctypes.data),
+                   "fa_build_speaker_database")
+        return {f"S{k + 1}": db[k].copy() for k in range(K) if counts[k] > 0}

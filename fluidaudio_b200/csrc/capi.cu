@@ -978,6 +978,17 @@ FA_API fa_status fa_build_segments(const float *weights, int32_t num_chunks, int
     FA_GUARD_END
 }
 
+FA_API fa_status fa_build_speaker_database(const int32_t *seg_cluster, int32_t segment_count, const double *centroids,
+                                           int32_t K, int32_t dim, float *database, int32_t *segment_counts) {
+    if (segment_count < 0 || K < 0 || dim < 0 || (segment_count > 0 && !seg_cluster) ||
+        (K > 0 && (!segment_counts || (dim > 0 && (!centroids || !database)))))
+        return FA_STATUS_INVALID_ARGUMENT;
+    FA_GUARD_BEGIN
+    reconstruct::build_speaker_database(seg_cluster, segment_count, centroids, K, dim, database, segment_counts);
+    return FA_STATUS_OK;
+    FA_GUARD_END
+}
+
 FA_API fa_status fa_speaker_constraints_resolve(int64_t num_embeddings, int64_t num_speakers, int64_t min_speakers,
                                                 int64_t max_speakers, int64_t *resolved_min, int64_t *resolved_max) {
     if (!resolved_min || !resolved_max) return FA_STATUS_INVALID_ARGUMENT;

@@ -160,5 +160,29 @@ void build_segments(const float *weights, int num_chunks, int num_frames, int nu
     }
 }
 
+void build_speaker_database(const int32_t *seg_cluster, int seg_count, const double *centroids, int K, int dim,
+                            float *database, int32_t *counts) {
+    std::fill(counts, counts + K, 0);
+    std::fill(database, database + (size_t)K * dim, 0.0f);
+    for (int s = 0; s < seg_count; ++s) {
+        const int k = seg_cluster[s];
+        if (k < 0 || k >= K) continue;                       // a cluster without centroid contributes a zero embedding
+        float *row = database + (size_t)k * dim;
+        const double *c = centroids + (size_t)k * dim;
+        if (counts[k] == 0) {
+            for (int q = 0; q < dim; ++q) row[q] = (float)c[q];           // sums[speaker] = segment.embedding (:330)
+        } else {
+            for (int q = 0; q < dim; ++q) row[q] = row[q] + (float)c[q];  // cblas_saxpy, alpha = 1 (:313-325)
+        }
+        ++counts[k];
+    }
+    for (int k = 0; k < K; ++k) {
+        if (counts[k] <= 0) continue;
+        const float scale = 1.0f / (float)counts[k];                     // vDSP_vsmul (:341-352)
+        float *row = database + (size_t)k * dim;
+        for (int q = 0; q < dim; ++q) row[q] *= scale;
+    }
+}
+
 } // namespace reconstruct
 } // namespace fa

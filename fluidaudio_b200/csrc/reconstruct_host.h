@@ -30,5 +30,9 @@ void build_segments(const float *weights, int num_chunks, int num_frames, int nu
                     int offsets_count, const int32_t *hard_clusters, int hard_rows, int centroid_count, const Config &cfg,
                     std::vector<Segment> &out);
 
+// buildSpeakerDatabase (:296-357): float32 mean of the segment embeddings (= Float(centroid)) per speaker.
+void build_speaker_database(const int32_t *seg_cluster, int seg_count, const double *centroids, int K, int dim,
+                            float *database, int32_t *counts);
+
 } // namespace reconstruct
 } // namespace fa

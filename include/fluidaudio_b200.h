@@ -251,6 +251,11 @@ fa_status fa_build_segments(const float *speaker_weights, int32_t num_chunks, in
                             int32_t *seg_cluster, float *seg_start, float *seg_end, float *seg_quality,
                             int32_t segment_cap, int32_t *segment_count);
 
+/* OfflineReconstruction.buildSpeakerDatabase (:296-357): database [K x dim] = per speaker the float32 mean of its segments'
+ * embeddings (a segment's embedding is Float(centroids[cluster])); segment_counts [K]; speakers without segment stay zero. */
+fa_status fa_build_speaker_database(const int32_t *seg_cluster, int32_t segment_count, const double *centroids, int32_t K,
+                                    int32_t dim, float *database, int32_t *segment_counts);
+
 /* KMeansClustering.clusterWithCentroidsNInit (Diarizer/Offline/Clustering/KMeansClustering.swift:39-130) on raw
  * embeddings [N x D]: labels [N], centroids (normalised space) [min(num_clusters, N) x D] -> *centroid_rows rows;
  * *best_init = index of the winning seed.  n_init <= 1 runs the single seeded clustering (:39-92).

@@ -434,6 +434,21 @@ def build_segments(speaker_weights, hard_clusters, centroid_count, frame_duratio
         cap = n
 
 
+def build_speaker_database(seg_clusters, centroids):
+    """OfflineReconstruction.buildSpeakerDatabase (:296-357) -> (database float32 [K x dim], segment counts [K])."""
+    cl = np.ascontiguousarray(seg_clusters, np.int32)
+    cen = np.ascontiguousarray(centroids, np.float64)
+    K, dim = cen.shape
+    db = np.zeros((K, dim), np.float32)
+    counts = np.zeros(K, np.int32)
+    L = lib()
+    L.oracle_build_speaker_database.restype = None
+    L.oracle_build_speaker_database.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.oracle_build_speaker_database(cl.ctypes.data if cl.size else None, cl.size, cen.ctypes.data, K, dim, db.ctypes.data,
+                                    counts.ctypes.data)
+    return db, counts
+
+
 def kmeans(emb: np.ndarray, num_clusters: int, max_iterations: int = 300, seed: int = 0):
     """KMeansClustering.clusterWithCentroids (:39-92): (labels, centroids, loop iterations)."""
     emb = np.ascontiguousarray(emb, np.float64)

@@ -1020,4 +1020,28 @@ int32_t oracle_build_segments(const float *weights, int32_t num_chunks, int32_t 
     return n;
 }
 
+
+// OfflineReconstruction.buildSpeakerDatabase (OfflineReconstruction.swift:296-357): per speaker the float32 mean of its
+// segments' embeddings; a segment's embedding is its cluster's centroid narrowed to Float (appendSegment :409-414, zeros
+// when the cluster has no centroid).  database: [K x dim], rows of speakers without segments stay zero; counts: [K].
+void oracle_build_speaker_database(const int32_t *seg_cluster, int32_t seg_count, const double *centroids, int32_t K,
+                                   int32_t dim, float *database, int32_t *counts) {
+    for (int32_t k = 0; k < K; ++k) counts[k] = 0;
+    for (int64_t i = 0; i < (int64_t)K * dim; ++i) database[i] = 0.0f;
+    for (int32_t s = 0; s < seg_count; ++s) {
+        const int32_t k = seg_cluster[s];
+        if (k < 0 || k >= K) continue;
+        for (int32_t q = 0; q < dim; ++q) {
+            const float e = (float)centroids[(int64_t)k * dim + q];
+            database[(int64_t)k * dim + q] = counts[k] == 0 ? e : database[(int64_t)k * dim + q] + e;   // first: copy (:330)
+        }
+        counts[k] += 1;
+    }
+    for (int32_t k = 0; k < K; ++k) {
+        if (counts[k] <= 0) continue;
+        const float scale = 1.0f / (float)counts[k];
+        for (int32_t q = 0; q < dim; ++q) database[(int64_t)k * dim + q] *= scale;
+    }
+}
+
 } // extern "C"

@@ -429,5 +429,11 @@ def test_timeline_reconstruction_matches_oracle(lib, oracle):
     assert abs(merged[0].quality_score - (0.9 * 2 + 0.8 * 1) / 3) < 1e-6          # duration-weighted blend
     assert OfflineReconstruction(0.0).build_segments(w, hard, 2) == []            # frameDuration <= 0 -> []
     assert OfflineReconstruction(0.5).build_segments(np.zeros((0, 0, 0), np.float32), [], 2) == []
+    cents = np.random.default_rng(0).standard_normal((2, 7))
+    db = OfflineReconstruction.build_speaker_database(merged + segs, cents)      # three segments, all of cluster 1
+    odb, ocnt = oracle.build_speaker_database([s.cluster for s in merged + segs], cents)
+    assert list(db) == ["S2"] and ocnt.tolist() == [0, 3] and db["S2"].tobytes() == odb[1].tobytes()
+    c32 = cents[1].astype(np.float32)
+    assert np.array_equal(db["S2"], ((c32 + c32) + c32) * np.float32(1.0 / 3.0))
     none = r.build_segments(w, np.full((2, 2), -2, np.int32), 2, [0.0, 2.0])
     assert all(s.cluster == 0 for s in none)     # zero votes everywhere: the ranking's tie-break picks cluster 0 (:177-186)
