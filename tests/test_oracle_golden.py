@@ -474,3 +474,70 @@ def test_next_row_goldens(oracle, golden_dir):
     f2, mean, cnt = oracle.lseend_features(cfg, a[4000 - 352:9000], mean, cnt)
     assert f1.tobytes() == g["lseend__f1"].tobytes() and f2.tobytes() == g["lseend__f2"].tobytes()
     assert mean.tobytes() == g["lseend__mean"].tobytes() and cnt == int(g["lseend__count"][0])
+
+
+def test_kmeans_against_independent_python_restatement(oracle):
+    """A second, independent restatement of KMeansClustering.clusterWithCentroids (:39-92) in plain Python floats —
+    seeded shuffle, first-k picks, strict-< assignment, index-order sums, empty-cluster re-seeding — must give the C++
+    oracle's labels and centroids bit for bit."""
+    def py_kmeans(emb, k, iters, seed):
+        n, d = len(emb), len(emb[0])
+        k = min(k, n)
+        if n <= k:
+            return list(range(n)), [list(map(float, e)) for e in emb]
+        rng = _SwiftLCG(seed)
+        x = []
+        for e in emb:
+            s = 0.0
+            for v in e:
+                s += v * v
+            norm = s ** 0.5
+            x.append([v * (1.0 / norm) for v in e] if norm > 1e-10 else list(e))
+        idx = list(range(n))
+        amount, cur = n, 0
+        while amount > 1:
+            r = rng.next_below(amount)
+            amount -= 1
+            idx[cur], idx[cur + r] = idx[cur + r], idx[cur]
+            cur += 1
+        cen = [list(x[i]) for i in idx[:k]]
+        assign = [0] * n
+        for _ in range(iters):
+            fresh = []
+            for p in x:
+                best, bd = 0, float("inf")
+                for j, c in enumerate(cen):
+                    dist = 0.0
+                    for a, b in zip(p, c):
+                        t = a - b
+                        dist += t * t
+                    if dist < bd:
+                        best, bd = j, dist
+                fresh.append(best)
+            if fresh == assign:
+                break
+            assign = fresh
+            sums = [[0.0] * d for _ in range(k)]
+            counts = [0] * k
+            for p, a in zip(x, assign):
+                counts[a] += 1
+                for q in range(d):
+                    sums[a][q] += p[q]
+            cen = []
+            for j in range(k):
+                if counts[j] > 0:
+                    inv = 1.0 / counts[j]
+                    cen.append([v * inv for v in sums[j]])
+                else:
+                    cen.append(list(x[rng.next_below(n)]))
+        return assign, cen
+
+    rng = np.random.default_rng(8)
+    for n, d, k, seed in ((12, 3, 3, 0), (40, 8, 5, 7), (25, 4, 6, 42), (9, 2, 9, 1), (30, 5, 4, 12345)):
+        emb = rng.standard_normal((n, d)) + 3.0 * rng.integers(0, 3, (n, 1))
+        if n == 25:
+            emb[5:15] = emb[5]                     # duplicates: provokes an empty cluster and its re-seeding
+        lab, cen, _ = oracle.kmeans(emb, k, 50, seed)
+        plab, pcen = py_kmeans(emb.tolist(), k, 50, seed)
+        assert lab.tolist() == plab
+        assert np.array(pcen, np.float64).tobytes() == cen.tobytes()
