@@ -35,6 +35,11 @@ class MelConfig(C.Structure):
                 ("log_floor_mode", C.c_int32), ("window_periodic", C.c_int32)]
 
 
+class AudioFormat(C.Structure):
+    _fields_ = [("in_rate", C.c_double), ("out_rate", C.c_double), ("channels", C.c_int32), ("format", C.c_int32),
+                ("interleaved", C.c_int32), ("algorithm", C.c_int32)]
+
+
 class VbxConfig(C.Structure):
     _fields_ = [("Fa", C.c_double), ("Fb", C.c_double), ("max_iterations", C.c_int32), ("epsilon", C.c_double),
                 ("init_smoothing", C.c_double)]
@@ -62,10 +67,11 @@ class ReconstructConfig(C.Structure):
 EXPORTED_SYMBOLS = [
     "fa_version", "fa_last_error", "fa_device_count", "fa_set_device", "fa_device_synchronize",
     "fa_kernel_launch_count", "fa_host_alloc", "fa_host_free", "fa_device_alloc", "fa_device_free", "fa_memcpy_h2d",
-    "fa_memcpy_d2h", "fa_timer_start", "fa_timer_stop_ms", "fa_mel_default_config", "fa_mel_create",
+    "fa_memcpy_d2h", "fa_memcpy_probe", "fa_timer_start", "fa_timer_stop_ms", "fa_mel_default_config", "fa_mel_create",
     "fa_mel_destroy", "fa_mel_get_window", "fa_mel_get_filterbank", "fa_mel_frame_count", "fa_mel_compute",
     "fa_mel_compute_device", "fa_mel_compute_batch", "fa_mel_compute_batch_device", "fa_mel_timer_start",
-    "fa_mel_timer_stop_ms", "fa_mel_normalize_per_feature", "fa_mel_unified_features", "fa_mel_lseend_features",
+    "fa_mel_timer_stop_ms", "fa_mel_set_precision", "fa_mel_get_precision", "fa_mel_normalize_per_feature", "fa_mel_unified_features", "fa_mel_lseend_features",
+    "fa_resample_output_count", "fa_audio_resample", "fa_audio_to_mel",
     "fa_linear_resample", "fa_l2_normalize_rows", "fa_ahc_cluster", "fa_dendrogram_cut", "fa_vbx_default_config",
     "fa_vbx_refine", "fa_compute_centroids", "fa_assign_embeddings", "fa_cluster_default_config",
     "fa_diarize_cluster", "fa_diarize_cluster_batch", "fa_ahc_last_stage_ms", "fa_diarize_cluster_chunks",
@@ -100,6 +106,7 @@ def load():
     L.fa_device_free.argtypes = [vp]
     L.fa_memcpy_h2d.argtypes = [vp, vp, sz]
     L.fa_memcpy_d2h.argtypes = [vp, vp, sz]
+    L.fa_memcpy_probe.argtypes = [vp, sz, vp, sz, i32, C.POINTER(f32)]
     L.fa_timer_stop_ms.argtypes = [C.POINTER(f32)]
     L.fa_mel_default_config.argtypes = [C.POINTER(MelConfig)]
     L.fa_mel_default_config.restype = None
@@ -114,11 +121,19 @@ def load():
     L.fa_mel_compute_device.argtypes = L.fa_mel_compute.argtypes
     L.fa_mel_compute_batch.argtypes = [vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]
     L.fa_mel_compute_batch_device.argtypes = L.fa_mel_compute_batch.argtypes
+    L.fa_mel_set_precision.argtypes = [vp, i32]
+    L.fa_mel_get_precision.argtypes = [vp]
+    L.fa_mel_get_precision.restype = i32
     L.fa_mel_timer_start.argtypes = [vp]
     L.fa_mel_timer_stop_ms.argtypes = [vp, C.POINTER(f32)]
     L.fa_mel_normalize_per_feature.argtypes = [vp, i64, i32, i64]
     L.fa_mel_unified_features.argtypes = [vp, vp, sz, sz, vp, sz, C.POINTER(i64), C.POINTER(i32)]
     L.fa_mel_lseend_features.argtypes = [vp, vp, sz, vp, C.POINTER(i64), vp, sz, C.POINTER(i64)]
+    L.fa_resample_output_count.argtypes = [C.POINTER(AudioFormat), i64]
+    L.fa_resample_output_count.restype = i64
+    L.fa_audio_resample.argtypes = [vp, i64, C.POINTER(AudioFormat), vp, i64, C.POINTER(i64)]
+    L.fa_audio_to_mel.argtypes = [vp, vp, i64, C.POINTER(AudioFormat), f32, i32, i32, vp, sz, C.POINTER(i64),
+                                  C.POINTER(i64), C.POINTER(i64)]
     L.fa_linear_resample.argtypes = [vp, i64, i32, f64, f64, vp, i64, C.POINTER(i64)]
     L.fa_l2_normalize_rows.argtypes = [vp, sz, sz, vp]
     L.fa_ahc_cluster.argtypes = [vp, sz, sz, f64, vp]

@@ -530,6 +530,40 @@ FA_API fa_status fa_memcpy_d2h(void *dst, const void *src, size_t bytes) {
     return FA_STATUS_OK;
 }
 
+// Bare copy-engine probe: `reps` rounds of an H2D copy of h2d_bytes and a D2H copy of d2h_bytes issued together on two
+// streams (device scratch allocated here), wall-clock per round.  bench.py uses it to name the floor under every
+// host-buffer (end-to-end) number: what the PCIe / host-memory path delivers with no kernel in the way.
+FA_API fa_status fa_memcpy_probe(const void *host_src, size_t h2d_bytes, void *host_dst, size_t d2h_bytes, int32_t reps,
+                                 float *ms_per_round) {
+    if (!ms_per_round || reps < 1 || (!host_src && h2d_bytes) || (!host_dst && d2h_bytes)) return FA_STATUS_INVALID_ARGUMENT;
+    API_REQUIRE_DEVICE();
+    struct R {
+        void *a = nullptr, *b = nullptr;
+        cudaStream_t s[2] = {nullptr, nullptr};
+        ~R() {
+            if (a) cudaFree(a);
+            if (b) cudaFree(b);
+            for (auto x : s)
+                if (x) cudaStreamDestroy(x);
+        }
+    } r;
+    API_CUDA_TRY(cudaMalloc(&r.a, h2d_bytes + 16));
+    API_CUDA_TRY(cudaMalloc(&r.b, d2h_bytes + 16));
+    API_CUDA_TRY(cudaMemset(r.b, 0, d2h_bytes + 16));
+    for (auto &x : r.s) API_CUDA_TRY(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+    API_CUDA_TRY(cudaDeviceSynchronize());
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < reps; ++i) {
+        if (h2d_bytes) API_CUDA_TRY(cudaMemcpyAsync(r.a, host_src, h2d_bytes, cudaMemcpyHostToDevice, r.s[0]));
+        if (d2h_bytes) API_CUDA_TRY(cudaMemcpyAsync(host_dst, r.b, d2h_bytes, cudaMemcpyDeviceToHost, r.s[1]));
+        API_CUDA_TRY(cudaStreamSynchronize(r.s[0]));
+        API_CUDA_TRY(cudaStreamSynchronize(r.s[1]));
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    *ms_per_round = (float)(std::chrono::duration<double, std::milli>(t1 - t0).count() / reps);
+    return FA_STATUS_OK;
+}
+
 // Events on the legacy default stream order against every blocking stream AND, because the library's own streams
 // are non-blocking, the timed entry points synchronise their streams before returning (device-side async calls
 // are timed by the caller bracketing fa_device_synchronize()).
@@ -604,6 +638,18 @@ FA_API fa_status fa_mel_get_filterbank(const fa_mel *mel, float *out, size_t len
 FA_API int64_t fa_mel_frame_count(const fa_mel *mel, int64_t n, int32_t padding_mode, int64_t expected) {
     if (!mel) return -1;
     return reinterpret_cast<const MelHandle *>(mel)->plan.frame_count(n, padding_mode, expected);
+}
+
+FA_API fa_status fa_mel_set_precision(fa_mel *mel, int32_t precision) {
+    if (!mel || (precision != FA_MEL_PRECISION_F64 && precision != FA_MEL_PRECISION_F32)) {
+        fa::set_error("precision must be FA_MEL_PRECISION_F64 (0) or FA_MEL_PRECISION_F32 (1)");
+        return FA_STATUS_INVALID_ARGUMENT;
+    }
+    reinterpret_cast<MelHandle *>(mel)->plan.precision = precision;
+    return FA_STATUS_OK;
+}
+FA_API int32_t fa_mel_get_precision(const fa_mel *mel) {
+    return mel ? reinterpret_cast<const MelHandle *>(mel)->plan.precision : -1;
 }
 
 static bool mel_args_ok(int32_t mode, int32_t layout) {
@@ -762,6 +808,94 @@ FA_API fa_status fa_mel_normalize_per_feature(float *x, int64_t frames, int32_t 
         for (int64_t t = 0; t < frames; ++t) x[t * n_mels + m] = t < valid ? (x[t * n_mels + m] - mean) / sd : 0.0f;
     }
     return FA_STATUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ AudioConverter stage
+static bool audio_format_ok(const fa_audio_format *f) {
+    if (!f || !(f->in_rate > 0) || !(f->out_rate > 0) || f->channels < 1 || f->channels > 64 ||
+        (f->format != FA_PCM_F32 && f->format != FA_PCM_I16) || f->algorithm < 0 || f->algorithm > 2) {
+        fa::set_error("audio format: rates must be positive, 1..64 channels, format F32/I16, algorithm 0..2");
+        return false;
+    }
+    return true;
+}
+static resample::AudioFormat to_format(const fa_audio_format *f) {
+    return resample::AudioFormat{f->in_rate, f->out_rate, f->channels, f->format, f->interleaved ? 1 : 0, f->algorithm};
+}
+
+FA_API int64_t fa_resample_output_count(const fa_audio_format *fmt, int64_t frames) {
+    if (!fmt || frames < 0 || !(fmt->in_rate > 0) || !(fmt->out_rate > 0)) return -1;
+    return resample::output_count(frames, fmt->in_rate, fmt->out_rate);
+}
+
+FA_API fa_status fa_audio_resample(const void *pcm, int64_t frames, const fa_audio_format *fmt, float *out,
+                                   int64_t out_cap, int64_t *out_count) {
+    if (!audio_format_ok(fmt) || frames < 0 || (!pcm && frames) || !out_count) return FA_STATUS_INVALID_ARGUMENT;
+    const long long n = resample::output_count(frames, fmt->in_rate, fmt->out_rate);
+    *out_count = n;
+    if (!out) return FA_STATUS_OK;
+    if (out_cap < n) return FA_STATUS_OUTPUT_TOO_SMALL;
+    if (n == 0) return FA_STATUS_OK;
+    API_REQUIRE_DEVICE();
+    FA_GUARD_BEGIN
+    const resample::AudioFormat f = to_format(fmt);
+    resample::Design d;
+    if (f.in_rate != f.out_rate) {
+        const int st = resample::make_design(f.in_rate, f.out_rate, d);
+        if (st != FA_OK) return (fa_status)st;
+    }
+    const size_t bytes = (size_t)frames * f.channels * (f.format == resample::kPcmI16 ? 2 : 4);
+    struct Bufs {
+        void *pcm = nullptr;
+        float *tab = nullptr, *out = nullptr;
+        cudaStream_t s = nullptr;
+        ~Bufs() {
+            if (pcm) cudaFree(pcm);
+            if (tab) cudaFree(tab);
+            if (out) cudaFree(out);
+            if (s) cudaStreamDestroy(s);
+        }
+    } b;
+    API_CUDA_TRY(cudaStreamCreateWithFlags(&b.s, cudaStreamNonBlocking));
+    API_CUDA_TRY(cudaMalloc(&b.pcm, bytes + 16));
+    API_CUDA_TRY(cudaMalloc(&b.out, (size_t)n * sizeof(float)));
+    if (!d.table.empty()) {
+        API_CUDA_TRY(cudaMalloc(&b.tab, d.table.size() * sizeof(float)));
+        API_CUDA_TRY(cudaMemcpyAsync(b.tab, d.table.data(), d.table.size() * sizeof(float), cudaMemcpyHostToDevice, b.s));
+    }
+    API_CUDA_TRY(cudaMemcpyAsync(b.pcm, pcm, bytes, cudaMemcpyHostToDevice, b.s));
+    long long launches = 0;
+    const int st = resample::launch_convert(b.pcm, frames, f, d, b.tab, b.out, 0, n, b.s, &launches);
+    g_launches += launches;
+    if (st != FA_OK) return (fa_status)st;
+    API_CUDA_TRY(cudaMemcpyAsync(out, b.out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, b.s));
+    API_CUDA_TRY(cudaStreamSynchronize(b.s));
+    return FA_STATUS_OK;
+    FA_GUARD_END
+}
+
+FA_API fa_status fa_audio_to_mel(fa_mel *mel, const void *pcm, int64_t frames, const fa_audio_format *fmt, float last,
+                                 int32_t mode, int32_t layout, float *out, size_t out_len, int64_t *mel_length,
+                                 int64_t *num_frames, int64_t *resampled_count) {
+    if (!mel || !out || frames < 0 || (!pcm && frames) || !audio_format_ok(fmt) || !mel_args_ok(mode, layout))
+        return FA_STATUS_INVALID_ARGUMENT;
+    FA_GUARD_BEGIN
+    auto *h = reinterpret_cast<MelHandle *>(mel);
+    if (fmt->out_rate != (double)h->plan.cfg.sample_rate) {
+        fa::set_error("fa_audio_to_mel: out_rate %.3f differs from the handle's sample_rate %d", fmt->out_rate,
+                      h->plan.cfg.sample_rate);
+        return FA_STATUS_INVALID_ARGUMENT;
+    }
+    long long ml = 0, nf = 0, rs = 0;
+    const long long before = h->plan.launches;
+    const int st = h->plan.compute_host_pcm(pcm, (long long)frames, to_format(fmt), last, mode, layout, out,
+                                            (long long)out_len, &ml, &nf, &rs);
+    g_launches += h->plan.launches - before;
+    if (mel_length) *mel_length = ml;
+    if (num_frames) *num_frames = nf;
+    if (resampled_count) *resampled_count = rs;
+    return (fa_status)st;
+    FA_GUARD_END
 }
 
 // AudioConverter.linearResample (AudioConverter.swift:388-442): boundary glue for >2-channel input.

@@ -104,13 +104,14 @@ __device__ __forceinline__ TileGeom tile_geom(const MelLaunch &P, int tile) {
     return g;
 }
 
-template <int kWarps>
+template <int kWarps, typename V>
 __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch P) {
+    constexpr int kF = vtraits<V>::kFrames;   // frames one warp transforms together (2: packed float32 pairs)
     extern __shared__ __align__(128) unsigned char smem[];
     float *raw0 = reinterpret_cast<float *>(smem);
     float *raw1 = raw0 + P.raw_cap;
     float *ptile = raw1 + P.raw_cap;
-    cpxd *fftbuf = reinterpret_cast<cpxd *>(ptile + P.pt_cap);   // kWarps * kFftPad complex doubles (16-byte aligned)
+    cpxv<V> *fftbuf = reinterpret_cast<cpxv<V> *>(ptile + P.pt_cap);   // kWarps * kFftPad complex values (16 bytes each)
     float *power = reinterpret_cast<float *>(fftbuf + kWarps * kFftPad);   // kTileFrames * kPowStride
     float *otile = power + kTileFrames * kPowStride;        // kTileFrames * (n_mels + 1)
     float *fbw = otile + kTileFrames * (P.n_mels + 1);      // fb_nnz_cap
@@ -128,11 +129,11 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
     for (int i = tid; i < P.n_mels; i += kWarps * 32)
         fbmeta[i] = make_int4(P.fb_lo[i], (P.fb_hi[i] - P.fb_lo[i]) >> 2, P.fb_off[i], 0);
     for (int i = tid; i < kTileFrames * kPowStride; i += kWarps * 32) power[i] = 0.0f;   // rows of partial tiles, pad columns
-    LaneTables T;
+    LaneTables<V> T;
     load_lane_tables(lane, P.win_tab, P.in_tab, T);
     __syncthreads();
 
-    cpxd *buf = fftbuf + warp * kFftPad;
+    cpxv<V> *buf = fftbuf + warp * kFftPad;
 
     auto issue = [&](int tile, int buf) {   // thread 0 only
         const TileGeom g = tile_geom(P, tile);
@@ -236,10 +237,10 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
 
         // ---- phase A: previous tile's copy-out, then one warp per frame: FP64 FFT256 + recombination + power ----
         if (pending_dst) copy_out(pending_dst, pending_total);
-        for (int fi = warp; fi < g.nf; fi += kWarps) {
+        for (int fi = warp * kF; fi < g.nf; fi += kWarps * kF) {   // kF == 2: frames fi and fi + 1 (kTileFrames is even)
             const float *pf = ptile + fi * P.hop;
-            double re[8], im[8];
-            if (P.mid_full) pass1<true>(lane, pf, T, buf); else pass1<false>(lane, pf, T, buf);
+            V re[8], im[8];
+            if (P.mid_full) pass1<true>(lane, pf, P.hop, T, buf); else pass1<false>(lane, pf, P.hop, T, buf);
             __syncwarp();
             pass2_load(lane, buf, re, im);
             __syncwarp();
@@ -363,6 +364,10 @@ void MelPlan::release() {
     fr(d_units);
     fr(d_audio);
     fr(d_out);
+    fr(d_pcm);
+    fr(d_rs_tab);
+    d_pcm_cap = 0;
+    rs_in = rs_out = 0.0;
     d_audio_cap = d_out_cap = 0;
     if (h_units) cudaFreeHost(h_units);
     h_units = nullptr;
@@ -461,7 +466,9 @@ int MelPlan::init(const MelConfig &c) {
                       (size_t)prop.sharedMemPerBlockOptin);
         return FA_UNSUPPORTED;
     }
-    FA_CUDA_TRY(cudaFuncSetAttribute(mel512_kernel<kWarpsPerCta>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FA_CUDA_TRY(cudaFuncSetAttribute(mel512_kernel<kWarpsPerCta, double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes));
+    FA_CUDA_TRY(cudaFuncSetAttribute(mel512_kernel<kWarpsPerCta, f32x2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_bytes));
     for (auto &s : streams) FA_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     return FA_OK;
@@ -548,7 +555,8 @@ int MelPlan::launch(const float *d_audio_base, float *d_out_base, int first, int
     }
     P.inv_n_mels = (unsigned)((0x100000000ull + (unsigned)cfg.n_mels - 1) / (unsigned)cfg.n_mels);
     const int grid = std::min(total_tiles, num_sms * kCtasPerSm);
-    mel512_kernel<kWarpsPerCta><<<grid, kWarpsPerCta * 32, smem_bytes, stream>>>(P);
+    if (precision == 1) mel512_kernel<kWarpsPerCta, f32x2><<<grid, kWarpsPerCta * 32, smem_bytes, stream>>>(P);
+    else mel512_kernel<kWarpsPerCta, double><<<grid, kWarpsPerCta * 32, smem_bytes, stream>>>(P);
     FA_CUDA_TRY(cudaGetLastError());
     ++launches;
     return FA_OK;
@@ -680,6 +688,135 @@ int MelPlan::compute_host(const float *audio, long long n, float last, int mode,
         const long long fb = h_units[c].frame_begin, fc = h_units[c].frame_count;
         if (layout == 0) {
             const long long rows = (c == chunks - 1) ? (Tp - fb) : fc;   // last unit also returns the zero pad rows
+            FA_CUDA_TRY(cudaMemcpyAsync(out + fb * cfg.n_mels, d_out + fb * cfg.n_mels, rows * cfg.n_mels * sizeof(float),
+                                        cudaMemcpyDeviceToHost, s_out));
+        } else {
+            const long long cols = (c == chunks - 1) ? (Tp - fb) : fc;
+            FA_CUDA_TRY(cudaMemcpy2DAsync(out + fb, Tp * sizeof(float), d_out + fb, Tp * sizeof(float),
+                                          cols * sizeof(float), cfg.n_mels, cudaMemcpyDeviceToHost, s_out));
+        }
+    }
+    FA_CUDA_TRY(cudaStreamSynchronize(s_out));
+    FA_CUDA_TRY(cudaStreamSynchronize(s_k));
+    return FA_OK;
+}
+
+int MelPlan::ensure_resampler(double in_rate, double out_rate) {
+    if (in_rate == out_rate || (in_rate == rs_in && out_rate == rs_out && d_rs_tab)) return FA_OK;
+    resample::Design d;
+    const int st = resample::make_design(in_rate, out_rate, d);
+    if (st != FA_OK) return st;
+    if (d_rs_tab) cudaFree(d_rs_tab);
+    d_rs_tab = nullptr;
+    FA_CUDA_TRY(cudaMalloc(&d_rs_tab, d.table.size() * sizeof(float)));
+    FA_CUDA_TRY(cudaMemcpy(d_rs_tab, d.table.data(), d.table.size() * sizeof(float), cudaMemcpyHostToDevice));
+    rs_design = std::move(d);
+    rs_in = in_rate;
+    rs_out = out_rate;
+    return FA_OK;
+}
+
+// AudioConverter.resample + computeFlatTransposed as one device pipeline.  The PCM is copied in chunks; as soon as a
+// chunk has landed the compute stream converts the samples it completes (mixdown + polyphase / linear, see
+// resample_kernels.cu) into the float buffer the mel kernel reads, runs the frames those samples complete, and the D2H
+// stream returns their rows — H2D of chunk c+1, kernels of chunk c and D2H of chunk c-1 overlap.
+int MelPlan::compute_host_pcm(const void *pcm, long long frames, const resample::AudioFormat &f, float last, int mode,
+                              int layout, float *out, long long out_len, long long *mel_length, long long *num_frames,
+                              long long *resampled) {
+    const long long n = resample::output_count(frames, f.in_rate, f.out_rate);
+    if (resampled) *resampled = n;
+    long long T, Tp;
+    if (!shape_of(*this, n, mode, -1, T, Tp)) {
+        if (mel_length) *mel_length = 0;
+        if (num_frames) *num_frames = mode == 2 ? 0 : 1;
+        if (mode != 2) {
+            if (out_len < cfg.n_mels) return FA_OUTPUT_TOO_SMALL;
+            for (int m = 0; m < cfg.n_mels; ++m) out[m] = 0.0f;
+        }
+        return FA_OK;
+    }
+    if (mel_length) *mel_length = T;
+    if (num_frames) *num_frames = Tp;
+    const long long need = Tp * cfg.n_mels;
+    if (out_len < need) {
+        fa::set_error("mel output needs %lld floats, buffer has %lld", need, out_len);
+        return FA_OUTPUT_TOO_SMALL;
+    }
+    int st = ensure_resampler(f.in_rate, f.out_rate);
+    if (st != FA_OK) return st;
+    st = ensure_staging((size_t)n + 8, (size_t)need);
+    if (st != FA_OK) return st;
+    const size_t bps = f.format == resample::kPcmI16 ? 2 : 4;
+    const size_t pcm_bytes = (size_t)frames * f.channels * bps;
+    if (pcm_bytes + 16 > d_pcm_cap) {
+        if (d_pcm) cudaFree(d_pcm);
+        d_pcm = nullptr;
+        d_pcm_cap = 0;
+        FA_CUDA_TRY(cudaMalloc(&d_pcm, pcm_bytes + 16));
+        d_pcm_cap = pcm_bytes + 16;
+    }
+    const long long kMinChunk = 4096, kMaxChunks = 24;
+    const long long chunk = std::max(kMinChunk, ceil_to((T + kMaxChunks - 1) / kMaxChunks, kTileFrames));
+    const int chunks = (int)((T + chunk - 1) / chunk);
+    st = ensure_units(chunks);
+    if (st != FA_OK) return st;
+    st = ensure_events(2 * (size_t)chunks);
+    if (st != FA_OK) return st;
+    cudaStream_t s_in = streams[0], s_k = streams[1], s_out = streams[2];
+    for (int c = 0; c < chunks; ++c) {
+        const long long fb = c * chunk, fc = std::min(chunk, T - fb);
+        h_units[c] = MelUnit{0, n, 0, Tp, fb, fc, last, 0};
+    }
+    FA_CUDA_TRY(cudaMemcpyAsync(d_units, h_units, chunks * sizeof(MelUnit), cudaMemcpyHostToDevice, s_k));
+    if (Tp > T) FA_CUDA_TRY(cudaMemsetAsync(d_out, 0, need * sizeof(float), s_k));
+    const long long pad = mode == 0 ? cfg.n_fft / 2 : 0;
+    const resample::Design &D = rs_design;
+    const bool linear = f.in_rate != f.out_rate && resample::resolve_algorithm(f) == resample::kAlgoLinear;
+    long long in_copied = 0, converted = 0;
+    for (int c = 0; c < chunks; ++c) {
+        const long long f_end = h_units[c].frame_begin + h_units[c].frame_count;
+        long long s_end = std::min(n, (f_end - 1) * cfg.hop_length + kNfft - pad);   // model-rate samples needed so far
+        if (c == chunks - 1) s_end = n;
+        // input frames those samples depend on
+        long long in_need = frames;
+        if (c != chunks - 1) {
+            if (f.in_rate == f.out_rate) in_need = s_end;
+            else if (linear) in_need = (long long)((double)(s_end + 1) * (f.in_rate / f.out_rate)) + 4;
+            else in_need = ((s_end + 2) * D.M) / D.L + D.half + 3;
+            in_need = std::min(frames, std::max(in_need, in_copied));
+        }
+        if (in_need > in_copied) {
+            const char *src = reinterpret_cast<const char *>(pcm);
+            char *dst = reinterpret_cast<char *>(d_pcm);
+            if (f.interleaved || f.channels == 1) {
+                const size_t a = (size_t)in_copied * f.channels * bps, b = (size_t)in_need * f.channels * bps;
+                FA_CUDA_TRY(cudaMemcpyAsync(dst + a, src + a, b - a, cudaMemcpyHostToDevice, s_in));
+            } else {
+                for (int ch = 0; ch < f.channels; ++ch) {
+                    const size_t a = ((size_t)ch * frames + in_copied) * bps, b = ((size_t)ch * frames + in_need) * bps;
+                    FA_CUDA_TRY(cudaMemcpyAsync(dst + a, src + a, b - a, cudaMemcpyHostToDevice, s_in));
+                }
+            }
+            in_copied = in_need;
+        }
+        FA_CUDA_TRY(cudaEventRecord(events[2 * c], s_in));
+        FA_CUDA_TRY(cudaStreamWaitEvent(s_k, events[2 * c], 0));
+        long long ready = resample::outputs_ready(f, D, frames, in_copied, n);
+        if (ready < s_end) {
+            fa::set_error("internal: resampler window accounting (%lld < %lld)", ready, s_end);
+            return FA_RUNTIME_ERROR;
+        }
+        ready = c == chunks - 1 ? n : s_end;
+        st = resample::launch_convert(d_pcm, frames, f, D, d_rs_tab, d_audio, converted, ready, s_k, &launches);
+        if (st != FA_OK) return st;
+        converted = std::max(converted, ready);
+        st = launch(d_audio, d_out, c, 1, tiles_of(h_units[c].frame_count), mode, layout, s_k, true);
+        if (st != FA_OK) return st;
+        FA_CUDA_TRY(cudaEventRecord(events[2 * c + 1], s_k));
+        FA_CUDA_TRY(cudaStreamWaitEvent(s_out, events[2 * c + 1], 0));
+        const long long fb = h_units[c].frame_begin, fc = h_units[c].frame_count;
+        if (layout == 0) {
+            const long long rows = (c == chunks - 1) ? (Tp - fb) : fc;
             FA_CUDA_TRY(cudaMemcpyAsync(out + fb * cfg.n_mels, d_out + fb * cfg.n_mels, rows * cfg.n_mels * sizeof(float),
                                         cudaMemcpyDeviceToHost, s_out));
         } else {

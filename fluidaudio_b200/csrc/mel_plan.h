@@ -2,6 +2,7 @@
 #pragma once
 
 #include "fa_common.cuh"
+#include "resample_plan.h"
 #include <cuda_runtime.h>
 #include <vector>
 
@@ -72,6 +73,7 @@ struct MelPlan {
     size_t smem_bytes = 0;
     int num_sms = 0;
     long long launches = 0;          // kernels launched through this plan (bench.py reports it)
+    int precision = 0;               // transform arithmetic: 0 = FP64 (one frame per warp), 1 = packed float32 pairs
 
     float *d_win_tab_mode[2] = {nullptr, nullptr};
     uint8_t *d_in_tab_mode[2] = {nullptr, nullptr};
@@ -82,6 +84,12 @@ struct MelPlan {
     int units_cap = 0;
     float *d_audio = nullptr, *d_out = nullptr;   // staging for the host-buffer entry points
     size_t d_audio_cap = 0, d_out_cap = 0;
+    // AudioConverter stage ahead of the kernel (fa_audio_to_mel): raw PCM staging + the polyphase table of the last ratio
+    void *d_pcm = nullptr;
+    size_t d_pcm_cap = 0;
+    resample::Design rs_design;
+    double rs_in = 0.0, rs_out = 0.0;
+    float *d_rs_tab = nullptr;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};   // h2d, compute, d2h
     std::vector<cudaEvent_t> events;
     cudaEvent_t timer[2] = {nullptr, nullptr};   // fa_mel_timer_*: events on the compute stream
@@ -103,6 +111,12 @@ struct MelPlan {
                        cudaStream_t stream);
     int compute_host(const float *audio, long long n, float last, int mode, long long expected, int layout,
                      float *out, long long out_len, long long *mel_length, long long *num_frames);
+    // PCM in any AudioFormat (host) -> [device: mixdown + resample to cfg.sample_rate] -> log-mel (host).  Only the raw
+    // PCM crosses PCIe on the way in (int16 halves the bytes); *resampled = samples at the model rate.
+    int compute_host_pcm(const void *pcm, long long frames, const resample::AudioFormat &f, float last, int mode,
+                         int layout, float *out, long long out_len, long long *mel_length, long long *num_frames,
+                         long long *resampled);
+    int ensure_resampler(double in_rate, double out_rate);
     int compute_batch_host(const float *audio, const long long *offsets, int count, const float *last, int mode,
                            int layout, float *out, const long long *out_offsets, long long *mel_lengths,
                            long long *num_frames);

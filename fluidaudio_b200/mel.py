@@ -24,6 +24,11 @@ class LogFloorMode(enum.IntEnum):
     clamped = 1
 
 
+class Precision(enum.IntEnum):
+    f64 = 0           # FA_MEL_PRECISION_F64: transform in FP64, rounded once (default; parity with the oracle ~5e-6)
+    f32 = 1           # FA_MEL_PRECISION_F32: float32 transform like vDSP_DFT, packed two frames per warp
+
+
 _TIME_MAJOR, _MEL_MAJOR = 0, 1
 _LEGACY = 2
 
@@ -31,7 +36,8 @@ _LEGACY = 2
 class AudioMelSpectrogram:
     def __init__(self, sample_rate: int = 16000, n_mels: int = 128, n_fft: int = 512, hop_length: int = 160,
                  win_length: int = 400, preemph: float = 0.97, pad_to: int = 0, log_floor: float = 2.0 ** -24,
-                 log_floor_mode: LogFloorMode = LogFloorMode.additive, window_periodic: bool = False):
+                 log_floor_mode: LogFloorMode = LogFloorMode.additive, window_periodic: bool = False,
+                 precision: Precision = Precision.f64):
         self.sample_rate, self.n_mels, self.n_fft = sample_rate, n_mels, n_fft
         self.hop_length, self.win_length, self.preemph = hop_length, win_length, preemph
         self.pad_to = max(1, pad_to)
@@ -41,6 +47,14 @@ class AudioMelSpectrogram:
         h = C.c_void_p()
         _lib.check(self._L.fa_mel_create(C.byref(cfg), C.byref(h)), "fa_mel_create")
         self._h = h
+        self.precision = Precision(precision)
+        if self.precision != Precision.f64:
+            self.set_precision(self.precision)
+
+    def set_precision(self, precision: Precision):
+        """Not part of the Swift class: selects the transform arithmetic (see include/fluidaudio_b200.h)."""
+        _lib.check(self._L.fa_mel_set_precision(self._h, int(precision)), "fa_mel_set_precision")
+        self.precision = Precision(precision)
 
     def close(self):
         if getattr(self, "_h", None) is not None:
@@ -103,6 +117,31 @@ class AudioMelSpectrogram:
         """``computeFlatTransposed`` → (mel flat [numFrames * nMels] time-major, melLength, numFrames)."""
         out, ml, nf = self._run(audio, last_audio_sample, padding_mode, expected_frame_count, _TIME_MAJOR, out)
         return out[: self.n_mels * nf], ml, nf
+
+    # ---- AudioConverter.resample + computeFlatTransposed fused on the device --------------------------------
+    def compute_from_pcm(self, pcm, input_rate: float, channels: int | None = None, interleaved: bool = False,
+                         last_audio_sample: float = 0.0, padding_mode: PaddingMode = PaddingMode.center,
+                         time_major: bool = True, algorithm: int = 0, out=None):
+        """PCM (float32 / int16, any channel count and rate) -> log-mel, one call: the raw PCM is the only thing that
+        crosses PCIe on the way in, mixdown + resampling to ``sample_rate`` + log-mel run back to back in HBM.
+        Returns (mel flat, melLength, numFrames, resampledCount)."""
+        from .audio_converter import _as_pcm, _format
+        a, frames, channels = _as_pcm(pcm, channels, interleaved)
+        fmt = _format(input_rate, self.sample_rate, channels, a.dtype, interleaved, algorithm)
+        n = int(self._L.fa_resample_output_count(C.byref(fmt), frames))
+        T = self.frame_count(n, padding_mode)
+        Tp = 1 if (T <= 0 or n == 0) else -(-T // self.pad_to) * self.pad_to
+        need = Tp * self.n_mels
+        if out is None:
+            out = np.empty(need, np.float32)
+        elif out.size < need:
+            raise ValueError(f"output buffer too small: need {need} floats")
+        ml, nf, rs = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self._L.fa_audio_to_mel(self._h, a.ctypes.data if a.size else None, frames, C.byref(fmt),
+                                           float(last_audio_sample), int(padding_mode), 0 if time_major else 1,
+                                           out.ctypes.data, out.size, C.byref(ml), C.byref(nf), C.byref(rs)),
+                   "fa_audio_to_mel")
+        return out[: self.n_mels * nf.value], int(ml.value), int(nf.value), int(rs.value)
 
     # ---- batch of independent clips (BASELINE config 4) -------------------------------------------------------
     def compute_batch(self, clips, last_samples=None, padding_mode: PaddingMode = PaddingMode.center,

@@ -8,7 +8,10 @@
  * Reference interfaces replaced (paths relative to the FluidAudio repository):
  *   fa_mel_*             Sources/FluidAudio/Shared/AudioMelSpectrogram.swift:18-121 (class + init),
  *                        :132 compute, :185 computeFlat, :299/:325 computeFlatTransposed, :486-493 getters
- *   fa_linear_resample   Sources/FluidAudio/Shared/AudioConverter.swift:388-442 (linearResample)
+ *   fa_audio_resample / fa_audio_to_mel / fa_resample_output_count
+ *                        Sources/FluidAudio/Shared/AudioConverter.swift:60-71 (resample), :299-370 (convertBuffer),
+ *                        :388-442 (linearResample) — the converter stage on the GPU, fused ahead of the log-mel kernel
+ *   fa_linear_resample   Sources/FluidAudio/Shared/AudioConverter.swift:388-442 (linearResample, host restatement)
  *   fa_l2_normalize_rows Sources/FluidAudio/Diarizer/Offline/Clustering/AHCClustering.swift:70-105
  *   fastcluster_compute_centroid_linkage  (declared in FastClusterWrapper.h, same symbol as the reference)
  *   fa_ahc_cluster       AHCClustering.swift:20-67  (AHCClustering.cluster)
@@ -65,6 +68,12 @@ fa_status fa_device_free(void *p);
 fa_status fa_memcpy_h2d(void *dst_device, const void *src_host, size_t bytes);
 fa_status fa_memcpy_d2h(void *dst_host, const void *src_device, size_t bytes);
 
+/* Bare copy-engine probe: `reps` rounds of one H2D copy (h2d_bytes from host_src) and one D2H copy (d2h_bytes into
+ * host_dst) issued together on two streams; *ms_per_round = wall clock per round.  The floor under every host-buffer
+ * ("end to end") number: what PCIe and the host memory path deliver with no kernel in between. */
+fa_status fa_memcpy_probe(const void *host_src, size_t h2d_bytes, void *host_dst, size_t d2h_bytes, int32_t reps,
+                          float *ms_per_round);
+
 /* Device-side timing of a region on the library's default stream (CUDA events). */
 fa_status fa_timer_start(void);
 fa_status fa_timer_stop_ms(float *elapsed_ms);
@@ -95,6 +104,16 @@ fa_status fa_mel_get_window(const fa_mel *mel, float *out, size_t len);       /*
 fa_status fa_mel_get_filterbank(const fa_mel *mel, float *out, size_t len);   /* getFilterbank(): n_mels x (n_fft/2+1) */
 /* frames the reference would produce; expected_frames < 0 means nil */
 int64_t fa_mel_frame_count(const fa_mel *mel, int64_t sample_count, int32_t padding_mode, int64_t expected_frames);
+
+/* Arithmetic of the 512-point transform (window product, |.|^2, filterbank and log are float32 in both, like the reference):
+ *   FA_MEL_PRECISION_F64  (default) DFT evaluated in FP64 and rounded once — the implementation-independent value,
+ *                         reproduces the oracle to ~5e-6 in the log domain whatever the signal's dynamic range;
+ *   FA_MEL_PRECISION_F32  DFT in float32 like the reference's own vDSP_DFT_zop (AudioMelSpectrogram.swift:459-481), two
+ *                         frames per warp on packed FFMA2/FADD2: ~2x the throughput; carries the float32 noise floor of
+ *                         any float32 FFT (measured max |delta log-mel| 6e-5 over BASELINE's hour of audio). */
+enum { FA_MEL_PRECISION_F64 = 0, FA_MEL_PRECISION_F32 = 1 };
+fa_status fa_mel_set_precision(fa_mel *mel, int32_t precision);
+int32_t fa_mel_get_precision(const fa_mel *mel);
 
 /* Host buffers in and out (the drop-in call).  On return *mel_length = valid frames, *num_frames = padded frames;
  * out receives num_frames*n_mels floats in `layout`.  Mirrors computeFlatTransposed / computeFlat / compute. */
@@ -135,6 +154,37 @@ fa_status fa_mel_lseend_features(fa_mel *mel, const float *chunk, size_t n, floa
 /* NeMo per-feature normalisation of a time-major [frames x n_mels] buffer, in place (host buffer).
  * UnifiedMelExtractor.normalizePerFeature, Sources/FluidAudio/ASR/Parakeet/Unified/UnifiedMelExtractor.swift:88-113 */
 fa_status fa_mel_normalize_per_feature(float *x, int64_t frames, int32_t n_mels, int64_t valid_frames);
+
+/* ---- AudioConverter stage on the GPU ---------------------------------------------------------------------
+ * PCM in any of the layouts AVAudioPCMBuffer / a WAV file hands over -> mono float32 at out_rate.
+ *   algorithm AUTO follows AudioConverter.convertBuffer (:299-305): more than two channels take linearResample
+ *   (:388-442, reproduced BIT FOR BIT: mean mixdown, src = i * ratio in double, two-tap float32 lerp); one or two
+ *   channels take the AVAudioConverter path, whose arithmetic is closed — replaced by a documented Kaiser-windowed-sinc
+ *   polyphase filter (24 zero crossings, beta 12, pass band 0.94 of the lower Nyquist; fluidaudio_b200/csrc/
+ *   resample_plan.h), "parity unpinned" against Apple's sample values.  in_rate == out_rate is the identity on the
+ *   samples (:66-68), after mixdown / int16 widening (v / 32768) when the input is not already mono float32.
+ *   Output length = Int(Double(frames) / (in_rate / out_rate)) (:417-418) for both algorithms: the reference's tests
+ *   accept +-1 % (AudioConverterTests.swift:129-176). */
+enum { FA_PCM_F32 = 0, FA_PCM_I16 = 1 };
+enum { FA_RESAMPLE_AUTO = 0, FA_RESAMPLE_SINC = 1, FA_RESAMPLE_LINEAR = 2 };
+typedef struct {
+    double in_rate;        /* e.g. 48000 */
+    double out_rate;       /* 16000 (AudioConverter's default target) */
+    int32_t channels;      /* >= 1 */
+    int32_t format;        /* FA_PCM_F32 / FA_PCM_I16 */
+    int32_t interleaved;   /* 1: [frames x channels] (WAV); 0: planar [channels x frames] (floatChannelData) */
+    int32_t algorithm;     /* FA_RESAMPLE_* */
+} fa_audio_format;
+int64_t fa_resample_output_count(const fa_audio_format *fmt, int64_t frames);
+/* AudioConverter.resample / resampleBuffer: host PCM in, host float32 mono out (conversion runs on the GPU). */
+fa_status fa_audio_resample(const void *pcm, int64_t frames, const fa_audio_format *fmt, float *out, int64_t out_cap,
+                            int64_t *out_count);
+/* AudioConverter.resample followed by AudioMelSpectrogram.computeFlatTransposed / computeFlat as ONE device pipeline:
+ * only the raw PCM crosses PCIe on the way in (int16 halves the bytes of the float path), the converted samples never
+ * leave HBM.  fmt->out_rate must equal the handle's sample_rate.  *resampled_count (may be NULL) = samples at out_rate. */
+fa_status fa_audio_to_mel(fa_mel *mel, const void *pcm, int64_t frames, const fa_audio_format *fmt,
+                          float last_audio_sample, int32_t padding_mode, int32_t layout, float *out, size_t out_len,
+                          int64_t *mel_length, int64_t *num_frames, int64_t *resampled_count);
 
 /* AudioConverter.linearResample: planar [channels x frames] -> mono at out_rate.  Returns the sample count
  * through *out_count; call with out == NULL to size the buffer. */

@@ -5,11 +5,11 @@ import numpy as np
 from fluidaudio_b200 import _lib, synth
 what = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-if what == "mel":
-    from fluidaudio_b200.mel import AudioMelSpectrogram
+if what in ("mel", "mel32"):
+    from fluidaudio_b200.mel import AudioMelSpectrogram, Precision
     n = 57_600_000
     a = synth.tone_noise_audio(n)
-    m = AudioMelSpectrogram(n_mels=80)
+    m = AudioMelSpectrogram(n_mels=80, precision=Precision.f32 if what == "mel32" else Precision.f64)
     d_a = _lib.DeviceBuffer(n * 4 + 64); d_a.upload(a)
     d_o = _lib.DeviceBuffer(360001 * 80 * 4)
     for _ in range(reps):

@@ -16,7 +16,7 @@ import pytest
 
 from fluidaudio_b200 import _lib, synth
 from fluidaudio_b200 import clustering as cl
-from fluidaudio_b200.mel import AudioMelSpectrogram, LogFloorMode, PaddingMode
+from fluidaudio_b200.mel import AudioMelSpectrogram, LogFloorMode, PaddingMode, Precision
 
 pytestmark = pytest.mark.gpu
 
@@ -189,6 +189,133 @@ def test_mel_one_hour_properties(gpu_lib, oracle):
     s0 = 200000 * 160
     ref, rml, _ = oracle.mel_flat_transposed(cfg, a[s0:s0 + 960000], last=float(a[s0 - 1]))
     assert np.abs(host[200000 + 2:200000 + rml - 3] - ref[2:rml - 3]).max() <= MEL_TOL
+
+
+def test_mel_float32_transform_option(gpu_lib, oracle):
+    """FA_MEL_PRECISION_F32: the transform in float32 like the reference's vDSP_DFT (two frames per warp, packed
+    FFMA2).  Same entry points, shapes and guards; values within the SAME 1e-4 bar on BASELINE's signal — checked over
+    the WHOLE hour against the FP64 path (itself within 5e-6 of the oracle) and directly against the oracle on windows."""
+    n = 57_600_000
+    a = synth.tone_noise_audio(n)
+    m64 = AudioMelSpectrogram(n_mels=80)
+    m32 = AudioMelSpectrogram(n_mels=80, precision=Precision.f32)
+    assert m32._L.fa_mel_get_precision(m32._h) == 1 and m64._L.fa_mel_get_precision(m64._h) == 0
+    h64, ml, nf = m64.compute_flat_transposed(a)
+    h32, ml2, nf2 = m32.compute_flat_transposed(a)
+    assert (ml, nf) == (ml2, nf2) == (360001, 360001)
+    d = np.abs(h32 - h64)
+    assert np.isfinite(h32).all() and d.max() <= MEL_TOL, d.max()
+    cfg = oracle.mel_config(n_mels=80)
+    h32 = h32.reshape(ml, 80)
+    ref, rml, _ = oracle.mel_flat_transposed(cfg, a[:960000])
+    assert np.abs(h32[:rml - 3] - ref[:rml - 3]).max() <= MEL_TOL
+    # every mode / layout / odd length, 128 mels, the harder fixture; frames are independent of their pair partner
+    sp = synth.speech_like_audio(16000 * 8)
+    m = AudioMelSpectrogram(n_mels=128, precision=Precision.f32)
+    cfg = oracle.mel_config(n_mels=128)
+    for sig in (sp, synth.tone_noise_audio(16000 * 5 + 77, seed=3), synth.tone_noise_audio(161), synth.tone_noise_audio(7)):
+        got, ml, nf = m.compute_flat_transposed(sig)
+        ref, rml, rnf = oracle.mel_flat_transposed(cfg, sig)
+        assert (ml, nf) == (rml, rnf) and np.abs(got.reshape(nf, 128) - ref).max() <= MEL_TOL
+        got, ml, nf = m.compute_flat(sig, last_audio_sample=0.25)
+        ref, rml, rnf = oracle.mel_flat(cfg, sig, last=0.25)
+        assert (ml, nf) == (rml, rnf) and np.abs(got.reshape(128, nf) - ref).max() <= MEL_TOL
+    got, ml = m.compute(sp)
+    ref, rml = oracle.mel_legacy(cfg, sp)
+    assert ml == rml and np.abs(got[0] - ref).max() <= MEL_TOL
+    got, ml, nf = m.compute_flat_transposed(sp, last_audio_sample=-0.1, padding_mode=PaddingMode.pre_padded, expected_frame_count=333)
+    ref, rml, rnf = oracle.mel_flat_transposed(cfg, sp, last=-0.1, padding_mode=1, expected_frames=333)
+    assert (ml, nf) == (rml, rnf) and np.abs(got.reshape(nf, 128) - ref).max() <= MEL_TOL
+    ex = sp[160 * 100:160 * 100 + 16000]
+    sub, sml, _ = m.compute_flat_transposed(ex, last_audio_sample=float(sp[160 * 100 - 1]))
+    full, fml, _ = m.compute_flat_transposed(sp)
+    assert np.array_equal(sub.reshape(sml, 128)[2:sml - 3], full.reshape(fml, 128)[102:100 + sml - 3])
+    with pytest.raises(_lib.FluidAudioError):
+        m.set_precision(7)
+
+
+# ================================================================================================ AudioConverter (R1)
+def _sine_pcm(rate, channels, seconds, seed=0):
+    """AudioConverterTests.swift createAudioBuffer: a 440 Hz sine of amplitude 0.5 per channel (here each channel gets its
+    own frequency and a little noise so that a wrong mixdown or channel order cannot hide)."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(int(rate * seconds)) / rate
+    return np.stack([(0.5 * np.sin(2 * np.pi * (440.0 + 110.0 * c) * t) + 0.01 * rng.standard_normal(t.size)).astype(np.float32)
+                     for c in range(channels)])
+
+
+def test_audio_converter_reference_tests_and_filter_spec(gpu_lib, oracle):
+    from fluidaudio_b200.audio_converter import AudioConverter
+    conv = AudioConverter()
+    # testConvertAlreadyCorrectFormat / resample(_:from:) identity (:66-68): same samples, bit for bit
+    x = _sine_pcm(16000, 1, 1.0)[0]
+    assert np.array_equal(conv.resample(x, 16000), x) and conv.resample(np.zeros(0, np.float32), 48000).size == 0
+    assert np.array_equal(conv.resample_buffer(x[None], 16000), x)
+    # lengths: 44.1k stereo 1 s, 48k mono 0.5 s, 8k mono 2 s within 1 % (AudioConverterTests.swift:129-176); short buffer
+    for rate, ch, dur, expect in ((44100, 2, 1.0, 16000), (48000, 1, 0.5, 8000), (8000, 1, 2.0, 32000), (44100, 1, 0.01, 160)):
+        y = conv.resample_buffer(_sine_pcm(rate, ch, dur), rate)
+        assert y.size > 0 and abs(y.size - expect) <= 0.01 * expect + 1 and np.abs(y).max() <= 0.6
+        assert y.size == oracle.resample_output_count(int(rate * dur), rate, 16000) == conv.output_count(int(rate * dur), rate)
+    # testConvertStereoToMono: same rate, 1000 frames -> 1000 frames, mean of the channels
+    st = _sine_pcm(16000, 2, 1000 / 16000)
+    assert np.array_equal(conv.resample_buffer(st, 16000), oracle.mixdown(st))
+    # values against the float64 evaluation of the documented filter (float32 taps and sums: <= 3e-6 of full scale)
+    for rate in (8000, 11025, 22050, 32000, 44100, 48000, 96000, 16001):
+        m = _sine_pcm(rate, 1, 0.35, seed=rate)[0]
+        got = conv.resample(m, rate)
+        ref = oracle.sinc_resample(m, rate, 16000)
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= (2e-5 if rate == 16001 else 3e-6), rate
+    # stereo, int16, interleaved and planar: mixdown + widening happen on the device
+    st = _sine_pcm(44100, 2, 0.4, seed=5)
+    i16 = np.round(st * 32767).astype(np.int16)
+    ref = oracle.sinc_resample(oracle.mixdown(i16), 44100, 16000)
+    assert np.abs(conv.resample_buffer(i16, 44100) - ref).max() <= 3e-6
+    assert np.array_equal(conv.resample_buffer(np.ascontiguousarray(i16.T), 44100, interleaved=True), conv.resample_buffer(i16, 44100))
+    assert np.abs(conv.resample_buffer(st, 44100) - oracle.sinc_resample(oracle.mixdown(st), 44100, 16000)).max() <= 3e-6
+    # > 2 channels: AudioConverter.linearResample, bit for bit (planar float32 as floatChannelData; interleaved too)
+    for ch, rate in ((3, 44100), (4, 48000), (6, 8000), (5, 16000)):
+        p = _sine_pcm(rate, ch, 0.2, seed=ch)
+        ref = oracle.linear_resample(p, rate, 16000)
+        assert np.array_equal(conv.resample_buffer(p, rate), ref)
+        assert np.array_equal(conv.resample_buffer(np.ascontiguousarray(p.T), rate, interleaved=True), ref)
+    # a tone above the new Nyquist is gone, one below it keeps its amplitude (what "Mastering quality" must deliver)
+    t = np.arange(48000) / 48000.0
+    for f0, lo, hi in ((1000.0, 0.4999, 0.5001), (10000.0, 0.0, 2e-6)):
+        y = conv.resample((0.5 * np.sin(2 * np.pi * f0 * t)).astype(np.float32), 48000)[2000:-2000]
+        amp = np.sqrt(2.0 * np.mean(y.astype(np.float64) ** 2))
+        assert lo <= amp <= hi, (f0, amp)
+    # guards
+    with pytest.raises(_lib.FluidAudioError):
+        conv.resample_buffer(np.zeros((65, 10), np.float32), 48000)
+
+
+def test_audio_to_mel_fused_pipeline(gpu_lib, oracle):
+    """fa_audio_to_mel == fa_mel_compute(fa_audio_resample(pcm)) bit for bit (the chunked PCM pipeline is invisible),
+    for float32 / int16, mono / stereo / 4 channels, every rate; 16 kHz mono float32 is the plain mel path."""
+    from fluidaudio_b200.audio_converter import AudioConverter
+    conv = AudioConverter()
+    m = AudioMelSpectrogram(n_mels=80)
+    cases = [(48000, 1, np.float32, 3.0), (44100, 2, np.int16, 2.5), (8000, 1, np.int16, 4.0), (48000, 4, np.float32, 1.0),
+             (16000, 1, np.int16, 2.0), (16000, 2, np.float32, 1.5), (16000, 1, np.float32, 1.0), (22050, 1, np.float32, 20.0)]
+    for rate, ch, dt, dur in cases:
+        p = _sine_pcm(rate, ch, dur, seed=rate + ch)
+        if dt == np.int16:
+            p = np.round(p * 32767).astype(np.int16)
+        inter = np.ascontiguousarray(p.T)
+        mono = conv.resample_buffer(p, rate)
+        ref, rml, rnf = m.compute_flat_transposed(mono, last_audio_sample=0.1)
+        got, ml, nf, rs = m.compute_from_pcm(inter, rate, interleaved=True, last_audio_sample=0.1)
+        assert (ml, nf, rs) == (rml, rnf, mono.size) and np.array_equal(got, ref), (rate, ch)
+        got2, _, _, _ = m.compute_from_pcm(p, rate, last_audio_sample=0.1, time_major=False)
+        assert np.array_equal(got2.reshape(80, nf).T, ref.reshape(nf, 80))
+    # the whole chain against the oracle: oracle filter (float64) -> oracle mel, within the mel bar
+    x = synth.tone_noise_audio(48000 * 4)[: 48000 * 4]
+    up = oracle.sinc_resample(x, 16000, 48000)          # a 48 kHz rendition of the fixture
+    got, ml, nf, rs = m.compute_from_pcm(up, 48000)
+    ref, rml, _ = oracle.mel_flat_transposed(oracle.mel_config(n_mels=80), oracle.sinc_resample(up, 48000, 16000))
+    assert ml == rml and np.abs(got.reshape(nf, 80) - ref).max() <= 2e-3   # float32 filter sums ahead of a log
+    with pytest.raises(_lib.FluidAudioError):
+        AudioMelSpectrogram(n_mels=80, sample_rate=8000).compute_from_pcm(np.zeros(100, np.float32), 16000, algorithm=9)
 
 
 # ================================================================================================ AHC

@@ -541,3 +541,44 @@ def test_kmeans_against_independent_python_restatement(oracle):
         plab, pcen = py_kmeans(emb.tolist(), k, 50, seed)
         assert lab.tolist() == plab
         assert np.array(pcen, np.float64).tobytes() == cen.tobytes()
+
+
+# ------------------------------------------------------------------------------------------------ AudioConverter stage
+def test_resampler_spec_and_reference_length_contract(oracle):
+    """The documented Kaiser-sinc filter (the library's stand-in for the closed AVAudioConverter: PARITY UNPINNED for
+    values) restated in float64: unit pass band, > 110 dB stop band, output length = Int(n / ratio) within 1 % of the
+    nominal count (AudioConverterTests.swift:129-176), mixdown = float32 mean in channel order (:401-409)."""
+    for rate, dur, expect in ((44100, 1.0, 16000), (48000, 0.5, 8000), (8000, 2.0, 32000)):
+        n = int(rate * dur)
+        assert abs(oracle.resample_output_count(n, rate, 16000) - expect) <= 0.01 * expect
+    assert oracle.resample_output_count(1000, 16000, 16000) == 1000
+    t = np.arange(48000) / 48000.0
+    for f0, lo, hi in ((1000.0, 0.9999, 1.0001), (6000.0, 0.999, 1.001), (9000.0, 0.0, 3e-6), (20000.0, 0.0, 3e-6)):
+        y = oracle.sinc_resample(np.sin(2 * np.pi * f0 * t).astype(np.float32), 48000, 16000)[2000:-2000].astype(np.float64)
+        assert y.size == 16000 - 4000 and lo <= np.sqrt(2 * np.mean(y * y)) <= hi, f0
+    x = np.random.default_rng(1).standard_normal(4000).astype(np.float32)
+    assert np.array_equal(oracle.sinc_resample(x, 16000, 16000), x)
+    L, M, half, fc = oracle.sinc_design(44100, 16000)
+    assert (L, M, half) == (160, 441, 67) and abs(fc - 0.94 * 160 / 441) < 1e-15
+    # constant in -> the same constant out (rows are normalised to unit DC gain), away from the edges
+    y = oracle.sinc_resample(np.full(5000, 0.25, np.float32), 44100, 16000)
+    assert np.abs(y[100:-100] - 0.25).max() < 1e-7
+    st = np.array([[1.0, 2.0, 3.0], [3.0, 2.0, -3.0]], np.float32)
+    assert np.array_equal(oracle.mixdown(st), np.array([2.0, 2.0, 0.0], np.float32))
+    i16 = np.array([[16384, -32768]], np.int16)
+    assert np.array_equal(oracle.mixdown(i16), np.array([0.5, -1.0], np.float32))
+    # one channel through linearResample's arithmetic equals the mono lerp
+    m = np.linspace(-1, 1, 1000, dtype=np.float32)
+    lin = oracle.linear_resample(np.stack([m, m, m]), 48000, 16000)
+    assert lin.size == 333 and np.abs(lin - m[::3][:333]).max() < 1e-6
+
+
+def test_timed_cpu_arm_matches_the_oracle(oracle):
+    """oracle_mel_fast.cpp — the float32-FFT, SIMD-across-frames CPU implementation bench.py times as the reference arm —
+    agrees with the parity oracle within the spread of two float32 FFTs (2e-4), frame counts exact."""
+    for nm, n, last in ((80, 16000 * 20 + 77, 0.0), (128, 16000 * 7, 0.25), (80, 401, 0.0), (80, 5, -0.5)):
+        a = synth.tone_noise_audio(n, seed=nm)
+        cfg = oracle.mel_config(n_mels=nm)
+        got, ml = oracle.mel_fast_flat_transposed(cfg, a, last)
+        ref, rml, _ = oracle.mel_flat_transposed(cfg, a, last=last)
+        assert ml == rml and got.shape == ref.shape and np.abs(got - ref).max() <= 2e-4
