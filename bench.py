@@ -1,27 +1,36 @@
 #!/usr/bin/env python
-"""bench.py — the reference's headline metric on its named configuration, one JSON line on rank 0.
+"""bench.py — the reference's headline metric on its named configurations, one JSON line on rank 0.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mel|cluster] [--impl ours|reference]
 
-Workload `mel` (default; BASELINE.json configs[1], the configuration the metric is quoted on):
+Main line (BASELINE.json configs[1], the configuration the metric is quoted on):
     log-mel of 1 h of synthetic 16 kHz mono audio, 25 ms / 10 ms frames, 512-point FFT, 80 mels -> [360 001 x 80].
-    A step = one pass over the hour.  `value` = audio-hours/s with audio and output resident in HBM (CUDA events on
-    the launching stream); `e2e` = the same through fa_mel_compute with pinned HOST buffers (H2D and D2H inside).
-Workload `cluster` (configs[2]): 10 000 x 256 embeddings -> normalise + AHC + cut + VBx + centroids + assignment.
-    Its numbers are ALSO attached to the default line under "cluster" so that one run reports both halves of the metric.
-With N > 1 (torchrun) every rank runs the same per-GPU workload on its own GPU: units are independent, there is no
-data-path collective, scaling is weak; timing is barrier + device sync on both sides, MAX over ranks.
+    A step = one pass over the hour.  `value` = audio-hours/s with audio and output resident in HBM (CUDA events on the
+    launching stream, exactly K steps); `sustained` = the same launch repeated for >= 1 s; `e2e` = the same through
+    fa_mel_compute with pinned HOST buffers (H2D and D2H inside); `e2e_i16` = int16 PCM through fa_audio_to_mel (the
+    AudioConverter stage on the device: half the H2D bytes); `copy_floor` = the bare copies of the same bytes.
+    The transform runs in float32 like the reference's vDSP_DFT (FA_MEL_PRECISION_F32: packed FFMA2, two frames per
+    warp); the run itself checks that choice against the FP64-transform path over the WHOLE hour (`parity`, bar 1e-4,
+    a failed bar fails the run) and reports the FP64 path's numbers under `f64_transform`.
+Attached sub-objects, each with its own parity field:
+    `cluster` configs[2]: 10 000 x 256 embeddings -> normalise + AHC + cut + VBx + centroids + assignment (per GPU, weak).
+    `c4`      configs[3]: 512 clips x 30 s SHARDED over the ranks (contiguous blocks), strong scaling, host buffers.
+    `c5`      configs[4]: 64 meetings x 5 000 x 256 SHARDED over the ranks (LPT), labels gathered over NCCL and hashed
+              against goldens produced by the compiled reference (tests/golden/c5_meetings.json): `labels_equal_ref`.
+    `streaming`: p50 / p99 latency of small `.prePadded` calls (the production callers' shape).
+With N > 1 (torchrun) units are independent: no data-path collective; NCCL carries the barrier, the MAX-reduction of
+times and the gather of labels / checksums.  Timing: barrier + device sync on both sides, MAX over ranks.
 
---impl reference: the reference's CPU implementation of the path timed on the host cores — the oracle port of
-AudioMelSpectrogram (no Swift toolchain exists) for `mel`, the UNMODIFIED FastClusterWrapper.cpp (oracle/_ref, when it
-was built) plus the oracle port of the Swift stages for `cluster`.  Rank 0 only.
+--impl reference: the reference's CPU implementation of the path on the host cores, rank 0 only — for `mel` the
+float32-FFT port of AudioMelSpectrogram vectorised across frames (oracle/oracle_mel_fast.cpp; no Swift toolchain
+exists), for `cluster` the UNMODIFIED FastClusterWrapper.cpp (oracle/_ref) plus the oracle port of the Swift stages.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -38,6 +47,9 @@ N_MELS = 80
 MEL_BYTES_PER_HOUR = 4 * MEL_SAMPLES + 4 * MEL_FRAMES * N_MELS            # 345 600 320 B
 CLUSTER_N, CLUSTER_D, CLUSTER_R, CLUSTER_K = 10_000, 256, 128, 8
 AHC_BYTES = 8.0 * CLUSTER_D * CLUSTER_N * CLUSTER_N                       # 2.048e11 B
+C4_CLIPS, C4_SAMPLES = 512, 480_000
+C5_MEETINGS, C5_N = 64, 5_000
+MEL_TOL = 1e-4
 
 
 def measured_peaks():
@@ -51,50 +63,67 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock, power and throttle reasons sampled IN PROCESS through NVML every ~2 ms while `active` (a 10 ms timed
+    region is invisible to a 100 ms nvidia-smi poll)."""
 
     def __init__(self, index: int):
-        self.index = index
-        self.rows = []
-        self.proc = None
-
-    def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+        self.rows, self.active, self.stop_flag, self.h, self.nv = [], False, False, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
         except Exception:
-            self.proc = None
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                      nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                      nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+                except Exception:
+                    pass
+            time.sleep(0.002)
 
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0.0, set()
+    def __enter__(self):
+        self.active = True
+        return self
+
+    def __exit__(self, *a):
+        self.active = False
+
+    def summary(self):
+        self.stop_flag = True
+        if self.h is None or not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        bits = 0
         for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            bits |= int(r[2])
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": self.max_sm,
+                "power_w_max": float(max(r[1] for r in self.rows)), "reasons": sorted(k for k, v in names.items() if bits & v),
+                "samples": len(sm), "how": "NVML in process, 2 ms period, timed regions only"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
-def cpu_mel(audio: np.ndarray, threads: int, repeats: int = 1):
-    """Oracle port of AudioMelSpectrogram on `threads` host threads: the audio cut into 30 s clips, every clip
-    processed `repeats` times, each thread working through its own share of the clips with its own output buffer
-    (one AudioMelSpectrogram-like instance per thread; ctypes releases the GIL inside the C++ call)."""
+def host_threads() -> int:
+    return max(1, min(os.cpu_count() or 1, 64))
+
+
+def cpu_mel(audio: np.ndarray, threads: int, repeats: int = 1, fast: bool = True):
+    """AudioMelSpectrogram on `threads` host threads: the audio cut into 30 s clips, every clip processed `repeats`
+    times, one instance and one output buffer per thread (ctypes releases the GIL inside the C++ call).
+    fast=True: the float32-FFT port vectorised across frames (oracle_mel_fast.cpp — the reference's arithmetic);
+    fast=False: the parity oracle itself (float64 DFT rounded once, scalar)."""
     import ctypes as C
     from oracle import oracle as O
     L = O.lib()
@@ -102,28 +131,34 @@ def cpu_mel(audio: np.ndarray, threads: int, repeats: int = 1):
     cfg = O.mel_config(n_mels=N_MELS)
     clip = 480_000
     pieces = [np.ascontiguousarray(audio[i:i + clip]) for i in range(0, audio.size, clip)] * repeats
-    shares = [pieces[t::threads] for t in range(threads)]
-    shares = [s for s in shares if s]
-    O.mel_flat_transposed(cfg, pieces[0][:16000])
-    ml0, nf0 = C.c_int64(), C.c_int64()
-    cap = max(int(L.oracle_mel_compute_flat_transposed(C.byref(cfg), p.ctypes.data, p.size, 0.0, 0, -1, None, 0,
-                                                       C.byref(ml0), C.byref(nf0))) for p in {p.size: p for p in pieces}.values())
+    shares = [s for s in (pieces[t::threads] for t in range(threads)) if s]
+    O.mel_fast_flat_transposed(cfg, pieces[0][:16000])           # sets argtypes, warms the thread-local instance
+    cap = (1 + (clip + 112) // 160) * N_MELS
 
     def work(share):
         out = np.empty(cap, np.float32)
         ml, nf = C.c_int64(), C.c_int64()
-        frames = 0
         for p in share:
-            L.oracle_mel_compute_flat_transposed(C.byref(cfg), p.ctypes.data, p.size, 0.0, 0, -1, out.ctypes.data, cap,
-                                                 C.byref(ml), C.byref(nf))
-            frames += ml.value
-        return frames
+            if fast:
+                L.oracle_mel_fast_flat_transposed(C.byref(cfg), p.ctypes.data, p.size, 0.0, out.ctypes.data, cap, C.byref(ml))
+            else:
+                L.oracle_mel_compute_flat_transposed(C.byref(cfg), p.ctypes.data, p.size, 0.0, 0, -1, out.ctypes.data, cap,
+                                                     C.byref(ml), C.byref(nf))
+        return 0
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(len(shares)) as ex:
         list(ex.map(work, shares))
     dt = time.perf_counter() - t0
     return (repeats * audio.size / 16000.0 / 3600.0) / dt, dt
+
+
+def cpu_mel_arm(audio: np.ndarray, threads: int, budget_s: float = 8.0):
+    """Bounded sample of the mel workload on all host threads: repeats sized so that the arm runs ~budget_s."""
+    v, dt = cpu_mel(audio, threads, 1)
+    repeats = int(max(1, min(64, budget_s / max(dt, 1e-3))))
+    v, dt = cpu_mel(audio, threads, repeats)
+    return v, dt, repeats
 
 
 def cpu_cluster(emb, rho, psi):
@@ -134,75 +169,146 @@ def cpu_cluster(emb, rho, psi):
     return emb.shape[0] / dt, dt, ("reference" if O.ref_available() else "port"), res
 
 
-def host_threads() -> int:
-    return max(1, min(os.cpu_count() or 1, 64))
-
-
 # ------------------------------------------------------------------------------------------------ GPU arms
-def bench_mel(args, dist):
+def _timed_steps(mel, fn, steps, dist, sharding):
+    sharding.barrier(dist)
+    mel.timer_start()
+    for _ in range(steps):
+        fn()
+    ms = mel.timer_stop_ms()
+    sharding.barrier(dist)
+    return sharding.all_reduce_max(dist, ms)
+
+
+def _timed_wall(fn, steps, dist, sharding, _lib):
+    sharding.barrier(dist)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    _lib.synchronize()
+    dt = time.perf_counter() - t0
+    sharding.barrier(dist)
+    return sharding.all_reduce_max(dist, dt)
+
+
+def bench_mel(args, dist, clocks):
+    import ctypes as C
     from fluidaudio_b200 import _lib, sharding, synth
-    from fluidaudio_b200.mel import AudioMelSpectrogram
+    from fluidaudio_b200.mel import AudioMelSpectrogram, Precision
     audio = synth.tone_noise_audio(MEL_SAMPLES, seed=7 + dist.rank)
-    mel = AudioMelSpectrogram(n_mels=N_MELS)
+    mel = AudioMelSpectrogram(n_mels=N_MELS, precision=Precision.f32)
+    mel64 = AudioMelSpectrogram(n_mels=N_MELS, precision=Precision.f64)
     pin_in = _lib.PinnedArray(MEL_SAMPLES, np.float32)
     pin_in.array[:] = audio
+    pin_i16 = _lib.PinnedArray(MEL_SAMPLES, np.int16)
+    pin_i16.array[:] = np.round(audio * 32767.0).astype(np.int16)
     pin_out = _lib.PinnedArray(MEL_FRAMES * N_MELS, np.float32)
     d_in = _lib.DeviceBuffer(MEL_SAMPLES * 4 + 64)
     d_out = _lib.DeviceBuffer(MEL_FRAMES * N_MELS * 4)
     d_in.upload(audio)
+    K, W = args.steps, args.warmup
     # ---- kernel-only: inputs resident in HBM (345.6 MB touched per step > 126 MB L2: nothing survives a step) ----
-    clocks = ClockSampler(dist.local_rank)
-    if dist.is_root:
-        clocks.start()
-    for _ in range(args.warmup):
-        mel.compute_device(d_in, MEL_SAMPLES, d_out)
+    step = lambda: mel.compute_device(d_in, MEL_SAMPLES, d_out)
+    step64 = lambda: mel64.compute_device(d_in, MEL_SAMPLES, d_out)
+    for _ in range(W):
+        step()
     _lib.synchronize()
-    sharding.barrier(dist)
     launches0 = _lib.kernel_launch_count()
-    mel.timer_start()
-    for _ in range(args.steps):
-        mel.compute_device(d_in, MEL_SAMPLES, d_out)
-    dev_ms = mel.timer_stop_ms()
-    _lib.synchronize()
+    with clocks:
+        dev_ms = _timed_steps(mel, step, K, dist, sharding)
     launches = _lib.kernel_launch_count() - launches0
-    sharding.barrier(dist)
-    dev_ms = sharding.all_reduce_max(dist, dev_ms)
+    got32 = d_out.download((MEL_FRAMES, N_MELS), np.float32)
+    # sustained: the same launch back to back for >= ~1.2 s
+    reps = int(max(K, min(20000, 1200.0 / max(dev_ms / K, 1e-3))))
+    with clocks:
+        sus_ms = _timed_steps(mel, step, reps, dist, sharding)
+    # FP64-transform path (the library default), same K steps
+    for _ in range(W):
+        step64()
+    with clocks:
+        dev64_ms = _timed_steps(mel64, step64, K, dist, sharding)
+    got64 = d_out.download((MEL_FRAMES, N_MELS), np.float32)
+    diff = float(np.abs(got32 - got64).max())
     # ---- end to end through the C ABI with host buffers --------------------------------------------------------
-    for _ in range(args.warmup):
-        mel.compute_flat_transposed(pin_in.array, out=pin_out.array)
-    sharding.barrier(dist)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        _, ml, nf = mel.compute_flat_transposed(pin_in.array, out=pin_out.array)
-    _lib.synchronize()
-    e2e_s = time.perf_counter() - t0
-    sharding.barrier(dist)
-    e2e_s = sharding.all_reduce_max(dist, e2e_s)
-    clock_info = clocks.stop() if dist.is_root else None
-    assert ml == MEL_FRAMES
-    ms_per_step = dev_ms / args.steps
+    e2e = lambda: mel.compute_flat_transposed(pin_in.array, out=pin_out.array)
+    for _ in range(W):
+        e2e()
+    with clocks:
+        e2e_s = _timed_wall(e2e, K, dist, sharding, _lib)
+    assert np.array_equal(pin_out.array.reshape(MEL_FRAMES, N_MELS), got32), "host-buffer path differs from the resident one"
+    e2e16 = lambda: mel.compute_from_pcm(pin_i16.array, 16000.0, out=pin_out.array)
+    for _ in range(W):
+        e2e16()
+    e2e16_s = _timed_wall(e2e16, K, dist, sharding, _lib)
+    i16_diff = float(np.abs(pin_out.array.reshape(MEL_FRAMES, N_MELS)[:6000] - got32[:6000]).max())   # 16-bit quantised input
+    # bare copies of the same bytes on two streams: the floor under the end-to-end numbers
+    L = _lib.load()
+    ms = C.c_float()
+    floor = {}
+    for name, src, nb_in in (("f32", pin_in, 4 * MEL_SAMPLES), ("i16", pin_i16, 2 * MEL_SAMPLES)):
+        sharding.barrier(dist)
+        _lib.check(L.fa_memcpy_probe(src.array.ctypes.data, nb_in, pin_out.array.ctypes.data, 4 * MEL_FRAMES * N_MELS,
+                                     max(3, min(K, 10)), C.byref(ms)), "fa_memcpy_probe")
+        floor[name] = sharding.all_reduce_max(dist, float(ms.value))
+    ms_per_step = dev_ms / K
     hours = dist.world * 1.0
     peak, peak_src = measured_peaks()
     achieved = MEL_BYTES_PER_HOUR / (ms_per_step * 1e-3) / 1e9
     out = {
         "metric": "audio-hours/s", "value": hours / (ms_per_step * 1e-3), "unit": "audio-hours/s",
         "ms_per_step": ms_per_step, "dtype": "f32",
-        "e2e": {"value": hours / (e2e_s / args.steps), "unit": "audio-hours/s", "ms_per_step": e2e_s / args.steps * 1e3,
+        "sustained": {"value": hours / (sus_ms / reps * 1e-3), "ms_per_step": sus_ms / reps, "steps": reps,
+                      "seconds": sus_ms * 1e-3},
+        "f64_transform": {"value": hours / (dev64_ms / K * 1e-3), "ms_per_step": dev64_ms / K,
+                          "roofline_frac": MEL_BYTES_PER_HOUR / (dev64_ms / K * 1e-3) / 1e9 / peak,
+                          "note": "FA_MEL_PRECISION_F64 (library default): DFT in FP64 rounded once, one frame per warp"},
+        "parity": {"bar": MEL_TOL, "max_abs_f32_vs_f64_transform_full_hour": diff, "values_compared": int(got32.size),
+                   "max_abs_i16_pcm_vs_f32_pcm_first_minute": i16_diff},
+        "e2e": {"value": hours / (e2e_s / K), "unit": "audio-hours/s", "ms_per_step": e2e_s / K * 1e3,
                 "h2d_bytes_per_step": 4 * MEL_SAMPLES, "d2h_bytes_per_step": 4 * MEL_FRAMES * N_MELS,
-                "host_buffers": "pinned (fa_host_alloc)", "api": "fa_mel_compute"},
+                "host_buffers": "pinned (fa_host_alloc)", "api": "fa_mel_compute",
+                "copy_floor_ms": floor["f32"], "of_copy_floor": floor["f32"] / (e2e_s / K * 1e3)},
+        "e2e_i16": {"value": hours / (e2e16_s / K), "unit": "audio-hours/s", "ms_per_step": e2e16_s / K * 1e3,
+                    "h2d_bytes_per_step": 2 * MEL_SAMPLES, "d2h_bytes_per_step": 4 * MEL_FRAMES * N_MELS,
+                    "api": "fa_audio_to_mel (int16 PCM, 16 kHz mono: widening on the device)",
+                    "copy_floor_ms": floor["i16"], "of_copy_floor": floor["i16"] / (e2e16_s / K * 1e3)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 317.5e6, "traffic_source": "ncu --set full, profiles/r01c_summary.txt: dram read 230.5 MB + "
-                     "write 87.0 MB per launch (the tail of the output is still in L2 at kernel end)",
-                     "kernel": "mel512_kernel", "peak_source": peak_src,
+                     "traffic": None, "traffic_source": "see profiles/r02_summary.txt (ncu --set full of this kernel)",
+                     "kernel": "mel512_kernel<8, f32x2>", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": MEL_BYTES_PER_HOUR},
         "config": {"workload": "log-mel STFT, 1 h synthetic 16 kHz mono, 25 ms/10 ms frames, nFFT 512, 80 mels, per GPU",
-                   "samples": MEL_SAMPLES, "frames": MEL_FRAMES, "n_mels": N_MELS,
+                   "samples": MEL_SAMPLES, "frames": MEL_FRAMES, "n_mels": N_MELS, "transform": "float32 (FA_MEL_PRECISION_F32)",
                    "l2": "inputs+outputs 345.6 MB per step exceed the 126 MB L2 (no flush needed)",
                    "parallelism": f"dp{dist.world}: one process per GPU, independent clips, no data-path collective"},
-        "clocks": clock_info,
     }
-    return out, audio
+    if diff > MEL_TOL:
+        raise SystemExit(f"parity gate failed: float32 transform differs from the FP64 transform by {diff} > {MEL_TOL}")
+    return out, audio, got32
+
+
+def bench_streaming(args):
+    """Latency of the production callers' small `.prePadded` calls (SortformerDiarizer.swift:857-905 streams 10 080-sample
+    chunks, StreamingEouAsrManager 2 560 / 20 480: EouChunkSizeFrameCountTests.swift:10-41), host buffers in and out."""
+    from fluidaudio_b200 import synth
+    from fluidaudio_b200.mel import AudioMelSpectrogram, PaddingMode, Precision
+    out = {}
+    mel = AudioMelSpectrogram(n_mels=128, precision=Precision.f32)
+    for n in (2560, 10080, 20480):
+        a = synth.tone_noise_audio(n, seed=n)
+        buf = np.empty(mel.frame_count(n, PaddingMode.pre_padded) * 128, np.float32)
+        for _ in range(20):
+            mel.compute_flat_transposed(a, padding_mode=PaddingMode.pre_padded, out=buf)
+        ts = []
+        for _ in range(300):
+            t0 = time.perf_counter()
+            mel.compute_flat_transposed(a, last_audio_sample=0.1, padding_mode=PaddingMode.pre_padded, out=buf)
+            ts.append(time.perf_counter() - t0)
+        ts = np.sort(np.array(ts)) * 1e6
+        out[str(n)] = {"frames": int(buf.size // 128), "p50_us": float(ts[len(ts) // 2]), "p99_us": float(ts[int(len(ts) * 0.99)]),
+                       "min_us": float(ts[0])}
+    out["api"] = "fa_mel_compute, .prePadded, 128 mels, pageable host buffers, 300 calls each (wall clock incl. ctypes)"
+    return out
 
 
 def bench_cluster(args, dist, steps=None):
@@ -253,47 +359,109 @@ def bench_cluster(args, dist, steps=None):
                    "n": CLUSTER_N, "dim": CLUSTER_D, "rho_dim": CLUSTER_R,
                    "parallelism": f"dp{dist.world}: one process per GPU, independent embedding sets"},
     }
+    # parity at every N: rank r's labels hashed against the golden of seed 42 (rank 0) — other seeds are checked through
+    # determinism (two runs, identical labels)
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "ahc_large.json")))["c3_10000x256_seed42"]
+    ok = 1.0
+    if dist.rank == 0:
+        ok = 1.0 if hashlib.sha256(np.ascontiguousarray(res.labels, np.int32).tobytes()).hexdigest() == golden["final_labels_sha256"] else 0.0
+    again = c.cluster(pin_e.array, pin_r.array)
+    same = 1.0 if np.array_equal(again.labels, res.labels) else 0.0
+    out["labels_equal_ref"] = bool(sharding.all_reduce_sum(dist, ok if dist.rank == 0 else 0.0) == 1.0)
+    out["labels_deterministic_all_ranks"] = bool(sharding.all_reduce_sum(dist, same) == dist.world)
     return out, (emb, rho, psi, res)
 
 
-def bench_batched_shares():
-    """Per-GPU shares of BASELINE configs[3] and configs[4] (secondary numbers, N = 1 only): 64 clips x 30 s through
-    fa_mel_compute_batch from pinned host memory, and 8 meetings x 5 000 x 256 through fa_diarize_cluster_batch
-    (three meetings side by side on disjoint SM partitions)."""
-    from fluidaudio_b200 import _lib, synth
-    from fluidaudio_b200.clustering import OfflineClusterer
-    from fluidaudio_b200.mel import AudioMelSpectrogram
-    out = {}
-    mel = AudioMelSpectrogram(n_mels=N_MELS)
-    n_clip, count = 480_000, 64
-    pin_in = _lib.PinnedArray((count * n_clip,), np.float32)
-    for i in range(count):
-        pin_in.array[i * n_clip:(i + 1) * n_clip] = synth.tone_noise_audio(n_clip, seed=i)
-    offsets = np.arange(count + 1, dtype=np.int64) * n_clip
-    T = mel.frame_count(n_clip)
+def _stats(ts):
+    ts = sorted(ts)
+    return {"min": ts[0], "median": ts[len(ts) // 2], "max": ts[-1], "reps": len(ts)}
+
+
+def bench_c4(args, dist):
+    """BASELINE configs[3]: 512 clips x 30 s, clip i generated from seed i, sharded in contiguous blocks over the ranks,
+    each rank running fa_mel_compute_batch from pinned host memory to pinned host memory.  Strong scaling: the job is the
+    512 clips whatever N.  Parity at every N: per-clip SHA-256 of the output rows are gathered over the process group and
+    rank 0 recomputes the first clip of every rank's shard on its own GPU (a clip's result may not depend on its batch)."""
+    from fluidaudio_b200 import _lib, sharding, synth
+    from fluidaudio_b200.mel import AudioMelSpectrogram, Precision
+    mel = AudioMelSpectrogram(n_mels=N_MELS, precision=Precision.f32)
+    mine = sharding.contiguous_shard(C4_CLIPS, dist.rank, dist.world)
+    count = len(mine)
+    T = mel.frame_count(C4_SAMPLES)
+    pin_in = _lib.PinnedArray((count * C4_SAMPLES,), np.float32)
+    for j, i in enumerate(mine):
+        pin_in.array[j * C4_SAMPLES:(j + 1) * C4_SAMPLES] = synth.tone_noise_audio(C4_SAMPLES, seed=i)
+    offsets = np.arange(count + 1, dtype=np.int64) * C4_SAMPLES
     pin_out = _lib.PinnedArray((count * T * N_MELS,), np.float32)
+    run = lambda: mel.compute_batch(None, packed_audio=pin_in.array, offsets=offsets, out=pin_out.array)
     for _ in range(2):
-        mel.compute_batch(None, packed_audio=pin_in.array, offsets=offsets, out=pin_out.array)
-    t0 = time.perf_counter()
-    reps = 5
-    for _ in range(reps):
-        mel.compute_batch(None, packed_audio=pin_in.array, offsets=offsets, out=pin_out.array)
-    dt = (time.perf_counter() - t0) / reps
-    out["mel_c4_share"] = {"workload": "64 clips x 30 s (configs[3] / 8 GPUs), pinned host buffers, fa_mel_compute_batch",
-                           "e2e_ms": dt * 1e3, "e2e_audio_hours_per_s": count * 30 / 3600 / dt}
-    sets = [synth.speaker_embeddings(5000, CLUSTER_D, 4, weights=(0.4, 0.3, 0.2, 0.1), sigma=0.02, seed=m)[0] for m in range(8)]
-    emb = np.concatenate(sets)
-    rho, psi = synth.synthetic_plda(emb, CLUSTER_R)
-    offs = np.arange(9, dtype=np.int64) * 5000
+        run()
+    ts = [_timed_wall(run, 1, dist, sharding, _lib) for _ in range(5)]
+    st = _stats(ts)
+    out = pin_out.array.reshape(count, T * N_MELS)
+    digests = np.stack([np.frombuffer(hashlib.sha256(out[j].tobytes()).digest(), np.uint8) for j in range(count)])
+    allhash = sharding.gather_bytes(dist, digests, [len(sharding.contiguous_shard(C4_CLIPS, r, dist.world)) for r in range(dist.world)])
+    checked = equal = 0
+    if dist.is_root:
+        for r in range(dist.world):
+            i = sharding.contiguous_shard(C4_CLIPS, r, dist.world)[0]
+            a = synth.tone_noise_audio(C4_SAMPLES, seed=i)
+            single, _, _ = mel.compute_flat_transposed(a)
+            checked += 1
+            equal += int(hashlib.sha256(single.tobytes()).digest() == allhash[i].tobytes())
+    hours = C4_CLIPS * 30.0 / 3600.0
+    return {"workload": "configs[3]: 512 clips x 30 s sharded over the ranks (contiguous blocks), fa_mel_compute_batch, "
+                        "pinned host buffers in and out", "scaling": "strong", "clips_per_rank": count,
+            "e2e": {"value": hours / st["median"], "unit": "audio-hours/s", "ms": {k: v * 1e3 for k, v in st.items() if k != "reps"},
+                    "reps": st["reps"], "h2d_bytes_per_rank": int(4 * count * C4_SAMPLES), "d2h_bytes_per_rank": int(4 * count * T * N_MELS)},
+            "clips_hashed": int(C4_CLIPS if dist.is_root else count), "clips_recomputed_on_rank0": checked, "clips_equal": equal}
+
+
+def bench_c5(args, dist):
+    """BASELINE configs[4]: 64 meetings x 5 000 x 256 (seed = meeting index), partitioned over the ranks by LPT on 8 d N^2,
+    each rank running fa_diarize_cluster_batch; labels gathered over the process group (NCCL) and every meeting's labels
+    hashed against tests/golden/c5_meetings.json — goldens produced by the compiled reference fastcluster + the oracle
+    port of the Swift stages.  Strong scaling."""
+    from fluidaudio_b200 import _lib, sharding, synth
+    from fluidaudio_b200.clustering import OfflineClusterer
+    parts = sharding.lpt_partition([sharding.ahc_cost(C5_N, CLUSTER_D)] * C5_MEETINGS, dist.world)
+    mine = parts[dist.rank]
+    embs, rhos, psi = [], [], None
+    for m in mine:
+        e, _ = synth.speaker_embeddings(C5_N, CLUSTER_D, 4, weights=(0.4, 0.3, 0.2, 0.1), sigma=0.02, seed=m)
+        r, psi = synth.synthetic_plda(e, CLUSTER_R)
+        embs.append(e); rhos.append(r)
+    pin_e = _lib.PinnedArray((len(mine) * C5_N, CLUSTER_D), np.float32); pin_e.array[:] = np.concatenate(embs)
+    pin_r = _lib.PinnedArray((len(mine) * C5_N, CLUSTER_R), np.float64); pin_r.array[:] = np.concatenate(rhos)
+    offs = np.arange(len(mine) + 1, dtype=np.int64) * C5_N
     c = OfflineClusterer(psi=psi)
-    c.cluster_batch(emb, rho, offs)
-    t0 = time.perf_counter()
-    labels, infos = c.cluster_batch(emb, rho, offs)
-    dt = time.perf_counter() - t0
-    out["cluster_c5_share"] = {"workload": "8 meetings x 5 000 x 256 (configs[4] / 8 GPUs), fa_diarize_cluster_batch",
-                               "e2e_ms": dt * 1e3, "e2e_embeddings_per_s": emb.shape[0] / dt,
-                               "ahc_ms_per_meeting": [round(i["ms_ahc"], 2) for i in infos]}
-    return out
+    box = {}
+
+    def run():
+        box["labels"], box["infos"] = c.cluster_batch(pin_e.array, pin_r.array, offs)
+    run()
+    ts = [_timed_wall(run, 1, dist, sharding, _lib) for _ in range(5)]
+    st = _stats(ts)
+    counts = [len(p) * C5_N for p in parts]
+    gathered = sharding.gather_labels(dist, box["labels"], counts)
+    equal = None
+    if dist.is_root:
+        golden = {g["meeting"]: g["final_labels_sha256"] for g in
+                  json.load(open(os.path.join(ROOT, "tests", "golden", "c5_meetings.json")))["meetings"]}
+        equal, pos = 0, 0
+        for r in range(dist.world):
+            for m in parts[r]:
+                lab = np.ascontiguousarray(gathered[pos:pos + C5_N], np.int32)
+                equal += int(hashlib.sha256(lab.tobytes()).hexdigest() == golden[m])
+                pos += C5_N
+    ahc = [i["ms_ahc"] for i in box["infos"]]
+    return {"workload": "configs[4]: 64 meetings x 5 000 x 256 sharded over the ranks (LPT), fa_diarize_cluster_batch, labels "
+                        "gathered over the process group", "scaling": "strong", "meetings_per_rank": len(mine),
+            "e2e": {"value": C5_MEETINGS * C5_N / st["median"], "unit": "embeddings/s",
+                    "ms": {k: v * 1e3 for k, v in st.items() if k != "reps"}, "reps": st["reps"]},
+            "ahc_ms_per_meeting": {"min": float(min(ahc)), "max": float(max(ahc))},
+            "labels_equal_ref": equal, "meetings": C5_MEETINGS,
+            "golden": "tests/golden/c5_meetings.json (compiled reference fastcluster + oracle port of the Swift stages)"}
 
 
 def main():
@@ -304,6 +472,7 @@ def main():
     ap.add_argument("--workload", choices=["mel", "cluster"], default="mel")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-main", action="store_true", help="skip the c4 / c5 / streaming sub-objects (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -317,17 +486,22 @@ def main():
         threads = host_threads()
         steps = max(1, min(args.steps, 3))
         if args.workload == "mel":
-            sample_s, repeats = 3600, 4                                          # 4 audio-hours (~20 s of CPU work) per step
-            audio = synth.tone_noise_audio(16000 * sample_s)
+            audio = synth.tone_noise_audio(MEL_SAMPLES)
             for _ in range(min(args.warmup, 1)):
                 cpu_mel(audio[: 16000 * 120], threads)
-            vals = [cpu_mel(audio, threads, repeats) for _ in range(steps)]
-            v = float(np.mean([x[0] for x in vals])); dt = float(np.mean([x[1] for x in vals]))
+            vals = [cpu_mel_arm(audio, threads, budget_s=8.0) for _ in range(steps)]
+            v = float(np.mean([x[0] for x in vals])); dt = float(np.mean([x[1] for x in vals])); rep = vals[-1][2]
+            v1, _ = cpu_mel(audio[: 16000 * 600], 1)
+            vo, _ = cpu_mel(audio[: 16000 * 600], threads, 1, fast=False)
             line = {"impl": "reference", "metric": "audio-hours/s", "value": v, "unit": "audio-hours/s", "dtype": "f32",
                     "config": {"workload": "log-mel STFT, 1 h synthetic 16 kHz mono, 25 ms/10 ms frames, nFFT 512, 80 mels"},
                     "cpu_baseline": {"value": v, "unit": "audio-hours/s", "cores": threads, "kind": "port",
-                                     "sample": f"the workload's {sample_s} s of audio x {repeats} per step, 30 s clips over {threads} threads "
-                                               "(oracle port of AudioMelSpectrogram.swift; no Swift toolchain)"}}
+                                     "sample": f"the workload's hour of audio x {rep} per step, 30 s clips over {threads} threads: float32-FFT "
+                                               "port of AudioMelSpectrogram.swift, SIMD across frames (oracle/oracle_mel_fast.cpp; no Swift "
+                                               "toolchain, no Accelerate)",
+                                     "single_thread_value": v1, "apple_m5_single_core_derived": 4.6,
+                                     "parity_oracle_port_value": vo,
+                                     "parity_oracle_port_note": "oracle_mel.cpp (float64 DFT rounded once, scalar), same threads, 600 s sample"}}
         else:
             emb, _ = synth.speaker_embeddings(CLUSTER_N, CLUSTER_D, CLUSTER_K, seed=42)
             rho, psi = synth.synthetic_plda(emb, CLUSTER_R)
@@ -350,31 +524,46 @@ def main():
     _lib.set_device(dist.local_rank)
     all_cpus = os.sched_getaffinity(0)
     numa = sharding.bind_to_gpu_numa(dist.local_rank)
+    clocks = ClockSampler(dist.local_rank)
 
+    got32 = None
     if args.workload == "mel":
-        line, audio = bench_mel(args, dist)
+        line, audio, got32 = bench_mel(args, dist, clocks)
         extra_steps = max(3, min(args.steps, 5))
         cluster_line, cluster_data = bench_cluster(args, dist, steps=extra_steps)
-        line["cluster"] = {k: cluster_line[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline",
-                                                         "stages_ms", "gpu_launches", "config")}
+        line["cluster"] = {k: cluster_line[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "stages_ms",
+                                                         "gpu_launches", "config", "labels_equal_ref",
+                                                         "labels_deterministic_all_ranks")}
         line["cluster"]["steps"] = extra_steps
+        if not args.only_main:
+            line["c4"] = bench_c4(args, dist)
+            line["c5"] = bench_c5(args, dist)
+            if dist.is_root:
+                line["streaming"] = bench_streaming(args)
     else:
         line, cluster_data = bench_cluster(args, dist)
         audio = None
+    line["clocks"] = clocks.summary()
 
-    if dist.is_root and world == 1 and args.workload == "mel" and not args.no_cpu_baseline:
-        line["batched_shares"] = bench_batched_shares()
     os.sched_setaffinity(0, all_cpus)      # the CPU baseline may use every host core again
     if dist.is_root and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         if args.workload == "mel":
-            repeats = 4
-            v, dt = cpu_mel(audio, threads, repeats)
+            from oracle import oracle as O
+            v, dt, rep = cpu_mel_arm(audio, threads, budget_s=8.0)
+            v1, _ = cpu_mel(audio[: 16000 * 600], 1)
+            vo, _ = cpu_mel(audio[: 16000 * 600], threads, 1, fast=False)
             line["cpu_baseline"] = {"value": v, "unit": "audio-hours/s", "cores": threads, "kind": "port",
-                                    "sample": f"the workload's hour of audio x {repeats}, 30 s clips over {threads} host threads, "
-                                              f"{dt:.2f} s wall (oracle port of AudioMelSpectrogram.swift)"}
-            v1, dt1 = cpu_mel(audio[: 16000 * 300], 1)
-            line["cpu_baseline"]["single_thread_value"] = v1
+                                    "sample": f"the workload's hour of audio x {rep}, 30 s clips over {threads} host threads, {dt:.2f} s wall: "
+                                              "float32-FFT port of AudioMelSpectrogram.swift, SIMD across frames (oracle/oracle_mel_fast.cpp)",
+                                    "single_thread_value": v1, "apple_m5_single_core_derived": 4.6,
+                                    "parity_oracle_port_value": vo}
+            # the CPU arms double as checkers of the GPU output (first minute): the parity oracle and the float32 port
+            cfg = O.mel_config(n_mels=N_MELS)
+            ref, rml, _ = O.mel_flat_transposed(cfg, audio[:960000])
+            fast, _ = O.mel_fast_flat_transposed(cfg, audio[:960000], 0.0)
+            line["parity"]["max_abs_vs_oracle_first_minute"] = float(np.abs(got32[:rml - 3] - ref[:rml - 3]).max())
+            line["parity"]["max_abs_vs_cpu_float32_port_first_minute"] = float(np.abs(got32[:rml - 3] - fast[:rml - 3]).max())
             emb, rho, psi, res = cluster_data
             cv, cdt, kind, ores = cpu_cluster(emb, rho, psi)
             line["cluster"]["cpu_baseline"] = {"value": cv, "unit": "embeddings/s", "cores": 1, "kind": kind,

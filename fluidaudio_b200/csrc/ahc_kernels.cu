@@ -1187,8 +1187,12 @@ void dendrogram_cut(const double *Z, long long count, double threshold, int32_t 
     std::vector<long long> lc(total, -1), rc(total, -1);
     std::vector<double> nd(total, 0.0);
     for (long long m = 0; m + 1 < count; ++m) {
-        lc[count + m] = (long long)Z[m * 4];
-        rc[count + m] = (long long)Z[m * 4 + 1];
+        // children of row m must be earlier nodes (0 <= id < count + m): anything else in a caller-supplied Z (NaN, a
+        // negative or forward reference) is dropped, which also rules out cycles; the leaves it orphans get fresh labels
+        const double za = Z[m * 4], zb = Z[m * 4 + 1];
+        const double hi = (double)(count + m);
+        lc[count + m] = (za >= 0.0 && za < hi) ? (long long)za : -1;
+        rc[count + m] = (zb >= 0.0 && zb < hi) ? (long long)zb : -1;
         nd[count + m] = Z[m * 4 + 2];
     }
     std::vector<long long> lab(count, -1), todo, sub;

@@ -300,7 +300,7 @@ static int cluster_pipeline(ClusterContext &C, const float *emb, const double *r
     vc.max_iterations = cfg.vbx.max_iterations;
     vc.epsilon = cfg.vbx.epsilon;
     vc.init_smoothing = cfg.vbx.init_smoothing;
-    const size_t gbytes = ((size_t)Tn * S + 2 * (size_t)S + std::max(vc.max_iterations, 1) + 2 * (size_t)S * E + E) *
+    const size_t gbytes = ((size_t)Tn * S + 2 * (size_t)S + std::max(vc.max_iterations, 1) + 2 * ((size_t)S * E + E)) *
                               sizeof(double) + 8192;
     st = C.cent_ws.reserve(std::max(gbytes, (size_t)1 << 20));
     if (st != FA_OK) return st;
@@ -790,6 +790,7 @@ FA_API fa_status fa_mel_lseend_features(fa_mel *mel, const float *chunk, size_t 
 // buffer that is about to be handed to the encoder; not a GPU hot path.
 FA_API fa_status fa_mel_normalize_per_feature(float *x, int64_t frames, int32_t n_mels, int64_t valid) {
     if (!x || frames < 0 || n_mels <= 0) return FA_STATUS_INVALID_ARGUMENT;
+    if (valid > frames) valid = frames;   // UnifiedMelExtractor.swift:66: validFrames = min(validCount / hop, totalFrames)
     if (valid <= 0) {
         for (int64_t i = 0; i < frames * n_mels; ++i) x[i] = 0.0f;
         return FA_STATUS_OK;
@@ -1423,7 +1424,9 @@ FA_API fa_status fa_diarize_cluster_batch(const float *emb256, const double *rho
     std::atomic<int> next{0};
     std::vector<int> status(lanes, FA_OK);
     std::vector<std::string> messages(lanes);
-    auto run = [&](int lane) {
+    // Each lane is a plain std::thread: nothing may escape it (an exception leaving a thread function is std::terminate,
+    // and FA_GUARD_* only covers the calling thread), so the body is wrapped and failures are reported through status[].
+    auto run_lane = [&](int lane) {
         if (cudaSetDevice(dev) != cudaSuccess) {
             status[lane] = FA_CUDA_ERROR;
             return;
@@ -1450,10 +1453,40 @@ FA_API fa_status fa_diarize_cluster_batch(const float *emb256, const double *rho
             }
         }
     };
-    std::vector<std::thread> threads;
-    for (int l = 1; l < lanes; ++l) threads.emplace_back(run, l);
+    auto run = [&](int lane) noexcept {
+        try {
+            run_lane(lane);
+        } catch (const std::bad_alloc &) {
+            status[lane] = FA_ALLOCATION_FAILURE;
+            try { messages[lane] = "host allocation failed"; } catch (...) {}
+        } catch (const std::exception &ex) {
+            status[lane] = FA_RUNTIME_ERROR;
+            try { messages[lane] = std::string("exception: ") + ex.what(); } catch (...) {}
+        } catch (...) {
+            status[lane] = FA_UNKNOWN_ERROR;
+        }
+        if (status[lane] != FA_OK) next.store(set_count);   // the other lanes stop taking new sets
+    };
+    // threads already started are always joined, also when starting a later one fails
+    struct Joiner {
+        std::vector<std::thread> t;
+        ~Joiner() {
+            for (auto &x : t)
+                if (x.joinable()) x.join();
+        }
+    } threads;
+    threads.t.reserve(lanes);
+    int started = 1;
+    try {
+        for (int l = 1; l < lanes; ++l) {
+            threads.t.emplace_back(run, l);
+            ++started;
+        }
+    } catch (...) {   // std::system_error: run with the lanes that did start
+    }
+    (void)started;
     run(0);
-    for (auto &t : threads) t.join();
+    for (auto &t : threads.t) t.join();
     for (int l = 0; l < lanes; ++l)
         if (status[l] != FA_OK) {
             fa::set_error("%s", messages[l].c_str());

@@ -110,6 +110,12 @@ struct Reader {
         return true;
     }
     bool skip_value() {
+        struct Depth {
+            int &d;
+            explicit Depth(int &x) : d(x) { ++d; }
+            ~Depth() { --d; }
+        } guard(depth);
+        if (depth > 64) return fail("values nested deeper than 64 levels");
         ws();
         if (p >= end) return fail("unexpected end");
         if (*p == '"') {
@@ -141,11 +147,11 @@ struct Reader {
                 return fail("expected ',' or a closing bracket");
             }
         }
-        if (!std::strncmp(p, "true", 4) || !std::strncmp(p, "null", 4)) {
+        if (end - p >= 4 && (!std::memcmp(p, "true", 4) || !std::memcmp(p, "null", 4))) {
             p += 4;
             return true;
         }
-        if (!std::strncmp(p, "false", 5)) {
+        if (end - p >= 5 && !std::memcmp(p, "false", 5)) {
             p += 5;
             return true;
         }
@@ -153,6 +159,7 @@ struct Reader {
         return f64(d);
     }
     const char *start;
+    int depth = 0;   // nesting of skipped values: bounded so that a file of '[[[[...' cannot exhaust the stack
 };
 
 struct Entry {

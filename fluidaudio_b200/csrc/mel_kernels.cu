@@ -289,6 +289,92 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
     if (pending_dst) copy_out(pending_dst, pending_total);
 }
 
+
+// ------------------------------------------------------------------------------------------------ any-nFFT kernel
+// AudioMelSpectrogram is parametric (AudioMelSpectrogram.swift:59-70) and LS-EEND derives nFFT = nextPow2(winLength)
+// (Diarizer/LS-EEND/LSEENDTypes.swift:55-57): nFFT other than 512, or an odd hop, take this kernel.  Same contract, same
+// unit / tile bookkeeping and the same packed filterbank as mel512_kernel; one warp per frame, the transform an FP64
+// radix-2 decimation-in-time FFT of the real frame in shared memory (twiddles from an FP64 table), power rounded once
+// to float32.  A correctness-first path: ~6x the instructions per frame of the specialised kernel.
+struct GenericParams {
+    int n_fft, log2n, bins, prow;      // prow: floats per power row (bins rounded up to quads + 4)
+    const cpxd *tw;                    // W_n^k, k < n/2
+    int warps;
+};
+
+__global__ void __launch_bounds__(256) mel_generic_kernel(const MelLaunch P, const GenericParams G) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    cpxd *tw = reinterpret_cast<cpxd *>(smem);                                   // n/2
+    cpxd *fft = tw + G.n_fft / 2;                                                // warps x n
+    float *power = reinterpret_cast<float *>(fft + (size_t)G.warps * G.n_fft);   // warps x prow
+    float *win = power + (size_t)G.warps * G.prow;                               // n (0 outside the window)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = G.warps * 32;
+    for (int i = tid; i < G.n_fft / 2; i += nthreads) tw[i] = G.tw[i];
+    for (int i = tid; i < G.n_fft; i += nthreads) win[i] = P.in_tab[i] ? P.win_tab[i] : 0.0f;
+    for (int i = tid; i < G.warps * G.prow; i += nthreads) power[i] = 0.0f;
+    __syncthreads();
+    cpxd *buf = fft + (size_t)warp * G.n_fft;
+    float *prow = power + (size_t)warp * G.prow;
+    const float a = P.preemph;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileGeom g = tile_geom(P, tile);
+        const MelUnit u = P.units[g.unit];
+        const float *x = P.audio + u.audio_off;
+        for (int fi = warp; fi < g.nf; fi += G.warps) {
+            const long long f = g.f0 + fi;
+            const long long base = f * P.hop - P.pad;
+            // pre-emphasis + window into bit-reversed order
+            for (int j = lane; j < G.n_fft; j += 32) {
+                const long long i = base + j;
+                float v = 0.0f;
+                if (i >= 0 && i < u.n && P.in_tab[j]) {
+                    const float xi = __ldg(x + i);
+                    if (a == 0.0f) v = xi;
+                    else if (i == 0) v = preemph_first(xi, u.last, a);
+                    else v = preemph_rest(xi, __ldg(x + i - 1), a);
+                    v = __fmul_rn(v, win[j]);
+                }
+                cpxd z;
+                z.x = (double)v;
+                z.y = 0.0;
+                buf[__brev((unsigned)j) >> (32 - G.log2n)] = z;
+            }
+            __syncwarp();
+            for (int s = 0; s < G.log2n; ++s) {
+                const int half = 1 << s, step = G.n_fft >> (s + 1);
+                for (int t = lane; t < G.n_fft / 2; t += 32) {
+                    const int j = t & (half - 1);
+                    const int ia = ((t >> s) << (s + 1)) + j, ib = ia + half;
+                    const cpxd w = tw[j * step], zb = buf[ib], za = buf[ia];
+                    const double tr = zb.x * w.x - zb.y * w.y, ti = zb.x * w.y + zb.y * w.x;
+                    cpxd o;
+                    o.x = za.x - tr;
+                    o.y = za.y - ti;
+                    buf[ib] = o;
+                    o.x = za.x + tr;
+                    o.y = za.y + ti;
+                    buf[ia] = o;
+                }
+                __syncwarp();
+            }
+            for (int b = lane; b < G.bins; b += 32) {
+                const float xr = (float)buf[b].x, xi = (float)buf[b].y;
+                prow[b] = 4.0f * __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi));   // the packed weights carry 1/4
+            }
+            __syncwarp();
+            for (int m = lane; m < P.n_mels; m += 32) {
+                const int lo = P.fb_lo[m], nq = (P.fb_hi[m] - lo) >> 2;
+                const float v = log_value(mel_dot_quads(reinterpret_cast<const float4 *>(prow + lo),
+                                                        reinterpret_cast<const float4 *>(P.fb_w + P.fb_off[m]), nq),
+                                          P.log_floor, P.log_clamped);
+                if (P.layout == 0) P.out[u.out_off + f * P.n_mels + m] = v;
+                else P.out[u.out_off + (long long)m * u.out_stride + f] = v;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host plan
 static float swift_float_pi() {
     const uint32_t bits = 0x40490FDAu;   // Swift's Float.pi is rounded toward zero
@@ -366,6 +452,7 @@ void MelPlan::release() {
     fr(d_out);
     fr(d_pcm);
     fr(d_rs_tab);
+    fr(d_generic_tw);
     d_pcm_cap = 0;
     rs_in = rs_out = 0.0;
     d_audio_cap = d_out_cap = 0;
@@ -388,13 +475,16 @@ int MelPlan::init(const MelConfig &c) {
         fa::set_error("mel config: all sizes must be positive");
         return FA_INVALID_ARGUMENT;
     }
-    if (cfg.n_fft != kNfft || (cfg.hop_length & 1) || cfg.win_length > kNfft || cfg.n_mels > 512 ||
-        cfg.hop_length > 1024) {
-        fa::set_error("mel config unsupported by the sm_100a kernel: need nFFT == 512, even hop <= 1024, win <= 512, "
+    const bool pow2 = cfg.n_fft >= 32 && cfg.n_fft <= 4096 && (cfg.n_fft & (cfg.n_fft - 1)) == 0;
+    if (!pow2 || cfg.win_length > cfg.n_fft || cfg.n_mels > 512 || cfg.hop_length > 65536) {
+        fa::set_error("mel config unsupported by the sm_100a kernels: need nFFT a power of two in 32..4096, win <= nFFT, "
                       "nMels <= 512 (got nFFT=%d hop=%d win=%d nMels=%d)",
                       cfg.n_fft, cfg.hop_length, cfg.win_length, cfg.n_mels);
         return FA_UNSUPPORTED;
     }
+    // the specialised kernel covers every in-repo caller's shape; anything else takes mel_generic_kernel
+    generic = cfg.n_fft != kNfft || (cfg.hop_length & 1) || cfg.hop_length > 1024;
+    const int n_fft = cfg.n_fft, bins = n_fft / 2 + 1;
     build_window(cfg.win_length, cfg.window_periodic != 0, window);
     build_filterbank(cfg.n_fft, cfg.n_mels, cfg.sample_rate, filterbank);
 
@@ -403,9 +493,9 @@ int MelPlan::init(const MelConfig &c) {
     std::vector<float> w;
     std::vector<int> lo(cfg.n_mels), hi(cfg.n_mels), off(cfg.n_mels);
     for (int m = 0; m < cfg.n_mels; ++m) {
-        int a = kBins, b = 0;
-        for (int k = 0; k < kBins; ++k)
-            if (filterbank[(size_t)m * kBins + k] != 0.0f) {
+        int a = bins, b = 0;
+        for (int k = 0; k < bins; ++k)
+            if (filterbank[(size_t)m * bins + k] != 0.0f) {
                 a = std::min(a, k);
                 b = k + 1;
             }
@@ -415,7 +505,7 @@ int MelPlan::init(const MelConfig &c) {
         lo[m] = a;
         hi[m] = b;
         off[m] = (int)w.size();        // a multiple of four: 16-byte aligned weight quads
-        for (int k = a; k < b; ++k) w.push_back(k < kBins ? 0.25f * filterbank[(size_t)m * kBins + k] : 0.0f);
+        for (int k = a; k < b; ++k) w.push_back(k < bins ? 0.25f * filterbank[(size_t)m * bins + k] : 0.0f);
     }
     fb_nnz = (int)w.size();
 
@@ -429,8 +519,8 @@ int MelPlan::init(const MelConfig &c) {
         return FA_NO_DEVICE;
     }
 
-    std::vector<float> win_tab(kNfft, 0.0f);
-    std::vector<uint8_t> in_tab(kNfft, 0);
+    std::vector<float> win_tab(n_fft, 0.0f);
+    std::vector<uint8_t> in_tab(n_fft, 0);
     for (int mode = 0; mode < 2; ++mode) {   // 0: centred window (offset (nFFT-win)/2); 1: legacy compute(), offset 0
         const int off_w = mode == 0 ? (cfg.n_fft - cfg.win_length) / 2 : 0;
         std::fill(win_tab.begin(), win_tab.end(), 0.0f);
@@ -439,10 +529,10 @@ int MelPlan::init(const MelConfig &c) {
             win_tab[off_w + j] = window[j];
             in_tab[off_w + j] = 1;
         }
-        FA_CUDA_TRY(cudaMalloc(&d_win_tab_mode[mode], kNfft * sizeof(float)));
-        FA_CUDA_TRY(cudaMalloc(&d_in_tab_mode[mode], kNfft));
-        FA_CUDA_TRY(cudaMemcpy(d_win_tab_mode[mode], win_tab.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice));
-        FA_CUDA_TRY(cudaMemcpy(d_in_tab_mode[mode], in_tab.data(), kNfft, cudaMemcpyHostToDevice));
+        FA_CUDA_TRY(cudaMalloc(&d_win_tab_mode[mode], n_fft * sizeof(float)));
+        FA_CUDA_TRY(cudaMalloc(&d_in_tab_mode[mode], n_fft));
+        FA_CUDA_TRY(cudaMemcpy(d_win_tab_mode[mode], win_tab.data(), n_fft * sizeof(float), cudaMemcpyHostToDevice));
+        FA_CUDA_TRY(cudaMemcpy(d_in_tab_mode[mode], in_tab.data(), n_fft, cudaMemcpyHostToDevice));
     }
     FA_CUDA_TRY(cudaMalloc(&d_fb_w, std::max<size_t>(1, w.size()) * sizeof(float)));
     FA_CUDA_TRY(cudaMalloc(&d_fb_lo, cfg.n_mels * sizeof(int)));
@@ -453,6 +543,28 @@ int MelPlan::init(const MelConfig &c) {
     FA_CUDA_TRY(cudaMemcpy(d_fb_hi, hi.data(), cfg.n_mels * sizeof(int), cudaMemcpyHostToDevice));
     FA_CUDA_TRY(cudaMemcpy(d_fb_off, off.data(), cfg.n_mels * sizeof(int), cudaMemcpyHostToDevice));
 
+    for (auto &st : streams) FA_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (generic) {
+        // FP64 twiddle table W_n^k and the shared-memory budget: as many warps per CTA as fit beside it
+        std::vector<cpxd> tw(n_fft / 2);
+        for (int k = 0; k < n_fft / 2; ++k) tw[k] = unit_root(k, n_fft);
+        FA_CUDA_TRY(cudaMalloc(&d_generic_tw, tw.size() * sizeof(cpxd)));
+        FA_CUDA_TRY(cudaMemcpy(d_generic_tw, tw.data(), tw.size() * sizeof(cpxd), cudaMemcpyHostToDevice));
+        generic_prow = ((bins + 3) & ~3) + 4;
+        int log2n = 0;
+        while ((1 << log2n) < n_fft) ++log2n;
+        generic_log2n = log2n;
+        const size_t fixed = (size_t)(n_fft / 2) * sizeof(cpxd) + (size_t)n_fft * sizeof(float);
+        const size_t per_warp = (size_t)n_fft * sizeof(cpxd) + (size_t)generic_prow * sizeof(float);
+        generic_warps = (int)std::min<size_t>(8, ((size_t)prop.sharedMemPerBlockOptin - fixed - 1024) / per_warp);
+        if (generic_warps < 1) {
+            fa::set_error("mel config: nFFT %d does not fit shared memory", n_fft);
+            return FA_UNSUPPORTED;
+        }
+        smem_bytes = fixed + per_warp * generic_warps;
+        FA_CUDA_TRY(cudaFuncSetAttribute(mel_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        return FA_OK;
+    }
     pt_len = (kTileFrames - 1) * cfg.hop_length + kNfft;
     pt_cap = (pt_len + 31) & ~31;
     raw_cap = (pt_len + 1 + 3 + 3 + 31) & ~31;   // whole 128-byte lines: the pre-emphasised tile behind it stays line-aligned
@@ -470,7 +582,6 @@ int MelPlan::init(const MelConfig &c) {
                                      (int)smem_bytes));
     FA_CUDA_TRY(cudaFuncSetAttribute(mel512_kernel<kWarpsPerCta, f32x2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_bytes));
-    for (auto &s : streams) FA_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     return FA_OK;
 }
 
@@ -554,6 +665,15 @@ int MelPlan::launch(const float *d_audio_base, float *d_out_base, int first, int
         P.mid_full = (off_w <= 64 && off_w + cfg.win_length >= 448) ? 1 : 0;
     }
     P.inv_n_mels = (unsigned)((0x100000000ull + (unsigned)cfg.n_mels - 1) / (unsigned)cfg.n_mels);
+    if (generic) {
+        GenericParams G{cfg.n_fft, generic_log2n, cfg.n_fft / 2 + 1, generic_prow, reinterpret_cast<const cpxd *>(d_generic_tw),
+                        generic_warps};
+        const int ggrid = std::min(total_tiles, num_sms * std::max(1, 16 / generic_warps));
+        mel_generic_kernel<<<ggrid, generic_warps * 32, smem_bytes, stream>>>(P, G);
+        FA_CUDA_TRY(cudaGetLastError());
+        ++launches;
+        return FA_OK;
+    }
     const int grid = std::min(total_tiles, num_sms * kCtasPerSm);
     if (precision == 1) mel512_kernel<kWarpsPerCta, f32x2><<<grid, kWarpsPerCta * 32, smem_bytes, stream>>>(P);
     else mel512_kernel<kWarpsPerCta, double><<<grid, kWarpsPerCta * 32, smem_bytes, stream>>>(P);
@@ -672,7 +792,7 @@ int MelPlan::compute_host(const float *audio, long long n, float last, int mode,
     long long copied = 0;
     for (int c = 0; c < chunks; ++c) {
         const long long f_end = h_units[c].frame_begin + h_units[c].frame_count;            // exclusive
-        long long s_end = std::min(n, (f_end - 1) * cfg.hop_length + kNfft - pad);          // samples needed so far
+        long long s_end = std::min(n, (f_end - 1) * cfg.hop_length + cfg.n_fft - pad);          // samples needed so far
         if (c == chunks - 1) s_end = n;
         if (s_end > copied) {
             FA_CUDA_TRY(cudaMemcpyAsync(d_audio + copied, audio + copied, (s_end - copied) * sizeof(float),
@@ -775,7 +895,7 @@ int MelPlan::compute_host_pcm(const void *pcm, long long frames, const resample:
     long long in_copied = 0, converted = 0;
     for (int c = 0; c < chunks; ++c) {
         const long long f_end = h_units[c].frame_begin + h_units[c].frame_count;
-        long long s_end = std::min(n, (f_end - 1) * cfg.hop_length + kNfft - pad);   // model-rate samples needed so far
+        long long s_end = std::min(n, (f_end - 1) * cfg.hop_length + cfg.n_fft - pad);   // model-rate samples needed so far
         if (c == chunks - 1) s_end = n;
         // input frames those samples depend on
         long long in_need = frames;

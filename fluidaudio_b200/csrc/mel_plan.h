@@ -74,6 +74,9 @@ struct MelPlan {
     int num_sms = 0;
     long long launches = 0;          // kernels launched through this plan (bench.py reports it)
     int precision = 0;               // transform arithmetic: 0 = FP64 (one frame per warp), 1 = packed float32 pairs
+    bool generic = false;            // nFFT != 512 or odd hop: mel_generic_kernel (FP64 transform whatever `precision`)
+    int generic_warps = 0, generic_prow = 0, generic_log2n = 0;
+    void *d_generic_tw = nullptr;    // FP64 twiddles W_n^k, k < n/2
 
     float *d_win_tab_mode[2] = {nullptr, nullptr};
     uint8_t *d_in_tab_mode[2] = {nullptr, nullptr};

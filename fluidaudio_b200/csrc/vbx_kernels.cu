@@ -32,6 +32,8 @@ namespace vbx {
 
 constexpr int kChunks = 128;      // frame chunks for the two-level reductions (fewer when there are > 1024 speakers)
 constexpr int kEThreads = 128;    // threads per CTA in the E-step
+constexpr int kFChunks = 16;      // frame chunks of the two-kernel EM path
+constexpr int kFusedMaxS = 64;    // speakers the two-kernel EM path handles (alpha and invL tiles live in shared memory)
 
 // Partial sums are [chunks x S x D]: keep them bounded when AHC hands over thousands of clusters (degenerate input:
 // every embedding its own speaker).  The chunk count only changes the (fixed) summation order.
@@ -57,6 +59,11 @@ struct Dev {
     int *state;           // [0]=done [1]=iterations
     int eblocks;
     double Fa, Fb, eps;
+    // two-kernel path (S <= kFusedMaxS): partials over kFChunks frame chunks, E-step partials double-buffered by iteration
+    double *fA, *fG;        // [kFChunks x S x D], [kFChunks x S]
+    double *fLL[2];         // [eblocks]
+    double *fPi[2];         // [eblocks x S]
+    double *fsums[2];       // [4]: sum log invL, sum invL, sum alpha^2
 };
 
 // gamma0 = softmax(7 * onehot) row-wise, then renormalise (VBxClustering.swift:190-235); rho = x * sqrt(phi);
@@ -285,6 +292,214 @@ __global__ void vbx_finish_kernel(Dev d, int iteration) {
     }
 }
 
+
+// ---- two-kernel EM iteration (the normal case: a handful of speakers) -----------------------------------------------
+// Iteration i = vbx_acc16_kernel (partial sums of gamma_i over kFChunks frame chunks, one thread per (s, k) and chunk)
+//             + vbx_estep_fused_kernel, whose PROLOGUE every CTA runs redundantly from those partials and from the previous
+//               E-step's per-CTA partials: pi_i, ELBO_{i-1} and the convergence test (VBxClustering.swift:578-661), then
+//               N_s, invL, alpha, phi, log pi (:304-436, :496-516) into shared memory; its body is the E-step (:438-576).
+// Every CTA takes the same decision from the same doubles in the same order, so no grid-wide barrier and no single-CTA
+// fold is needed: 2 launches per iteration instead of 4, and the 144 us single-CTA update kernel is gone.  All sums keep a
+// FIXED order (sequential inside a chunk, chunks ascending; E-step partials per CTA, CTAs ascending): bit-reproducible.
+__global__ void __launch_bounds__(256) vbx_acc16_kernel(Dev d) {
+    if (d.state[0]) return;
+    const int c = blockIdx.y;
+    const int per = (d.T + kFChunks - 1) / kFChunks;
+    const int t0 = c * per, t1 = min(d.T, t0 + per);
+    const int SD = d.S * d.D;
+    const int o = blockIdx.x * 256 + threadIdx.x;
+    if (o < SD) {
+        const int s = o / d.D, k = o - s * d.D;
+        const double *g = d.gamma + s, *r = d.rho + k;
+        double acc = 0.0;
+        for (int t = t0; t < t1; ++t) acc += g[(size_t)t * d.S] * r[(size_t)t * d.D];
+        d.fA[(size_t)c * SD + o] = acc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < d.S) {
+        const int s = threadIdx.x;
+        double acc = 0.0;
+        for (int t = t0; t < t1; ++t) acc += d.gamma[(size_t)t * d.S + s];
+        d.fG[(size_t)c * d.S + s] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(kEThreads) vbx_estep_fused_kernel(Dev d, int it) {
+    if (d.state[0]) return;   // converged in an earlier launch
+    extern __shared__ double sm[];
+    const int S = d.S, D = d.D, SD = S * D, tid = threadIdx.x;
+    double *a_s = sm;                 // [S x D] alpha
+    double *il_s = a_s + SD;          // [S x D] invL
+    double *off_s = il_s + SD;        // [S] -0.5 phiTerm
+    double *lpi_s = off_s + S;        // [S] log pi
+    double *pi_s = lpi_s + S;         // [S]
+    double *gs_s = pi_s + S;          // [S] N_s
+    double *red = gs_s + S;           // [kEThreads] (+ 3 x kEThreads for the ELBO sums in CTA 0)
+    __shared__ double sh_scalar[2];
+    __shared__ int sh_done;
+    const int prev = (it + 1) & 1, cur = it & 1;
+    // (1) pi_i: column sums of gamma_i from the previous E-step's per-CTA partials, CTAs ascending (:578-621)
+    for (int s = tid; s < S; s += kEThreads) {
+        double v;
+        if (it == 0) v = d.pi[s];
+        else {
+            v = 0.0;
+            for (int b = 0; b < d.eblocks; ++b) v += d.fPi[prev][(size_t)b * S + s];
+        }
+        pi_s[s] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        sh_done = 0;
+        if (it > 0) {
+            double ps = 0.0;
+            for (int s = 0; s < S; ++s) ps += pi_s[s];
+            sh_scalar[0] = ps;
+            // (2) ELBO_{i-1} (:623-647) and the convergence test (:653-659)
+            double ll = 0.0;
+            for (int b = 0; b < d.eblocks; ++b) ll += d.fLL[prev][b];
+            const double *q = d.fsums[prev];
+            const double elbo = ll + d.Fb * 0.5 * (q[0] - q[1] - q[2] + (double)SD);
+            sh_scalar[1] = elbo;
+            if (it > 1 && fabs(elbo - d.elbos[it - 2]) < d.eps) sh_done = 1;
+        }
+    }
+    __syncthreads();
+    if (it > 0) {
+        const double ps = sh_scalar[0];
+        for (int s = tid; s < S; s += kEThreads) pi_s[s] = (ps > 0.0 && isfinite(ps)) ? pi_s[s] * (1.0 / ps) : 1.0 / (double)S;
+        if (blockIdx.x == 0) {
+            for (int s = tid; s < S; s += kEThreads) d.pi[s] = (ps > 0.0 && isfinite(ps)) ? pi_s[s] : 1.0 / (double)S;
+            if (tid == 0) {
+                d.elbos[it - 1] = sh_scalar[1];
+                d.state[1] = it;
+                if (sh_done) d.state[0] = 1;   // read only by LATER launches; this launch decides from sh_done
+            }
+        }
+    }
+    if (sh_done) return;
+    // (3) N_s, invL, alpha from the chunk partials (chunks ascending), phi and log pi
+    const double ratio = d.Fa / d.Fb;
+    for (int s = tid; s < S; s += kEThreads) {
+        double acc = 0.0;
+        for (int c = 0; c < kFChunks; ++c) acc += d.fG[(size_t)c * S + s];
+        gs_s[s] = acc;
+    }
+    __syncthreads();
+    for (int o = tid; o < SD; o += kEThreads) {
+        const int s = o / D, k = o - s * D;
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < kFChunks; ++c) acc += d.fA[(size_t)c * SD + o];
+        const double il = 1.0 / fmax(1.0 + (ratio * gs_s[s]) * d.phi_c[k], 1e-12);
+        il_s[o] = il;
+        a_s[o] = (acc * il) * ratio;
+    }
+    __syncthreads();
+    for (int s = tid; s < S; s += kEThreads) {
+        double p = 0.0;
+        for (int k = 0; k < D; ++k) {
+            const double a = a_s[s * D + k];
+            p += (a * a + il_s[s * D + k]) * d.phi_c[k];
+        }
+        off_s[s] = p * -0.5;
+        lpi_s[s] = log(fmax(pi_s[s], 1e-8));
+    }
+    if (blockIdx.x == 0) {   // the three ELBO sums of this iteration: thread-strided partials, folded in thread order
+        double l = 0.0, i2 = 0.0, a2 = 0.0;
+        for (int o = tid; o < SD; o += kEThreads) {
+            const double il = il_s[o], a = a_s[o];
+            l += log(il);
+            i2 += il;
+            a2 += a * a;
+        }
+        red[kEThreads + tid] = l;
+        red[2 * kEThreads + tid] = i2;
+        red[3 * kEThreads + tid] = a2;
+        __syncthreads();
+        if (tid == 0) {
+            double x0 = 0, x1 = 0, x2 = 0;
+            for (int i = 0; i < kEThreads; ++i) {
+                x0 += red[kEThreads + i];
+                x1 += red[2 * kEThreads + i];
+                x2 += red[3 * kEThreads + i];
+            }
+            d.fsums[cur][0] = x0;
+            d.fsums[cur][1] = x1;
+            d.fsums[cur][2] = x2;
+        }
+    }
+    __syncthreads();
+    // (4) E-step, thread per frame
+    const int t = blockIdx.x * kEThreads + tid;
+    double ll = 0.0;
+    if (t < d.T) {
+        double *g = d.gamma + (size_t)t * S;
+        const double Gt = d.G[t];
+        double mx = -1.7976931348623157e308;
+        for (int s = 0; s < S; ++s) {
+            double acc = 0.0;
+            const double *a = a_s + (size_t)s * D;
+            for (int k = 0; k < D; ++k) acc += d.rhoT[(size_t)k * d.Tp + t] * a[k];
+            const double v = ((acc + off_s[s]) + Gt) * d.Fa + lpi_s[s];
+            g[s] = v;
+            mx = fmax(mx, v);
+        }
+        double sum = 0.0;
+        for (int s = 0; s < S; ++s) {
+            const double e = exp(g[s] - mx);
+            g[s] = e;
+            sum += e;
+        }
+        if (sum <= 0.0 || !isfinite(sum)) {
+            for (int s = 0; s < S; ++s) g[s] = 1.0 / (double)S;
+            ll = mx;
+        } else {
+            const double inv = 1.0 / sum;
+            for (int s = 0; s < S; ++s) g[s] *= inv;
+            ll = mx + log(sum);
+        }
+    }
+    red[tid] = ll;
+    __syncthreads();
+    if (tid == 0) {
+        double acc = 0.0;
+        for (int i = 0; i < kEThreads; ++i) acc += red[i];
+        d.fLL[cur][blockIdx.x] = acc;
+    }
+    const int t0 = blockIdx.x * kEThreads, t1 = min(d.T, t0 + kEThreads);
+    for (int s = tid; s < S; s += kEThreads) {
+        double acc = 0.0;
+        for (int tt = t0; tt < t1; ++tt) acc += d.gamma[(size_t)tt * S + s];
+        d.fPi[cur][(size_t)blockIdx.x * S + s] = acc;
+    }
+}
+
+// after the last launched iteration: if no launch saw convergence, close the books of iteration max_it - 1
+__global__ void vbx_final_fused_kernel(Dev d, int max_it) {
+    if (d.state[0] || max_it <= 0) return;
+    const int S = d.S, cur = (max_it - 1) & 1;
+    __shared__ double ps_sh;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        double v = 0.0;
+        for (int b = 0; b < d.eblocks; ++b) v += d.fPi[cur][(size_t)b * S + s];
+        d.pi[s] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ps = 0.0;
+        for (int s = 0; s < S; ++s) ps += d.pi[s];
+        ps_sh = ps;
+        double ll = 0.0;
+        for (int b = 0; b < d.eblocks; ++b) ll += d.fLL[cur][b];
+        const double *q = d.fsums[cur];
+        d.elbos[max_it - 1] = ll + d.Fb * 0.5 * (q[0] - q[1] - q[2] + (double)(S * d.D));
+        d.state[1] = max_it;
+    }
+    __syncthreads();
+    const double ps = ps_sh;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) d.pi[s] = (ps > 0.0 && isfinite(ps)) ? d.pi[s] * (1.0 / ps) : 1.0 / (double)S;
+}
+
 // first maximum wins (VBxClustering.swift:144-146)
 __global__ void vbx_hard_kernel(const double *__restrict__ gamma, int T, int S, int *__restrict__ hard) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -356,34 +571,126 @@ __global__ void centroid_finish_kernel(const double *__restrict__ pnum, const do
     }
 }
 
-// thread per embedding: cosine against every centroid, strict '>' (:800-822).  scores optional [N x K].
-__global__ void assign_kernel(const double *__restrict__ emb, int N, int E, const double *__restrict__ cent_n,
-                              const int *__restrict__ count_ptr, int K_fixed, int *__restrict__ labels,
-                              double *__restrict__ scores) {
+// ---- centroids, parallel path (S <= kFusedMaxS): the same sums over kFChunks chunks, thread per (s, k) and chunk; the
+// fold over chunks and the division run thread-per-output on many CTAs, the normalisation thread-per-centroid.
+__global__ void __launch_bounds__(256) centroid_acc16_kernel(const double *__restrict__ emb, const double *__restrict__ gamma,
+                                                             int T, int E, int S, double *__restrict__ pnum,
+                                                             double *__restrict__ pden) {
+    const int c = blockIdx.y;
+    const int per = (T + kFChunks - 1) / kFChunks;
+    const int t0 = c * per, t1 = min(T, t0 + per);
+    const int SE = S * E, o = blockIdx.x * 256 + threadIdx.x;
+    if (o < SE) {
+        const int s = o / E, k = o - s * E;
+        double acc = 0.0;
+        for (int t = t0; t < t1; ++t) {
+            const double w = gamma[(size_t)t * S + s];
+            if (w > 0.0) acc += w * emb[(size_t)t * E + k];
+        }
+        pnum[(size_t)c * SE + o] = acc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < S) {
+        const int s = threadIdx.x;
+        double acc = 0.0;
+        for (int t = t0; t < t1; ++t) {
+            const double w = gamma[(size_t)t * S + s];
+            if (w > 0.0) acc += w;
+        }
+        pden[(size_t)c * S + s] = acc;
+    }
+}
+__global__ void __launch_bounds__(256) centroid_fold_kernel(const double *__restrict__ pnum, const double *__restrict__ pden,
+                                                            const double *__restrict__ pi, int E, int S,
+                                                            double *__restrict__ cent) {
+    const int o = blockIdx.x * 256 + threadIdx.x;
+    if (o >= S * E) return;
+    const int s = o / E, k = o - s * E;
+    if (!(pi[s] > 1e-7)) return;
+    int slot = 0;
+    for (int j = 0; j < s; ++j) slot += pi[j] > 1e-7 ? 1 : 0;
+    double num = 0.0, den = 0.0;
+#pragma unroll
+    for (int c = 0; c < kFChunks; ++c) {
+        num += pnum[(size_t)c * S * E + o];
+        den += pden[(size_t)c * S + s];
+    }
+    cent[(size_t)slot * E + k] = den > 0.0 ? num / den : 0.0;
+}
+__global__ void centroid_norm_kernel(const double *__restrict__ pi, int E, int S, const double *__restrict__ cent,
+                                     double *__restrict__ cent_n, int *__restrict__ count) {
+    int K = 0;
+    for (int s = 0; s < S; ++s) K += pi[s] > 1e-7 ? 1 : 0;
+    if (threadIdx.x == 0) *count = K;
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {   // normalize (:824-860): unchanged if |c|^2 <= 0
+        const double *v = cent + (size_t)c * E;
+        double ss = 0.0;
+        for (int k = 0; k < E; ++k) ss = __dadd_rn(ss, __dmul_rn(v[k], v[k]));
+        const double sc = ss > 0.0 ? __ddiv_rn(1.0, __dsqrt_rn(ss)) : 1.0;
+        for (int k = 0; k < E; ++k) cent_n[(size_t)c * E + k] = __dmul_rn(v[k], sc);
+    }
+}
+
+// thread per embedding: cosine against every centroid, strict '>' (OfflineDiarizerManager.swift:800-822), scores optional
+// [N x K].  Tiled: 128 embeddings per CTA, 32 dimensions at a time through a padded shared-memory tile so that
+// the row-major embeddings are read coalesced; eight centroids per pass share one sweep over the row.  Per (n, c) the
+// arithmetic is the reference's scalar loop (individually rounded operations, k ascending): exact ties resolve the same way.
+constexpr int kATile = 32, kARows = 128, kAGroup = 8;
+__global__ void __launch_bounds__(kARows) assign_tiled_kernel(const double *__restrict__ emb, int N, int E,
+                                                              const double *__restrict__ cent_n,
+                                                              const int *__restrict__ count_ptr, int K_fixed,
+                                                              int *__restrict__ labels, double *__restrict__ scores) {
+    __shared__ double tile[kARows][kATile + 1];
     const int K = count_ptr ? *count_ptr : K_fixed;
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    const int n0 = blockIdx.x * kARows, r = threadIdx.x, n = n0 + r;
     if (K <= 0) {
-        labels[n] = 0;
+        if (n < N) labels[n] = 0;
         return;
     }
-    const double *e = emb + (size_t)n * E;
-    double ss = 0.0;   // individually rounded operations in the reference's order: exact ties resolve the same way
-    for (int k = 0; k < E; ++k) ss = __dadd_rn(ss, __dmul_rn(e[k], e[k]));
+    auto load_tile = [&](int k0) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < kARows * kATile; idx += kARows) {
+            const int rr = idx / kATile, j = idx - rr * kATile;
+            tile[rr][j] = (n0 + rr < N && k0 + j < E) ? emb[(size_t)(n0 + rr) * E + k0 + j] : 0.0;
+        }
+        __syncthreads();
+    };
+    double ss = 0.0;
+    for (int k0 = 0; k0 < E; k0 += kATile) {
+        load_tile(k0);
+        const int lim = min(kATile, E - k0);
+        for (int j = 0; j < lim; ++j) ss = __dadd_rn(ss, __dmul_rn(tile[r][j], tile[r][j]));
+    }
     const double sc = ss > 0.0 ? __ddiv_rn(1.0, __dsqrt_rn(ss)) : 1.0;
     int best = 0;
     double best_score = -INFINITY;
-    for (int c = 0; c < K; ++c) {
-        const double *v = cent_n + (size_t)c * E;
-        double dot = 0.0;
-        for (int k = 0; k < E; ++k) dot = __dadd_rn(dot, __dmul_rn(__dmul_rn(e[k], sc), v[k]));
-        if (scores) scores[(size_t)n * K + c] = dot;
-        if (dot > best_score) {
-            best_score = dot;
-            best = c;
+    for (int c0 = 0; c0 < K; c0 += kAGroup) {
+        const int gc = min(kAGroup, K - c0);
+        double dot[kAGroup];
+#pragma unroll
+        for (int q = 0; q < kAGroup; ++q) dot[q] = 0.0;
+        for (int k0 = 0; k0 < E; k0 += kATile) {
+            load_tile(k0);
+            const int lim = min(kATile, E - k0);
+            for (int j = 0; j < lim; ++j) {
+                const double ek = __dmul_rn(tile[r][j], sc);
+#pragma unroll
+                for (int q = 0; q < kAGroup; ++q)
+                    if (q < gc) dot[q] = __dadd_rn(dot[q], __dmul_rn(ek, __ldg(cent_n + (size_t)(c0 + q) * E + k0 + j)));
+            }
+        }
+        if (n < N) {
+#pragma unroll
+            for (int q = 0; q < kAGroup; ++q) {
+                if (q >= gc) break;
+                if (scores) scores[(size_t)n * K + c0 + q] = dot[q];
+                if (dot[q] > best_score) {
+                    best_score = dot[q];
+                    best = c0 + q;
+                }
+            }
         }
     }
-    labels[n] = best;
+    if (n < N) labels[n] = best;
 }
 
 __global__ void onehot_kernel(const int *__restrict__ labels, int T, int S, double *__restrict__ gamma,
@@ -469,8 +776,18 @@ size_t refine_bytes(int T, int D, int S, int max_it) {
     c.take<double>(std::max(max_it, 1));
     c.take<double>(8);
     c.take<int>(8);
+    c.take<double>((size_t)kFChunks * S * D);
+    c.take<double>((size_t)kFChunks * S);
+    for (int i = 0; i < 2; ++i) {
+        c.take<double>(eblocks);
+        c.take<double>((size_t)eblocks * S);
+        c.take<double>(4);
+    }
     return c.off + 512;
 }
+
+static size_t fused_smem_bytes(int S, int D) { return sizeof(double) * (2 * (size_t)S * D + 4 * (size_t)S + 4 * kEThreads); }
+static bool fused_path(int S, int D) { return S <= kFusedMaxS && fused_smem_bytes(S, D) <= 200 * 1024; }
 
 // d_x: [T x D] device, h_psi: [D] HOST (already identity-substituted by the caller if lengths mismatch),
 // d_init: [T] device labels (or nullptr), d_gamma [T x S], d_pi [S], d_elbos [max(max_it,1)], d_hard [T].
@@ -507,6 +824,13 @@ int refine_device(Workspace &ws, const double *d_x, int T, int D, const double *
     (void)c.take<double>(std::max(max_it, 1));
     d.scal = c.take<double>(8);
     d.state = c.take<int>(8);
+    d.fA = c.take<double>((size_t)kFChunks * S * D);
+    d.fG = c.take<double>((size_t)kFChunks * S);
+    for (int i = 0; i < 2; ++i) {
+        d.fLL[i] = c.take<double>(d.eblocks);
+        d.fPi[i] = c.take<double>((size_t)d.eblocks * S);
+        d.fsums[i] = c.take<double>(4);
+    }
     d.gamma = d_gamma;
     d.pi = d_pi;
     d.elbos = d_elbos;
@@ -530,6 +854,33 @@ int refine_device(Workspace &ws, const double *d_x, int T, int D, const double *
     vbx_init_kernel<<<(T + 127) / 128, 128, 0, stream>>>(d, d_init, cfg.init_smoothing);
     FA_CUDA_TRY(cudaGetLastError());
     long long n_launch = 1;
+    if (fused_path(S, D)) {
+        static std::once_flag once_f;
+        static cudaError_t attr_err_f = cudaSuccess;
+        std::call_once(once_f, [&]() {
+            attr_err_f = cudaFuncSetAttribute(vbx_estep_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        });
+        FA_CUDA_TRY(attr_err_f);
+        const size_t fsmem = fused_smem_bytes(S, D);
+        const dim3 agrid((unsigned)((S * D + 255) / 256), kFChunks);
+        for (int it = 0; it < max_it; ++it) {
+            vbx_acc16_kernel<<<agrid, 256, 0, stream>>>(d);
+            vbx_estep_fused_kernel<<<d.eblocks, kEThreads, fsmem, stream>>>(d, it);
+            n_launch += 2;
+        }
+        vbx_final_fused_kernel<<<1, 128, 0, stream>>>(d, max_it);
+        vbx_hard_kernel<<<(T + 127) / 128, 128, 0, stream>>>(d_gamma, T, S, d_hard);
+        FA_CUDA_TRY(cudaGetLastError());
+        n_launch += 2;
+        if (launches) *launches += n_launch;
+        if (iterations_host) {
+            int h_state[2] = {0, 0};
+            FA_CUDA_TRY(cudaMemcpyAsync(h_state, d.state, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            FA_CUDA_TRY(cudaStreamSynchronize(stream));
+            *iterations_host = h_state[1];
+        }
+        return FA_OK;
+    }
     const size_t esmem_full = sizeof(double) * ((size_t)S * D + 2 * S + kEThreads);
     const bool alpha_smem = esmem_full <= 200 * 1024;
     const size_t esmem = alpha_smem ? esmem_full : sizeof(double) * kEThreads;
@@ -576,6 +927,15 @@ int centroids_device(Workspace &ws, const double *d_emb, int T, int E, const dou
     double *pnum = c.take<double>((size_t)chunks * S * E);
     double *pden = c.take<double>((size_t)chunks * S);
     int *map = c.take<int>(S);
+    if (S <= kFusedMaxS) {   // kFChunks <= chunks: the same buffers hold the smaller partial arrays
+        const unsigned tiles = (unsigned)((S * E + 255) / 256);
+        centroid_acc16_kernel<<<dim3(tiles, kFChunks), 256, 0, stream>>>(d_emb, d_gamma, T, E, S, pnum, pden);
+        centroid_fold_kernel<<<tiles, 256, 0, stream>>>(pnum, pden, d_pi, E, S, d_cent);
+        centroid_norm_kernel<<<1, 64, 0, stream>>>(d_pi, E, S, d_cent, d_cent_n, d_count);
+        FA_CUDA_TRY(cudaGetLastError());
+        if (launches) *launches += 3;
+        return FA_OK;
+    }
     centroid_accumulate_kernel<<<chunks, 256, 0, stream>>>(d_emb, d_gamma, T, E, S, chunks, pnum, pden);
     centroid_finish_kernel<<<1, 256, 0, stream>>>(pnum, pden, d_pi, E, S, chunks, map, d_cent, d_cent_n, d_count);
     FA_CUDA_TRY(cudaGetLastError());
@@ -586,7 +946,8 @@ int centroids_device(Workspace &ws, const double *d_emb, int T, int E, const dou
 int assign_device(const double *d_emb, int N, int E, const double *d_cent_n, const int *d_count, int K_fixed,
                   int *d_labels, double *d_scores, cudaStream_t stream, long long *launches) {
     if (N <= 0) return FA_OK;
-    assign_kernel<<<(N + 127) / 128, 128, 0, stream>>>(d_emb, N, E, d_cent_n, d_count, K_fixed, d_labels, d_scores);
+    assign_tiled_kernel<<<(N + kARows - 1) / kARows, kARows, 0, stream>>>(d_emb, N, E, d_cent_n, d_count, K_fixed, d_labels,
+                                                                          d_scores);
     FA_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;
     return FA_OK;

@@ -150,6 +150,27 @@ def gather_labels(d: Dist, local: np.ndarray, counts: list[int]) -> np.ndarray |
     return np.concatenate([bucket[r][: counts[r]].cpu().numpy() for r in range(d.world)]) if width else local
 
 
+def gather_bytes(d: Dist, local: np.ndarray, counts: list[int]) -> np.ndarray | None:
+    """Gathers per-rank uint8 rows (e.g. one 32-byte SHA-256 digest per clip) on rank 0, in rank order.
+    ``local`` is [counts[rank] x width]; returns [sum(counts) x width] on rank 0, None elsewhere."""
+    local = np.ascontiguousarray(local, np.uint8)
+    if d.world == 1:
+        return local
+    import torch
+    import torch.distributed as dist
+    width = local.shape[1] if local.ndim == 2 else 0
+    rows = max(counts) if counts else 0
+    dev = torch.device("cuda", d.local_rank) if d.backend == "nccl" else torch.device("cpu")
+    mine = torch.zeros((rows, width), dtype=torch.uint8, device=dev)
+    if local.size:
+        mine[: local.shape[0]] = torch.from_numpy(local).to(dev)
+    bucket = [torch.empty_like(mine) for _ in range(d.world)]
+    dist.all_gather(bucket, mine)
+    if not d.is_root:
+        return None
+    return np.concatenate([bucket[r][: counts[r]].cpu().numpy() for r in range(d.world)])
+
+
 def finalize(d: Dist) -> None:
     if d.world > 1:
         import torch.distributed as dist

@@ -95,14 +95,59 @@ def test_mel_all_entry_points_and_modes(gpu_lib, oracle):
     assert (ml, nf) == (26, 32) and np.all(got.reshape(80, 32)[:, 26:] == 0)
     ref, _, _ = oracle.mel_flat(oracle.mel_config(n_mels=80, pad_to=16), a[:4000])
     assert np.abs(got.reshape(80, 32) - ref).max() <= MEL_TOL
-    # LS-EEND style configuration (LSEENDPreprocessor.swift:70-81)
-    m = AudioMelSpectrogram(n_mels=23, hop_length=80, win_length=200, preemph=0.0, log_floor=1e-10,
-                            log_floor_mode=LogFloorMode.clamped, window_periodic=True)
-    cfg = oracle.mel_config(n_mels=23, hop_length=80, win_length=200, preemph=0.0, log_floor=1e-10, log_floor_mode=1,
-                            window_periodic=True)
-    got, ml, nf = m.compute_flat_transposed(sp[:40000], padding_mode=PaddingMode.pre_padded)
-    ref, rml, rnf = oracle.mel_flat_transposed(cfg, sp[:40000], padding_mode=1)
-    assert (ml, nf) == (rml, rnf) and np.abs(got.reshape(nf, 23) - ref).max() <= MEL_TOL
+    # LS-EEND style configuration (LSEENDPreprocessor.swift:70-81) with the nFFT the reference derives from the window,
+    # nFFT = nextPow2(winLength) (LSEENDTypes.swift:55-57): 200 -> 256 (8 kHz model), 400 -> 512 (16 kHz model)
+    for win, hop, nfft in ((200, 80, 256), (400, 160, 512)):
+        m = AudioMelSpectrogram(n_mels=23, n_fft=nfft, hop_length=hop, win_length=win, preemph=0.0, log_floor=1e-10,
+                                log_floor_mode=LogFloorMode.clamped, window_periodic=True)
+        cfg = oracle.mel_config(n_mels=23, n_fft=nfft, hop_length=hop, win_length=win, preemph=0.0, log_floor=1e-10,
+                                log_floor_mode=1, window_periodic=True)
+        got, ml, nf = m.compute_flat_transposed(sp[:40000], padding_mode=PaddingMode.pre_padded)
+        ref, rml, rnf = oracle.mel_flat_transposed(cfg, sp[:40000], padding_mode=1)
+        assert (ml, nf) == (rml, rnf) and np.abs(got.reshape(nf, 23) - ref).max() <= MEL_TOL
+
+
+def test_mel_any_power_of_two_nfft_and_odd_hop(gpu_lib, oracle):
+    """AudioMelSpectrogram is parametric (AudioMelSpectrogram.swift:59-70): nFFT 256 / 1024 / 2048, odd hops, windows
+    shorter than nFFT, every entry point and both layouts — the any-nFFT kernel against the oracle at the same bar."""
+    a = synth.tone_noise_audio(16000 * 3 + 41, seed=5)
+    sp = synth.speech_like_audio(16000 * 3)
+    cases = [dict(n_fft=256, win_length=200, hop_length=80, n_mels=23), dict(n_fft=1024, win_length=800, hop_length=320, n_mels=80),
+             dict(n_fft=512, win_length=400, hop_length=161, n_mels=80), dict(n_fft=2048, win_length=1200, hop_length=441, n_mels=128),
+             dict(n_fft=64, win_length=64, hop_length=17, n_mels=10), dict(n_fft=1024, win_length=1024, hop_length=256, n_mels=64,
+                                                                      preemph=0.0, window_periodic=True)]
+    for kw in cases:
+        m = AudioMelSpectrogram(**kw)
+        okw = dict(kw)
+        if "window_periodic" in okw:
+            okw["window_periodic"] = 1
+        cfg = oracle.mel_config(**okw)
+        nm, bins = kw["n_mels"], kw["n_fft"] // 2 + 1
+        assert np.array_equal(m.get_filterbank(), oracle.mel_filterbank(kw["n_fft"], nm)) and m.get_filterbank().shape == (nm, bins)
+        for sig in (a, sp, a[:kw["n_fft"] // 2 + 3]):
+            got, ml, nf = m.compute_flat_transposed(sig, last_audio_sample=0.2)
+            ref, rml, rnf = oracle.mel_flat_transposed(cfg, sig, last=0.2)
+            assert (ml, nf) == (rml, rnf) and np.abs(got.reshape(nf, nm) - ref).max() <= MEL_TOL, kw
+            got, ml, nf = m.compute_flat(sig)
+            ref, rml, rnf = oracle.mel_flat(cfg, sig)
+            assert (ml, nf) == (rml, rnf) and np.abs(got.reshape(nm, nf) - ref).max() <= MEL_TOL, kw
+        got, ml, nf = m.compute_flat_transposed(a, padding_mode=PaddingMode.pre_padded)
+        ref, rml, rnf = oracle.mel_flat_transposed(cfg, a, padding_mode=1)
+        assert (ml, nf) == (rml, rnf) and np.abs(got.reshape(nf, nm) - ref).max() <= MEL_TOL, kw
+        got, ml = m.compute(a)
+        ref, rml = oracle.mel_legacy(cfg, a)
+        assert ml == rml and np.abs(got[0] - ref).max() <= MEL_TOL, kw
+    # batch entry point on the generic path == one by one
+    m = AudioMelSpectrogram(n_fft=256, win_length=200, hop_length=80, n_mels=23)
+    clips = [a[:5000], sp[:12345], a[:90]]
+    out, offs, ml, nf = m.compute_batch(clips)
+    for i, c in enumerate(clips):
+        single, _, _ = m.compute_flat_transposed(c)
+        assert np.array_equal(single, out[offs[i]:offs[i + 1]])
+    for bad in (dict(n_fft=400), dict(n_fft=8192), dict(n_fft=256, win_length=400)):
+        with pytest.raises(_lib.FluidAudioError) as e:
+            AudioMelSpectrogram(**bad)
+        assert e.value.status == 8
 
 
 def test_mel_guards_silence_and_unsupported(gpu_lib):

@@ -238,9 +238,19 @@ sharding.barrier(d)
 mx = sharding.all_reduce_max(d, 1.5 + d.rank)
 sm = sharding.all_reduce_sum(d, len(mine))
 got = sharding.gather_labels(d, labels, [len(sharding.contiguous_shard(10, r, d.world)) for r in range(d.world)])
+import hashlib
+digests = np.stack([np.frombuffer(hashlib.sha256(bytes([i])).digest(), np.uint8) for i in mine])
+allh = sharding.gather_bytes(d, digests, [len(sharding.contiguous_shard(10, r, d.world)) for r in range(d.world)])
+# the C5 plan: 64 equal meetings over the ranks by LPT, labels come back in partition order
+parts = sharding.lpt_partition([sharding.ahc_cost(5000)] * 64, d.world)
+mine5 = np.concatenate([np.full(3, m, np.int32) for m in parts[d.rank]])
+got5 = sharding.gather_labels(d, mine5, [3 * len(p) for p in parts])
 if d.is_root:
     assert mx == 2.5 and sm == 10.0, (mx, sm)
     assert got.tolist() == [0, 1, 2, 3, 4, 105, 106, 107, 108, 109], got.tolist()
+    assert allh.shape == (10, 32) and all(allh[i].tobytes() == hashlib.sha256(bytes([i])).digest() for i in range(10))
+    assert sorted(sum(parts, [])) == list(range(64)) and all(len(p) == 32 for p in parts)
+    assert got5.tolist() == [m for p in parts for m in p for _ in range(3)]
     print("GLOO_OK")
 sharding.finalize(d)
 """
