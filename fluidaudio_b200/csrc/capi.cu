@@ -648,6 +648,11 @@ FA_API fa_status fa_mel_set_precision(fa_mel *mel, int32_t precision) {
     reinterpret_cast<MelHandle *>(mel)->plan.precision = precision;
     return FA_STATUS_OK;
 }
+FA_API fa_status fa_mel_set_pipeline_chunks(fa_mel *mel, int32_t chunks) {
+    if (!mel || chunks < 1 || chunks > 1024) return FA_STATUS_INVALID_ARGUMENT;
+    reinterpret_cast<MelHandle *>(mel)->plan.pipeline_chunks = chunks;
+    return FA_STATUS_OK;
+}
 FA_API int32_t fa_mel_get_precision(const fa_mel *mel) {
     return mel ? reinterpret_cast<const MelHandle *>(mel)->plan.precision : -1;
 }

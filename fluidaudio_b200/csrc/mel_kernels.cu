@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -79,14 +80,16 @@ struct TileGeom {
     long long gs, ge;  // bulk-copied audio range [gs, ge), both multiples of 4 (empty if ge <= gs)
 };
 
+__device__ __forceinline__ const MelUnit &unit_at(const MelLaunch &P, int idx) { return P.inline_unit ? P.unit0 : P.units[idx]; }
+
 __device__ __forceinline__ TileGeom tile_geom(const MelLaunch &P, int tile) {
     // units are sorted by tile_begin; binary search for the unit that owns this tile
-    int lo = 0, hi = P.num_units - 1;
+    int lo = 0, hi = P.inline_unit ? 0 : P.num_units - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
         if (P.units[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
     }
-    const MelUnit &u = P.units[lo];
+    const MelUnit &u = P.inline_unit ? P.unit0 : P.units[lo];
     TileGeom g;
     g.unit = lo;
     g.f0 = u.frame_begin + (long long)kTileFrames * (tile - u.tile_begin);
@@ -129,8 +132,9 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
     for (int i = tid; i < P.n_mels; i += kWarps * 32)
         fbmeta[i] = make_int4(P.fb_lo[i], (P.fb_hi[i] - P.fb_lo[i]) >> 2, P.fb_off[i], 0);
     for (int i = tid; i < kTileFrames * kPowStride; i += kWarps * 32) power[i] = 0.0f;   // rows of partial tiles, pad columns
-    LaneTables<V> T;
-    load_lane_tables(lane, P.win_tab, P.in_tab, T);
+    // per-lane constants (window slots, twiddles, butterfly addresses): built on the host once per plan (FP64 sin / cos
+    // inlined here cost ~3 % of the kernel and 9 000 SASS lines), one struct copy per thread
+    const LaneTables<V> T = reinterpret_cast<const LaneTables<V> *>(P.lane_tab)[lane];
     __syncthreads();
 
     cpxv<V> *buf = fftbuf + warp * kFftPad;
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
         const TileGeom g = tile_geom(P, tile);
         float *dst = buf ? raw1 : raw0;
         if (g.ge > g.gs) {
-            const MelUnit &u = P.units[g.unit];
+            const MelUnit &u = unit_at(P, g.unit);
             const uint32_t bytes = (uint32_t)((g.ge - g.gs) * 4);
             mbar_expect_tx(&bars[buf], bytes);
             bulk_g2s(dst + (g.gs - g.base), P.audio + u.audio_off + g.gs, bytes, &bars[buf]);
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
     }
     {
         const TileGeom g0 = tile_geom(P, first);
-        const MelUnit u0 = P.units[g0.unit];
+        const MelUnit u0 = unit_at(P, g0.unit);
         mbar_wait(&bars[0], 0);
         preemphasize(g0, u0, raw0);
     }
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
     int it = 0;
     for (int tile = first; tile < P.total_tiles; tile += stride, ++it) {
         const TileGeom g = tile_geom(P, tile);
-        const MelUnit u = P.units[g.unit];
+        const MelUnit u = unit_at(P, g.unit);
 
         // ---- phase A: previous tile's copy-out, then one warp per frame: FP64 FFT256 + recombination + power ----
         if (pending_dst) copy_out(pending_dst, pending_total);
@@ -280,7 +284,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
         if (next < P.total_tiles) {
             const int nb = (it + 1) & 1;
             const TileGeom gn = tile_geom(P, next);
-            const MelUnit un = P.units[gn.unit];
+            const MelUnit un = unit_at(P, gn.unit);
             mbar_wait(&bars[nb], (uint32_t)((it + 1) >> 1) & 1u);
             preemphasize(gn, un, nb ? raw1 : raw0);
         }
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(256) mel_generic_kernel(const MelLaunch P, con
     const float a = P.preemph;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const TileGeom g = tile_geom(P, tile);
-        const MelUnit u = P.units[g.unit];
+        const MelUnit u = unit_at(P, g.unit);
         const float *x = P.audio + u.audio_off;
         for (int fi = warp; fi < g.nf; fi += G.warps) {
             const long long f = g.f0 + fi;
@@ -442,6 +446,8 @@ void MelPlan::release() {
     for (int m = 0; m < 2; ++m) {
         fr(d_win_tab_mode[m]);
         fr(d_in_tab_mode[m]);
+        fr(d_lane_tab[m][0]);
+        fr(d_lane_tab[m][1]);
     }
     fr(d_fb_w);
     fr(d_fb_lo);
@@ -533,6 +539,27 @@ int MelPlan::init(const MelConfig &c) {
         FA_CUDA_TRY(cudaMalloc(&d_in_tab_mode[mode], n_fft));
         FA_CUDA_TRY(cudaMemcpy(d_win_tab_mode[mode], win_tab.data(), n_fft * sizeof(float), cudaMemcpyHostToDevice));
         FA_CUDA_TRY(cudaMemcpy(d_in_tab_mode[mode], in_tab.data(), n_fft, cudaMemcpyHostToDevice));
+    }
+    if (!generic) {
+        for (int mode = 0; mode < 2; ++mode) {
+            const int off_w = mode == 0 ? (cfg.n_fft - cfg.win_length) / 2 : 0;
+            std::fill(win_tab.begin(), win_tab.end(), 0.0f);
+            std::fill(in_tab.begin(), in_tab.end(), 0);
+            for (int j = 0; j < cfg.win_length; ++j) {
+                win_tab[off_w + j] = window[j];
+                in_tab[off_w + j] = 1;
+            }
+            std::vector<LaneTables<double>> t64(32);
+            std::vector<LaneTables<f32x2>> t32(32);
+            for (int l = 0; l < 32; ++l) {
+                load_lane_tables(l, win_tab.data(), in_tab.data(), t64[l]);
+                load_lane_tables(l, win_tab.data(), in_tab.data(), t32[l]);
+            }
+            FA_CUDA_TRY(cudaMalloc(&d_lane_tab[mode][0], 32 * sizeof(LaneTables<double>)));
+            FA_CUDA_TRY(cudaMalloc(&d_lane_tab[mode][1], 32 * sizeof(LaneTables<f32x2>)));
+            FA_CUDA_TRY(cudaMemcpy(d_lane_tab[mode][0], t64.data(), 32 * sizeof(LaneTables<double>), cudaMemcpyHostToDevice));
+            FA_CUDA_TRY(cudaMemcpy(d_lane_tab[mode][1], t32.data(), 32 * sizeof(LaneTables<f32x2>), cudaMemcpyHostToDevice));
+        }
     }
     FA_CUDA_TRY(cudaMalloc(&d_fb_w, std::max<size_t>(1, w.size()) * sizeof(float)));
     FA_CUDA_TRY(cudaMalloc(&d_fb_lo, cfg.n_mels * sizeof(int)));
@@ -640,6 +667,8 @@ int MelPlan::launch(const float *d_audio_base, float *d_out_base, int first, int
     P.out = d_out_base;
     P.units = d_units + first;
     P.num_units = count;
+    P.inline_unit = (inline_unit && count == 1) ? 1 : 0;
+    if (P.inline_unit) P.unit0 = h_units[first];
     P.total_tiles = total_tiles;
     P.hop = cfg.hop_length;
     P.pad = mode == 0 ? cfg.n_fft / 2 : 0;
@@ -648,6 +677,7 @@ int MelPlan::launch(const float *d_audio_base, float *d_out_base, int first, int
     P.log_floor = cfg.log_floor;
     P.log_clamped = cfg.log_floor_mode;
     P.layout = layout;
+    P.lane_tab = d_lane_tab[mode == 2 ? 1 : 0][precision == 1 ? 1 : 0];
     P.win_tab = d_win_tab_mode[mode == 2 ? 1 : 0];
     P.in_tab = d_in_tab_mode[mode == 2 ? 1 : 0];
     P.fb_w = d_fb_w;
@@ -774,14 +804,28 @@ int MelPlan::compute_host(const float *audio, long long n, float last, int mode,
     }
     int st = ensure_staging((size_t)n + 8, (size_t)need);
     if (st != FA_OK) return st;
-    const long long kMinChunk = 4096, kMaxChunks = 24;
+    const long long kMinChunk = 4096, kMaxChunks = pipeline_chunks;
     long long chunk = std::max(kMinChunk, ceil_to((T + kMaxChunks - 1) / kMaxChunks, kTileFrames));
     const int chunks = (int)((T + chunk - 1) / chunk);
     st = ensure_units(chunks);
     if (st != FA_OK) return st;
+    cudaStream_t s_in = streams[0], s_k = streams[1], s_out = streams[2];
+    if (chunks == 1) {
+        // the streaming callers' shape (a few thousand samples, SortformerDiarizer.swift:857-905): nothing to overlap, so
+        // one stream, no events, the unit descriptor passed in the kernel parameters, one synchronisation
+        FA_CUDA_TRY(cudaMemcpyAsync(d_audio, audio, n * sizeof(float), cudaMemcpyHostToDevice, s_k));
+        if (Tp > T) FA_CUDA_TRY(cudaMemsetAsync(d_out, 0, need * sizeof(float), s_k));
+        h_units[0] = MelUnit{0, n, 0, Tp, 0, T, last, 0};
+        inline_unit = true;
+        st = launch(d_audio, d_out, 0, 1, tiles_of(T), mode, layout, s_k, true);
+        inline_unit = false;
+        if (st != FA_OK) return st;
+        FA_CUDA_TRY(cudaMemcpyAsync(out, d_out, need * sizeof(float), cudaMemcpyDeviceToHost, s_k));
+        FA_CUDA_TRY(cudaStreamSynchronize(s_k));
+        return FA_OK;
+    }
     st = ensure_events(2 * (size_t)chunks);
     if (st != FA_OK) return st;
-    cudaStream_t s_in = streams[0], s_k = streams[1], s_out = streams[2];
     for (int c = 0; c < chunks; ++c) {
         const long long fb = c * chunk, fc = std::min(chunk, T - fb);
         h_units[c] = MelUnit{0, n, 0, Tp, fb, fc, last, 0};
@@ -875,7 +919,7 @@ int MelPlan::compute_host_pcm(const void *pcm, long long frames, const resample:
         FA_CUDA_TRY(cudaMalloc(&d_pcm, pcm_bytes + 16));
         d_pcm_cap = pcm_bytes + 16;
     }
-    const long long kMinChunk = 4096, kMaxChunks = 24;
+    const long long kMinChunk = 4096, kMaxChunks = pipeline_chunks;
     const long long chunk = std::max(kMinChunk, ceil_to((T + kMaxChunks - 1) / kMaxChunks, kTileFrames));
     const int chunks = (int)((T + chunk - 1) / chunk);
     st = ensure_units(chunks);

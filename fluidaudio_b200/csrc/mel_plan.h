@@ -51,6 +51,7 @@ struct MelLaunch {
     float log_floor;
     int log_clamped;
     int layout;         // 0 time-major [T x nMels], 1 mel-major [nMels x stride]
+    const void *lane_tab;   // [32] LaneTables<V> of the launch's window placement and precision (mel_core.cuh)
     const float *win_tab;
     const uint8_t *in_tab;
     const float *fb_w;
@@ -62,6 +63,8 @@ struct MelLaunch {
     int use_tma;
     int mid_full;          // window covers buffer positions [64, 448): pass 1 skips the in-window select for slots 1..6
     unsigned inv_n_mels;   // ceil(2^32 / n_mels): idx / n_mels == umulhi(idx, inv) for idx < 2^16
+    int inline_unit;       // single-unit launch: the descriptor travels in the kernel parameters (unit0), units is not read
+    MelUnit unit0;
 };
 
 struct MelPlan {
@@ -74,10 +77,13 @@ struct MelPlan {
     int num_sms = 0;
     long long launches = 0;          // kernels launched through this plan (bench.py reports it)
     int precision = 0;               // transform arithmetic: 0 = FP64 (one frame per warp), 1 = packed float32 pairs
+    int pipeline_chunks = 24;        // units a long host-buffer call is cut into (H2D / kernel / D2H overlap)
+    bool inline_unit = false;        // next launch() passes its (single) unit in the kernel parameters
     bool generic = false;            // nFFT != 512 or odd hop: mel_generic_kernel (FP64 transform whatever `precision`)
     int generic_warps = 0, generic_prow = 0, generic_log2n = 0;
     void *d_generic_tw = nullptr;    // FP64 twiddles W_n^k, k < n/2
 
+    void *d_lane_tab[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [window placement][precision]
     float *d_win_tab_mode[2] = {nullptr, nullptr};
     uint8_t *d_in_tab_mode[2] = {nullptr, nullptr};
     float *d_fb_w = nullptr;

@@ -60,10 +60,9 @@ struct Dev {
     int eblocks;
     double Fa, Fb, eps;
     // two-kernel path (S <= kFusedMaxS): partials over kFChunks frame chunks, E-step partials double-buffered by iteration
-    double *fA, *fG;        // [kFChunks x S x D], [kFChunks x S]
-    double *fLL[2];         // [eblocks]
-    double *fPi[2];         // [eblocks x S]
-    double *fsums[2];       // [4]: sum log invL, sum invL, sum alpha^2
+    double *fA, *fG;        // [eblocks x S x D], [eblocks x S]: per-frame-block gamma^T rho and column sums of gamma
+    double *fLL;            // [eblocks] per-block log-likelihood
+    double *fsums[2];       // [3 x S] per speaker: sum log invL, sum invL, sum alpha^2 (double-buffered by iteration)
 };
 
 // gamma0 = softmax(7 * onehot) row-wise, then renormalise (VBxClustering.swift:190-235); rho = x * sqrt(phi);
@@ -294,210 +293,211 @@ __global__ void vbx_finish_kernel(Dev d, int iteration) {
 
 
 // ---- two-kernel EM iteration (the normal case: a handful of speakers) -----------------------------------------------
-// Iteration i = vbx_acc16_kernel (partial sums of gamma_i over kFChunks frame chunks, one thread per (s, k) and chunk)
-//             + vbx_estep_fused_kernel, whose PROLOGUE every CTA runs redundantly from those partials and from the previous
-//               E-step's per-CTA partials: pi_i, ELBO_{i-1} and the convergence test (VBxClustering.swift:578-661), then
-//               N_s, invL, alpha, phi, log pi (:304-436, :496-516) into shared memory; its body is the E-step (:438-576).
-// Every CTA takes the same decision from the same doubles in the same order, so no grid-wide barrier and no single-CTA
-// fold is needed: 2 launches per iteration instead of 4, and the 144 us single-CTA update kernel is gone.  All sums keep a
-// FIXED order (sequential inside a chunk, chunks ascending; E-step partials per CTA, CTAs ascending): bit-reproducible.
-__global__ void __launch_bounds__(256) vbx_acc16_kernel(Dev d) {
-    if (d.state[0]) return;
-    const int c = blockIdx.y;
-    const int per = (d.T + kFChunks - 1) / kFChunks;
-    const int t0 = c * per, t1 = min(d.T, t0 + per);
-    const int SD = d.S * d.D;
-    const int o = blockIdx.x * 256 + threadIdx.x;
-    if (o < SD) {
-        const int s = o / d.D, k = o - s * d.D;
-        const double *g = d.gamma + s, *r = d.rho + k;
+// The EM loop is tiny (C3: 2 x 10 MFLOP per iteration) and was bound by LATENCY: one-accumulator chains of hundreds of
+// dependent loads and a single CTA folding 128 partials.  Here every chain carries kSG = 8 speakers at once (eight
+// independent FP64 accumulators per thread: one load feeds eight FMAs) and no fold is longer than the number of frame
+// blocks, spread over S CTAs:
+//   vbx_update_kernel2 (S CTAs)      CTA s: pi and N_s from the per-block column sums, ELBO of the previous iteration and
+//                                    the convergence test (VBxClustering.swift:578-661), then A[s][.] folded over the
+//                                    frame blocks, invL, alpha, phi_s, log pi_s and this speaker's share of the ELBO sums
+//                                    (:304-436, :496-516, :623-644).
+//   vbx_estep_kernel2 (T/128 CTAs)   thread per frame: log-likelihood row (k outer, speakers in registers), soft-max,
+//                                    gamma (:438-576); then, with the block's new gamma rows in shared memory, the block's
+//                                    partial sums for the NEXT update: column sums, LL, gamma^T rho (thread per dimension).
+// All sums keep a FIXED order (k ascending; frames ascending inside a block; blocks ascending): bit-reproducible.
+constexpr int kSG = 8;   // speakers per register group
+
+// partial sums of one frame block from the gamma rows in shared memory: fG[b][s], fA[b][s][k]
+__device__ __forceinline__ void vbx_block_partials(const Dev &d, const double *g_s, int t0, int rows, int b) {
+    const int S = d.S, D = d.D, tid = threadIdx.x;
+    for (int s = tid; s < S; s += kEThreads) {
         double acc = 0.0;
-        for (int t = t0; t < t1; ++t) acc += g[(size_t)t * d.S] * r[(size_t)t * d.D];
-        d.fA[(size_t)c * SD + o] = acc;
+        for (int r = 0; r < rows; ++r) acc += g_s[r * S + s];
+        d.fG[(size_t)b * S + s] = acc;
     }
-    if (blockIdx.x == 0 && threadIdx.x < d.S) {
-        const int s = threadIdx.x;
-        double acc = 0.0;
-        for (int t = t0; t < t1; ++t) acc += d.gamma[(size_t)t * d.S + s];
-        d.fG[(size_t)c * d.S + s] = acc;
+    for (int k = tid; k < D; k += kEThreads) {
+        const double *rk = d.rho + (size_t)t0 * D + k;
+        for (int s0 = 0; s0 < S; s0 += kSG) {
+            double acc[kSG];
+#pragma unroll
+            for (int q = 0; q < kSG; ++q) acc[q] = 0.0;
+            for (int r = 0; r < rows; ++r) {
+                const double x = rk[(size_t)r * D];
+                const double *g = g_s + r * S + s0;
+#pragma unroll
+                for (int q = 0; q < kSG; ++q)
+                    if (s0 + q < S) acc[q] += g[q] * x;
+            }
+#pragma unroll
+            for (int q = 0; q < kSG; ++q)
+                if (s0 + q < S) d.fA[((size_t)b * S + s0 + q) * D + k] = acc[q];
+        }
     }
 }
 
-__global__ void __launch_bounds__(kEThreads) vbx_estep_fused_kernel(Dev d, int it) {
-    if (d.state[0]) return;   // converged in an earlier launch
+// partials of the INITIAL gamma (before the first update)
+__global__ void __launch_bounds__(kEThreads) vbx_partials0_kernel(Dev d) {
     extern __shared__ double sm[];
-    const int S = d.S, D = d.D, SD = S * D, tid = threadIdx.x;
-    double *a_s = sm;                 // [S x D] alpha
-    double *il_s = a_s + SD;          // [S x D] invL
-    double *off_s = il_s + SD;        // [S] -0.5 phiTerm
-    double *lpi_s = off_s + S;        // [S] log pi
-    double *pi_s = lpi_s + S;         // [S]
-    double *gs_s = pi_s + S;          // [S] N_s
-    double *red = gs_s + S;           // [kEThreads] (+ 3 x kEThreads for the ELBO sums in CTA 0)
-    __shared__ double sh_scalar[2];
-    __shared__ int sh_done;
+    const int S = d.S, b = blockIdx.x, t0 = b * kEThreads, rows = min(kEThreads, d.T - t0);
+    for (int i = threadIdx.x; i < rows * S; i += kEThreads) sm[i] = d.gamma[(size_t)t0 * S + i];
+    __syncthreads();
+    vbx_block_partials(d, sm, t0, rows, b);
+}
+
+// closing == 1: only the pi / ELBO bookkeeping of the last E-step (after max_iterations launches)
+__global__ void __launch_bounds__(kEThreads) vbx_update_kernel2(Dev d, int it, int closing) {
+    if (d.state[0]) return;   // converged in an earlier launch
+    __shared__ double pi_sh[kFusedMaxS];
+    __shared__ double red[kEThreads];
+    __shared__ double scal[4];
+    __shared__ int done_sh;
+    const int S = d.S, D = d.D, tid = threadIdx.x, s = blockIdx.x, nb = d.eblocks;
     const int prev = (it + 1) & 1, cur = it & 1;
-    // (1) pi_i: column sums of gamma_i from the previous E-step's per-CTA partials, CTAs ascending (:578-621)
-    for (int s = tid; s < S; s += kEThreads) {
-        double v;
-        if (it == 0) v = d.pi[s];
-        else {
-            v = 0.0;
-            for (int b = 0; b < d.eblocks; ++b) v += d.fPi[prev][(size_t)b * S + s];
+    // column sums of gamma_it per speaker, blocks ascending (every CTA folds all S columns: S * nb loads)
+    for (int c = tid; c < S; c += kEThreads) {
+        double v = 0.0;
+#pragma unroll 8
+        for (int b = 0; b < nb; ++b) v += d.fG[(size_t)b * S + c];
+        pi_sh[c] = v;
+    }
+    if (tid == 0) done_sh = 0;
+    __syncthreads();
+    if (tid == 0) {
+        double ps = 0.0;
+        for (int c = 0; c < S; ++c) ps += pi_sh[c];
+        scal[0] = ps;
+        if (it > 0) {   // ELBO_{it-1} (:623-647) and the convergence test (:653-659)
+            double ll = 0.0;
+#pragma unroll 8
+            for (int b = 0; b < nb; ++b) ll += d.fLL[b];
+            double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+            for (int c = 0; c < S; ++c) {
+                x0 += d.fsums[prev][3 * c];
+                x1 += d.fsums[prev][3 * c + 1];
+                x2 += d.fsums[prev][3 * c + 2];
+            }
+            const double elbo = ll + d.Fb * 0.5 * (x0 - x1 - x2 + (double)(S * D));
+            scal[1] = elbo;
+            if (closing || (it > 1 && fabs(elbo - d.elbos[it - 2]) < d.eps)) done_sh = 1;
         }
-        pi_s[s] = v;
+    }
+    __syncthreads();
+    const double ps = scal[0];
+    const double Ns = pi_sh[s];                                   // N_s = sum_t gamma_ts (:304-328)
+    const bool ok = ps > 0.0 && isfinite(ps);
+    const double pi_s = it == 0 ? d.pi[s] : (ok ? Ns * (1.0 / ps) : 1.0 / (double)S);   // pi (:578-621); 1/S initially (:237)
+    if (it > 0 && tid == 0) {
+        d.pi[s] = pi_s;
+        if (s == 0) {
+            d.elbos[it - 1] = scal[1];
+            d.state[1] = it;
+            if (done_sh && !closing) d.state[0] = 1;
+        }
+    }
+    if (done_sh || closing) return;
+    // A[s][k] over the frame blocks (ascending), invL, alpha
+    const double ratio = d.Fa / d.Fb;
+    double p_part = 0.0, l_part = 0.0, i_part = 0.0, a_part = 0.0;
+    for (int k = tid; k < D; k += kEThreads) {
+        double acc = 0.0;
+#pragma unroll 8
+        for (int b = 0; b < nb; ++b) acc += d.fA[((size_t)b * S + s) * D + k];
+        const double il = 1.0 / fmax(1.0 + (ratio * Ns) * d.phi_c[k], 1e-12);
+        const double al = (acc * il) * ratio;
+        d.alpha[(size_t)s * D + k] = al;
+        p_part += (al * al + il) * d.phi_c[k];
+        l_part += log(il);
+        i_part += il;
+        a_part += al * al;
+    }
+    // four block sums in thread order (fixed)
+    double *outs[4] = {&scal[0], &scal[1], &scal[2], &scal[3]};
+    const double parts[4] = {p_part, l_part, i_part, a_part};
+    for (int q = 0; q < 4; ++q) {
+        __syncthreads();
+        red[tid] = parts[q];
+        __syncthreads();
+        if (tid == 0) {
+            double acc = 0.0;
+            for (int i = 0; i < kEThreads; ++i) acc += red[i];
+            *outs[q] = acc;
+        }
     }
     __syncthreads();
     if (tid == 0) {
-        sh_done = 0;
-        if (it > 0) {
-            double ps = 0.0;
-            for (int s = 0; s < S; ++s) ps += pi_s[s];
-            sh_scalar[0] = ps;
-            // (2) ELBO_{i-1} (:623-647) and the convergence test (:653-659)
-            double ll = 0.0;
-            for (int b = 0; b < d.eblocks; ++b) ll += d.fLL[prev][b];
-            const double *q = d.fsums[prev];
-            const double elbo = ll + d.Fb * 0.5 * (q[0] - q[1] - q[2] + (double)SD);
-            sh_scalar[1] = elbo;
-            if (it > 1 && fabs(elbo - d.elbos[it - 2]) < d.eps) sh_done = 1;
-        }
+        d.phiTerm[s] = scal[0];
+        d.logPi[s] = log(fmax(pi_s, 1e-8));
+        d.fsums[cur][3 * s] = scal[1];
+        d.fsums[cur][3 * s + 1] = scal[2];
+        d.fsums[cur][3 * s + 2] = scal[3];
+    }
+}
+
+__global__ void __launch_bounds__(kEThreads) vbx_estep_kernel2(Dev d) {
+    if (d.state[0]) return;
+    extern __shared__ double sm[];
+    const int S = d.S, D = d.D, tid = threadIdx.x, b = blockIdx.x;
+    double *a_s = sm;                        // [S x D] alpha
+    double *off_s = a_s + (size_t)S * D;     // [S] -0.5 phi
+    double *lpi_s = off_s + S;               // [S]
+    double *g_s = lpi_s + S;                 // [kEThreads x S] this block's new gamma rows
+    double *red = g_s + (size_t)kEThreads * S;   // [kEThreads]
+    for (int o = tid; o < S * D; o += kEThreads) a_s[o] = d.alpha[o];
+    for (int c = tid; c < S; c += kEThreads) {
+        off_s[c] = d.phiTerm[c] * -0.5;
+        lpi_s[c] = d.logPi[c];
     }
     __syncthreads();
-    if (it > 0) {
-        const double ps = sh_scalar[0];
-        for (int s = tid; s < S; s += kEThreads) pi_s[s] = (ps > 0.0 && isfinite(ps)) ? pi_s[s] * (1.0 / ps) : 1.0 / (double)S;
-        if (blockIdx.x == 0) {
-            for (int s = tid; s < S; s += kEThreads) d.pi[s] = (ps > 0.0 && isfinite(ps)) ? pi_s[s] : 1.0 / (double)S;
-            if (tid == 0) {
-                d.elbos[it - 1] = sh_scalar[1];
-                d.state[1] = it;
-                if (sh_done) d.state[0] = 1;   // read only by LATER launches; this launch decides from sh_done
-            }
-        }
-    }
-    if (sh_done) return;
-    // (3) N_s, invL, alpha from the chunk partials (chunks ascending), phi and log pi
-    const double ratio = d.Fa / d.Fb;
-    for (int s = tid; s < S; s += kEThreads) {
-        double acc = 0.0;
-        for (int c = 0; c < kFChunks; ++c) acc += d.fG[(size_t)c * S + s];
-        gs_s[s] = acc;
-    }
-    __syncthreads();
-    for (int o = tid; o < SD; o += kEThreads) {
-        const int s = o / D, k = o - s * D;
-        double acc = 0.0;
-#pragma unroll
-        for (int c = 0; c < kFChunks; ++c) acc += d.fA[(size_t)c * SD + o];
-        const double il = 1.0 / fmax(1.0 + (ratio * gs_s[s]) * d.phi_c[k], 1e-12);
-        il_s[o] = il;
-        a_s[o] = (acc * il) * ratio;
-    }
-    __syncthreads();
-    for (int s = tid; s < S; s += kEThreads) {
-        double p = 0.0;
-        for (int k = 0; k < D; ++k) {
-            const double a = a_s[s * D + k];
-            p += (a * a + il_s[s * D + k]) * d.phi_c[k];
-        }
-        off_s[s] = p * -0.5;
-        lpi_s[s] = log(fmax(pi_s[s], 1e-8));
-    }
-    if (blockIdx.x == 0) {   // the three ELBO sums of this iteration: thread-strided partials, folded in thread order
-        double l = 0.0, i2 = 0.0, a2 = 0.0;
-        for (int o = tid; o < SD; o += kEThreads) {
-            const double il = il_s[o], a = a_s[o];
-            l += log(il);
-            i2 += il;
-            a2 += a * a;
-        }
-        red[kEThreads + tid] = l;
-        red[2 * kEThreads + tid] = i2;
-        red[3 * kEThreads + tid] = a2;
-        __syncthreads();
-        if (tid == 0) {
-            double x0 = 0, x1 = 0, x2 = 0;
-            for (int i = 0; i < kEThreads; ++i) {
-                x0 += red[kEThreads + i];
-                x1 += red[2 * kEThreads + i];
-                x2 += red[3 * kEThreads + i];
-            }
-            d.fsums[cur][0] = x0;
-            d.fsums[cur][1] = x1;
-            d.fsums[cur][2] = x2;
-        }
-    }
-    __syncthreads();
-    // (4) E-step, thread per frame
-    const int t = blockIdx.x * kEThreads + tid;
+    const int t0 = b * kEThreads, rows = min(kEThreads, d.T - t0), t = t0 + tid;
     double ll = 0.0;
     if (t < d.T) {
-        double *g = d.gamma + (size_t)t * S;
+        double *g = g_s + (size_t)tid * S;
         const double Gt = d.G[t];
+        const double *xr = d.rhoT + t;
         double mx = -1.7976931348623157e308;
-        for (int s = 0; s < S; ++s) {
-            double acc = 0.0;
-            const double *a = a_s + (size_t)s * D;
-            for (int k = 0; k < D; ++k) acc += d.rhoT[(size_t)k * d.Tp + t] * a[k];
-            const double v = ((acc + off_s[s]) + Gt) * d.Fa + lpi_s[s];
-            g[s] = v;
-            mx = fmax(mx, v);
+        for (int s0 = 0; s0 < S; s0 += kSG) {
+            double acc[kSG];
+#pragma unroll
+            for (int q = 0; q < kSG; ++q) acc[q] = 0.0;
+            for (int k = 0; k < D; ++k) {
+                const double x = xr[(size_t)k * d.Tp];
+#pragma unroll
+                for (int q = 0; q < kSG; ++q)
+                    if (s0 + q < S) acc[q] += x * a_s[(size_t)(s0 + q) * D + k];
+            }
+#pragma unroll
+            for (int q = 0; q < kSG; ++q)
+                if (s0 + q < S) {
+                    const double v = ((acc[q] + off_s[s0 + q]) + Gt) * d.Fa + lpi_s[s0 + q];
+                    g[s0 + q] = v;
+                    mx = fmax(mx, v);
+                }
         }
         double sum = 0.0;
-        for (int s = 0; s < S; ++s) {
-            const double e = exp(g[s] - mx);
-            g[s] = e;
+        for (int c = 0; c < S; ++c) {
+            const double e = exp(g[c] - mx);
+            g[c] = e;
             sum += e;
         }
         if (sum <= 0.0 || !isfinite(sum)) {
-            for (int s = 0; s < S; ++s) g[s] = 1.0 / (double)S;
+            for (int c = 0; c < S; ++c) g[c] = 1.0 / (double)S;
             ll = mx;
         } else {
             const double inv = 1.0 / sum;
-            for (int s = 0; s < S; ++s) g[s] *= inv;
+            for (int c = 0; c < S; ++c) g[c] *= inv;
             ll = mx + log(sum);
         }
+        double *gout = d.gamma + (size_t)t * S;
+        for (int c = 0; c < S; ++c) gout[c] = g[c];
     }
     red[tid] = ll;
     __syncthreads();
     if (tid == 0) {
         double acc = 0.0;
         for (int i = 0; i < kEThreads; ++i) acc += red[i];
-        d.fLL[cur][blockIdx.x] = acc;
+        d.fLL[b] = acc;
     }
-    const int t0 = blockIdx.x * kEThreads, t1 = min(d.T, t0 + kEThreads);
-    for (int s = tid; s < S; s += kEThreads) {
-        double acc = 0.0;
-        for (int tt = t0; tt < t1; ++tt) acc += d.gamma[(size_t)tt * S + s];
-        d.fPi[cur][(size_t)blockIdx.x * S + s] = acc;
-    }
-}
-
-// after the last launched iteration: if no launch saw convergence, close the books of iteration max_it - 1
-__global__ void vbx_final_fused_kernel(Dev d, int max_it) {
-    if (d.state[0] || max_it <= 0) return;
-    const int S = d.S, cur = (max_it - 1) & 1;
-    __shared__ double ps_sh;
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
-        double v = 0.0;
-        for (int b = 0; b < d.eblocks; ++b) v += d.fPi[cur][(size_t)b * S + s];
-        d.pi[s] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double ps = 0.0;
-        for (int s = 0; s < S; ++s) ps += d.pi[s];
-        ps_sh = ps;
-        double ll = 0.0;
-        for (int b = 0; b < d.eblocks; ++b) ll += d.fLL[cur][b];
-        const double *q = d.fsums[cur];
-        d.elbos[max_it - 1] = ll + d.Fb * 0.5 * (q[0] - q[1] - q[2] + (double)(S * d.D));
-        d.state[1] = max_it;
-    }
-    __syncthreads();
-    const double ps = ps_sh;
-    for (int s = threadIdx.x; s < S; s += blockDim.x) d.pi[s] = (ps > 0.0 && isfinite(ps)) ? d.pi[s] * (1.0 / ps) : 1.0 / (double)S;
+    vbx_block_partials(d, g_s, t0, rows, b);
 }
 
 // first maximum wins (VBxClustering.swift:144-146)
@@ -776,17 +776,18 @@ size_t refine_bytes(int T, int D, int S, int max_it) {
     c.take<double>(std::max(max_it, 1));
     c.take<double>(8);
     c.take<int>(8);
-    c.take<double>((size_t)kFChunks * S * D);
-    c.take<double>((size_t)kFChunks * S);
-    for (int i = 0; i < 2; ++i) {
-        c.take<double>(eblocks);
+    if (S <= kFusedMaxS) {
+        c.take<double>((size_t)eblocks * S * D);
         c.take<double>((size_t)eblocks * S);
-        c.take<double>(4);
+        c.take<double>(eblocks);
+        for (int i = 0; i < 2; ++i) c.take<double>(3 * (size_t)S);
     }
     return c.off + 512;
 }
 
-static size_t fused_smem_bytes(int S, int D) { return sizeof(double) * (2 * (size_t)S * D + 4 * (size_t)S + 4 * kEThreads); }
+static size_t fused_smem_bytes(int S, int D) {
+    return sizeof(double) * ((size_t)S * D + 2 * (size_t)S + (size_t)kEThreads * S + kEThreads);
+}
 static bool fused_path(int S, int D) { return S <= kFusedMaxS && fused_smem_bytes(S, D) <= 200 * 1024; }
 
 // d_x: [T x D] device, h_psi: [D] HOST (already identity-substituted by the caller if lengths mismatch),
@@ -824,12 +825,11 @@ int refine_device(Workspace &ws, const double *d_x, int T, int D, const double *
     (void)c.take<double>(std::max(max_it, 1));
     d.scal = c.take<double>(8);
     d.state = c.take<int>(8);
-    d.fA = c.take<double>((size_t)kFChunks * S * D);
-    d.fG = c.take<double>((size_t)kFChunks * S);
-    for (int i = 0; i < 2; ++i) {
-        d.fLL[i] = c.take<double>(d.eblocks);
-        d.fPi[i] = c.take<double>((size_t)d.eblocks * S);
-        d.fsums[i] = c.take<double>(4);
+    if (S <= kFusedMaxS) {
+        d.fA = c.take<double>((size_t)d.eblocks * S * D);
+        d.fG = c.take<double>((size_t)d.eblocks * S);
+        d.fLL = c.take<double>(d.eblocks);
+        for (int i = 0; i < 2; ++i) d.fsums[i] = c.take<double>(3 * (size_t)S);
     }
     d.gamma = d_gamma;
     d.pi = d_pi;
@@ -858,20 +858,26 @@ int refine_device(Workspace &ws, const double *d_x, int T, int D, const double *
         static std::once_flag once_f;
         static cudaError_t attr_err_f = cudaSuccess;
         std::call_once(once_f, [&]() {
-            attr_err_f = cudaFuncSetAttribute(vbx_estep_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_err_f = cudaFuncSetAttribute(vbx_estep_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (attr_err_f == cudaSuccess)
+                attr_err_f = cudaFuncSetAttribute(vbx_partials0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         });
         FA_CUDA_TRY(attr_err_f);
         const size_t fsmem = fused_smem_bytes(S, D);
-        const dim3 agrid((unsigned)((S * D + 255) / 256), kFChunks);
+        vbx_partials0_kernel<<<d.eblocks, kEThreads, sizeof(double) * (size_t)kEThreads * S, stream>>>(d);
+        ++n_launch;
         for (int it = 0; it < max_it; ++it) {
-            vbx_acc16_kernel<<<agrid, 256, 0, stream>>>(d);
-            vbx_estep_fused_kernel<<<d.eblocks, kEThreads, fsmem, stream>>>(d, it);
+            vbx_update_kernel2<<<S, kEThreads, 0, stream>>>(d, it, 0);
+            vbx_estep_kernel2<<<d.eblocks, kEThreads, fsmem, stream>>>(d);
             n_launch += 2;
         }
-        vbx_final_fused_kernel<<<1, 128, 0, stream>>>(d, max_it);
+        if (max_it > 0) {
+            vbx_update_kernel2<<<S, kEThreads, 0, stream>>>(d, max_it, 1);   // books of the last E-step (no-op if converged)
+            ++n_launch;
+        }
         vbx_hard_kernel<<<(T + 127) / 128, 128, 0, stream>>>(d_gamma, T, S, d_hard);
         FA_CUDA_TRY(cudaGetLastError());
-        n_launch += 2;
+        ++n_launch;
         if (launches) *launches += n_launch;
         if (iterations_host) {
             int h_state[2] = {0, 0};

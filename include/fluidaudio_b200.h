@@ -114,6 +114,9 @@ int64_t fa_mel_frame_count(const fa_mel *mel, int64_t sample_count, int32_t padd
 enum { FA_MEL_PRECISION_F64 = 0, FA_MEL_PRECISION_F32 = 1 };
 fa_status fa_mel_set_precision(fa_mel *mel, int32_t precision);
 int32_t fa_mel_get_precision(const fa_mel *mel);
+/* Host-buffer calls on long clips are cut into `chunks` units whose H2D copy, kernels and D2H copy overlap on three
+ * streams (default 24; 1 = no overlap).  Results do not depend on it. */
+fa_status fa_mel_set_pipeline_chunks(fa_mel *mel, int32_t chunks);
 
 /* Host buffers in and out (the drop-in call).  On return *mel_length = valid frames, *num_frames = padded frames;
  * out receives num_frames*n_mels floats in `layout`.  Mirrors computeFlatTransposed / computeFlat / compute. */

@@ -582,3 +582,43 @@ def test_timed_cpu_arm_matches_the_oracle(oracle):
         got, ml = oracle.mel_fast_flat_transposed(cfg, a, last)
         ref, rml, _ = oracle.mel_flat_transposed(cfg, a, last=last)
         assert ml == rml and got.shape == ref.shape and np.abs(got - ref).max() <= 2e-4
+
+
+def test_oracle_against_a_nemo_style_torch_stft_featurizer(oracle):
+    """The one external claim the reference makes about its mel values: NemotronMelExtractor matches NeMo's PyTorch
+    log-mel to max |delta| ~ 9e-3 (Documentation/Benchmarks.md:149).  NeMo's AudioToMelSpectrogramPreprocessor is
+    pre-emphasis 0.97 -> torch.stft(n_fft 512, hop 160, win 400, symmetric Hann, centred) -> |.|^2 -> librosa Slaney
+    filterbank (norm='slaney', htk=False) -> log(x + 2^-24).  Rebuilt here from torch.stft (float32, zero padding like the
+    Swift code) and an independent float64 restatement of librosa.filters.mel: the oracle must sit well inside the
+    reference's own tolerance, and its float32 filterbank within float32 rounding of librosa's formula."""
+    torch = pytest.importorskip("torch")
+
+    def hz_to_mel(f):
+        f = np.asarray(f, float)
+        return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-10) / 1000.0) / (np.log(6.4) / 27.0), f / (200.0 / 3))
+
+    def mel_to_hz(m):
+        m = np.asarray(m, float)
+        return np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), (200.0 / 3) * m)
+
+    def librosa_slaney(n_mels):
+        fftfreqs = np.linspace(0, 8000, 257)
+        mel_f = mel_to_hz(np.linspace(hz_to_mel(0.0), hz_to_mel(8000.0), n_mels + 2))
+        fdiff, ramps = np.diff(mel_f), mel_f[:, None] - fftfreqs[None, :]
+        w = np.stack([np.maximum(0, np.minimum(-ramps[i] / fdiff[i], ramps[i + 2] / fdiff[i + 1])) for i in range(n_mels)])
+        return w * (2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels]))[:, None]
+
+    for gen, seconds in ((synth.tone_noise_audio, 4), (synth.speech_like_audio, 3)):
+        a = gen(16000 * seconds)
+        x = torch.from_numpy(a)
+        y = torch.cat([x[:1], x[1:] - 0.97 * x[:-1]])
+        spec = torch.stft(y, 512, 160, 400, window=torch.hann_window(400, periodic=False), center=True, pad_mode="constant",
+                          return_complex=True)
+        power = (spec.real ** 2 + spec.imag ** 2).numpy().astype(np.float64)
+        for nm in (80, 128):
+            fb = librosa_slaney(nm)
+            assert np.abs(fb - oracle.mel_filterbank(512, nm)).max() <= 5e-7
+            nemo = np.log(fb @ power + 2.0 ** -24).T
+            ref, T, _ = oracle.mel_flat_transposed(oracle.mel_config(n_mels=nm), a)
+            assert nemo.shape == ref.shape
+            assert np.abs(nemo - ref).max() <= 1e-3            # measured 5e-5 .. 1.5e-4; the reference documents 9e-3
