@@ -70,7 +70,7 @@ EXPORTED_SYMBOLS = [
     "fa_memcpy_d2h", "fa_memcpy_probe", "fa_timer_start", "fa_timer_stop_ms", "fa_mel_default_config", "fa_mel_create",
     "fa_mel_destroy", "fa_mel_get_window", "fa_mel_get_filterbank", "fa_mel_frame_count", "fa_mel_compute",
     "fa_mel_compute_device", "fa_mel_compute_batch", "fa_mel_compute_batch_device", "fa_mel_timer_start",
-    "fa_mel_timer_stop_ms", "fa_mel_set_precision", "fa_mel_get_precision", "fa_mel_set_pipeline_chunks", "fa_mel_normalize_per_feature", "fa_mel_unified_features", "fa_mel_lseend_features",
+    "fa_mel_timer_stop_ms", "fa_mel_set_precision", "fa_mel_get_precision", "fa_mel_set_pipeline_chunks", "fa_mel_set_zero_copy_output", "fa_mel_normalize_per_feature", "fa_mel_unified_features", "fa_mel_lseend_features",
     "fa_resample_output_count", "fa_audio_resample", "fa_audio_to_mel",
     "fa_linear_resample", "fa_l2_normalize_rows", "fa_ahc_cluster", "fa_dendrogram_cut", "fa_vbx_default_config",
     "fa_vbx_refine", "fa_compute_centroids", "fa_assign_embeddings", "fa_cluster_default_config",
@@ -123,6 +123,7 @@ def load():
     L.fa_mel_compute_batch_device.argtypes = L.fa_mel_compute_batch.argtypes
     L.fa_mel_set_precision.argtypes = [vp, i32]
     L.fa_mel_set_pipeline_chunks.argtypes = [vp, i32]
+    L.fa_mel_set_zero_copy_output.argtypes = [vp, i32]
     L.fa_mel_get_precision.argtypes = [vp]
     L.fa_mel_get_precision.restype = i32
     L.fa_mel_timer_start.argtypes = [vp]

@@ -946,6 +946,25 @@ int Solver::ensure_pool(int N, int D) {
     return FA_OK;
 }
 
+// FA_AHC_* environment hooks (test / tuning only: fall-back placements at small N, trace, candidate spacing), read once.
+struct Hooks {
+    bool force_global = false, force_stream = false;
+    int slot_shift = 3, flags = 0;
+};
+static const Hooks &hooks() {
+    static const Hooks h = [] {
+        Hooks x;
+        const char *g = std::getenv("FA_AHC_FORCE_GLOBAL_MASTER"), *s = std::getenv("FA_AHC_FORCE_STREAMED");
+        const char *sh = std::getenv("FA_AHC_SLOT_SHIFT"), *f = std::getenv("FA_AHC_FLAGS");
+        x.force_global = g && g[0] == '1';
+        x.force_stream = s && s[0] == '1';
+        if (sh) x.slot_shift = std::min(3, std::max(0, std::atoi(sh)));
+        if (f) x.flags = std::atoi(f);
+        return x;
+    }();
+    return h;
+}
+
 int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     if (N < 2) return FA_OK;
     const int Ns = (N + 31) & ~31;
@@ -956,9 +975,10 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
         for (int l = 1; l <= 3; ++l)
             if (master_smem_bytes(N, l) <= smem_cap) level = l;
     // test hooks: exercise the fall-back placements at small N (tests/test_gpu_parity.py)
-    const char *force_global = std::getenv("FA_AHC_FORCE_GLOBAL_MASTER");
-    const char *force_stream = std::getenv("FA_AHC_FORCE_STREAMED");
-    if (force_global && force_global[0] == '1') level = 0;
+    // (all FA_AHC_* hooks are read ONCE per process, see hooks(): stray variables cannot change behaviour mid-run)
+    const Hooks &hk = hooks();
+    const bool force_global = hk.force_global, force_stream = hk.force_stream;
+    if (force_global) level = 0;
     const bool idx16 = level >= 1;
     // worker placement: resident (each CTA keeps <= 128 node vectors in shared memory) when the whole problem fits
     // into max_workers CTAs, else streamed from the k-major global copy
@@ -969,7 +989,7 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     }
     const int cap_slots = (int)std::min<size_t>(kMergeThreads, (smem_cap - worker_fixed) / (sizeof(double) * (size_t)D));
     bool resident = cap_slots >= 1 && (long long)cap_slots * max_workers >= N;
-    if (force_stream && force_stream[0] == '1') resident = false;
+    if (force_stream) resident = false;
     int workers, slots_per_cta = 0;
     size_t worker_smem = worker_fixed;
     if (resident) {
@@ -1010,10 +1030,7 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     P.cmd = reinterpret_cast<unsigned long long *>(base + L.cmd);
     P.threshold = reinterpret_cast<unsigned long long *>(base + L.threshold);
     P.results = reinterpret_cast<ResultSlot *>(base + L.results);
-    {
-        const char *f = std::getenv("FA_AHC_SLOT_SHIFT");   // tuning hook: 0 = packed, 1 = 32 B, 3 = 128 B per candidate
-        P.slot_shift = f ? std::min(3, std::max(0, std::atoi(f))) : 3;
-    }
+    P.slot_shift = hk.slot_shift;   // tuning hook: 0 = packed, 1 = 32 B, 3 = 128 B per candidate (default)
     P.result_stride = (max_workers + 1) << P.slot_shift;
     P.error = reinterpret_cast<int *>(base + L.error);
     P.trace = reinterpret_cast<unsigned long long *>(base + L.trace);
@@ -1021,10 +1038,7 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     P.slots_per_cta = slots_per_cta;
     P.idx16 = idx16 ? 1 : 0;
     P.smem_level = level;
-    {
-        const char *f = std::getenv("FA_AHC_FLAGS");   // tuning hooks: 4 = globaltimer trace, 8 = never self-issue
-        P.flags = f ? std::atoi(f) : 0;
-    }
+    P.flags = hk.flags;             // tuning hooks: 4 = globaltimer trace, 8 = never self-issue
     Cand *init_partial = reinterpret_cast<Cand *>(base + L.init_partial);
     Problem *d_prob = reinterpret_cast<Problem *>(base + L.problem);
 
@@ -1038,11 +1052,17 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
     int *h_mb = h_ma + N;
     int *h_err = h_mb + N;
 
-    cudaEvent_t ev[4];
-    for (auto &e : ev) FA_CUDA_TRY(cudaEventCreate(&e));
-    auto drop_events = [&]() {
-        for (auto &e : ev) cudaEventDestroy(e);
-    };
+    // timing events live in a guard: every early return below (FA_CUDA_TRY) releases them
+    struct Events {
+        cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+        ~Events() {
+            for (auto x : e)
+                if (x) cudaEventDestroy(x);
+        }
+        cudaEvent_t &operator[](int i) { return e[i]; }
+    } ev;
+    for (int i = 0; i < 4; ++i) FA_CUDA_TRY(cudaEventCreate(&ev.e[i]));
+    auto drop_events = [&]() {};
 
     FA_CUDA_TRY(cudaMemsetAsync(base + L.cmd, 0, 256, stream));
     FA_CUDA_TRY(cudaMemsetAsync(base + L.threshold, 0, 256, stream));

@@ -653,6 +653,11 @@ FA_API fa_status fa_mel_set_pipeline_chunks(fa_mel *mel, int32_t chunks) {
     reinterpret_cast<MelHandle *>(mel)->plan.pipeline_chunks = chunks;
     return FA_STATUS_OK;
 }
+FA_API fa_status fa_mel_set_zero_copy_output(fa_mel *mel, int32_t enabled) {
+    if (!mel) return FA_STATUS_INVALID_ARGUMENT;
+    reinterpret_cast<MelHandle *>(mel)->plan.zero_copy_out = enabled != 0;
+    return FA_STATUS_OK;
+}
 FA_API int32_t fa_mel_get_precision(const fa_mel *mel) {
     return mel ? reinterpret_cast<const MelHandle *>(mel)->plan.precision : -1;
 }
@@ -836,10 +841,14 @@ FA_API int64_t fa_resample_output_count(const fa_audio_format *fmt, int64_t fram
 
 FA_API fa_status fa_audio_resample(const void *pcm, int64_t frames, const fa_audio_format *fmt, float *out,
                                    int64_t out_cap, int64_t *out_count) {
-    if (!audio_format_ok(fmt) || frames < 0 || (!pcm && frames) || !out_count) return FA_STATUS_INVALID_ARGUMENT;
+    if (!audio_format_ok(fmt) || frames < 0 || !out_count) return FA_STATUS_INVALID_ARGUMENT;
     const long long n = resample::output_count(frames, fmt->in_rate, fmt->out_rate);
     *out_count = n;
-    if (!out) return FA_STATUS_OK;
+    if (!out) return FA_STATUS_OK;            // sizing call: pcm may be NULL
+    if (!pcm && frames) {
+        fa::set_error("fa_audio_resample: pcm is NULL");
+        return FA_STATUS_INVALID_ARGUMENT;
+    }
     if (out_cap < n) return FA_STATUS_OUTPUT_TOO_SMALL;
     if (n == 0) return FA_STATUS_OK;
     API_REQUIRE_DEVICE();

@@ -107,6 +107,25 @@ __device__ __forceinline__ TileGeom tile_geom(const MelLaunch &P, int tile) {
     return g;
 }
 
+// Geometry + the unit fields a tile needs, computed ONCE per tile by thread 0 and broadcast through shared memory (three
+// rotating slots): every thread recomputing it (binary search, 64-bit index math, a 56-byte struct copy) three times per
+// tile was 6 % of the kernel's instructions (profiles/r02_mel.md).
+struct TileInfo {
+    TileGeom g;
+    long long audio_off, n, out_off, out_stride;
+    float last;
+    int pad_;
+};
+__device__ __forceinline__ void make_tile_info(const MelLaunch &P, int tile, TileInfo &ti) {
+    ti.g = tile_geom(P, tile);
+    const MelUnit &u = unit_at(P, ti.g.unit);
+    ti.audio_off = u.audio_off;
+    ti.n = u.n;
+    ti.out_off = u.out_off;
+    ti.out_stride = u.out_stride;
+    ti.last = u.last;
+}
+
 template <int kWarps, typename V>
 __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch P) {
     constexpr int kF = vtraits<V>::kFrames;   // frames one warp transforms together (2: packed float32 pairs)
@@ -120,6 +139,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
     float *fbw = otile + kTileFrames * (P.n_mels + 1);      // fb_nnz_cap
     int4 *fbmeta = reinterpret_cast<int4 *>(fbw + P.fb_cap);   // n_mels x {first bin, quads, weight offset, -}
     uint64_t *bars = reinterpret_cast<uint64_t *>(fbmeta + P.n_mels);
+    TileInfo *tinfo = reinterpret_cast<TileInfo *>(bars + 2);   // [3]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -139,21 +159,22 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
 
     cpxv<V> *buf = fftbuf + warp * kFftPad;
 
-    auto issue = [&](int tile, int buf) {   // thread 0 only
-        const TileGeom g = tile_geom(P, tile);
+    auto issue = [&](int tile, int buf, TileInfo &slot) {   // thread 0 only: publishes the tile's info, starts its bulk copy
+        make_tile_info(P, tile, slot);
+        const TileGeom &g = slot.g;
         float *dst = buf ? raw1 : raw0;
         if (g.ge > g.gs) {
-            const MelUnit &u = unit_at(P, g.unit);
             const uint32_t bytes = (uint32_t)((g.ge - g.gs) * 4);
             mbar_expect_tx(&bars[buf], bytes);
-            bulk_g2s(dst + (g.gs - g.base), P.audio + u.audio_off + g.gs, bytes, &bars[buf]);
+            bulk_g2s(dst + (g.gs - g.base), P.audio + slot.audio_off + g.gs, bytes, &bars[buf]);
         } else {
             mbar_arrive(&bars[buf]);
         }
     };
 
     // pre-emphasis of one tile from its raw buffer into ptile (zero outside [0, n))
-    auto preemphasize = [&](const TileGeom &g, const MelUnit &u, const float *raw) {
+    auto preemphasize = [&](const TileInfo &u, const float *raw) {   // u.n / u.last / u.audio_off: the owning clip
+        const TileGeom &g = u.g;
         const float a = P.preemph;
         const bool interior = g.a0 >= 1 && g.a0 - 1 >= g.gs && g.a0 + P.pt_len <= g.ge && g.a0 + P.pt_len <= u.n;
         if (interior) {
@@ -222,26 +243,23 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
     const int first = blockIdx.x, stride = gridDim.x;
     if (first >= P.total_tiles) return;
     if (tid == 0) {
-        issue(first, 0);
-        if (first + stride < P.total_tiles) issue(first + stride, 1);
+        issue(first, 0, tinfo[0]);
+        if (first + stride < P.total_tiles) issue(first + stride, 1, tinfo[1]);
     }
-    {
-        const TileGeom g0 = tile_geom(P, first);
-        const MelUnit u0 = unit_at(P, g0.unit);
-        mbar_wait(&bars[0], 0);
-        preemphasize(g0, u0, raw0);
-    }
+    __syncthreads();
+    mbar_wait(&bars[0], 0);
+    preemphasize(tinfo[0], raw0);
     __syncthreads();
     float *pending_dst = nullptr;
     int pending_total = 0;
-    int it = 0;
-    for (int tile = first; tile < P.total_tiles; tile += stride, ++it) {
-        const TileGeom g = tile_geom(P, tile);
-        const MelUnit u = unit_at(P, g.unit);
+    int it = 0, slot = 0;   // slot = it % 3
+    for (int tile = first; tile < P.total_tiles; tile += stride, ++it, slot = slot == 2 ? 0 : slot + 1) {
+        const TileInfo &u = tinfo[slot];
+        const int nf = u.g.nf;
 
-        // ---- phase A: previous tile's copy-out, then one warp per frame: FP64 FFT256 + recombination + power ----
+        // ---- phase A: previous tile's copy-out, then one warp per frame (pair): FFT256 + recombination + power ----
         if (pending_dst) copy_out(pending_dst, pending_total);
-        for (int fi = warp * kF; fi < g.nf; fi += kWarps * kF) {   // kF == 2: frames fi and fi + 1 (kTileFrames is even)
+        for (int fi = warp * kF; fi < nf; fi += kWarps * kF) {   // kF == 2: frames fi and fi + 1 (kTileFrames is even)
             const float *pf = ptile + fi * P.hop;
             V re[8], im[8];
             if (P.mid_full) pass1<true>(lane, pf, P.hop, T, buf); else pass1<false>(lane, pf, P.hop, T, buf);
@@ -257,16 +275,17 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
 
         // ---- phase B: mel filterbank + log; a warp covers kTileFrames frames x (32 / kTileFrames) mel bins -------
         const int next = tile + stride;
+        const int slot1 = slot == 2 ? 0 : slot + 1, slot2 = slot1 == 2 ? 0 : slot1 + 1;
         if (tid == 0 && next + stride < P.total_tiles) {
             fence_proxy_async();   // generic-proxy reads of this raw buffer (pre-emphasis, previous phase B) precede the async write
-            issue(next + stride, it & 1);
+            issue(next + stride, it & 1, tinfo[slot2]);   // slot2 held tile it-1: nobody reads it any more
         }
         {
             constexpr int kGroup = 32 / kTileFrames;               // mel bins handled concurrently by one warp
             const int fl = lane % kTileFrames, mg = lane / kTileFrames;
-            const bool live = fl < g.nf;
+            const bool live = fl < nf;
             const float *prow = power + fl * kPowStride;
-            const long long f = g.f0 + fl;
+            const long long f = u.g.f0 + fl;
             for (int m = warp * kGroup + mg; m < P.n_mels; m += kWarps * kGroup) {
                 const int4 md = fbmeta[m];
                 // rows beyond the tile's last frame hold finite leftovers: computed and dropped, no divergent branch
@@ -278,15 +297,13 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             }
         }
         if (P.layout == 0) {
-            pending_dst = P.out + u.out_off + g.f0 * P.n_mels;
-            pending_total = g.nf * P.n_mels;
+            pending_dst = P.out + u.out_off + u.g.f0 * P.n_mels;
+            pending_total = nf * P.n_mels;
         }
         if (next < P.total_tiles) {
             const int nb = (it + 1) & 1;
-            const TileGeom gn = tile_geom(P, next);
-            const MelUnit un = unit_at(P, gn.unit);
             mbar_wait(&bars[nb], (uint32_t)((it + 1) >> 1) & 1u);
-            preemphasize(gn, un, nb ? raw1 : raw0);
+            preemphasize(tinfo[slot1], nb ? raw1 : raw0);
         }
         __syncthreads();
     }
@@ -599,7 +616,7 @@ int MelPlan::init(const MelConfig &c) {
     smem_bytes = sizeof(float) * ((size_t)2 * raw_cap + pt_cap + 0 +
                                   (size_t)kTileFrames * kPowStride + (size_t)kTileFrames * (cfg.n_mels + 1) + fb_cap) +
                  sizeof(cpxd) * (size_t)kWarpsPerCta * kFftPad + sizeof(int) * 4 * (size_t)cfg.n_mels + 8 +
-                 2 * sizeof(uint64_t);
+                 2 * sizeof(uint64_t) + 3 * sizeof(TileInfo) + 16;
     if (smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
         fa::set_error("mel config needs %zu bytes of shared memory per CTA, device allows %zu", smem_bytes,
                       (size_t)prop.sharedMemPerBlockOptin);
@@ -781,6 +798,18 @@ int MelPlan::compute_batch_device(const float *d_in, const long long *offsets, i
     return launch(d_in, d_out_buf, 0, used, tiles, mode, layout, stream, aligned);
 }
 
+// A pinned (page-locked, mapped) host buffer has a device alias under UVA: the kernel can then store its output rows
+// straight into host memory (coalesced 16-byte stores become posted PCIe writes), which removes the D2H copy stage and its
+// cross-stream hand-offs from the pipeline.  Pageable memory returns nullptr and takes the staged copy.
+static float *device_alias_if_pinned(float *host) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return (a.type == cudaMemoryTypeHost && a.devicePointer) ? static_cast<float *>(a.devicePointer) : nullptr;
+}
+
 // Host buffers in, host buffers out.  A long clip is cut into units of `chunk` frames: unit c's samples are copied
 // on the H2D stream while unit c-1 runs on the compute stream and unit c-2's rows return on the D2H stream.
 int MelPlan::compute_host(const float *audio, long long n, float last, int mode, long long expected, int layout,
@@ -807,6 +836,9 @@ int MelPlan::compute_host(const float *audio, long long n, float last, int mode,
     const long long kMinChunk = 4096, kMaxChunks = pipeline_chunks;
     long long chunk = std::max(kMinChunk, ceil_to((T + kMaxChunks - 1) / kMaxChunks, kTileFrames));
     const int chunks = (int)((T + chunk - 1) / chunk);
+    float *out_alias = (zero_copy_out && layout == 0 && chunks > 1) ? device_alias_if_pinned(out) : nullptr;
+    float *k_out = out_alias ? out_alias : d_out;   // where the kernel writes
+    if (out_alias && Tp > T) std::memset(out + T * cfg.n_mels, 0, (size_t)(Tp - T) * cfg.n_mels * sizeof(float));
     st = ensure_units(chunks);
     if (st != FA_OK) return st;
     cudaStream_t s_in = streams[0], s_k = streams[1], s_out = streams[2];
@@ -831,7 +863,7 @@ int MelPlan::compute_host(const float *audio, long long n, float last, int mode,
         h_units[c] = MelUnit{0, n, 0, Tp, fb, fc, last, 0};
     }
     FA_CUDA_TRY(cudaMemcpyAsync(d_units, h_units, chunks * sizeof(MelUnit), cudaMemcpyHostToDevice, s_k));
-    if (Tp > T) FA_CUDA_TRY(cudaMemsetAsync(d_out, 0, need * sizeof(float), s_k));
+    if (Tp > T && !out_alias) FA_CUDA_TRY(cudaMemsetAsync(d_out, 0, need * sizeof(float), s_k));
     const long long pad = mode == 0 ? cfg.n_fft / 2 : 0;
     long long copied = 0;
     for (int c = 0; c < chunks; ++c) {
@@ -845,8 +877,9 @@ int MelPlan::compute_host(const float *audio, long long n, float last, int mode,
         }
         FA_CUDA_TRY(cudaEventRecord(events[2 * c], s_in));
         FA_CUDA_TRY(cudaStreamWaitEvent(s_k, events[2 * c], 0));
-        st = launch(d_audio, d_out, c, 1, tiles_of(h_units[c].frame_count), mode, layout, s_k, true);
+        st = launch(d_audio, k_out, c, 1, tiles_of(h_units[c].frame_count), mode, layout, s_k, true);
         if (st != FA_OK) return st;
+        if (out_alias) continue;   // the kernel stored its rows in the caller's pinned buffer: no D2H stage
         FA_CUDA_TRY(cudaEventRecord(events[2 * c + 1], s_k));
         FA_CUDA_TRY(cudaStreamWaitEvent(s_out, events[2 * c + 1], 0));
         const long long fb = h_units[c].frame_begin, fc = h_units[c].frame_count;
@@ -919,9 +952,15 @@ int MelPlan::compute_host_pcm(const void *pcm, long long frames, const resample:
         FA_CUDA_TRY(cudaMalloc(&d_pcm, pcm_bytes + 16));
         d_pcm_cap = pcm_bytes + 16;
     }
-    const long long kMinChunk = 4096, kMaxChunks = pipeline_chunks;
+    // pipeline depth: ~10 MB of PCM per chunk (the copy engines' fixed cost per transfer and the host's enqueue rate make
+    // finer chunks slower: int16 hour 3.08 ms at 8-12 chunks, 3.44 at 24, 3.61 at 96 — profiles/r02_mel.md)
+    const long long kMinChunk = 4096;
+    const long long kMaxChunks = std::max<long long>(1, std::min<long long>(pipeline_chunks, (long long)(pcm_bytes / (10u << 20)) + 1));
     const long long chunk = std::max(kMinChunk, ceil_to((T + kMaxChunks - 1) / kMaxChunks, kTileFrames));
     const int chunks = (int)((T + chunk - 1) / chunk);
+    float *out_alias = (zero_copy_out && layout == 0) ? device_alias_if_pinned(out) : nullptr;
+    float *k_out = out_alias ? out_alias : d_out;   // where the kernel writes
+    if (out_alias && Tp > T) std::memset(out + T * cfg.n_mels, 0, (size_t)(Tp - T) * cfg.n_mels * sizeof(float));
     st = ensure_units(chunks);
     if (st != FA_OK) return st;
     st = ensure_events(2 * (size_t)chunks);
@@ -932,7 +971,7 @@ int MelPlan::compute_host_pcm(const void *pcm, long long frames, const resample:
         h_units[c] = MelUnit{0, n, 0, Tp, fb, fc, last, 0};
     }
     FA_CUDA_TRY(cudaMemcpyAsync(d_units, h_units, chunks * sizeof(MelUnit), cudaMemcpyHostToDevice, s_k));
-    if (Tp > T) FA_CUDA_TRY(cudaMemsetAsync(d_out, 0, need * sizeof(float), s_k));
+    if (Tp > T && !out_alias) FA_CUDA_TRY(cudaMemsetAsync(d_out, 0, need * sizeof(float), s_k));
     const long long pad = mode == 0 ? cfg.n_fft / 2 : 0;
     const resample::Design &D = rs_design;
     const bool linear = f.in_rate != f.out_rate && resample::resolve_algorithm(f) == resample::kAlgoLinear;
@@ -974,8 +1013,9 @@ int MelPlan::compute_host_pcm(const void *pcm, long long frames, const resample:
         st = resample::launch_convert(d_pcm, frames, f, D, d_rs_tab, d_audio, converted, ready, s_k, &launches);
         if (st != FA_OK) return st;
         converted = std::max(converted, ready);
-        st = launch(d_audio, d_out, c, 1, tiles_of(h_units[c].frame_count), mode, layout, s_k, true);
+        st = launch(d_audio, k_out, c, 1, tiles_of(h_units[c].frame_count), mode, layout, s_k, true);
         if (st != FA_OK) return st;
+        if (out_alias) continue;   // the kernel stored its rows in the caller's pinned buffer: no D2H stage
         FA_CUDA_TRY(cudaEventRecord(events[2 * c + 1], s_k));
         FA_CUDA_TRY(cudaStreamWaitEvent(s_out, events[2 * c + 1], 0));
         const long long fb = h_units[c].frame_begin, fc = h_units[c].frame_count;

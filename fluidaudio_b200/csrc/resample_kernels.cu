@@ -54,12 +54,13 @@ int make_design(double in_rate, double out_rate, Design &d) {
     d.taps = 2 * d.half;
     d.exact = d.L <= kMaxExactPhases;
     d.phases = d.exact ? (int)d.L : kInterpPhases;
-    if ((255.0 * (double)d.M / (double)d.L + d.taps + 4) * sizeof(float) > 200.0 * 1024.0) {
+    if ((255.0 * (double)d.M / (double)d.L + d.taps + 8) * sizeof(float) > 200.0 * 1024.0) {
         fa::set_error("resampling ratio %lld/%lld needs a filter window larger than shared memory", d.L, d.M);
         return FA_UNSUPPORTED;
     }
     const int rows = d.exact ? d.phases : d.phases + 1;
-    d.table.assign((size_t)rows * d.taps, 0.0f);
+    d.row_stride = (d.taps + 3) & ~3;   // rows padded with zero taps to whole float4s (16-byte aligned coefficient loads)
+    d.table.assign((size_t)rows * d.row_stride, 0.0f);
     const double pi = 3.14159265358979323846, i0b = bessel_i0(kBeta);
     std::vector<double> row(d.taps);
     for (int p = 0; p < rows; ++p) {
@@ -77,7 +78,7 @@ int make_design(double in_rate, double out_rate, Design &d) {
             row[k] = g;
             sum += g;
         }
-        for (int k = 0; k < d.taps; ++k) d.table[(size_t)p * d.taps + k] = (float)(row[k] / sum);
+        for (int k = 0; k < d.taps; ++k) d.table[(size_t)p * d.row_stride + k] = (float)(row[k] / sum);
     }
     return FA_OK;
 }
@@ -120,6 +121,13 @@ struct Source {
 // mono sample n: float32 sum over channels in channel order, times 1/channels (AudioConverter.swift:403-409).
 // int16 is widened like AVAudioPCMBuffer's int16 -> float conversion: v / 32768.
 __device__ __forceinline__ float mono_at(const Source &s, long long n) {
+    if (s.channels == 1)   // the common mono cases without the channel loop
+        return s.format == kPcmI16 ? (float)__ldg(reinterpret_cast<const short *>(s.pcm) + n) * (1.0f / 32768.0f)
+                                   : __ldg(reinterpret_cast<const float *>(s.pcm) + n);
+    if (s.channels == 2 && s.interleaved && s.format == kPcmI16) {   // stereo WAV: one 32-bit load per frame
+        const short2 v = __ldg(reinterpret_cast<const short2 *>(s.pcm) + n);
+        return __fmul_rn(__fadd_rn(__fadd_rn(0.0f, (float)v.x * (1.0f / 32768.0f)), (float)v.y * (1.0f / 32768.0f)), s.weight);
+    }
     float sum = 0.0f;
     for (int c = 0; c < s.channels; ++c) {
         const long long at = s.interleaved ? n * s.channels + c : (long long)c * s.frames + n;
@@ -152,44 +160,63 @@ __global__ void __launch_bounds__(256) linear_kernel(Source s, double ratio, flo
 }
 
 // Kaiser-windowed-sinc polyphase.  One CTA = 256 consecutive outputs; their input span (mixed down, widened) is staged
-// in shared memory once, every thread then runs its 2H-tap dot product out of shared memory, coefficients through the
-// read-only path (a single row when L == 1, i.e. integer decimation: every lane reads the same address).
+// in shared memory once, every thread then runs its 2H-tap dot product out of shared memory: coefficients as 16-byte
+// loads through the read-only path (a single row when L == 1, i.e. integer decimation: every lane reads the same
+// address), four independent accumulators, 32-bit index arithmetic relative to one 64-bit division per CTA.
 __global__ void __launch_bounds__(256)
-sinc_kernel(Source s, long long L, long long M, int half, int phases, int exact, const float *__restrict__ tab, float *out,
-            long long o_begin, long long o_end) {
+sinc_kernel(Source s, long long L, long long M, int half, int phases, int exact, int row_stride,
+            const float *__restrict__ tab, float *out, long long o_begin, long long o_end) {
     extern __shared__ float xs[];
-    const int taps = 2 * half;
+    __shared__ long long base_n0;
+    __shared__ unsigned base_ph;
     const long long i0 = o_begin + (long long)blockIdx.x * 256;
-    const long long i_last = min(i0 + 255, o_end - 1);
-    const long long n_lo = (i0 * M) / L - half + 1;
-    const long long n_hi = (i_last * M) / L + half;
-    const int span = (int)(n_hi - n_lo + 1);
-    for (int j = threadIdx.x; j < span; j += 256) {
+    if (threadIdx.x == 0) {
+        const long long num = i0 * M;
+        base_n0 = num / L;
+        base_ph = (unsigned)(num - base_n0 * L);
+    }
+    __syncthreads();
+    const unsigned uL = (unsigned)L, uM = (unsigned)M;   // L, M < 2^22 (rates on a 1/1000 Hz grid): 255 * M + L < 2^31
+    const int last = (int)(min(i0 + 255, o_end - 1) - i0);
+    const long long n_lo = base_n0 - half + 1;
+    const int span = (int)((base_ph + (unsigned)last * uM) / uL) + 2 * half;
+    for (int j = threadIdx.x; j < span + 4; j += 256) {
         const long long n = n_lo + j;
-        xs[j] = (n >= 0 && n < s.frames) ? mono_at(s, n) : 0.0f;
+        xs[j] = (j < span && n >= 0 && n < s.frames) ? mono_at(s, n) : 0.0f;
     }
     __syncthreads();
     const long long i = i0 + threadIdx.x;
     if (i >= o_end) return;
-    const long long num = i * M;
-    const long long n0 = num / L;
-    const long long ph = num - n0 * L;
-    const float *x = xs + (int)(n0 - half + 1 - n_lo);
-    float acc = 0.0f;
+    const unsigned t = base_ph + threadIdx.x * uM;
+    const unsigned dn = t / uL, ph = t - dn * uL;
+    const float *x = xs + dn;          // input n0 - H + 1 + k sits at xs[dn + k]
+    const int nq = row_stride >> 2;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
     if (exact) {
-        const float *row = tab + (size_t)ph * taps;
-        for (int k = 0; k < taps; ++k) acc = fmaf(__ldg(row + k), x[k], acc);
+        const float4 *row = reinterpret_cast<const float4 *>(tab + (size_t)ph * row_stride);
+#pragma unroll 4
+        for (int q = 0; q < nq; ++q) {
+            const float4 c = __ldg(row + q);
+            a0 = fmaf(c.x, x[4 * q], a0);
+            a1 = fmaf(c.y, x[4 * q + 1], a1);
+            a2 = fmaf(c.z, x[4 * q + 2], a2);
+            a3 = fmaf(c.w, x[4 * q + 3], a3);
+        }
     } else {
         const double pos = (double)ph / (double)L * (double)phases;
         const int p = (int)pos;
         const float a = (float)(pos - (double)p);
-        const float *r0 = tab + (size_t)p * taps, *r1 = r0 + taps;
-        for (int k = 0; k < taps; ++k) {
-            const float c0 = __ldg(r0 + k);
-            acc = fmaf(fmaf(a, __ldg(r1 + k) - c0, c0), x[k], acc);
+        const float4 *r0 = reinterpret_cast<const float4 *>(tab + (size_t)p * row_stride), *r1 = r0 + nq;
+#pragma unroll 2
+        for (int q = 0; q < nq; ++q) {
+            const float4 c0 = __ldg(r0 + q), c1 = __ldg(r1 + q);
+            a0 = fmaf(fmaf(a, c1.x - c0.x, c0.x), x[4 * q], a0);
+            a1 = fmaf(fmaf(a, c1.y - c0.y, c0.y), x[4 * q + 1], a1);
+            a2 = fmaf(fmaf(a, c1.z - c0.z, c0.z), x[4 * q + 2], a2);
+            a3 = fmaf(fmaf(a, c1.w - c0.w, c0.w), x[4 * q + 3], a3);
         }
     }
-    out[i] = acc;
+    out[i] = (a0 + a1) + (a2 + a3);
 }
 
 int launch_convert(const void *d_pcm, long long frames, const AudioFormat &f, const Design &d, const float *d_tab,
@@ -202,10 +229,11 @@ int launch_convert(const void *d_pcm, long long frames, const AudioFormat &f, co
     } else if (resolve_algorithm(f) == kAlgoLinear) {
         linear_kernel<<<grid, 256, 0, stream>>>(s, f.in_rate / f.out_rate, d_out, o_begin, o_end);
     } else {
-        const size_t smem = sizeof(float) * (size_t)((255 * d.M) / d.L + d.taps + 4);
+        const size_t smem = sizeof(float) * (size_t)((255 * d.M) / d.L + d.taps + 12);
         if (smem > 48 * 1024)
             FA_CUDA_TRY(cudaFuncSetAttribute(sinc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sinc_kernel<<<grid, 256, smem, stream>>>(s, d.L, d.M, d.half, d.phases, d.exact ? 1 : 0, d_tab, d_out, o_begin, o_end);
+        sinc_kernel<<<grid, 256, smem, stream>>>(s, d.L, d.M, d.half, d.phases, d.exact ? 1 : 0, d.row_stride, d_tab, d_out,
+                                                 o_begin, o_end);
     }
     FA_CUDA_TRY(cudaGetLastError());
     if (launches) ++*launches;

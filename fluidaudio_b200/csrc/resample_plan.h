@@ -54,10 +54,11 @@ struct Design {
     long long L = 1, M = 1;   // out/in = L/M
     int half = 0;             // H
     int taps = 0;             // 2H
+    int row_stride = 0;       // floats per table row: taps rounded up to a multiple of four (zero padded)
     int phases = 1;           // P (rows; P + 1 rows stored when interpolating)
     bool exact = true;        // every output lands on a row
     double fc = 1.0;
-    std::vector<float> table; // [(exact ? P : P + 1) x taps]
+    std::vector<float> table; // [(exact ? P : P + 1) x row_stride]
 };
 
 // out/in reduced to L/M when both rates are integers (in Hz) — otherwise a 1/1000 Hz grid

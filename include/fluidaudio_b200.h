@@ -117,6 +117,10 @@ int32_t fa_mel_get_precision(const fa_mel *mel);
 /* Host-buffer calls on long clips are cut into `chunks` units whose H2D copy, kernels and D2H copy overlap on three
  * streams (default 24; 1 = no overlap).  Results do not depend on it. */
 fa_status fa_mel_set_pipeline_chunks(fa_mel *mel, int32_t chunks);
+/* When the caller's time-major output buffer is pinned host memory (fa_host_alloc / cudaHostAlloc), the kernel stores its rows
+ * straight into it over PCIe instead of staging them in HBM and copying.  Default OFF: on B200 + PCIe 5 the SM-issued posted writes
+ * measured slower than the copy engine (4.72 vs 4.53 ms per audio-hour, profiles/r02_mel.md); pageable buffers always take the copy. */
+fa_status fa_mel_set_zero_copy_output(fa_mel *mel, int32_t enabled);
 
 /* Host buffers in and out (the drop-in call).  On return *mel_length = valid frames, *num_frames = padded frames;
  * out receives num_frames*n_mels floats in `layout`.  Mirrors computeFlatTransposed / computeFlat / compute. */

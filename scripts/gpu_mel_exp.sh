@@ -19,11 +19,23 @@ def t(fn, reps=10):
     _lib.synchronize(); t0 = time.perf_counter()
     for _ in range(reps): fn()
     _lib.synchronize(); return (time.perf_counter() - t0) / reps * 1e3
-for chunks in (1, 2, 4, 8, 12, 16, 24, 32, 48, 96, 192):
-    _lib.check(L.fa_mel_set_pipeline_chunks(m._h, chunks), "chunks")
-    f = t(lambda: m.compute_flat_transposed(pin_in.array, out=pin_out.array))
-    i = t(lambda: m.compute_from_pcm(pin_16.array, 16000.0, out=pin_out.array))
-    print(f"chunks={chunks:4d}  e2e f32 {f:.3f} ms   e2e i16 {i:.3f} ms", flush=True)
+d_a = _lib.DeviceBuffer(n * 4 + 64); d_a.upload(a)
+d_o = _lib.DeviceBuffer(T * 80 * 4)
+for _ in range(3): m.compute_device(d_a, n, d_o)
+m.timer_start()
+for _ in range(20): m.compute_device(d_a, n, d_o)
+print(f"kernel-only f32: {m.timer_stop_ms()/20:.4f} ms/h", flush=True)
+ref = None
+for zc in (1, 0):
+    _lib.check(L.fa_mel_set_zero_copy_output(m._h, zc), "zc")
+    for chunks in (2, 4, 8, 12, 16, 24, 32, 48, 96):
+        _lib.check(L.fa_mel_set_pipeline_chunks(m._h, chunks), "chunks")
+        f = t(lambda: m.compute_flat_transposed(pin_in.array, out=pin_out.array))
+        if ref is None: ref = pin_out.array.copy()
+        assert np.array_equal(ref, pin_out.array)
+        i = t(lambda: m.compute_from_pcm(pin_16.array, 16000.0, out=pin_out.array))
+        print(f"zero_copy={zc} chunks={chunks:4d}  e2e f32 {f:.3f} ms   e2e i16 {i:.3f} ms", flush=True)
+_lib.check(L.fa_mel_set_zero_copy_output(m._h, 1), "zc")
 ms = C.c_float()
 for nb_in, nb_out in ((4*n, 4*T*80), (2*n, 4*T*80), (4*n, 0), (2*n, 0), (0, 4*T*80)):
     L.fa_memcpy_probe(pin_in.array.ctypes.data, nb_in, pin_out.array.ctypes.data, nb_out, 10, C.byref(ms))

@@ -15,6 +15,13 @@ public final class AudioMelSpectrogram {
     private let padTo: Int
     private let winLength: Int
     private var handle: OpaquePointer?
+    internal var rawHandle: OpaquePointer? { handle }   // for the fused AudioConverter + mel entry (AudioConverter.swift)
+    internal var melBins: Int { nMels }
+    /// Transform arithmetic: false (default) = FP64 transform rounded once; true = float32 transform like vDSP_DFT
+    /// (fa_mel_set_precision, ~1.4x the throughput).  Not part of the reference class.
+    public var float32Transform: Bool = false {
+        didSet { _ = fa_mel_set_precision(handle, float32Transform ? 1 : 0) }
+    }
 
     public init(
         sampleRate: Int = 16000, nMels: Int = 128, nFFT: Int = 512, hopLength: Int = 160, winLength: Int = 400,
