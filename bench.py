@@ -274,7 +274,8 @@ def bench_mel(args, dist, clocks):
                     "copy_floor_ms": floor["i16"], "of_copy_floor": floor["i16"] / (e2e16_s / K * 1e3)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "traffic_source": "see profiles/r02_summary.txt (ncu --set full of this kernel)",
+                     "traffic": 316.8e6, "traffic_source": "ncu --set full, profiles/r02_summary.txt: dram read 230.5 MB + write "
+                     "86.3 MB per launch (the tail of the output is still in L2 at kernel end)",
                      "kernel": "mel512_kernel<8, f32x2>", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": MEL_BYTES_PER_HOUR},
         "config": {"workload": "log-mel STFT, 1 h synthetic 16 kHz mono, 25 ms/10 ms frames, nFFT 512, 80 mels, per GPU",

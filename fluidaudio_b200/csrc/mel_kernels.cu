@@ -126,7 +126,7 @@ __device__ __forceinline__ void make_tile_info(const MelLaunch &P, int tile, Til
     ti.last = u.last;
 }
 
-template <int kWarps, typename V>
+template <int kWarps, typename V, int kLayout>   // kLayout: 0 time-major [T x nMels], 1 mel-major [nMels x stride]
 __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch P) {
     constexpr int kF = vtraits<V>::kFrames;   // frames one warp transforms together (2: packed float32 pairs)
     extern __shared__ __align__(128) unsigned char smem[];
@@ -285,18 +285,19 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             const int fl = lane % kTileFrames, mg = lane / kTileFrames;
             const bool live = fl < nf;
             const float *prow = power + fl * kPowStride;
-            const long long f = u.g.f0 + fl;
+            float *orow = otile + fl * (P.n_mels + 1);
+            float *gout = kLayout == 1 ? P.out + u.out_off + u.g.f0 + fl : nullptr;   // mel-major: column of this frame
             for (int m = warp * kGroup + mg; m < P.n_mels; m += kWarps * kGroup) {
                 const int4 md = fbmeta[m];
                 // rows beyond the tile's last frame hold finite leftovers: computed and dropped, no divergent branch
                 const float v = log_value(mel_dot_quads(reinterpret_cast<const float4 *>(prow + md.x),
                                                         reinterpret_cast<const float4 *>(fbw + md.z), md.y),
                                           P.log_floor, P.log_clamped);
-                if (P.layout == 0) otile[fl * (P.n_mels + 1) + m] = v;
-                else if (live) P.out[u.out_off + (long long)m * u.out_stride + f] = v;
+                if (kLayout == 0) orow[m] = v;
+                else if (live) gout[(long long)m * u.out_stride] = v;
             }
         }
-        if (P.layout == 0) {
+        if (kLayout == 0) {
             pending_dst = P.out + u.out_off + u.g.f0 * P.n_mels;
             pending_total = nf * P.n_mels;
         }
@@ -622,10 +623,10 @@ int MelPlan::init(const MelConfig &c) {
                       (size_t)prop.sharedMemPerBlockOptin);
         return FA_UNSUPPORTED;
     }
-    FA_CUDA_TRY(cudaFuncSetAttribute(mel512_kernel<kWarpsPerCta, double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem_bytes));
-    FA_CUDA_TRY(cudaFuncSetAttribute(mel512_kernel<kWarpsPerCta, f32x2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem_bytes));
+    FA_CUDA_TRY(cudaFuncSetAttribute(mel512_kernel<kWarpsPerCta, double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    FA_CUDA_TRY(cudaFuncSetAttribute(mel512_kernel<kWarpsPerCta, double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    FA_CUDA_TRY(cudaFuncSetAttribute(mel512_kernel<kWarpsPerCta, f32x2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    FA_CUDA_TRY(cudaFuncSetAttribute(mel512_kernel<kWarpsPerCta, f32x2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     return FA_OK;
 }
 
@@ -722,8 +723,14 @@ int MelPlan::launch(const float *d_audio_base, float *d_out_base, int first, int
         return FA_OK;
     }
     const int grid = std::min(total_tiles, num_sms * kCtasPerSm);
-    if (precision == 1) mel512_kernel<kWarpsPerCta, f32x2><<<grid, kWarpsPerCta * 32, smem_bytes, stream>>>(P);
-    else mel512_kernel<kWarpsPerCta, double><<<grid, kWarpsPerCta * 32, smem_bytes, stream>>>(P);
+    const dim3 blk(kWarpsPerCta * 32);
+    if (precision == 1) {
+        if (layout == 0) mel512_kernel<kWarpsPerCta, f32x2, 0><<<grid, blk, smem_bytes, stream>>>(P);
+        else mel512_kernel<kWarpsPerCta, f32x2, 1><<<grid, blk, smem_bytes, stream>>>(P);
+    } else {
+        if (layout == 0) mel512_kernel<kWarpsPerCta, double, 0><<<grid, blk, smem_bytes, stream>>>(P);
+        else mel512_kernel<kWarpsPerCta, double, 1><<<grid, blk, smem_bytes, stream>>>(P);
+    }
     FA_CUDA_TRY(cudaGetLastError());
     ++launches;
     return FA_OK;

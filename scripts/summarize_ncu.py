@@ -48,7 +48,7 @@ def launches(path):
     return agg
 
 with open(f"profiles/{tag}_summary.txt", "w") as f:
-    for name in ("launches_mel.csv", "launches_cluster.csv"):
+    for name in ("launches_bench.csv", "launches_mel.csv", "launches_cluster.csv"):
         p = os.path.join("gpurun_out", name)
         if not os.path.exists(p): continue
         agg = launches(p); tot = sum(a[1] for a in agg.values())
@@ -56,7 +56,7 @@ with open(f"profiles/{tag}_summary.txt", "w") as f:
         for n, (c, t) in agg.items():
             f.write(f"  {n:58s} launches={c:4d} total={t/1e6:10.3f} ms  share={t/tot*100:5.1f}%\n")
         f.write("\n")
-    for rep in ("prof_mel.ncu-rep", "prof_ahc.ncu-rep"):
+    for rep in ("prof_mel_f32.ncu-rep", "prof_mel.ncu-rep", "prof_ahc.ncu-rep"):
         p = os.path.join("gpurun_out", rep)
         if not os.path.exists(p): continue
         hdr, units, rows = raw(p)
@@ -71,7 +71,7 @@ with open(f"profiles/{tag}_summary.txt", "w") as f:
                 rd = float(r[hdr.index("dram__bytes_read.sum")]); wr = float(r[hdr.index("dram__bytes_write.sum")])
                 f.write(f"   traffic = dram read + write = {rd + wr:.3f} {units[hdr.index('dram__bytes_read.sum')]}\n")
             except Exception: pass
-        for kr in ({"prof_mel.ncu-rep": ["mel512"], "prof_ahc.ncu-rep": ["ahc_init_nn", "ahc_merge"]}[rep]):
+        for kr in ({"prof_mel_f32.ncu-rep": ["mel512"], "prof_mel.ncu-rep": ["mel512"], "prof_ahc.ncu-rep": ["ahc_init_nn", "ahc_merge"]}[rep]):
             h = opcode_hist(p, kr)
             if not h: continue
             op, smp, tot, ts = h
