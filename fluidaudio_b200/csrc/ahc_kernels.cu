@@ -176,6 +176,160 @@ __global__ void ahc_init_reduce_kernel(const Cand *__restrict__ partial, int N, 
     nn[i] = arg;
 }
 
+// ------------------------------------------------------------------------------------------------ initial NN, filtered
+// The exact pass above evaluates all N(N-1)/2 bit-exact chains (3.6 ms at N = 10 000, FP64 pipe 76 % busy).  The filter
+// path finds the same (min, argmin) per row with far fewer chains:
+//   1. d2~(i,j) = |x_i|^2 + |x_j|^2 - 2 <x_i, x_j>, the inner product in float32 (tiled SIMT GEMM on float copies), with a
+//      RIGOROUS error bound E_ij = c1 r_i r_j + c2 (n_i + n_j): c1 = 2.02 (D + 3) 2^-24 covers the float conversion of the
+//      inputs and a D-term float32 accumulation in any order (|fl(sum) - sum| <= gamma_D sum |x y| <= gamma_D r_i r_j), c2
+//      covers the double arithmetic of the combination and the rounding of the exact chain itself;
+//   2. U_i = min_j (d2~ + E) is an upper bound of row i's true minimum; every j with d2~ - E <= U_i is a CANDIDATE (the
+//      true argmin, and every exact tie of it, always is);
+//   3. only the candidates run the reference's sequential chain (same sq_step arithmetic as the exact pass), and the
+//      lexicographic (distance, j) minimum over them is the reference's (min, first argmin).
+// Two passes over the lower-triangular 64 x 64 tiles (the float32 products are recomputed rather than stored: N^2 / 2
+// floats would be 200 MB at N = 10 000).  Non-finite or huge inputs, or a candidate list that overflows (thousands of
+// exact duplicates), fall back to the exact pass — the result is bit-identical either way.
+constexpr int kFT = 64;    // tile edge
+constexpr int kFK = 16;    // k chunk
+struct FilterBufs {
+    float *cf;                      // [D x Ns] float copy of cols
+    double *nrm2;                   // [N] |x_i|^2
+    float *rn;                      // [N] |x_i| rounded up
+    unsigned long long *U;          // [N] bits of the row's upper bound (non-negative doubles order like their bits)
+    unsigned long long *best_d;     // [N] bits of the exact minimum
+    int *best_j;                    // [N]
+    int2 *cand;                     // [cap] (i, j)
+    double *cand_d;                 // [cap]
+    int *counters;                  // [0] candidates appended, [1] bad input, [2] overflow
+    int cap;
+    double c1, c2;
+};
+
+__global__ void ahc_filter_prep_kernel(const double *__restrict__ cols, int N, int D, int Ns, FilterBufs F) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Ns) return;
+    double n = 0.0;
+    bool bad = false;
+    for (int k = 0; k < D; ++k) {
+        const double v = i < N ? cols[(size_t)k * Ns + i] : 0.0;
+        F.cf[(size_t)k * Ns + i] = (float)v;
+        n = fma(v, v, n);
+        if (!(fabs(v) <= 1e17)) bad = true;   // also NaN / Inf
+    }
+    if (i < N) {
+        F.nrm2[i] = n;
+        F.rn[i] = __fmul_ru(__double2float_ru(sqrt(n)), 1.000001f);
+        F.U[i] = ~0ull;
+        F.best_d[i] = ~0ull;
+        F.best_j[i] = INT_MAX;
+        if (bad) atomicExch(&F.counters[1], 1);
+    }
+}
+
+template <bool kCollect>
+__global__ void __launch_bounds__(256) ahc_filter_tile_kernel(int N, int D, int Ns, FilterBufs F) {
+    __shared__ __align__(16) float As[kFK][kFT], Bs[kFK][kFT];
+    // lower-triangular tile pair (ti >= tj) from the linear block index
+    const int b = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((long long)ti * (ti + 1) / 2 > b) --ti;
+    while ((long long)(ti + 1) * (ti + 2) / 2 <= b) ++ti;
+    const int tj = b - (int)((long long)ti * (ti + 1) / 2);
+    const int i0 = ti * kFT, j0 = tj * kFT;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.0f;
+    for (int k0 = 0; k0 < D; k0 += kFK) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < kFK * kFT; idx += 256) {
+            const int kk = idx / kFT, ii = idx % kFT, k = k0 + kk;
+            As[kk][ii] = (k < D && i0 + ii < Ns) ? F.cf[(size_t)k * Ns + i0 + ii] : 0.0f;
+            Bs[kk][ii] = (k < D && j0 + ii < Ns) ? F.cf[(size_t)k * Ns + j0 + ii] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kFK; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = i0 + ty * 4 + a;
+        double rowmin = 1.7976931348623157e308;
+        const double ni = i < N ? F.nrm2[i] : 0.0;
+        const double ri = i < N ? (double)F.rn[i] : 0.0;
+        const double Ui = (kCollect && i < N) ? __longlong_as_double((long long)F.U[i]) : 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = j0 + tx * 4 + c;
+            if (i < N && j < i) {
+                const double nj = F.nrm2[j];
+                const double approx = (ni + nj) - 2.0 * (double)acc[a][c];
+                const double E = F.c1 * ri * (double)F.rn[j] + F.c2 * (ni + nj);
+                if (!kCollect) {
+                    rowmin = fmin(rowmin, fmax(approx + E, 0.0));
+                } else if (approx - E <= Ui) {
+                    const int slot = atomicAdd(&F.counters[0], 1);
+                    if (slot < F.cap) F.cand[slot] = make_int2(i, j);
+                    else F.counters[2] = 1;
+                }
+            }
+        }
+        if (!kCollect) {   // the 16 threads of a row group are one half-warp: fold, one atomic per (row, tile)
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) rowmin = fmin(rowmin, __shfl_xor_sync(0xffffffffu, rowmin, o));
+            if (tx == 0 && i < N && rowmin < 1.7976931348623157e308)
+                atomicMin(&F.U[i], (unsigned long long)__double_as_longlong(rowmin));
+        }
+    }
+}
+
+// the reference's chain for every candidate; its minimum per row as an integer atomic on the distance bits
+__global__ void ahc_filter_exact_kernel(const double *__restrict__ cols, int D, int Ns, FilterBufs F) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int count = min(F.counters[0], F.cap);
+    if (slot >= count) return;
+    const int2 c = F.cand[slot];
+    double sum = 0.0;
+    for (int k = 0; k < D; ++k) sum = sq_step(sum, cols[(size_t)k * Ns + c.x], cols[(size_t)k * Ns + c.y]);
+    F.cand_d[slot] = sum;
+    if (sum != sum) F.counters[1] = 1;
+    else atomicMin(&F.best_d[c.x], (unsigned long long)__double_as_longlong(sum));
+}
+__global__ void ahc_filter_argmin_kernel(FilterBufs F) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int count = min(F.counters[0], F.cap);
+    if (slot >= count) return;
+    const int2 c = F.cand[slot];
+    if ((unsigned long long)__double_as_longlong(F.cand_d[slot]) == F.best_d[c.x]) atomicMin(&F.best_j[c.x], c.y);
+}
+__global__ void ahc_filter_finish_kernel(int N, FilterBufs F, double *key, int *nn, int *node_weight) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    node_weight[i] = 1;
+    if (i < 1) {
+        key[0] = INFINITY;
+        nn[0] = 0;
+        return;
+    }
+    if (F.best_j[i] == INT_MAX) {   // cannot happen with a valid bound: force the exact fall-back
+        F.counters[2] = 1;
+        return;
+    }
+    key[i] = __longlong_as_double((long long)F.best_d[i]);
+    nn[i] = F.best_j[i];
+}
+
 // ------------------------------------------------------------------------------------------------ merge loop
 constexpr int kMergeThreads = 128;
 constexpr int kMaxRounds = 16;    // streamed mode only: slots per thread
@@ -874,7 +1028,8 @@ struct Carver {
 struct Layout {
     size_t rows, cols, node_weight, key, nn, heap_at, heap_where, node_of, slot_of, live_bits, merge_a, merge_b, merge_d,
         cmd, threshold, results, error, trace, init_partial, problem, total;
-    int ranges;
+    size_t f_cf, f_nrm2, f_rn, f_U, f_best_d, f_best_j, f_cand, f_cand_d, f_counters;
+    int ranges, filter_cap;
 };
 Layout make_layout(int N, int D, int Ns, int workers) {
     Layout L{};
@@ -900,6 +1055,17 @@ Layout make_layout(int N, int D, int Ns, int workers) {
     L.ranges = (N + kJR - 1) / kJR;
     L.init_partial = c.take<Cand>((size_t)L.ranges * N);
     L.problem = c.take<Problem>(1);
+    // float32 filter of the initial nearest-neighbour pass (N >= kFilterMinN only, but sized unconditionally: small)
+    L.filter_cap = (int)std::min<long long>(64LL * N, 1 << 24);
+    L.f_cf = c.take<float>((size_t)D * Ns);
+    L.f_nrm2 = c.take<double>((size_t)N);
+    L.f_rn = c.take<float>((size_t)N);
+    L.f_U = c.take<unsigned long long>((size_t)N);
+    L.f_best_d = c.take<unsigned long long>((size_t)N);
+    L.f_best_j = c.take<int>((size_t)N);
+    L.f_cand = c.take<int2>((size_t)L.filter_cap);
+    L.f_cand_d = c.take<double>((size_t)L.filter_cap);
+    L.f_counters = c.take<int>(64);
     L.total = (c.off + 255) & ~size_t(255);
     return L;
 }
@@ -950,6 +1116,7 @@ int Solver::ensure_pool(int N, int D) {
 struct Hooks {
     bool force_global = false, force_stream = false;
     int slot_shift = 3, flags = 0;
+    int filter_min_n = 2048;   // FA_AHC_FILTER_MIN_N: problems at least this large take the float32 filter (0 = never)
 };
 static const Hooks &hooks() {
     static const Hooks h = [] {
@@ -960,6 +1127,7 @@ static const Hooks &hooks() {
         x.force_stream = s && s[0] == '1';
         if (sh) x.slot_shift = std::min(3, std::max(0, std::atoi(sh)));
         if (f) x.flags = std::atoi(f);
+        if (const char *m = std::getenv("FA_AHC_FILTER_MIN_N")) x.filter_min_n = std::atoi(m);
         return x;
     }();
     return h;
@@ -1074,13 +1242,55 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
         dim3 grid((Ns + 31) / 32, (D + 31) / 32), block(32, 8);
         ahc_stage_kernel<<<grid, block, 0, stream>>>(d_rows, P.rows, P.cols, N, D, Ns);
         FA_CUDA_TRY(cudaGetLastError());
+        launches += 1;
+    }
+    auto exact_init = [&]() -> int {
         dim3 g2((N + kTI - 1) / kTI, L.ranges);
         ahc_init_nn_kernel<<<g2, kTI, 0, stream>>>(P.cols, N, D, Ns, init_partial, P.error);
         FA_CUDA_TRY(cudaGetLastError());
         ahc_init_reduce_kernel<<<(N + 127) / 128, 128, 0, stream>>>(init_partial, N, L.ranges, P.key, P.nn,
                                                                      P.node_weight);
         FA_CUDA_TRY(cudaGetLastError());
-        launches += 3;
+        launches += 2;
+        return FA_OK;
+    };
+    const bool use_filter = hk.filter_min_n > 0 && N >= hk.filter_min_n;
+    int *h_fc = h_err + 1;   // [3] filter counters (pinned)
+    if (use_filter) {
+        FilterBufs F{};
+        F.cf = reinterpret_cast<float *>(base + L.f_cf);
+        F.nrm2 = reinterpret_cast<double *>(base + L.f_nrm2);
+        F.rn = reinterpret_cast<float *>(base + L.f_rn);
+        F.U = reinterpret_cast<unsigned long long *>(base + L.f_U);
+        F.best_d = reinterpret_cast<unsigned long long *>(base + L.f_best_d);
+        F.best_j = reinterpret_cast<int *>(base + L.f_best_j);
+        F.cand = reinterpret_cast<int2 *>(base + L.f_cand);
+        F.cand_d = reinterpret_cast<double *>(base + L.f_cand_d);
+        F.counters = reinterpret_cast<int *>(base + L.f_counters);
+        F.cap = L.filter_cap;
+        F.c1 = 2.02 * (double)(D + 3) * 5.9604644775390625e-08;   // 2^-24
+        F.c2 = 2e-12;
+        FA_CUDA_TRY(cudaMemsetAsync(F.counters, 0, 64 * sizeof(int), stream));
+        ahc_filter_prep_kernel<<<(Ns + 127) / 128, 128, 0, stream>>>(P.cols, N, D, Ns, F);
+        const int nt = (N + kFT - 1) / kFT;
+        const unsigned tiles = (unsigned)((long long)nt * (nt + 1) / 2);
+        ahc_filter_tile_kernel<false><<<tiles, 256, 0, stream>>>(N, D, Ns, F);
+        ahc_filter_tile_kernel<true><<<tiles, 256, 0, stream>>>(N, D, Ns, F);
+        const unsigned cgrid = (unsigned)((F.cap + 255) / 256);
+        ahc_filter_exact_kernel<<<cgrid, 256, 0, stream>>>(P.cols, D, Ns, F);
+        ahc_filter_argmin_kernel<<<cgrid, 256, 0, stream>>>(F);
+        ahc_filter_finish_kernel<<<(N + 127) / 128, 128, 0, stream>>>(N, F, P.key, P.nn, P.node_weight);
+        FA_CUDA_TRY(cudaGetLastError());
+        launches += 6;
+        FA_CUDA_TRY(cudaMemcpyAsync(h_fc, F.counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        FA_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (h_fc[1] || h_fc[2]) {   // non-finite / huge input, or more candidates than the list holds: the exact pass decides
+            const int st2 = exact_init();
+            if (st2 != FA_OK) return st2;
+        }
+    } else {
+        const int st2 = exact_init();
+        if (st2 != FA_OK) return st2;
     }
     FA_CUDA_TRY(cudaEventRecord(ev[1], stream));
     FA_CUDA_TRY(cudaMemcpyAsync(h_key, P.key, sizeof(double) * N, cudaMemcpyDeviceToHost, stream));

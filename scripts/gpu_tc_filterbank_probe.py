@@ -47,13 +47,20 @@ torch.backends.cuda.matmul.allow_tf32 = True
 rows.append(("TF32 tensor GEMM x1", timeit(lambda: power @ fb), (torch.log(power @ fb + 2.0 ** -24) - ref).abs().max().item()))
 torch.backends.cuda.matmul.allow_tf32 = False
 ph, pm, pl = split3(power); fh, fm, fl = split3(fb)
+# torch returns bf16 from a bf16 matmul (the fp32 accumulator is rounded on the way out): TIMES come from the real bf16
+# GEMMs, ACCURACY from float32 GEMMs of the same bf16-rounded operands (products exact, fp32 accumulate — what a tcgen05
+# kind::f16 MMA with an fp32 accumulator in TMEM delivers)
 one = lambda: (ph @ fh).float()
-rows.append(("bf16 tensor GEMM x1", timeit(one), (torch.log(one() + 2.0 ** -24) - ref).abs().max().item()))
+one_acc = lambda: ph.float() @ fh.float()
+rows.append(("bf16 tensor GEMM x1", timeit(one), (torch.log(one_acc() + 2.0 ** -24) - ref).abs().max().item()))
 def six():
     acc = (ph @ fh).float(); acc += (ph @ fm).float(); acc += (pm @ fh).float()
     acc += (ph @ fl).float(); acc += (pl @ fh).float(); acc += (pm @ fm).float()
     return acc
-rows.append(("bf16x3 tensor GEMM x6 (operands pre-split)", timeit(six), (torch.log(six() + 2.0 ** -24) - ref).abs().max().item()))
+def six_acc():
+    P = [x.float() for x in (ph, pm, pl)]; F = [x.float() for x in (fh, fm, fl)]
+    return P[0] @ F[0] + P[0] @ F[1] + P[1] @ F[0] + P[0] @ F[2] + P[2] @ F[0] + P[1] @ F[1]
+rows.append(("bf16x3 tensor GEMM x6 (operands pre-split)", timeit(six), (torch.log(six_acc() + 2.0 ** -24) - ref).abs().max().item()))
 rows.append(("  + splitting the power tile into 3 bf16 planes (elementwise)", timeit(lambda: split3(power)), float("nan")))
 print(f"dense filterbank product on tensor cores, T={T}, K={KP} (257 bins), N={NM}; ms per audio-hour, max |d log-mel| vs float64")
 for name, ms, err in rows:

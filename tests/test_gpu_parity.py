@@ -443,6 +443,32 @@ def test_linkage_fallback_placements_are_bit_exact(gpu_lib, oracle):
         assert "FALLBACK_OK" in out.stdout, (env, out.stdout[-500:], out.stderr[-1500:])
 
 
+def test_linkage_float32_filter_is_bit_exact(gpu_lib, golden_dir, oracle):
+    """The float32 GEMM-form filter of the initial nearest-neighbour pass (ahc_filter_*_kernel: rigorous error bound,
+    exact chains only for candidates) forced on at every size (FA_AHC_FILTER_MIN_N=2): the reference's goldens — exact
+    ties on a lattice, duplicates, a line — and fresh inputs incl. zero vectors, huge and non-finite values (which must
+    fall back to the exact pass and keep the reference's status codes) stay bit-identical."""
+    code = (
+        "import sys, os, numpy as np; sys.path.insert(0, %r);"
+        "from fluidaudio_b200 import clustering as cl; from oracle import oracle as O;"
+        "g = np.load(os.path.join(%r, 'ahc_reference.npz')); ok = True\n"
+        "for k in [k[:-3] for k in g.files if k.endswith('__x')]:\n"
+        "    st, z = cl.centroid_linkage(g[k + '__x']); ok = ok and st == 0 and np.array_equal(z, g[k + '__z'])\n"
+        "rng = np.random.default_rng(9)\n"
+        "cases = [rng.standard_normal((700, 64)), np.repeat(rng.standard_normal((40, 8)), 30, axis=0), rng.standard_normal((513, 256)) * 1e-9,"
+        " np.concatenate([np.zeros((5, 16)), rng.standard_normal((300, 16))]), rng.standard_normal((200, 16)) * 1e30]\n"
+        "from fluidaudio_b200 import synth\n"
+        "e, _ = synth.speaker_embeddings(3000, 256, 4, seed=2); cases.append(O.l2_normalize_rows(e.astype(np.float64)))\n"
+        "for x in cases:\n"
+        "    st, z = cl.centroid_linkage(x); st2, z2 = O.centroid_linkage(x, use_ref=O.ref_available()); ok = ok and st == st2 and np.array_equal(z, z2)\n"
+        "bad = rng.standard_normal((100, 8)); bad[50, 3] = np.nan\n"
+        "ok = ok and cl.centroid_linkage(bad)[0] == O.centroid_linkage(bad, use_ref=O.ref_available())[0] == 5\n"
+        "print('FILTER_OK' if ok else 'FILTER_BAD')" % (ROOT, golden_dir))
+    for env in ({"FA_AHC_FILTER_MIN_N": "2"}, {"FA_AHC_FILTER_MIN_N": "0"}):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+        assert "FILTER_OK" in out.stdout, (env, out.stdout[-500:], out.stderr[-1500:])
+
+
 def test_linkage_is_reentrant(gpu_lib, oracle):
     rng = np.random.default_rng(4)
     xs = [rng.standard_normal((400 + 50 * i, 32)) for i in range(6)]
