@@ -308,7 +308,10 @@ __global__ void vbx_finish_kernel(Dev d, int iteration) {
 constexpr int kSG = 8;   // speakers per register group
 
 // partial sums of one frame block from the gamma rows in shared memory: fG[b][s], fA[b][s][k]
-__device__ __forceinline__ void vbx_block_partials(const Dev &d, const double *g_s, int t0, int rows, int b) {
+// tile: optional shared-memory copy of the block's rho, k-major with stride kEThreads + 1 (tile[k * (kEThreads + 1) + r]);
+// nullptr = read rho from global memory
+__device__ __forceinline__ void vbx_block_partials(const Dev &d, const double *g_s, int t0, int rows, int b,
+                                                   const double *tile = nullptr) {
     const int S = d.S, D = d.D, tid = threadIdx.x;
     for (int s = tid; s < S; s += kEThreads) {
         double acc = 0.0;
@@ -322,7 +325,7 @@ __device__ __forceinline__ void vbx_block_partials(const Dev &d, const double *g
 #pragma unroll
             for (int q = 0; q < kSG; ++q) acc[q] = 0.0;
             for (int r = 0; r < rows; ++r) {
-                const double x = rk[(size_t)r * D];
+                const double x = tile ? tile[k * (kEThreads + 1) + r] : rk[(size_t)r * D];
                 const double *g = g_s + r * S + s0;
 #pragma unroll
                 for (int q = 0; q < kSG; ++q)
@@ -353,23 +356,34 @@ __global__ void __launch_bounds__(kEThreads) vbx_update_kernel2(Dev d, int it, i
     __shared__ int done_sh;
     const int S = d.S, D = d.D, tid = threadIdx.x, s = blockIdx.x, nb = d.eblocks;
     const int prev = (it + 1) & 1, cur = it & 1;
-    // column sums of gamma_it per speaker, blocks ascending (every CTA folds all S columns: S * nb loads)
-    for (int c = tid; c < S; c += kEThreads) {
-        double v = 0.0;
-#pragma unroll 8
-        for (int b = 0; b < nb; ++b) v += d.fG[(size_t)b * S + c];
-        pi_sh[c] = v;
-    }
+    // column sums of gamma_it per speaker and the log-likelihood, frame blocks ascending.  The per-block partials are
+    // first staged in shared memory by ALL threads (coalesced, one latency), then summed in block order from there:
+    // the same fixed order as a sequential fold, without 79 dependent global loads per speaker on one thread.
+    __shared__ double stage[64 * (kFusedMaxS + 1)];
+    for (int c = tid; c < S; c += kEThreads) pi_sh[c] = 0.0;
+    double ll = 0.0;   // thread 0 only
     if (tid == 0) done_sh = 0;
+    for (int b0 = 0; b0 < nb; b0 += 64) {
+        const int cnt = min(64, nb - b0);
+        __syncthreads();
+        for (int i = tid; i < cnt * S; i += kEThreads) stage[i] = d.fG[(size_t)b0 * S + i];
+        if (it > 0)
+            for (int i = tid; i < cnt; i += kEThreads) stage[64 * S + i] = d.fLL[b0 + i];
+        __syncthreads();
+        for (int c = tid; c < S; c += kEThreads) {
+            double v = pi_sh[c];
+            for (int b = 0; b < cnt; ++b) v += stage[b * S + c];
+            pi_sh[c] = v;
+        }
+        if (tid == 0 && it > 0)
+            for (int b = 0; b < cnt; ++b) ll += stage[64 * S + b];
+    }
     __syncthreads();
     if (tid == 0) {
         double ps = 0.0;
         for (int c = 0; c < S; ++c) ps += pi_sh[c];
         scal[0] = ps;
         if (it > 0) {   // ELBO_{it-1} (:623-647) and the convergence test (:653-659)
-            double ll = 0.0;
-#pragma unroll 8
-            for (int b = 0; b < nb; ++b) ll += d.fLL[b];
             double x0 = 0.0, x1 = 0.0, x2 = 0.0;
             for (int c = 0; c < S; ++c) {
                 x0 += d.fsums[prev][3 * c];
@@ -400,7 +414,7 @@ __global__ void __launch_bounds__(kEThreads) vbx_update_kernel2(Dev d, int it, i
     double p_part = 0.0, l_part = 0.0, i_part = 0.0, a_part = 0.0;
     for (int k = tid; k < D; k += kEThreads) {
         double acc = 0.0;
-#pragma unroll 8
+#pragma unroll 16
         for (int b = 0; b < nb; ++b) acc += d.fA[((size_t)b * S + s) * D + k];
         const double il = 1.0 / fmax(1.0 + (ratio * Ns) * d.phi_c[k], 1e-12);
         const double al = (acc * il) * ratio;
@@ -410,18 +424,20 @@ __global__ void __launch_bounds__(kEThreads) vbx_update_kernel2(Dev d, int it, i
         i_part += il;
         a_part += al * al;
     }
-    // four block sums in thread order (fixed)
-    double *outs[4] = {&scal[0], &scal[1], &scal[2], &scal[3]};
-    const double parts[4] = {p_part, l_part, i_part, a_part};
+    // four block sums: a fixed shuffle tree inside each warp, then the warps' partials in warp order
+    double parts[4] = {p_part, l_part, i_part, a_part};
+    __syncthreads();   // every thread has read scal[0] (ps)
+#pragma unroll
     for (int q = 0; q < 4; ++q) {
-        __syncthreads();
-        red[tid] = parts[q];
-        __syncthreads();
-        if (tid == 0) {
-            double acc = 0.0;
-            for (int i = 0; i < kEThreads; ++i) acc += red[i];
-            *outs[q] = acc;
-        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) parts[q] += __shfl_xor_sync(0xffffffffu, parts[q], o);
+        if ((tid & 31) == 0) red[q * (kEThreads / 32) + (tid >> 5)] = parts[q];
+    }
+    __syncthreads();
+    if (tid < 4) {
+        double acc = 0.0;
+        for (int w = 0; w < kEThreads / 32; ++w) acc += red[tid * (kEThreads / 32) + w];
+        scal[tid] = acc;
     }
     __syncthreads();
     if (tid == 0) {
@@ -433,7 +449,9 @@ __global__ void __launch_bounds__(kEThreads) vbx_update_kernel2(Dev d, int it, i
     }
 }
 
-__global__ void __launch_bounds__(kEThreads) vbx_estep_kernel2(Dev d) {
+// use_tile: the block's rho [D x 128 frames] is staged in shared memory once (coalesced, every load in flight at once) and
+// feeds both the E-step and the partial sums: the per-thread chains then wait on shared memory, not on L2.
+__global__ void __launch_bounds__(kEThreads) vbx_estep_kernel2(Dev d, int use_tile) {
     if (d.state[0]) return;
     extern __shared__ double sm[];
     const int S = d.S, D = d.D, tid = threadIdx.x, b = blockIdx.x;
@@ -442,6 +460,14 @@ __global__ void __launch_bounds__(kEThreads) vbx_estep_kernel2(Dev d) {
     double *lpi_s = off_s + S;               // [S]
     double *g_s = lpi_s + S;                 // [kEThreads x S] this block's new gamma rows
     double *red = g_s + (size_t)kEThreads * S;   // [kEThreads]
+    double *tile = use_tile ? red + kEThreads : nullptr;   // [D x (kEThreads + 1)]
+    if (use_tile) {
+        const int t0 = b * kEThreads;
+        for (int i = tid; i < D * kEThreads; i += kEThreads) {
+            const int k = i / kEThreads, r = i - k * kEThreads;
+            tile[k * (kEThreads + 1) + r] = (t0 + r < d.T) ? d.rhoT[(size_t)k * d.Tp + t0 + r] : 0.0;
+        }
+    }
     for (int o = tid; o < S * D; o += kEThreads) a_s[o] = d.alpha[o];
     for (int c = tid; c < S; c += kEThreads) {
         off_s[c] = d.phiTerm[c] * -0.5;
@@ -460,7 +486,7 @@ __global__ void __launch_bounds__(kEThreads) vbx_estep_kernel2(Dev d) {
 #pragma unroll
             for (int q = 0; q < kSG; ++q) acc[q] = 0.0;
             for (int k = 0; k < D; ++k) {
-                const double x = xr[(size_t)k * d.Tp];
+                const double x = tile ? tile[k * (kEThreads + 1) + tid] : xr[(size_t)k * d.Tp];
 #pragma unroll
                 for (int q = 0; q < kSG; ++q)
                     if (s0 + q < S) acc[q] += x * a_s[(size_t)(s0 + q) * D + k];
@@ -497,7 +523,7 @@ __global__ void __launch_bounds__(kEThreads) vbx_estep_kernel2(Dev d) {
         for (int i = 0; i < kEThreads; ++i) acc += red[i];
         d.fLL[b] = acc;
     }
-    vbx_block_partials(d, g_s, t0, rows, b);
+    vbx_block_partials(d, g_s, t0, rows, b, tile);
 }
 
 // first maximum wins (VBxClustering.swift:144-146)
@@ -573,48 +599,62 @@ __global__ void centroid_finish_kernel(const double *__restrict__ pnum, const do
 
 // ---- centroids, parallel path (S <= kFusedMaxS): the same sums over kFChunks chunks, thread per (s, k) and chunk; the
 // fold over chunks and the division run thread-per-output on many CTAs, the normalisation thread-per-centroid.
+// per block of kCBlock frames: num[b][s][k] = sum_t (gamma > 0) gamma[t][s] e[t][k] (thread per dimension k, eight speakers
+// at a time in registers: one embedding load feeds eight predicated FMAs), den[b][s] = sum_t gamma   (:642-674)
+constexpr int kCBlock = 128;
 __global__ void __launch_bounds__(256) centroid_acc16_kernel(const double *__restrict__ emb, const double *__restrict__ gamma,
                                                              int T, int E, int S, double *__restrict__ pnum,
                                                              double *__restrict__ pden) {
-    const int c = blockIdx.y;
-    const int per = (T + kFChunks - 1) / kFChunks;
-    const int t0 = c * per, t1 = min(T, t0 + per);
-    const int SE = S * E, o = blockIdx.x * 256 + threadIdx.x;
-    if (o < SE) {
-        const int s = o / E, k = o - s * E;
+    extern __shared__ double g_s[];   // [kCBlock x S] this block's gamma rows
+    const int b = blockIdx.x, t0 = b * kCBlock, rows = min(kCBlock, T - t0);
+    for (int i = threadIdx.x; i < rows * S; i += 256) g_s[i] = gamma[(size_t)t0 * S + i];
+    __syncthreads();
+    for (int s = threadIdx.x; s < S; s += 256) {
         double acc = 0.0;
-        for (int t = t0; t < t1; ++t) {
-            const double w = gamma[(size_t)t * S + s];
-            if (w > 0.0) acc += w * emb[(size_t)t * E + k];
-        }
-        pnum[(size_t)c * SE + o] = acc;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < S) {
-        const int s = threadIdx.x;
-        double acc = 0.0;
-        for (int t = t0; t < t1; ++t) {
-            const double w = gamma[(size_t)t * S + s];
+        for (int r = 0; r < rows; ++r) {
+            const double w = g_s[r * S + s];
             if (w > 0.0) acc += w;
         }
-        pden[(size_t)c * S + s] = acc;
+        pden[(size_t)b * S + s] = acc;
+    }
+    for (int k = threadIdx.x; k < E; k += 256) {
+        const double *ek = emb + (size_t)t0 * E + k;
+        for (int s0 = 0; s0 < S; s0 += kSG) {
+            double acc[kSG];
+#pragma unroll
+            for (int q = 0; q < kSG; ++q) acc[q] = 0.0;
+            for (int r = 0; r < rows; ++r) {
+                const double x = ek[(size_t)r * E];
+                const double *g = g_s + r * S + s0;
+#pragma unroll
+                for (int q = 0; q < kSG; ++q)
+                    if (s0 + q < S) {
+                        const double w = g[q];
+                        if (w > 0.0) acc[q] += w * x;
+                    }
+            }
+#pragma unroll
+            for (int q = 0; q < kSG; ++q)
+                if (s0 + q < S) pnum[((size_t)b * S + s0 + q) * E + k] = acc[q];
+        }
     }
 }
 __global__ void __launch_bounds__(256) centroid_fold_kernel(const double *__restrict__ pnum, const double *__restrict__ pden,
-                                                            const double *__restrict__ pi, int E, int S,
+                                                            const double *__restrict__ pi, int E, int S, int blocks,
                                                             double *__restrict__ cent) {
     const int o = blockIdx.x * 256 + threadIdx.x;
     if (o >= S * E) return;
-    const int s = o / E, k = o - s * E;
+    const int s = o / E;
     if (!(pi[s] > 1e-7)) return;
     int slot = 0;
     for (int j = 0; j < s; ++j) slot += pi[j] > 1e-7 ? 1 : 0;
     double num = 0.0, den = 0.0;
-#pragma unroll
-    for (int c = 0; c < kFChunks; ++c) {
-        num += pnum[(size_t)c * S * E + o];
-        den += pden[(size_t)c * S + s];
+#pragma unroll 8
+    for (int b = 0; b < blocks; ++b) {   // blocks ascending
+        num += pnum[(size_t)b * S * E + o];
+        den += pden[(size_t)b * S + s];
     }
-    cent[(size_t)slot * E + k] = den > 0.0 ? num / den : 0.0;
+    cent[(size_t)slot * E + (o - s * E)] = den > 0.0 ? num / den : 0.0;
 }
 __global__ void centroid_norm_kernel(const double *__restrict__ pi, int E, int S, const double *__restrict__ cent,
                                      double *__restrict__ cent_n, int *__restrict__ count) {
@@ -863,12 +903,14 @@ int refine_device(Workspace &ws, const double *d_x, int T, int D, const double *
                 attr_err_f = cudaFuncSetAttribute(vbx_partials0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         });
         FA_CUDA_TRY(attr_err_f);
-        const size_t fsmem = fused_smem_bytes(S, D);
+        const size_t tile_bytes = sizeof(double) * (size_t)D * (kEThreads + 1);
+        const bool use_tile = fused_smem_bytes(S, D) + tile_bytes <= 200 * 1024;
+        const size_t fsmem = fused_smem_bytes(S, D) + (use_tile ? tile_bytes : 0);
         vbx_partials0_kernel<<<d.eblocks, kEThreads, sizeof(double) * (size_t)kEThreads * S, stream>>>(d);
         ++n_launch;
         for (int it = 0; it < max_it; ++it) {
             vbx_update_kernel2<<<S, kEThreads, 0, stream>>>(d, it, 0);
-            vbx_estep_kernel2<<<d.eblocks, kEThreads, fsmem, stream>>>(d);
+            vbx_estep_kernel2<<<d.eblocks, kEThreads, fsmem, stream>>>(d, use_tile ? 1 : 0);
             n_launch += 2;
         }
         if (max_it > 0) {
@@ -920,23 +962,31 @@ int refine_device(Workspace &ws, const double *d_x, int T, int D, const double *
     return FA_OK;
 }
 
-size_t centroid_bytes(int E, int S) {
-    return ((size_t)chunks_for(S) * S * E + (size_t)chunks_for(S) * S) * sizeof(double) + (size_t)S * sizeof(int) + 2048;
+size_t centroid_bytes(int T, int E, int S) {
+    const size_t parts = S <= kFusedMaxS ? (size_t)((T + kCBlock - 1) / kCBlock) : (size_t)chunks_for(S);
+    return (parts * S * E + parts * S) * sizeof(double) + (size_t)S * sizeof(int) + 2048;
 }
 
 int centroids_device(Workspace &ws, const double *d_emb, int T, int E, const double *d_gamma, const double *d_pi, int S,
                      double *d_cent, double *d_cent_n, int *d_count, cudaStream_t stream, long long *launches) {
-    const int chunks = chunks_for(S);
-    int st = ws.reserve(centroid_bytes(E, S));
+    const int chunks = S <= kFusedMaxS ? (T + kCBlock - 1) / kCBlock : chunks_for(S);
+    int st = ws.reserve(centroid_bytes(T, E, S));
     if (st != FA_OK) return st;
     Carver c{static_cast<char *>(ws.pool)};
     double *pnum = c.take<double>((size_t)chunks * S * E);
     double *pden = c.take<double>((size_t)chunks * S);
     int *map = c.take<int>(S);
-    if (S <= kFusedMaxS) {   // kFChunks <= chunks: the same buffers hold the smaller partial arrays
+    if (S <= kFusedMaxS) {
+        static std::once_flag once_c;
+        static cudaError_t attr_err_c = cudaSuccess;
+        std::call_once(once_c, [&]() {
+            attr_err_c = cudaFuncSetAttribute(centroid_acc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(sizeof(double) * kCBlock * kFusedMaxS));
+        });
+        FA_CUDA_TRY(attr_err_c);
         const unsigned tiles = (unsigned)((S * E + 255) / 256);
-        centroid_acc16_kernel<<<dim3(tiles, kFChunks), 256, 0, stream>>>(d_emb, d_gamma, T, E, S, pnum, pden);
-        centroid_fold_kernel<<<tiles, 256, 0, stream>>>(pnum, pden, d_pi, E, S, d_cent);
+        centroid_acc16_kernel<<<chunks, 256, sizeof(double) * (size_t)kCBlock * S, stream>>>(d_emb, d_gamma, T, E, S, pnum, pden);
+        centroid_fold_kernel<<<tiles, 256, 0, stream>>>(pnum, pden, d_pi, E, S, chunks, d_cent);
         centroid_norm_kernel<<<1, 64, 0, stream>>>(d_pi, E, S, d_cent, d_cent_n, d_count);
         FA_CUDA_TRY(cudaGetLastError());
         if (launches) *launches += 3;
