@@ -202,6 +202,8 @@ struct FilterBufs {
     int2 *cand;                     // [cap] (i, j)
     double *cand_d;                 // [cap]
     int *counters;                  // [0] candidates appended, [1] bad input, [2] overflow
+    float *tmin;                    // [N x NT] per (row, column tile): min_j (d2~ - E) rounded down, or nullptr (not kept)
+    int nt;                         // column tiles per row
     int cap;
     double c1, c2;
 };
@@ -238,6 +240,14 @@ __global__ void __launch_bounds__(256) ahc_filter_tile_kernel(int N, int D, int 
     const int tj = b - (int)((long long)ti * (ti + 1) / 2);
     const int i0 = ti * kFT, j0 = tj * kFT;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    if (kCollect && F.tmin) {   // skip tiles in which no row can have a candidate (almost all of them)
+        int any = 0;
+        if (threadIdx.x < kFT) {
+            const int i = i0 + threadIdx.x;
+            if (i < N && i > j0) any = (double)F.tmin[(size_t)i * F.nt + tj] <= __longlong_as_double((long long)F.U[i]);
+        }
+        if (!__syncthreads_or(any)) return;
+    }
     float acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -265,7 +275,7 @@ __global__ void __launch_bounds__(256) ahc_filter_tile_kernel(int N, int D, int 
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int i = i0 + ty * 4 + a;
-        double rowmin = 1.7976931348623157e308;
+        double rowmin = 1.7976931348623157e308, rowlo = 1.7976931348623157e308;
         const double ni = i < N ? F.nrm2[i] : 0.0;
         const double ri = i < N ? (double)F.rn[i] : 0.0;
         const double Ui = (kCollect && i < N) ? __longlong_as_double((long long)F.U[i]) : 0.0;
@@ -278,6 +288,7 @@ __global__ void __launch_bounds__(256) ahc_filter_tile_kernel(int N, int D, int 
                 const double E = F.c1 * ri * (double)F.rn[j] + F.c2 * (ni + nj);
                 if (!kCollect) {
                     rowmin = fmin(rowmin, fmax(approx + E, 0.0));
+                    rowlo = fmin(rowlo, approx - E);
                 } else if (approx - E <= Ui) {
                     const int slot = atomicAdd(&F.counters[0], 1);
                     if (slot < F.cap) F.cand[slot] = make_int2(i, j);
@@ -287,9 +298,15 @@ __global__ void __launch_bounds__(256) ahc_filter_tile_kernel(int N, int D, int 
         }
         if (!kCollect) {   // the 16 threads of a row group are one half-warp: fold, one atomic per (row, tile)
 #pragma unroll
-            for (int o = 8; o >= 1; o >>= 1) rowmin = fmin(rowmin, __shfl_xor_sync(0xffffffffu, rowmin, o));
-            if (tx == 0 && i < N && rowmin < 1.7976931348623157e308)
-                atomicMin(&F.U[i], (unsigned long long)__double_as_longlong(rowmin));
+            for (int o = 8; o >= 1; o >>= 1) {
+                rowmin = fmin(rowmin, __shfl_xor_sync(0xffffffffu, rowmin, o));
+                rowlo = fmin(rowlo, __shfl_xor_sync(0xffffffffu, rowlo, o));
+            }
+            if (tx == 0 && i < N) {
+                if (rowmin < 1.7976931348623157e308) atomicMin(&F.U[i], (unsigned long long)__double_as_longlong(rowmin));
+                // what pass 2 needs to know about this (row, tile): can any pair in it be a candidate?
+                if (F.tmin) F.tmin[(size_t)i * F.nt + tj] = rowlo < 1.7976931348623157e308 ? __double2float_rd(rowlo) : 3.0e38f;
+            }
         }
     }
 }
@@ -1028,7 +1045,8 @@ struct Carver {
 struct Layout {
     size_t rows, cols, node_weight, key, nn, heap_at, heap_where, node_of, slot_of, live_bits, merge_a, merge_b, merge_d,
         cmd, threshold, results, error, trace, init_partial, problem, total;
-    size_t f_cf, f_nrm2, f_rn, f_U, f_best_d, f_best_j, f_cand, f_cand_d, f_counters;
+    size_t f_cf, f_nrm2, f_rn, f_U, f_best_d, f_best_j, f_cand, f_cand_d, f_counters, f_tmin;
+    bool f_keep_tmin;
     int ranges, filter_cap;
 };
 Layout make_layout(int N, int D, int Ns, int workers) {
@@ -1066,6 +1084,11 @@ Layout make_layout(int N, int D, int Ns, int workers) {
     L.f_cand = c.take<int2>((size_t)L.filter_cap);
     L.f_cand_d = c.take<double>((size_t)L.filter_cap);
     L.f_counters = c.take<int>(64);
+    {
+        const long long nt = (N + 63) / 64;
+        L.f_keep_tmin = (long long)N * nt <= (16LL << 20);   // <= 64 MB
+        L.f_tmin = c.take<float>(L.f_keep_tmin ? (size_t)((long long)N * nt) : 1);
+    }
     L.total = (c.off + 255) & ~size_t(255);
     return L;
 }
@@ -1268,6 +1291,8 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
         F.cand_d = reinterpret_cast<double *>(base + L.f_cand_d);
         F.counters = reinterpret_cast<int *>(base + L.f_counters);
         F.cap = L.filter_cap;
+        F.nt = (N + kFT - 1) / kFT;
+        F.tmin = L.f_keep_tmin ? reinterpret_cast<float *>(base + L.f_tmin) : nullptr;
         F.c1 = 2.02 * (double)(D + 3) * 5.9604644775390625e-08;   // 2^-24
         F.c2 = 2e-12;
         FA_CUDA_TRY(cudaMemsetAsync(F.counters, 0, 64 * sizeof(int), stream));
