@@ -903,8 +903,15 @@ FA_API fa_status fa_audio_to_mel(fa_mel *mel, const void *pcm, int64_t frames, c
     }
     long long ml = 0, nf = 0, rs = 0;
     const long long before = h->plan.launches;
-    const int st = h->plan.compute_host_pcm(pcm, (long long)frames, to_format(fmt), last, mode, layout, out,
-                                            (long long)out_len, &ml, &nf, &rs);
+    const resample::AudioFormat f = to_format(fmt);
+    int st;
+    if (resample::is_identity(f)) {   // mono float32 at the model rate: AudioConverter returns the samples as they are (:66-68)
+        rs = frames;
+        st = h->plan.compute_host(static_cast<const float *>(pcm), (long long)frames, last, mode, -1, layout, out,
+                                  (long long)out_len, &ml, &nf);
+    } else {
+        st = h->plan.compute_host_pcm(pcm, (long long)frames, f, last, mode, layout, out, (long long)out_len, &ml, &nf, &rs);
+    }
     g_launches += h->plan.launches - before;
     if (mel_length) *mel_length = ml;
     if (num_frames) *num_frames = nf;
