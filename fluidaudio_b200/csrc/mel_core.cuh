@@ -57,7 +57,11 @@ constexpr int kHalf = 256;
 constexpr int kBins = 257;
 constexpr int kFftPad = 304;      // complex values per warp buffer (max layout extent 296 + Z[0] mirror at 288)
 constexpr int kTileFrames = 16;   // frames per CTA tile; the mel stage maps 32 / kTileFrames mel bins onto one warp
-constexpr int kPowStride = 260;   // rows 16-byte aligned; stride = 4 (mod 32) floats: 8 lanes x 16 B of one bin quad hit distinct banks
+// Power tile: one row per frame PAIR, the two frames' values of a bin side by side: row[2 * bin + slot], slot = frame & 1.
+// The float32-pair transform stores both frames of a bin with ONE 64-bit store, and the filterbank stage runs two frames
+// per lane on packed FFMA2 with the weight as a broadcast scalar.  Row stride 524 floats = 2 x 260 bins + 4: 16-byte
+// aligned and = 12 (mod 32) banks, so the 8 lanes (pairs) of a quarter-warp reading the same bin quad hit disjoint banks.
+constexpr int kPairStride = 524;
 
 struct alignas(8) cpx {
     float x, y;
@@ -393,8 +397,8 @@ FA_HD void pass2_store(int l, const LaneTables<V> &T, V (&re)[8], V (&im)[8], cp
     twiddle_pass2(base, re, im, T, buf);
 }
 
-// Real-FFT recombination + power, one bin PAIR (b, 256 - b) per step (see the header).  prow -> this frame's row of
-// the power tile (frame B's row follows at + kPowStride); receives 4 |X[b]|^2 for b = 0..256.
+// Real-FFT recombination + power, one bin PAIR (b, 256 - b) per step (see the header).  prow -> this frame's slot in its
+// pair row of the power tile (FP64 path: row + (frame & 1); float32 pairs: the row itself); receives 4 |X[b]|^2, b = 0..256.
 FA_HD void pair_power(double zbx, double zby, double zcx, double zcy, double wx, double wy, float *prow, int ib, int ic) {
     const double sr = zbx + zcx, si = zby - zcy;             // S
     const double dr = zby + zcy, di = zcx - zbx;             // (D.y, -D.x)
@@ -402,12 +406,12 @@ FA_HD void pair_power(double zbx, double zby, double zcx, double zcy, double wx,
     const float xr = (float)(sr + tr), xi = (float)(si + ti);    // single rounding of the exact-arithmetic DFT (x2)
     const float yr = (float)(sr - tr), yi = (float)(si - ti);
 #if defined(__CUDA_ARCH__)
-    prow[ib] = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi));
-    prow[ic] = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
+    prow[2 * ib] = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi));
+    prow[2 * ic] = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
 #else
     const float a = xr * xr, b = xi * xi, c = yr * yr, d = yi * yi;
-    prow[ib] = a + b;
-    prow[ic] = c + d;
+    prow[2 * ib] = a + b;
+    prow[2 * ic] = c + d;
 #endif
 }
 FA_HD void pair_power(f32x2 zbx, f32x2 zby, f32x2 zcx, f32x2 zcy, float wx, float wy, float *prow, int ib, int ic) {
@@ -419,15 +423,13 @@ FA_HD void pair_power(f32x2 zbx, f32x2 zby, f32x2 zcx, f32x2 zcy, float wx, floa
 #if defined(__CUDA_ARCH__)
     const float2 pb = __ffma2_rn(as_f2(xr), as_f2(xr), __fmul2_rn(as_f2(xi), as_f2(xi)));
     const float2 pc = __ffma2_rn(as_f2(yr), as_f2(yr), __fmul2_rn(as_f2(yi), as_f2(yi)));
-    prow[ib] = pb.x;
-    prow[ic] = pc.x;
-    prow[kPowStride + ib] = pb.y;
-    prow[kPowStride + ic] = pc.y;
+    *reinterpret_cast<float2 *>(prow + 2 * ib) = pb;   // (frame A, frame B) of bin ib: one 64-bit store
+    *reinterpret_cast<float2 *>(prow + 2 * ic) = pc;
 #else
-    prow[ib] = fmaf(xr.a, xr.a, xi.a * xi.a);
-    prow[ic] = fmaf(yr.a, yr.a, yi.a * yi.a);
-    prow[kPowStride + ib] = fmaf(xr.b, xr.b, xi.b * xi.b);
-    prow[kPowStride + ic] = fmaf(yr.b, yr.b, yi.b * yi.b);
+    prow[2 * ib] = fmaf(xr.a, xr.a, xi.a * xi.a);
+    prow[2 * ic] = fmaf(yr.a, yr.a, yi.a * yi.a);
+    prow[2 * ib + 1] = fmaf(xr.b, xr.b, xi.b * xi.b);
+    prow[2 * ic + 1] = fmaf(yr.b, yr.b, yi.b * yi.b);
 #endif
 }
 
@@ -503,6 +505,20 @@ FA_HD float mel_dot(const float *prow, const float *w, int lo, int hi) {
     return acc;
 }
 #if defined(__CUDACC__)
+// Two frames at once out of a pair row: p4 -> (bin, slot) interleaved values of the band's first quad (two float4 per bin
+// quad), w4 -> packed weights; four FFMA2 per quad with the weight as a broadcast scalar operand.
+__device__ __forceinline__ float2 mel_dot_pairs(const float4 *p4, const float4 *w4, int nq) {
+    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+    for (int b = 0; b < nq; ++b) {
+        const float4 x01 = p4[2 * b], x23 = p4[2 * b + 1], c = w4[b];
+        acc = __ffma2_rn(make_float2(x01.x, x01.y), make_float2(c.x, c.x), acc);
+        acc = __ffma2_rn(make_float2(x01.z, x01.w), make_float2(c.y, c.y), acc);
+        acc = __ffma2_rn(make_float2(x23.x, x23.y), make_float2(c.z, c.z), acc);
+        acc = __ffma2_rn(make_float2(x23.z, x23.w), make_float2(c.w, c.w), acc);
+    }
+    return acc;
+}
 // p4 / w4: first quad of the band in the power row / in the packed weights; nq quads.  Not unrolled: bands are 1..6
 // quads long and the unrolled remainder ladder cost ~100 instructions per dot product (profiles/r01c_mel.md).
 __device__ __forceinline__ float mel_dot_quads(const float4 *p4, const float4 *w4, int nq) {

@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
     float *raw1 = raw0 + P.raw_cap;
     float *ptile = raw1 + P.raw_cap;
     cpxv<V> *fftbuf = reinterpret_cast<cpxv<V> *>(ptile + P.pt_cap);   // kWarps * kFftPad complex values (16 bytes each)
-    float *power = reinterpret_cast<float *>(fftbuf + kWarps * kFftPad);   // kTileFrames * kPowStride
-    float *otile = power + kTileFrames * kPowStride;        // kTileFrames * (n_mels + 1)
+    float *power = reinterpret_cast<float *>(fftbuf + kWarps * kFftPad);   // (kTileFrames / 2) pair rows x kPairStride
+    float *otile = power + (kTileFrames / 2) * kPairStride;  // kTileFrames * (n_mels + 1)
     float *fbw = otile + kTileFrames * (P.n_mels + 1);      // fb_nnz_cap
     int4 *fbmeta = reinterpret_cast<int4 *>(fbw + P.fb_cap);   // n_mels x {first bin, quads, weight offset, -}
     uint64_t *bars = reinterpret_cast<uint64_t *>(fbmeta + P.n_mels);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
     for (int i = tid; i < P.fb_nnz; i += kWarps * 32) fbw[i] = P.fb_w[i];
     for (int i = tid; i < P.n_mels; i += kWarps * 32)
         fbmeta[i] = make_int4(P.fb_lo[i], (P.fb_hi[i] - P.fb_lo[i]) >> 2, P.fb_off[i], 0);
-    for (int i = tid; i < kTileFrames * kPowStride; i += kWarps * 32) power[i] = 0.0f;   // rows of partial tiles, pad columns
+    for (int i = tid; i < (kTileFrames / 2) * kPairStride; i += kWarps * 32) power[i] = 0.0f;   // rows of partial tiles, pad columns
     // per-lane constants (window slots, twiddles, butterfly addresses): built on the host once per plan (FP64 sin / cos
     // inlined here cost ~3 % of the kernel and 9 000 SASS lines), one struct copy per thread
     const LaneTables<V> T = reinterpret_cast<const LaneTables<V> *>(P.lane_tab)[lane];
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             __syncwarp();
             pass2_store(lane, T, re, im, buf);
             __syncwarp();
-            pass3_post(lane, buf, T, power + fi * kPowStride);
+            pass3_post(lane, buf, T, power + (fi >> 1) * kPairStride + (fi & 1));   // pair row (+ slot on the FP64 path)
             __syncwarp();
         }
         __syncthreads();
@@ -281,20 +281,26 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             issue(next + stride, it & 1, tinfo[slot2]);   // slot2 held tile it-1: nobody reads it any more
         }
         {
-            constexpr int kGroup = 32 / kTileFrames;               // mel bins handled concurrently by one warp
-            const int fl = lane % kTileFrames, mg = lane / kTileFrames;
-            const bool live = fl < nf;
-            const float *prow = power + fl * kPowStride;
-            float *orow = otile + fl * (P.n_mels + 1);
-            float *gout = kLayout == 1 ? P.out + u.out_off + u.g.f0 + fl : nullptr;   // mel-major: column of this frame
+            constexpr int kPairs = kTileFrames / 2, kGroup = 32 / kPairs;   // lane = (frame pair, one of kGroup mel bins)
+            const int pl = lane % kPairs, mg = lane / kPairs;
+            const float *prow = power + pl * kPairStride;
+            float *orow = otile + (2 * pl) * (P.n_mels + 1);
+            float *gout = kLayout == 1 ? P.out + u.out_off + u.g.f0 + 2 * pl : nullptr;   // mel-major: this pair's columns
             for (int m = warp * kGroup + mg; m < P.n_mels; m += kWarps * kGroup) {
                 const int4 md = fbmeta[m];
-                // rows beyond the tile's last frame hold finite leftovers: computed and dropped, no divergent branch
-                const float v = log_value(mel_dot_quads(reinterpret_cast<const float4 *>(prow + md.x),
-                                                        reinterpret_cast<const float4 *>(fbw + md.z), md.y),
-                                          P.log_floor, P.log_clamped);
-                if (kLayout == 0) orow[m] = v;
-                else if (live) gout[(long long)m * u.out_stride] = v;
+                // two frames per lane on packed FFMA2; rows beyond the tile's last frame hold finite leftovers: computed and
+                // dropped, no divergent branch
+                const float2 a2 = mel_dot_pairs(reinterpret_cast<const float4 *>(prow + 2 * md.x),
+                                                reinterpret_cast<const float4 *>(fbw + md.z), md.y);
+                const float v0 = log_value(a2.x, P.log_floor, P.log_clamped), v1 = log_value(a2.y, P.log_floor, P.log_clamped);
+                if (kLayout == 0) {
+                    orow[m] = v0;
+                    orow[P.n_mels + 1 + m] = v1;
+                } else {
+                    float *g = gout + (long long)m * u.out_stride;
+                    if (2 * pl < nf) g[0] = v0;
+                    if (2 * pl + 1 < nf) g[1] = v1;
+                }
             }
         }
         if (kLayout == 0) {
@@ -524,7 +530,7 @@ int MelPlan::init(const MelConfig &c) {
                 b = k + 1;
             }
         if (b == 0) a = 0;
-        a &= ~3;                       // whole bin quads: 16-byte aligned reads of the power row (stride kPowStride)
+        a &= ~3;                       // whole bin quads: 16-byte aligned reads of the power row (pair rows, kPairStride)
         b = (b + 3) & ~3;              // may reach 260 > 257: the tile's pad columns are zero, so are these weights
         lo[m] = a;
         hi[m] = b;
@@ -615,7 +621,7 @@ int MelPlan::init(const MelConfig &c) {
     raw_cap = (pt_len + 1 + 3 + 3 + 31) & ~31;   // whole 128-byte lines: the pre-emphasised tile behind it stays line-aligned
     fb_cap = (fb_nnz + 3) & ~3;
     smem_bytes = sizeof(float) * ((size_t)2 * raw_cap + pt_cap + 0 +
-                                  (size_t)kTileFrames * kPowStride + (size_t)kTileFrames * (cfg.n_mels + 1) + fb_cap) +
+                                  (size_t)(kTileFrames / 2) * kPairStride + (size_t)kTileFrames * (cfg.n_mels + 1) + fb_cap) +
                  sizeof(cpxd) * (size_t)kWarpsPerCta * kFftPad + sizeof(int) * 4 * (size_t)cfg.n_mels + 8 +
                  2 * sizeof(uint64_t) + 3 * sizeof(TileInfo) + 16;
     if (smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {

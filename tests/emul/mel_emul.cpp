@@ -45,7 +45,7 @@ static int mel_emul_t(const float *audio, long long n, float last, int hop, int 
     alignas(16) cpxv<V> buf[kFftPad];
     std::vector<float> pfv((size_t)kNfft + hop + 8);
     float *pf = pfv.data();
-    std::vector<float> prow(2 * kPowStride);
+    std::vector<float> prow2(kPairStride), prow(2 * 260);   // the device's pair row, de-interleaved for the host dot product
     for (long long f = 0; f < T; f += kF) {
         for (int j = 0; j < kNfft + (kF - 1) * hop; ++j) {
             const long long i = f * hop + j - pad;
@@ -64,10 +64,14 @@ static int mel_emul_t(const float *audio, long long n, float last, int hop, int 
         }
         for (int l = 0; l < 32; ++l) pass2_load(l, buf, re[l], im[l]);
         for (int l = 0; l < 32; ++l) pass2_store(l, tabs[l], re[l], im[l], buf);
-        for (int l = 0; l < 32; ++l) pass3_post(l, buf, tabs[l], prow.data());
+        for (int l = 0; l < 32; ++l) pass3_post(l, buf, tabs[l], prow2.data());
+        for (int b = 0; b < kBins; ++b) {
+            prow[b] = prow2[2 * b];
+            prow[260 + b] = prow2[2 * b + 1];
+        }
         for (int k = 0; k < kF && f + k < T; ++k)
             for (int m = 0; m < n_mels; ++m) {
-                const float acc = mel_dot(prow.data() + k * kPowStride, fbq.data() + (size_t)m * kBins + lo[m], lo[m], hi[m]);
+                const float acc = mel_dot(prow.data() + k * 260, fbq.data() + (size_t)m * kBins + lo[m], lo[m], hi[m]);
                 out[(f + k) * n_mels + m] = log_value(acc, log_floor, clamped);
             }
     }

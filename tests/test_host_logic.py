@@ -181,6 +181,16 @@ def test_kernel_lane_math_matches_oracle(tmp_path, oracle):
         assert L.mel_emul(a, a.size, 0.0, 160, 400, 56, 256, np.float32(0.97), nm, oracle.mel_filterbank(512, nm),
                           oracle.hann_window(), np.float32(2.0 ** -24), 0, T, out) == 0
         assert np.abs(out - ref).max() <= 1e-4
+    # the float32-pair value type (two frames per warp, FA_MEL_PRECISION_F32) through the same per-lane code: index math of
+    # the pair rows, exact-rounded twiddle scalars; float32 transform noise stays inside the bar on these fixtures
+    L.mel_emul_f32x2.argtypes = L.mel_emul.argtypes
+    for nm, gen, n in ((80, synth.tone_noise_audio, 16000 * 4 + 137), (128, synth.speech_like_audio, 16000 * 3)):
+        a = gen(n)
+        ref, T, _ = oracle.mel_flat_transposed(oracle.mel_config(n_mels=nm), a)
+        out = np.zeros((T, nm), np.float32)
+        assert L.mel_emul_f32x2(a, a.size, 0.0, 160, 400, 56, 256, np.float32(0.97), nm, oracle.mel_filterbank(512, nm),
+                                oracle.hann_window(), np.float32(2.0 ** -24), 0, T, out) == 0
+        assert np.abs(out - ref).max() <= 1e-4
     # legacy compute(): window at offset 0, no padding, no pre-emphasis
     a = synth.tone_noise_audio(8000)
     ref, T = oracle.mel_legacy(oracle.mel_config(n_mels=80), a)
