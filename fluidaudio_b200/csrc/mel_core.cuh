@@ -536,12 +536,17 @@ __device__ __forceinline__ float mel_dot_quads(const float4 *p4, const float4 *w
 #endif
 
 // log of a mel value.  Device: one MUFU.LG2 and one multiply (|error| <= ~2 ulp of the result: 4e-6 at log(2^-24),
-// against the 1e-4 bar); host emulator: libm.
-FA_HD float log_value(float v, float floor_, int clamped) {
+// against the 1e-4 bar); host emulator: libm.  normal_floor: the floor is a normal float, so the argument never is a
+// denormal and the denormal pre-scaling of __log2f (three more instructions) can be skipped.
+FA_HD float log_value(float v, float floor_, int clamped, int normal_floor = 0) {
     const float x = clamped ? (v > floor_ ? v : floor_) : v + floor_;
 #if defined(__CUDA_ARCH__)
-    return __log2f(x) * 0.693147180559945309417f;
+    float l;
+    if (normal_floor) asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    else l = __log2f(x);
+    return l * 0.693147180559945309417f;
 #else
+    (void)normal_floor;
     return logf(x);
 #endif
 }

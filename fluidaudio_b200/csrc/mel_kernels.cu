@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
     float *power = reinterpret_cast<float *>(fftbuf + kWarps * kFftPad);   // (kTileFrames / 2) pair rows x kPairStride
     float *otile = power + (kTileFrames / 2) * kPairStride;  // kTileFrames * (n_mels + 1)
     float *fbw = otile + kTileFrames * (P.n_mels + 1);      // fb_nnz_cap
-    int4 *fbmeta = reinterpret_cast<int4 *>(fbw + P.fb_cap);   // n_mels x {first bin, quads, weight offset, -}
-    uint64_t *bars = reinterpret_cast<uint64_t *>(fbmeta + P.n_mels);
+    int4 *fbmeta = reinterpret_cast<int4 *>(fbw + P.fb_cap);   // n_slots x {first bin, quads, weight offset, mel bin or -1}
+    uint64_t *bars = reinterpret_cast<uint64_t *>(fbmeta + P.n_slots);
     TileInfo *tinfo = reinterpret_cast<TileInfo *>(bars + 2);   // [3]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,8 +149,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P.fb_nnz; i += kWarps * 32) fbw[i] = P.fb_w[i];
-    for (int i = tid; i < P.n_mels; i += kWarps * 32)
-        fbmeta[i] = make_int4(P.fb_lo[i], (P.fb_hi[i] - P.fb_lo[i]) >> 2, P.fb_off[i], 0);
+    for (int i = tid; i < P.n_slots; i += kWarps * 32) fbmeta[i] = P.fb_slots[i];
     for (int i = tid; i < (kTileFrames / 2) * kPairStride; i += kWarps * 32) power[i] = 0.0f;   // rows of partial tiles, pad columns
     // per-lane constants (window slots, twiddles, butterfly addresses): built on the host once per plan (FP64 sin / cos
     // inlined here cost ~3 % of the kernel and 9 000 SASS lines), one struct copy per thread
@@ -286,13 +285,18 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             const float *prow = power + pl * kPairStride;
             float *orow = otile + (2 * pl) * (P.n_mels + 1);
             float *gout = kLayout == 1 ? P.out + u.out_off + u.g.f0 + 2 * pl : nullptr;   // mel-major: this pair's columns
-            for (int m = warp * kGroup + mg; m < P.n_mels; m += kWarps * kGroup) {
-                const int4 md = fbmeta[m];
+            // slots, not mel bins: the plan deals the groups of four filters to the warps by band width (LPT), so that the
+            // warp with the widest (highest) filters does not hold the block barrier; md.w = the slot's mel bin, -1 = empty
+            for (int slot = warp * kGroup + mg; slot < P.n_slots; slot += kWarps * kGroup) {
+                const int4 md = fbmeta[slot];
                 // two frames per lane on packed FFMA2; rows beyond the tile's last frame hold finite leftovers: computed and
                 // dropped, no divergent branch
                 const float2 a2 = mel_dot_pairs(reinterpret_cast<const float4 *>(prow + 2 * md.x),
                                                 reinterpret_cast<const float4 *>(fbw + md.z), md.y);
-                const float v0 = log_value(a2.x, P.log_floor, P.log_clamped), v1 = log_value(a2.y, P.log_floor, P.log_clamped);
+                const float v0 = log_value(a2.x, P.log_floor, P.log_clamped, P.log_normal),
+                            v1 = log_value(a2.y, P.log_floor, P.log_clamped, P.log_normal);
+                const int m = md.w;
+                if (m < 0) continue;
                 if (kLayout == 0) {
                     orow[m] = v0;
                     orow[P.n_mels + 1 + m] = v1;
@@ -474,6 +478,7 @@ void MelPlan::release() {
         fr(d_lane_tab[m][1]);
     }
     fr(d_fb_w);
+    fr(d_fb_slots);
     fr(d_fb_lo);
     fr(d_fb_hi);
     fr(d_fb_off);
@@ -538,6 +543,38 @@ int MelPlan::init(const MelConfig &c) {
         for (int k = a; k < b; ++k) w.push_back(k < bins ? 0.25f * filterbank[(size_t)m * bins + k] : 0.0f);
     }
     fb_nnz = (int)w.size();
+    // filterbank-stage schedule of mel512_kernel: groups of four consecutive filters, dealt to the 8 warps longest first
+    // (cost = widest band of the group, in quads); slot = (iteration * 8 + warp) * 4 + member
+    std::vector<int4> slots;
+    {
+        const int groups = (cfg.n_mels + 3) / 4;
+        std::vector<int> cost(groups, 0), order(groups);
+        for (int g = 0; g < groups; ++g) {
+            for (int m = 4 * g; m < std::min(cfg.n_mels, 4 * g + 4); ++m) cost[g] = std::max(cost[g], (hi[m] - lo[m]) >> 2);
+            order[g] = g;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+        std::vector<std::vector<int>> mine(kWarpsPerCta);
+        std::vector<long long> load(kWarpsPerCta, 0);
+        load[0] = 6;   // warp 0's lane 0 also computes the next tile's geometry and issues its bulk copy in this phase
+        for (int g : order) {
+            int best = 0;
+            for (int wv = 1; wv < kWarpsPerCta; ++wv)
+                if (load[wv] + 2 * (long long)mine[wv].size() < load[best] + 2 * (long long)mine[best].size()) best = wv;
+            mine[best].push_back(g);
+            load[best] += cost[g] + 4;   // + per-iteration control
+        }
+        size_t iters = 0;
+        for (auto &v : mine) iters = std::max(iters, v.size());
+        slots.assign(iters * kWarpsPerCta * 4, make_int4(0, 0, 0, -1));
+        for (int wv = 0; wv < kWarpsPerCta; ++wv)
+            for (size_t it = 0; it < mine[wv].size(); ++it)
+                for (int q = 0; q < 4; ++q) {
+                    const int m = 4 * mine[wv][it] + q;
+                    if (m < cfg.n_mels) slots[(it * kWarpsPerCta + wv) * 4 + q] = make_int4(lo[m], (hi[m] - lo[m]) >> 2, off[m], m);
+                }
+    }
+    n_slots = (int)slots.size();
 
     int dev = 0;
     FA_CUDA_TRY(cudaGetDevice(&dev));
@@ -586,6 +623,9 @@ int MelPlan::init(const MelConfig &c) {
         }
     }
     FA_CUDA_TRY(cudaMalloc(&d_fb_w, std::max<size_t>(1, w.size()) * sizeof(float)));
+    FA_CUDA_TRY(cudaMalloc(&d_fb_slots, std::max<size_t>(1, slots.size()) * sizeof(int4)));
+    if (!slots.empty())
+        FA_CUDA_TRY(cudaMemcpy(d_fb_slots, slots.data(), slots.size() * sizeof(int4), cudaMemcpyHostToDevice));
     FA_CUDA_TRY(cudaMalloc(&d_fb_lo, cfg.n_mels * sizeof(int)));
     FA_CUDA_TRY(cudaMalloc(&d_fb_hi, cfg.n_mels * sizeof(int)));
     FA_CUDA_TRY(cudaMalloc(&d_fb_off, cfg.n_mels * sizeof(int)));
@@ -622,7 +662,7 @@ int MelPlan::init(const MelConfig &c) {
     fb_cap = (fb_nnz + 3) & ~3;
     smem_bytes = sizeof(float) * ((size_t)2 * raw_cap + pt_cap + 0 +
                                   (size_t)(kTileFrames / 2) * kPairStride + (size_t)kTileFrames * (cfg.n_mels + 1) + fb_cap) +
-                 sizeof(cpxd) * (size_t)kWarpsPerCta * kFftPad + sizeof(int) * 4 * (size_t)cfg.n_mels + 8 +
+                 sizeof(cpxd) * (size_t)kWarpsPerCta * kFftPad + sizeof(int) * 4 * (size_t)n_slots + 8 +
                  2 * sizeof(uint64_t) + 3 * sizeof(TileInfo) + 16;
     if (smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
         fa::set_error("mel config needs %zu bytes of shared memory per CTA, device allows %zu", smem_bytes,
@@ -700,11 +740,14 @@ int MelPlan::launch(const float *d_audio_base, float *d_out_base, int first, int
     P.n_mels = cfg.n_mels;
     P.log_floor = cfg.log_floor;
     P.log_clamped = cfg.log_floor_mode;
+    P.log_normal = cfg.log_floor >= 1e-37f ? 1 : 0;   // mel energies are >= 0: log's argument is then never a denormal
     P.layout = layout;
     P.lane_tab = d_lane_tab[mode == 2 ? 1 : 0][precision == 1 ? 1 : 0];
     P.win_tab = d_win_tab_mode[mode == 2 ? 1 : 0];
     P.in_tab = d_in_tab_mode[mode == 2 ? 1 : 0];
     P.fb_w = d_fb_w;
+    P.fb_slots = reinterpret_cast<const int4 *>(d_fb_slots);
+    P.n_slots = n_slots;
     P.fb_lo = d_fb_lo;
     P.fb_hi = d_fb_hi;
     P.fb_off = d_fb_off;

@@ -50,6 +50,7 @@ struct MelLaunch {
     int n_mels;
     float log_floor;
     int log_clamped;
+    int log_normal;     // log_floor is a normal float: the denormal handling of the device log can be skipped
     int layout;         // 0 time-major [T x nMels], 1 mel-major [nMels x stride]
     const void *lane_tab;   // [32] LaneTables<V> of the launch's window placement and precision (mel_core.cuh)
     const float *win_tab;
@@ -58,6 +59,8 @@ struct MelLaunch {
     const int *fb_lo;
     const int *fb_hi;
     const int *fb_off;
+    const int4 *fb_slots;   // mel512_kernel's filterbank schedule: {first bin, quads, weight offset, mel bin or -1} per slot
+    int n_slots;
     int fb_nnz, fb_cap;
     int pt_len, pt_cap, raw_cap;
     int use_tma;
@@ -90,6 +93,8 @@ struct MelPlan {
     uint8_t *d_in_tab_mode[2] = {nullptr, nullptr};
     float *d_fb_w = nullptr;
     int *d_fb_lo = nullptr, *d_fb_hi = nullptr, *d_fb_off = nullptr;
+    void *d_fb_slots = nullptr;
+    int n_slots = 0;
 
     MelUnit *d_units = nullptr, *h_units = nullptr;
     int units_cap = 0;
