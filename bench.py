@@ -241,15 +241,19 @@ def bench_mel(args, dist, clocks):
         e2e16()
     e2e16_s = _timed_wall(e2e16, K, dist, sharding, _lib)
     i16_diff = float(np.abs(pin_out.array.reshape(MEL_FRAMES, N_MELS)[:6000] - got32[:6000]).max())   # 16-bit quantised input
-    # bare copies of the same bytes on two streams: the floor under the end-to-end numbers
+    # bare copies of the same bytes on two streams: the floor under the end-to-end numbers; each direction alone as well,
+    # all ranks copying at the same time (at N = 8 four GPUs share a socket: this names the limiter of the e2e scaling)
     L = _lib.load()
     ms = C.c_float()
     floor = {}
-    for name, src, nb_in in (("f32", pin_in, 4 * MEL_SAMPLES), ("i16", pin_i16, 2 * MEL_SAMPLES)):
+    nb_out = 4 * MEL_FRAMES * N_MELS
+    for name, src, nb_in, nb_o in (("f32", pin_in, 4 * MEL_SAMPLES, nb_out), ("i16", pin_i16, 2 * MEL_SAMPLES, nb_out),
+                                    ("h2d_only", pin_in, 4 * MEL_SAMPLES, 0), ("d2h_only", pin_in, 0, nb_out)):
         sharding.barrier(dist)
-        _lib.check(L.fa_memcpy_probe(src.array.ctypes.data, nb_in, pin_out.array.ctypes.data, 4 * MEL_FRAMES * N_MELS,
+        _lib.check(L.fa_memcpy_probe(src.array.ctypes.data, nb_in, pin_out.array.ctypes.data, nb_o,
                                      max(3, min(K, 10)), C.byref(ms)), "fa_memcpy_probe")
         floor[name] = sharding.all_reduce_max(dist, float(ms.value))
+    numa = sharding.numa_node_of(pin_in.array.ctypes.data)
     ms_per_step = dev_ms / K
     hours = dist.world * 1.0
     peak, peak_src = measured_peaks()
@@ -267,7 +271,10 @@ def bench_mel(args, dist, clocks):
         "e2e": {"value": hours / (e2e_s / K), "unit": "audio-hours/s", "ms_per_step": e2e_s / K * 1e3,
                 "h2d_bytes_per_step": 4 * MEL_SAMPLES, "d2h_bytes_per_step": 4 * MEL_FRAMES * N_MELS,
                 "host_buffers": "pinned (fa_host_alloc)", "api": "fa_mel_compute",
-                "copy_floor_ms": floor["f32"], "of_copy_floor": floor["f32"] / (e2e_s / K * 1e3)},
+                "copy_floor_ms": floor["f32"], "of_copy_floor": floor["f32"] / (e2e_s / K * 1e3),
+                "copy_floor_h2d_only_ms": floor["h2d_only"], "copy_floor_d2h_only_ms": floor["d2h_only"],
+                "copy_floor_note": "fa_memcpy_probe: bare cudaMemcpyAsync of the same bytes on two streams, all ranks at once, MAX over ranks",
+                "pinned_input_numa_node": numa},
         "e2e_i16": {"value": hours / (e2e16_s / K), "unit": "audio-hours/s", "ms_per_step": e2e16_s / K * 1e3,
                     "h2d_bytes_per_step": 2 * MEL_SAMPLES, "d2h_bytes_per_step": 4 * MEL_FRAMES * N_MELS,
                     "api": "fa_audio_to_mel (int16 PCM, 16 kHz mono: widening on the device)",

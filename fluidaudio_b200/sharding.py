@@ -95,6 +95,20 @@ def bind_to_gpu_numa(local_rank: int) -> str:
         return f"unbound ({type(e).__name__})"
 
 
+def numa_node_of(address: int):
+    """NUMA node holding the page at `address` (move_pages(2) query through libc; None when it cannot be told): lets a
+    bench line state that its pinned buffers are local to the GPU's socket."""
+    try:
+        import ctypes as C
+        libc = C.CDLL(None, use_errno=True)
+        page = C.c_void_p(address & ~4095)
+        status = C.c_int(-1)
+        rc = libc.syscall(279, 0, 1, C.byref(page), None, C.byref(status), 0)   # __NR_move_pages on x86-64
+        return int(status.value) if rc == 0 and status.value >= 0 else None
+    except Exception:
+        return None
+
+
 def _tensor(values, d: Dist, dtype):
     import torch
     dev = torch.device("cuda", d.local_rank) if d.backend == "nccl" else torch.device("cpu")

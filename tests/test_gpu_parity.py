@@ -204,6 +204,33 @@ def test_mel_batch_and_device_paths(gpu_lib, oracle):
     assert np.array_equal(d_o.download((T * 80,), np.float32), host)
 
 
+def test_mel_pipeline_knobs_do_not_change_results(gpu_lib):
+    """fa_mel_set_pipeline_chunks / fa_mel_set_zero_copy_output only move data differently: every depth, the kernel storing
+    straight into the caller's pinned buffer or staging + D2H, float32 and int16 PCM entry points — bit-identical rows."""
+    n = 16000 * 150
+    a = synth.tone_noise_audio(n)
+    pin_in = _lib.PinnedArray(n, np.float32); pin_in.array[:] = a
+    pin_16 = _lib.PinnedArray(n, np.int16); pin_16.array[:] = np.round(a * 32767).astype(np.int16)
+    for prec in (Precision.f64, Precision.f32):
+        m = AudioMelSpectrogram(n_mels=80, precision=prec)
+        T = m.frame_count(n)
+        pin_out = _lib.PinnedArray(T * 80, np.float32)
+        ref, _, _ = m.compute_flat_transposed(a)                     # pageable buffers, default depth
+        ref16, _, _, _ = m.compute_from_pcm(pin_16.array.copy(), 16000.0)
+        for zc in (0, 1):
+            _lib.check(m._L.fa_mel_set_zero_copy_output(m._h, zc), "zero copy")
+            for chunks in (1, 2, 7, 24, 200):
+                _lib.check(m._L.fa_mel_set_pipeline_chunks(m._h, chunks), "chunks")
+                pin_out.array[:] = -1.0
+                got, ml, nf = m.compute_flat_transposed(pin_in.array, out=pin_out.array)
+                assert np.array_equal(got, ref), (prec, zc, chunks)
+                pin_out.array[:] = -1.0
+                got, ml, nf, rs = m.compute_from_pcm(pin_16.array, 16000.0, out=pin_out.array)
+                assert rs == n and np.array_equal(got, ref16), (prec, zc, chunks)
+    with pytest.raises(_lib.FluidAudioError):
+        _lib.check(m._L.fa_mel_set_pipeline_chunks(m._h, 0), "chunks")
+
+
 def test_mel_one_hour_properties(gpu_lib, oracle):
     """BASELINE config 2 at full size: 1 h of 16 kHz audio, 80 mels."""
     n = 57_600_000
