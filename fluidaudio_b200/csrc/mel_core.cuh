@@ -62,6 +62,13 @@ constexpr int kTileFrames = 16;   // frames per CTA tile; the mel stage maps 32 
 // per lane on packed FFMA2 with the weight as a broadcast scalar.  Row stride 524 floats = 2 x 260 bins + 4: 16-byte
 // aligned and = 12 (mod 32) banks, so the 8 lanes (pairs) of a quarter-warp reading the same bin quad hit disjoint banks.
 constexpr int kPairStride = 524;
+// Inside a pair row bin b sits at position pow_pos(b) = b ^ ((b >> 4) & 3): the two low bits are XORed with bits 4-5, a
+// permutation INSIDE each aligned bin quad (the filterbank stage still reads whole quads at 4 * Q; the plan permutes the
+// packed weights the same way).  Pass 3 stores bins k0 + 64 k2 with k0 = a + 8 j over the lanes of a quarter-warp: without
+// the swizzle they hit only two 8-byte bank pairs (4-way conflicts, 24 excess wavefronts per frame on the pipe that bounds
+// the kernel); with it the eight lanes hit eight distinct ones.  For a lane the XOR mask is a constant, so the swizzled
+// store positions are k0s + 64 k2 and kc0s - 64 k2 with two per-lane integers.
+FA_HD int pow_pos(int bin) { return bin ^ ((bin >> 4) & 3); }
 
 struct alignas(8) cpx {
     float x, y;
@@ -144,6 +151,7 @@ struct LaneCommon {
     float win[16];     // window coefficient at buffer positions j = 2(l+32r) [slot 2r] and j+1 [slot 2r+1]
     uint32_t in_win;   // bit s set  <=>  slot s lies inside [off, off+win)
     int a1, a2, k0;    // layout-B addresses of the lane's two mirror-image radix-4 butterflies; first output index
+    int k0s, kc0s;     // swizzled power-row positions: bin k0 + 64 k2 -> k0s + 64 k2, bin 256 - k0 - 64 k2 -> kc0s - 64 k2
 };
 template <typename V>
 struct LaneTables;
@@ -212,6 +220,8 @@ FA_HD void load_lane_common(int l, const float *win_tab, const uint8_t *in_tab, 
     T.a1 = 9 * (c1 >> 3) + (c1 & 7);
     T.a2 = 9 * (c2 >> 3) + (c2 & 7);
     T.k0 = (c1 >> 3) + 8 * (c1 & 7);
+    T.k0s = pow_pos(T.k0);
+    T.kc0s = pow_pos(kHalf - T.k0);
 }
 FA_HD void load_lane_tables(int l, const float *win_tab, const uint8_t *in_tab, LaneTables<double> &T) {
     load_lane_common(l, win_tab, in_tab, T);
@@ -476,17 +486,18 @@ FA_HD void pass3_post(int l, const cpxv<V> *buf, const LaneTables<V> &T, float *
     S wx[4], wy[4];
     recombination_roots(T, wx, wy);
     // slot 0
-    pair_power(ar[0], ai[0], z ? ar[0] : br[3], z ? ai[0] : bi[3], wx[0], wy[0], prow, T.k0, kHalf - T.k0);
+    // (positions: see pow_pos; 64 k2 never reaches the two swizzled bits, and their mask (bits 4-5) is the lane's constant)
+    pair_power(ar[0], ai[0], z ? ar[0] : br[3], z ? ai[0] : bi[3], wx[0], wy[0], prow, T.k0s, T.kc0s);
     // slot 1
-    pair_power(ar[1], ai[1], z ? ar[3] : br[2], z ? ai[3] : bi[2], wx[1], wy[1], prow, T.k0 + 64, kHalf - 64 - T.k0);
+    pair_power(ar[1], ai[1], z ? ar[3] : br[2], z ? ai[3] : bi[2], wx[1], wy[1], prow, T.k0s + 64, T.kc0s - 64);
     // slot 2
-    pair_power(ar[2], ai[2], z ? ar[2] : br[1], z ? ai[2] : bi[1], wx[2], wy[2], prow, T.k0 + 128, kHalf - 128 - T.k0);
+    pair_power(ar[2], ai[2], z ? ar[2] : br[1], z ? ai[2] : bi[1], wx[2], wy[2], prow, T.k0s + 128, T.kc0s - 128);
     // slot 3 (lane 0: bins 32 / 224, W512^32 = W16)
-    const int b3 = z ? 32 : T.k0 + 192;
+    const int b3 = z ? pow_pos(32) : T.k0s + 192, c3 = z ? pow_pos(224) : T.kc0s - 192;
     pair_power(z ? br[0] : ar[3], z ? bi[0] : ai[3], z ? br[3] : br[0], z ? bi[3] : bi[0], z ? c1 : wx[3],
-               z ? (S)(-s1) : wy[3], prow, b3, kHalf - b3);
+               z ? (S)(-s1) : wy[3], prow, b3, c3);
     if (z) {                     // bins 96 / 160, W512^96 = W16^3
-        pair_power(br[1], bi[1], br[2], bi[2], s1, (S)(-c1), prow, 96, 160);
+        pair_power(br[1], bi[1], br[2], bi[2], s1, (S)(-c1), prow, pow_pos(96), pow_pos(160));
     }
 }
 

@@ -540,7 +540,12 @@ int MelPlan::init(const MelConfig &c) {
         lo[m] = a;
         hi[m] = b;
         off[m] = (int)w.size();        // a multiple of four: 16-byte aligned weight quads
-        for (int k = a; k < b; ++k) w.push_back(k < bins ? 0.25f * filterbank[(size_t)m * bins + k] : 0.0f);
+        // packed in the order the kernel finds the bins in its power tile: mel512_kernel swizzles inside each bin quad
+        // (pow_pos, mel_core.cuh), the any-nFFT kernel keeps the natural order
+        for (int k = a; k < b; ++k) {
+            const int src = generic ? k : ((k & ~3) | ((k & 3) ^ ((k >> 4) & 3)));   // position k holds bin src: pow_pos is an involution
+            w.push_back(src < bins ? 0.25f * filterbank[(size_t)m * bins + src] : 0.0f);
+        }
     }
     fb_nnz = (int)w.size();
     // filterbank-stage schedule of mel512_kernel: groups of four consecutive filters, dealt to the 8 warps longest first

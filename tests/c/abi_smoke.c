@@ -47,6 +47,20 @@ int main(void) {
         if (count != 1 || cl[0] != 1 || st[0] != 0.0f || en[0] != 2.0f) return 11;
     }
 
+    {   /* converter stage: sizing and argument checks are host-side (AudioConverter.swift:417-418: Int(n / ratio)) */
+        fa_audio_format af;
+        int64_t n_out = -1;
+        af.in_rate = 44100.0;
+        af.out_rate = 16000.0;
+        af.channels = 2;
+        af.format = FA_PCM_I16;
+        af.interleaved = 1;
+        af.algorithm = FA_RESAMPLE_AUTO;
+        if (fa_resample_output_count(&af, 44100) != 16000) return 12;
+        if (fa_audio_resample(NULL, 44100, &af, NULL, 0, &n_out) != FA_STATUS_OK || n_out != 16000) return 13;
+        af.channels = 0;
+        if (fa_audio_resample(NULL, 44100, &af, NULL, 0, &n_out) != FA_STATUS_INVALID_ARGUMENT) return 14;
+    }
     printf("abi ok: %s, devices visible: %d\n", v, fa_device_count());
     return 0;
 }

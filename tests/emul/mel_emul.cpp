@@ -66,8 +66,8 @@ static int mel_emul_t(const float *audio, long long n, float last, int hop, int 
         for (int l = 0; l < 32; ++l) pass2_store(l, tabs[l], re[l], im[l], buf);
         for (int l = 0; l < 32; ++l) pass3_post(l, buf, tabs[l], prow2.data());
         for (int b = 0; b < kBins; ++b) {
-            prow[b] = prow2[2 * b];
-            prow[260 + b] = prow2[2 * b + 1];
+            prow[b] = prow2[2 * pow_pos(b)];
+            prow[260 + b] = prow2[2 * pow_pos(b) + 1];
         }
         for (int k = 0; k < kF && f + k < T; ++k)
             for (int m = 0; m < n_mels; ++m) {
