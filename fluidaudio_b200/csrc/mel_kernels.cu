@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
     float *ptile = raw1 + P.raw_cap;
     cpxv<V> *fftbuf = reinterpret_cast<cpxv<V> *>(ptile + P.pt_cap);   // kWarps * kFftPad complex values (16 bytes each)
     float *power = reinterpret_cast<float *>(fftbuf + kWarps * kFftPad);   // (kTileFrames / 2) pair rows x kPairStride
-    float *otile = power + (kTileFrames / 2) * kPairStride;  // kTileFrames * (n_mels + 1)
-    float *fbw = otile + kTileFrames * (P.n_mels + 1);      // fb_nnz_cap
+    float *otile = power + (kTileFrames / 2) * kPairStride;  // kTileFrames rows of ot_stride floats
+    const int ot_stride = P.ot_stride;                       // n_mels + 4 (rows stay 16-byte aligned) or n_mels + 1
+    float *fbw = otile + kTileFrames * ot_stride;            // fb_nnz_cap
     int4 *fbmeta = reinterpret_cast<int4 *>(fbw + P.fb_cap);   // n_slots x {first bin, quads, weight offset, mel bin or -1}
     uint64_t *bars = reinterpret_cast<uint64_t *>(fbmeta + P.n_slots);
     TileInfo *tinfo = reinterpret_cast<TileInfo *>(bars + 2);   // [3]
@@ -182,11 +183,16 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             if (((g.a0 - g.base) & 3) == 0 && (P.pt_len & 3) == 0) {   // 16-byte aligned rows: four samples per step
                 const float4 *s4 = reinterpret_cast<const float4 *>(src);
                 float4 *d4 = reinterpret_cast<float4 *>(ptile);
-                for (int q = tid; q < (P.pt_len >> 2); q += kWarps * 32) {
-                    const float4 x = s4[q];
+                for (int q = tid; q < ((P.pt_len >> 2) + 31 & ~31); q += kWarps * 32) {   // whole warps: shuffle below
+                    const bool in = q < (P.pt_len >> 2);
+                    const float4 x = in ? s4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 y = x;
+                    // x[4q - 1] is the left neighbour lane's .w (a 16-byte-strided scalar load was a 4-way bank conflict)
+                    float prev = __shfl_up_sync(0xffffffffu, x.w, 1);
+                    if (lane == 0 && in) prev = src[4 * q - 1];
+                    if (!in) continue;
                     if (a != 0.0f) {
-                        y.x = preemph_rest(x.x, src[4 * q - 1], a);
+                        y.x = preemph_rest(x.x, prev, a);
                         y.y = preemph_rest(x.y, x.x, a);
                         y.z = preemph_rest(x.z, x.y, a);
                         y.w = preemph_rest(x.w, x.z, a);
@@ -224,8 +230,8 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             float4 *d4 = reinterpret_cast<float4 *>(dst);
             for (int q = tid; q < (total >> 2); q += kWarps * 32) {
                 const int e = 4 * q;
-                const float *src = otile + e + (int)__umulhi((unsigned)e, P.inv_n_mels);   // + row: stride n_mels + 1
-                d4[q] = make_float4(src[0], src[1], src[2], src[3]);
+                const int row = (int)__umulhi((unsigned)e, P.inv_n_mels);                  // e / n_mels
+                d4[q] = *reinterpret_cast<const float4 *>(otile + e + 4 * row);             // row stride n_mels + 4: one LDS.128
             }
         } else {
             for (int idx = tid; idx < total; idx += kWarps * 32) {
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             constexpr int kPairs = kTileFrames / 2, kGroup = 32 / kPairs;   // lane = (frame pair, one of kGroup mel bins)
             const int pl = lane % kPairs, mg = lane / kPairs;
             const float *prow = power + pl * kPairStride;
-            float *orow = otile + (2 * pl) * (P.n_mels + 1);
+            float *orow = otile + (2 * pl) * ot_stride;
             float *gout = kLayout == 1 ? P.out + u.out_off + u.g.f0 + 2 * pl : nullptr;   // mel-major: this pair's columns
             // slots, not mel bins: the plan deals the groups of four filters to the warps by band width (LPT), so that the
             // warp with the widest (highest) filters does not hold the block barrier; md.w = the slot's mel bin, -1 = empty
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
                 if (m < 0) continue;
                 if (kLayout == 0) {
                     orow[m] = v0;
-                    orow[P.n_mels + 1 + m] = v1;
+                    orow[ot_stride + m] = v1;
                 } else {
                     float *g = gout + (long long)m * u.out_stride;
                     if (2 * pl < nf) g[0] = v0;
@@ -666,7 +672,7 @@ int MelPlan::init(const MelConfig &c) {
     raw_cap = (pt_len + 1 + 3 + 3 + 31) & ~31;   // whole 128-byte lines: the pre-emphasised tile behind it stays line-aligned
     fb_cap = (fb_nnz + 3) & ~3;
     smem_bytes = sizeof(float) * ((size_t)2 * raw_cap + pt_cap + 0 +
-                                  (size_t)(kTileFrames / 2) * kPairStride + (size_t)kTileFrames * (cfg.n_mels + 1) + fb_cap) +
+                                  (size_t)(kTileFrames / 2) * kPairStride + (size_t)kTileFrames * (cfg.n_mels + 4) + fb_cap) +
                  sizeof(cpxd) * (size_t)kWarpsPerCta * kFftPad + sizeof(int) * 4 * (size_t)n_slots + 8 +
                  2 * sizeof(uint64_t) + 3 * sizeof(TileInfo) + 16;
     if (smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
@@ -745,6 +751,7 @@ int MelPlan::launch(const float *d_audio_base, float *d_out_base, int first, int
     P.n_mels = cfg.n_mels;
     P.log_floor = cfg.log_floor;
     P.log_clamped = cfg.log_floor_mode;
+    P.ot_stride = (cfg.n_mels & 3) == 0 ? cfg.n_mels + 4 : cfg.n_mels + 1;
     P.log_normal = cfg.log_floor >= 1e-37f ? 1 : 0;   // mel energies are >= 0: log's argument is then never a denormal
     P.layout = layout;
     P.lane_tab = d_lane_tab[mode == 2 ? 1 : 0][precision == 1 ? 1 : 0];

@@ -50,6 +50,7 @@ struct MelLaunch {
     int n_mels;
     float log_floor;
     int log_clamped;
+    int ot_stride;      // floats per row of the staged output tile: n_mels + 4 (16-byte aligned rows) or n_mels + 1
     int log_normal;     // log_floor is a normal float: the denormal handling of the device log can be skipped
     int layout;         // 0 time-major [T x nMels], 1 mel-major [nMels x stride]
     const void *lane_tab;   // [32] LaneTables<V> of the launch's window placement and precision (mel_core.cuh)
