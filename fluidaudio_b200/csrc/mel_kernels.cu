@@ -183,14 +183,11 @@ __global__ void __launch_bounds__(kWarps * 32, 2) mel512_kernel(const MelLaunch 
             if (((g.a0 - g.base) & 3) == 0 && (P.pt_len & 3) == 0) {   // 16-byte aligned rows: four samples per step
                 const float4 *s4 = reinterpret_cast<const float4 *>(src);
                 float4 *d4 = reinterpret_cast<float4 *>(ptile);
-                for (int q = tid; q < ((P.pt_len >> 2) + 31 & ~31); q += kWarps * 32) {   // whole warps: shuffle below
-                    const bool in = q < (P.pt_len >> 2);
-                    const float4 x = in ? s4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = tid; q < (P.pt_len >> 2); q += kWarps * 32) {
+                    const float4 x = s4[q];
                     float4 y = x;
-                    // x[4q - 1] is the left neighbour lane's .w (a 16-byte-strided scalar load was a 4-way bank conflict)
-                    float prev = __shfl_up_sync(0xffffffffu, x.w, 1);
-                    if (lane == 0 && in) prev = src[4 * q - 1];
-                    if (!in) continue;
+                    const float prev = src[4 * q - 1];   // (a shuffle from the neighbour lane saves 4 wavefronts per frame but costs
+                                                         //  more instructions than it saves: measured 0.3135 vs 0.3096 ms)
                     if (a != 0.0f) {
                         y.x = preemph_rest(x.x, prev, a);
                         y.y = preemph_rest(x.y, x.x, a);
