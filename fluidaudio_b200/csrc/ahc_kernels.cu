@@ -311,6 +311,173 @@ __global__ void __launch_bounds__(256) ahc_filter_tile_kernel(int N, int D, int 
     }
 }
 
+// Pass 1 at full SIMT rate: 128 x 128 tiles of the lower triangle, 8 x 8 inner products per thread held as packed
+// float pairs (FFMA2: one issue slot per two FMAs), k in chunks of eight through double-buffered shared memory with the
+// next chunk's two float4 global loads in flight during the arithmetic.  Rows / columns of a thread: {ty*4..+3, 64+ty*4..+3}
+// x {tx*4..+3, 64+tx*4..+3}, so the per-k operand loads are four LDS.128 (two of them warp-wide broadcasts) for 32 FFMA2.
+// The bounds keep the 64-column granularity of pass 2: a tile feeds column tiles 2*TJ and 2*TJ+1.
+constexpr int kGT = 128, kGK = 8;
+
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ float2 ffma2_bcast(float a, float2 b, float2 c) {
+    return __ffma2_rn(make_float2(a, a), b, c);
+}
+
+__global__ void __launch_bounds__(256, 2) ahc_filter_tile128_kernel(int N, int D, int Ns, FilterBufs F) {
+    __shared__ __align__(16) float As[2][kGK][kGT], Bs[2][kGK][kGT];
+    const int b = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((long long)ti * (ti + 1) / 2 > b) --ti;
+    while ((long long)(ti + 1) * (ti + 2) / 2 <= b) ++ti;
+    const int tj = b - (int)((long long)ti * (ti + 1) / 2);
+    const int i0 = ti * kGT, j0 = tj * kGT;
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int lk = t >> 5, lc = (t & 31) * 4;   // this thread's float4 of a [8 x 128] chunk
+    const bool a_in = i0 + lc < Ns, b_in = j0 + lc < Ns;   // Ns is a multiple of 32: a float4 is inside or outside as a whole
+    const float *ga = F.cf + (size_t)lk * Ns + i0 + lc, *gb = F.cf + (size_t)lk * Ns + j0 + lc;
+    float2 acc[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = make_float2(0.0f, 0.0f);
+    // chunk k0 -> buffer: asynchronous 16-byte copies straight into shared memory (zero-filled outside the matrix), so
+    // the prefetch holds no registers
+    auto stage = [&](int k0, int bufi) {
+        const bool kin = k0 + lk < D;
+        cp_async16_zfill(&As[bufi][lk][lc], a_in && kin ? ga + (size_t)k0 * Ns : F.cf, a_in && kin);
+        cp_async16_zfill(&Bs[bufi][lk][lc], b_in && kin ? gb + (size_t)k0 * Ns : F.cf, b_in && kin);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, 0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < D; k0 += kGK) {
+        const bool more = k0 + kGK < D;
+        if (more) stage(k0 + kGK, buf ^ 1);   // that buffer was last read a full chunk (and a barrier) ago
+#pragma unroll
+        for (int kk = 0; kk < kGK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                  make_float2(b1.z, b1.w)};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = ffma2_bcast(av[a], bv[c], acc[a][c]);
+        }
+        if (more) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+    // bounds per (row, 64-column tile); the 16 tx threads of a row group are one half-warp.  The columns' norms go
+    // through shared memory (the operand buffers are free now) instead of 24 more live registers.
+    __syncthreads();
+    double *nj = reinterpret_cast<double *>(&As[0][0][0]);   // [128]
+    float *rj = &Bs[0][0][0];                                // [128]
+    if (t < kGT) {
+        const int j = j0 + t;
+        nj[t] = j < N ? F.nrm2[j] : 0.0;
+        rj[t] = j < N ? F.rn[j] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int i = i0 + (a >> 2) * 64 + ty * 4 + (a & 3);
+        const double ni = i < N ? F.nrm2[i] : 0.0;
+        const double ri = i < N ? (double)F.rn[i] : 0.0;
+        double rowmin = 1.7976931348623157e308;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double rowlo = 1.7976931348623157e308;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = j0 + h * 64 + tx * 4 + c;
+                if (i < N && j < i) {
+                    const float2 p = acc[a][h * 2 + (c >> 1)];
+                    const double dot = (double)((c & 1) ? p.y : p.x);
+                    const double njc = nj[h * 64 + tx * 4 + c];
+                    const double approx = (ni + njc) - 2.0 * dot;
+                    const double E = F.c1 * ri * (double)rj[h * 64 + tx * 4 + c] + F.c2 * (ni + njc);
+                    rowmin = fmin(rowmin, fmax(approx + E, 0.0));
+                    rowlo = fmin(rowlo, approx - E);
+                }
+            }
+            if (F.tmin) {
+#pragma unroll
+                for (int o = 8; o >= 1; o >>= 1) rowlo = fmin(rowlo, __shfl_xor_sync(0xffffffffu, rowlo, o));
+                const int t64 = 2 * tj + h;
+                if (tx == 0 && i < N && t64 < F.nt)
+                    F.tmin[(size_t)i * F.nt + t64] = rowlo < 1.7976931348623157e308 ? __double2float_rd(rowlo) : 3.0e38f;
+            }
+        }
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) rowmin = fmin(rowmin, __shfl_xor_sync(0xffffffffu, rowmin, o));
+        if (tx == 0 && i < N && rowmin < 1.7976931348623157e308)
+            atomicMin(&F.U[i], (unsigned long long)__double_as_longlong(rowmin));
+    }
+}
+
+// Pass 2, sparse form (when pass 1 kept its per (row, column tile) lower bounds): one warp per row.  The warp scans its
+// row's bounds (a few of ~N/64 tiles can hold a candidate), and for every such tile evaluates the row's 64 float32 inner
+// products itself (two columns per lane, x_i from shared memory, the columns coalesced from the k-major float copy) and
+// appends the pairs inside the band.  Re-running the dense tile GEMM and exiting early still recomputed ~half the tiles
+// (any of a tile's 64 rows keeps it alive); this does ~1.5 tiles' worth of one row per row.
+__global__ void __launch_bounds__(256) ahc_filter_rows_kernel(int N, int D, int Ns, FilterBufs F) {
+    extern __shared__ float xrow[];   // [8 warps x D]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= N || i < 1) return;
+    float *xi = xrow + (size_t)warp * D;
+    for (int k = lane; k < D; k += 32) xi[k] = F.cf[(size_t)k * Ns + i];
+    __syncwarp();
+    const double Ui = __longlong_as_double((long long)F.U[i]);
+    const double ni = F.nrm2[i], ri = (double)F.rn[i];
+    const int nt_row = i / kFT + 1;   // column tiles that hold some j < i
+    for (int t0 = 0; t0 < nt_row; t0 += 32) {
+        const int t = t0 + lane;
+        const bool hit = t < nt_row && (double)F.tmin[(size_t)i * F.nt + t] <= Ui;
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+            const int tt = t0 + __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int j0 = tt * kFT + lane, j1 = j0 + 32;   // this lane's two columns of the tile
+            float a0 = 0.0f, a1 = 0.0f;
+            const float *c0 = F.cf + j0, *c1 = F.cf + j1;   // (j < Ns always: Ns is a multiple of 32 >= N; zero beyond N)
+            const bool in0 = j0 < Ns, in1 = j1 < Ns;
+            for (int k = 0; k < D; ++k) {
+                const float x = xi[k];
+                if (in0) a0 = fmaf(x, c0[(size_t)k * Ns], a0);
+                if (in1) a1 = fmaf(x, c1[(size_t)k * Ns], a1);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = h ? j1 : j0;
+                if (j < i) {
+                    const double nj = F.nrm2[j];
+                    const double approx = (ni + nj) - 2.0 * (double)(h ? a1 : a0);
+                    const double E = F.c1 * ri * (double)F.rn[j] + F.c2 * (ni + nj);
+                    if (approx - E <= Ui) {
+                        const int slot = atomicAdd(&F.counters[0], 1);
+                        if (slot < F.cap) F.cand[slot] = make_int2(i, j);
+                        else F.counters[2] = 1;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // the reference's chain for every candidate; its minimum per row as an integer atomic on the distance bits
 __global__ void ahc_filter_exact_kernel(const double *__restrict__ cols, int D, int Ns, FilterBufs F) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1140,6 +1307,7 @@ struct Hooks {
     bool force_global = false, force_stream = false;
     int slot_shift = 3, flags = 0;
     int filter_min_n = 2048;   // FA_AHC_FILTER_MIN_N: problems at least this large take the float32 filter (0 = never)
+    int filter_impl = 0;       // FA_AHC_FILTER_IMPL: bit 0 = 64 x 64 tiles in pass 1, bit 1 = dense pass 2 (A/B measurements)
 };
 static const Hooks &hooks() {
     static const Hooks h = [] {
@@ -1151,6 +1319,7 @@ static const Hooks &hooks() {
         if (sh) x.slot_shift = std::min(3, std::max(0, std::atoi(sh)));
         if (f) x.flags = std::atoi(f);
         if (const char *m = std::getenv("FA_AHC_FILTER_MIN_N")) x.filter_min_n = std::atoi(m);
+        if (const char *m = std::getenv("FA_AHC_FILTER_IMPL")) x.filter_impl = std::atoi(m);
         return x;
     }();
     return h;
@@ -1299,8 +1468,16 @@ int Solver::linkage_device(const double *d_rows, int N, int D, double *Z) {
         ahc_filter_prep_kernel<<<(Ns + 127) / 128, 128, 0, stream>>>(P.cols, N, D, Ns, F);
         const int nt = (N + kFT - 1) / kFT;
         const unsigned tiles = (unsigned)((long long)nt * (nt + 1) / 2);
-        ahc_filter_tile_kernel<false><<<tiles, 256, 0, stream>>>(N, D, Ns, F);
-        ahc_filter_tile_kernel<true><<<tiles, 256, 0, stream>>>(N, D, Ns, F);
+        if (hk.filter_impl & 1) {
+            ahc_filter_tile_kernel<false><<<tiles, 256, 0, stream>>>(N, D, Ns, F);
+        } else {
+            const int nt2 = (N + kGT - 1) / kGT;
+            ahc_filter_tile128_kernel<<<(unsigned)((long long)nt2 * (nt2 + 1) / 2), 256, 0, stream>>>(N, D, Ns, F);
+        }
+        if (!(hk.filter_impl & 2) && F.tmin && (size_t)8 * D * sizeof(float) <= 48 * 1024)
+            ahc_filter_rows_kernel<<<(N + 7) / 8, 256, (size_t)8 * D * sizeof(float), stream>>>(N, D, Ns, F);
+        else
+            ahc_filter_tile_kernel<true><<<tiles, 256, 0, stream>>>(N, D, Ns, F);
         const unsigned cgrid = (unsigned)((F.cap + 255) / 256);
         ahc_filter_exact_kernel<<<cgrid, 256, 0, stream>>>(P.cols, D, Ns, F);
         ahc_filter_argmin_kernel<<<cgrid, 256, 0, stream>>>(F);

@@ -1,7 +1,10 @@
 #!/bin/bash
+# final profiles of round 2: launch lists (bench command, cluster call) + ncu --set full of the mel kernel (both value types)
+# and of the filter GEMM
 mkdir -p gpurun_out
-bash scripts/gpu_tests_only.sh -k "vbx or cluster or pipeline or batch or constrained or export or kmeans or speaker or next_rows"
-timeout 600 python bench.py --workload cluster --steps 5 --warmup 3 2>gpurun_out/benchc.err | python -c "
-import json,sys
-d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('cluster', round(d['value']), d['ms_per_step'], d['stages_ms'], d.get('labels_equal_ref'), d.get('labels_equal_cpu'))"
-tail -c 300 gpurun_out/benchc.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --only-main > gpurun_out/ncu_bench_list.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mel512 -s 2 -c 1 -f -o gpurun_out/prof_mel_f32 python scripts/profile_target.py mel32 3 > gpurun_out/ncu_mel32_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mel512 -s 2 -c 1 -f -o gpurun_out/prof_mel python scripts/profile_target.py mel 3 > gpurun_out/ncu_mel_full.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_cluster.csv python scripts/profile_target.py cluster 2 > gpurun_out/ncu_cluster_list.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:tile128 -s 1 -c 1 -f -o gpurun_out/prof_ahc_filter python scripts/profile_target.py cluster 2 > gpurun_out/ncu_filter_full.log 2>&1
+ls -la gpurun_out | head -40

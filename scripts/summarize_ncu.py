@@ -9,7 +9,7 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
            "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum",
+           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum",
            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
@@ -56,7 +56,7 @@ with open(f"profiles/{tag}_summary.txt", "w") as f:
         for n, (c, t) in agg.items():
             f.write(f"  {n:58s} launches={c:4d} total={t/1e6:10.3f} ms  share={t/tot*100:5.1f}%\n")
         f.write("\n")
-    for rep in ("prof_mel_f32.ncu-rep", "prof_mel.ncu-rep", "prof_ahc.ncu-rep"):
+    for rep in ("prof_mel_f32.ncu-rep", "prof_mel.ncu-rep", "prof_ahc.ncu-rep", "prof_ahc_filter.ncu-rep"):
         p = os.path.join("gpurun_out", rep)
         if not os.path.exists(p): continue
         hdr, units, rows = raw(p)
@@ -71,7 +71,7 @@ with open(f"profiles/{tag}_summary.txt", "w") as f:
                 rd = float(r[hdr.index("dram__bytes_read.sum")]); wr = float(r[hdr.index("dram__bytes_write.sum")])
                 f.write(f"   traffic = dram read + write = {rd + wr:.3f} {units[hdr.index('dram__bytes_read.sum')]}\n")
             except Exception: pass
-        for kr in ({"prof_mel_f32.ncu-rep": ["mel512"], "prof_mel.ncu-rep": ["mel512"], "prof_ahc.ncu-rep": ["ahc_init_nn", "ahc_merge"]}[rep]):
+        for kr in ({"prof_mel_f32.ncu-rep": ["mel512"], "prof_mel.ncu-rep": ["mel512"], "prof_ahc.ncu-rep": ["ahc_init_nn", "ahc_merge"], "prof_ahc_filter.ncu-rep": ["tile128"]}[rep]):
             h = opcode_hist(p, kr)
             if not h: continue
             op, smp, tot, ts = h
