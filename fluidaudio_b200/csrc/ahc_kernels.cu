@@ -219,6 +219,7 @@ __global__ void ahc_filter_prep_kernel(const double *__restrict__ cols, int N, i
         n = fma(v, v, n);
         if (!(fabs(v) <= 1e17)) bad = true;   // also NaN / Inf
     }
+    for (int k = D; k < ((D + 7) & ~7); ++k) F.cf[(size_t)k * Ns + i] = 0.0f;
     if (i < N) {
         F.nrm2[i] = n;
         F.rn[i] = __fmul_ru(__double2float_ru(sqrt(n)), 1.000001f);
@@ -338,28 +339,35 @@ __global__ void __launch_bounds__(256, 2) ahc_filter_tile128_kernel(int N, int D
     const int i0 = ti * kGT, j0 = tj * kGT;
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
     const int lk = t >> 5, lc = (t & 31) * 4;   // this thread's float4 of a [8 x 128] chunk
-    const bool a_in = i0 + lc < Ns, b_in = j0 + lc < Ns;   // Ns is a multiple of 32: a float4 is inside or outside as a whole
-    const float *ga = F.cf + (size_t)lk * Ns + i0 + lc, *gb = F.cf + (size_t)lk * Ns + j0 + lc;
+    // Ns is a multiple of 32: a float4 is inside or outside the matrix as a whole; cf has its row count rounded up to a
+    // multiple of eight with zero rows, so k needs no bound check
+    const int a_bytes = i0 + lc < Ns ? 16 : 0, b_bytes = j0 + lc < Ns ? 16 : 0;
+    const float *ga = a_bytes ? F.cf + (size_t)lk * Ns + i0 + lc : F.cf;
+    const float *gb = b_bytes ? F.cf + (size_t)lk * Ns + j0 + lc : F.cf;
+    const size_t gstep = a_bytes ? (size_t)kGK * Ns : 0, gstep_b = b_bytes ? (size_t)kGK * Ns : 0;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(&As[0][lk][lc]), sb = (unsigned)__cvta_generic_to_shared(&Bs[0][lk][lc]);
+    constexpr unsigned kBufBytes = kGK * kGT * sizeof(float);
     float2 acc[8][4];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[a][c] = make_float2(0.0f, 0.0f);
-    // chunk k0 -> buffer: asynchronous 16-byte copies straight into shared memory (zero-filled outside the matrix), so
-    // the prefetch holds no registers
-    auto stage = [&](int k0, int bufi) {
-        const bool kin = k0 + lk < D;
-        cp_async16_zfill(&As[bufi][lk][lc], a_in && kin ? ga + (size_t)k0 * Ns : F.cf, a_in && kin);
-        cp_async16_zfill(&Bs[bufi][lk][lc], b_in && kin ? gb + (size_t)k0 * Ns : F.cf, b_in && kin);
+    // chunk -> buffer: asynchronous 16-byte copies straight into shared memory (zero-filled outside the matrix): the
+    // prefetch holds no registers
+    auto stage = [&](int bufi) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa + bufi * kBufBytes), "l"(ga), "r"(a_bytes) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sb + bufi * kBufBytes), "l"(gb), "r"(b_bytes) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
+        ga += gstep;
+        gb += gstep_b;
     };
-    stage(0, 0);
+    stage(0);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     int buf = 0;
     for (int k0 = 0; k0 < D; k0 += kGK) {
         const bool more = k0 + kGK < D;
-        if (more) stage(k0 + kGK, buf ^ 1);   // that buffer was last read a full chunk (and a barrier) ago
+        if (more) stage(buf ^ 1);   // that buffer was last read a full chunk (and a barrier) ago
 #pragma unroll
         for (int kk = 0; kk < kGK; ++kk) {
             const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 4]);
@@ -380,51 +388,57 @@ __global__ void __launch_bounds__(256, 2) ahc_filter_tile128_kernel(int N, int D
             buf ^= 1;
         }
     }
-    // bounds per (row, 64-column tile); the 16 tx threads of a row group are one half-warp.  The columns' norms go
-    // through shared memory (the operand buffers are free now) instead of 24 more live registers.
+    // Bounds per (row, 64-column tile) in float32 INTERVAL arithmetic (every operation rounded towards the safe side), so
+    // that the epilogue is ~12 instructions per pair instead of ~35 in double: with s = n_i + n_j,
+    //   lo = RD(RD(-2 dot + RD(s)) - E^),  hi = RU(RU(-2 dot + RU(s)) + E^),  E^ = RU(c1r_i^ r_j + RU(c2^ RU(s))) >= E.
+    // Rounding the bounds to float widens the band by < 1 % of E (2^-24 * 4 against c1 ~ 3e-5).  The columns' norms go
+    // through shared memory (the operand buffers are free now); the 16 tx threads of a row group are one half-warp.
     __syncthreads();
-    double *nj = reinterpret_cast<double *>(&As[0][0][0]);   // [128]
-    float *rj = &Bs[0][0][0];                                // [128]
+    float *nlo = &As[0][0][0], *nhi = nlo + kGT, *rj = nhi + kGT;   // [128] each
     if (t < kGT) {
         const int j = j0 + t;
-        nj[t] = j < N ? F.nrm2[j] : 0.0;
+        const double nj = j < N ? F.nrm2[j] : 0.0;
+        nlo[t] = __double2float_rd(nj);
+        nhi[t] = __double2float_ru(nj);
         rj[t] = j < N ? F.rn[j] : 0.0f;
     }
     __syncthreads();
+    const float c1up = __double2float_ru(F.c1), c2up = __double2float_ru(F.c2);
+    const float kInf = __int_as_float(0x7f800000);
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
         const int i = i0 + (a >> 2) * 64 + ty * 4 + (a & 3);
         const double ni = i < N ? F.nrm2[i] : 0.0;
-        const double ri = i < N ? (double)F.rn[i] : 0.0;
-        double rowmin = 1.7976931348623157e308;
+        const float ni_lo = __double2float_rd(ni), ni_hi = __double2float_ru(ni);
+        const float c1ri = __fmul_ru(c1up, i < N ? F.rn[i] : 0.0f);
+        float rowmin = kInf;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            double rowlo = 1.7976931348623157e308;
+            float rowlo = kInf;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const int j = j0 + h * 64 + tx * 4 + c;
-                if (i < N && j < i) {
-                    const float2 p = acc[a][h * 2 + (c >> 1)];
-                    const double dot = (double)((c & 1) ? p.y : p.x);
-                    const double njc = nj[h * 64 + tx * 4 + c];
-                    const double approx = (ni + njc) - 2.0 * dot;
-                    const double E = F.c1 * ri * (double)rj[h * 64 + tx * 4 + c] + F.c2 * (ni + njc);
-                    rowmin = fmin(rowmin, fmax(approx + E, 0.0));
-                    rowlo = fmin(rowlo, approx - E);
-                }
+                const int jl = h * 64 + tx * 4 + c, j = j0 + jl;
+                const float2 p = acc[a][h * 2 + (c >> 1)];
+                const float dot = (c & 1) ? p.y : p.x;
+                const float s_lo = __fadd_rd(ni_lo, nlo[jl]), s_hi = __fadd_ru(ni_hi, nhi[jl]);
+                const float e = __fmaf_ru(c1ri, rj[jl], __fmul_ru(c2up, s_hi));
+                const float hi = __fadd_ru(__fmaf_ru(-2.0f, dot, s_hi), e);
+                const float lo = __fsub_rd(__fmaf_rd(-2.0f, dot, s_lo), e);
+                const bool live = i < N && j < i;
+                rowmin = fminf(rowmin, live ? fmaxf(hi, 0.0f) : kInf);
+                rowlo = fminf(rowlo, live ? lo : kInf);
             }
             if (F.tmin) {
 #pragma unroll
-                for (int o = 8; o >= 1; o >>= 1) rowlo = fmin(rowlo, __shfl_xor_sync(0xffffffffu, rowlo, o));
+                for (int o = 8; o >= 1; o >>= 1) rowlo = fminf(rowlo, __shfl_xor_sync(0xffffffffu, rowlo, o));
                 const int t64 = 2 * tj + h;
-                if (tx == 0 && i < N && t64 < F.nt)
-                    F.tmin[(size_t)i * F.nt + t64] = rowlo < 1.7976931348623157e308 ? __double2float_rd(rowlo) : 3.0e38f;
+                if (tx == 0 && i < N && t64 < F.nt) F.tmin[(size_t)i * F.nt + t64] = rowlo < kInf ? rowlo : 3.0e38f;
             }
         }
 #pragma unroll
-        for (int o = 8; o >= 1; o >>= 1) rowmin = fmin(rowmin, __shfl_xor_sync(0xffffffffu, rowmin, o));
-        if (tx == 0 && i < N && rowmin < 1.7976931348623157e308)
-            atomicMin(&F.U[i], (unsigned long long)__double_as_longlong(rowmin));
+        for (int o = 8; o >= 1; o >>= 1) rowmin = fminf(rowmin, __shfl_xor_sync(0xffffffffu, rowmin, o));
+        if (tx == 0 && i < N && rowmin < kInf)
+            atomicMin(&F.U[i], (unsigned long long)__double_as_longlong((double)rowmin));
     }
 }
 
@@ -1242,7 +1256,7 @@ Layout make_layout(int N, int D, int Ns, int workers) {
     L.problem = c.take<Problem>(1);
     // float32 filter of the initial nearest-neighbour pass (N >= kFilterMinN only, but sized unconditionally: small)
     L.filter_cap = (int)std::min<long long>(64LL * N, 1 << 24);
-    L.f_cf = c.take<float>((size_t)D * Ns);
+    L.f_cf = c.take<float>((size_t)((D + 7) & ~7) * Ns);   // rows rounded up to the GEMM's k-chunk (zero rows)
     L.f_nrm2 = c.take<double>((size_t)N);
     L.f_rn = c.take<float>((size_t)N);
     L.f_U = c.take<unsigned long long>((size_t)N);

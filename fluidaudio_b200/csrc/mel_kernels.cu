@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -877,6 +878,73 @@ static float *device_alias_if_pinned(float *host) {
 
 // Host buffers in, host buffers out.  A long clip is cut into units of `chunk` frames: unit c's samples are copied
 // on the H2D stream while unit c-1 runs on the compute stream and unit c-2's rows return on the D2H stream.
+// FA_MEL_TRACE_PIPELINE=1: device timestamps (timing events) at the end of every unit's H2D, kernels and D2H, printed to
+// stderr after the call — the tool behind profiles/r02_mel.md's pipeline timeline.  Off: no events, no cost.
+struct PipelineTrace {
+    bool on = false;
+    cudaEvent_t t0 = nullptr;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> tag;   // unit * 4 + stage (0 H2D done, 1 kernels done, 2 D2H done)
+    PipelineTrace() {
+        static const bool want = [] { const char *e = std::getenv("FA_MEL_TRACE_PIPELINE"); return e && *e && *e != '0'; }();
+        on = want;
+    }
+    void start(cudaStream_t s) {
+        if (!on) return;
+        cudaEventCreate(&t0);
+        cudaEventRecord(t0, s);
+    }
+    void mark(cudaStream_t s, int unit, int stage) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.push_back(e);
+        tag.push_back(unit * 4 + stage);
+    }
+    void dump(const char *what) {
+        if (!on) return;
+        static const char *names[3] = {"h2d", "kern", "d2h"};
+        std::fprintf(stderr, "[pipeline %s]", what);
+        for (size_t i = 0; i < ev.size(); ++i) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, t0, ev[i]);
+            std::fprintf(stderr, " u%d.%s=%.3f", tag[i] / 4, names[tag[i] & 3], ms);
+            cudaEventDestroy(ev[i]);
+        }
+        std::fprintf(stderr, "\n");
+        cudaEventDestroy(t0);
+    }
+};
+
+// Frame ranges of the pipeline's units.  The pipeline's fixed cost is its ramp: nothing can be computed before the first
+// unit's samples have landed, and the last unit's kernel + D2H run after the last byte of input.  So the units at both ends
+// are small (1 : 2 : 4 ... 4 : 2 : 1) and the ones in between large enough to amortise the per-transfer cost.  Bounds are
+// multiples of the tile height; no unit is shorter than min_unit frames (fewer units otherwise).
+static std::vector<long long> unit_bounds(long long T, long long max_units, long long min_unit) {
+    std::vector<long long> b{0};
+    long long K = std::max<long long>(1, std::min(max_units, T / std::max<long long>(1, min_unit)));
+    auto weight = [&](long long c, long long k) -> long long {
+        if (k < 6) return 4;
+        const long long e = std::min(c, k - 1 - c);
+        return e == 0 ? 1 : (e == 1 ? 2 : 4);
+    };
+    for (; K > 1; --K) {   // the smallest unit must still hold min_unit frames
+        long long sum = 0;
+        for (long long c = 0; c < K; ++c) sum += weight(c, K);
+        if (T * weight(0, K) / sum >= min_unit) break;
+    }
+    long long sum = 0, acc = 0;
+    for (long long c = 0; c < K; ++c) sum += weight(c, K);
+    for (long long c = 0; c + 1 < K; ++c) {
+        acc += weight(c, K);
+        const long long e = std::min(T, ceil_to((long long)((double)T * (double)acc / (double)sum), kTileFrames));
+        if (e > b.back() && e < T) b.push_back(e);
+    }
+    b.push_back(T);
+    return b;
+}
+
 int MelPlan::compute_host(const float *audio, long long n, float last, int mode, long long expected, int layout,
                           float *out, long long out_len, long long *mel_length, long long *num_frames) {
     long long T, Tp;
@@ -898,9 +966,8 @@ int MelPlan::compute_host(const float *audio, long long n, float last, int mode,
     }
     int st = ensure_staging((size_t)n + 8, (size_t)need);
     if (st != FA_OK) return st;
-    const long long kMinChunk = 4096, kMaxChunks = pipeline_chunks;
-    long long chunk = std::max(kMinChunk, ceil_to((T + kMaxChunks - 1) / kMaxChunks, kTileFrames));
-    const int chunks = (int)((T + chunk - 1) / chunk);
+    const std::vector<long long> bounds = unit_bounds(T, pipeline_chunks, 4096);
+    const int chunks = (int)bounds.size() - 1;
     float *out_alias = (zero_copy_out && layout == 0 && chunks > 1) ? device_alias_if_pinned(out) : nullptr;
     float *k_out = out_alias ? out_alias : d_out;   // where the kernel writes
     if (out_alias && Tp > T) std::memset(out + T * cfg.n_mels, 0, (size_t)(Tp - T) * cfg.n_mels * sizeof(float));
@@ -923,10 +990,7 @@ int MelPlan::compute_host(const float *audio, long long n, float last, int mode,
     }
     st = ensure_events(2 * (size_t)chunks);
     if (st != FA_OK) return st;
-    for (int c = 0; c < chunks; ++c) {
-        const long long fb = c * chunk, fc = std::min(chunk, T - fb);
-        h_units[c] = MelUnit{0, n, 0, Tp, fb, fc, last, 0};
-    }
+    for (int c = 0; c < chunks; ++c) h_units[c] = MelUnit{0, n, 0, Tp, bounds[c], bounds[c + 1] - bounds[c], last, 0};
     FA_CUDA_TRY(cudaMemcpyAsync(d_units, h_units, chunks * sizeof(MelUnit), cudaMemcpyHostToDevice, s_k));
     if (Tp > T && !out_alias) FA_CUDA_TRY(cudaMemsetAsync(d_out, 0, need * sizeof(float), s_k));
     const long long pad = mode == 0 ? cfg.n_fft / 2 : 0;
@@ -1019,10 +1083,9 @@ int MelPlan::compute_host_pcm(const void *pcm, long long frames, const resample:
     }
     // pipeline depth: ~10 MB of PCM per chunk (the copy engines' fixed cost per transfer and the host's enqueue rate make
     // finer chunks slower: int16 hour 3.08 ms at 8-12 chunks, 3.44 at 24, 3.61 at 96 — profiles/r02_mel.md)
-    const long long kMinChunk = 4096;
     const long long kMaxChunks = std::max<long long>(1, std::min<long long>(pipeline_chunks, (long long)(pcm_bytes / (10u << 20)) + 1));
-    const long long chunk = std::max(kMinChunk, ceil_to((T + kMaxChunks - 1) / kMaxChunks, kTileFrames));
-    const int chunks = (int)((T + chunk - 1) / chunk);
+    const std::vector<long long> bounds = unit_bounds(T, kMaxChunks, 4096);
+    const int chunks = (int)bounds.size() - 1;
     float *out_alias = (zero_copy_out && layout == 0) ? device_alias_if_pinned(out) : nullptr;
     float *k_out = out_alias ? out_alias : d_out;   // where the kernel writes
     if (out_alias && Tp > T) std::memset(out + T * cfg.n_mels, 0, (size_t)(Tp - T) * cfg.n_mels * sizeof(float));
@@ -1031,16 +1094,15 @@ int MelPlan::compute_host_pcm(const void *pcm, long long frames, const resample:
     st = ensure_events(2 * (size_t)chunks);
     if (st != FA_OK) return st;
     cudaStream_t s_in = streams[0], s_k = streams[1], s_out = streams[2];
-    for (int c = 0; c < chunks; ++c) {
-        const long long fb = c * chunk, fc = std::min(chunk, T - fb);
-        h_units[c] = MelUnit{0, n, 0, Tp, fb, fc, last, 0};
-    }
+    for (int c = 0; c < chunks; ++c) h_units[c] = MelUnit{0, n, 0, Tp, bounds[c], bounds[c + 1] - bounds[c], last, 0};
     FA_CUDA_TRY(cudaMemcpyAsync(d_units, h_units, chunks * sizeof(MelUnit), cudaMemcpyHostToDevice, s_k));
     if (Tp > T && !out_alias) FA_CUDA_TRY(cudaMemsetAsync(d_out, 0, need * sizeof(float), s_k));
     const long long pad = mode == 0 ? cfg.n_fft / 2 : 0;
     const resample::Design &D = rs_design;
     const bool linear = f.in_rate != f.out_rate && resample::resolve_algorithm(f) == resample::kAlgoLinear;
     long long in_copied = 0, converted = 0;
+    PipelineTrace trace;
+    trace.start(s_in);
     for (int c = 0; c < chunks; ++c) {
         const long long f_end = h_units[c].frame_begin + h_units[c].frame_count;
         long long s_end = std::min(n, (f_end - 1) * cfg.hop_length + cfg.n_fft - pad);   // model-rate samples needed so far
@@ -1068,6 +1130,7 @@ int MelPlan::compute_host_pcm(const void *pcm, long long frames, const resample:
             in_copied = in_need;
         }
         FA_CUDA_TRY(cudaEventRecord(events[2 * c], s_in));
+        trace.mark(s_in, c, 0);
         FA_CUDA_TRY(cudaStreamWaitEvent(s_k, events[2 * c], 0));
         long long ready = resample::outputs_ready(f, D, frames, in_copied, n);
         if (ready < s_end) {
@@ -1080,6 +1143,7 @@ int MelPlan::compute_host_pcm(const void *pcm, long long frames, const resample:
         converted = std::max(converted, ready);
         st = launch(d_audio, k_out, c, 1, tiles_of(h_units[c].frame_count), mode, layout, s_k, true);
         if (st != FA_OK) return st;
+        trace.mark(s_k, c, 1);
         if (out_alias) continue;   // the kernel stored its rows in the caller's pinned buffer: no D2H stage
         FA_CUDA_TRY(cudaEventRecord(events[2 * c + 1], s_k));
         FA_CUDA_TRY(cudaStreamWaitEvent(s_out, events[2 * c + 1], 0));
@@ -1093,9 +1157,11 @@ int MelPlan::compute_host_pcm(const void *pcm, long long frames, const resample:
             FA_CUDA_TRY(cudaMemcpy2DAsync(out + fb, Tp * sizeof(float), d_out + fb, Tp * sizeof(float),
                                           cols * sizeof(float), cfg.n_mels, cudaMemcpyDeviceToHost, s_out));
         }
+        trace.mark(s_out, c, 2);
     }
     FA_CUDA_TRY(cudaStreamSynchronize(s_out));
     FA_CUDA_TRY(cudaStreamSynchronize(s_k));
+    trace.dump("pcm");
     return FA_OK;
 }
 

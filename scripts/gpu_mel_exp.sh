@@ -26,7 +26,7 @@ m.timer_start()
 for _ in range(20): m.compute_device(d_a, n, d_o)
 print(f"kernel-only f32: {m.timer_stop_ms()/20:.4f} ms/h", flush=True)
 ref = None
-for zc in (1, 0):
+for zc in ((1, 0) if "ZC" in __import__("os").environ else (0,)):
     _lib.check(L.fa_mel_set_zero_copy_output(m._h, zc), "zc")
     for chunks in (2, 4, 8, 12, 16, 24, 32, 48, 96):
         _lib.check(L.fa_mel_set_pipeline_chunks(m._h, chunks), "chunks")
