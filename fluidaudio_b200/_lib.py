@@ -74,7 +74,7 @@ EXPORTED_SYMBOLS = [
     "fa_resample_output_count", "fa_audio_resample", "fa_audio_to_mel",
     "fa_linear_resample", "fa_l2_normalize_rows", "fa_ahc_cluster", "fa_dendrogram_cut", "fa_vbx_default_config",
     "fa_vbx_refine", "fa_compute_centroids", "fa_assign_embeddings", "fa_cluster_default_config",
-    "fa_diarize_cluster", "fa_diarize_cluster_batch", "fa_ahc_last_stage_ms", "fa_diarize_cluster_chunks",
+    "fa_diarize_cluster", "fa_diarize_cluster_batch", "fa_diarize_cluster_batch_chunks", "fa_ahc_last_stage_ms", "fa_diarize_cluster_chunks",
     "fa_hungarian_solve", "fa_max_score_assignment", "fa_constrained_assign", "fa_build_chunk_assignments",
     "fa_export_shape", "fa_export_read", "fa_export_write", "fa_kmeans_cluster", "fa_speaker_constraints_resolve",
     "fa_reconstruct_default_config", "fa_build_segments", "fa_build_speaker_database",
@@ -150,6 +150,7 @@ def load():
     L.fa_diarize_cluster.argtypes = [vp, vp, sz, sz, sz, vp, C.POINTER(ClusterConfig), vp, vp, vp, i32,
                                      C.POINTER(ClusterInfo)]
     L.fa_diarize_cluster_batch.argtypes = [vp, vp, vp, i32, sz, sz, vp, C.POINTER(ClusterConfig), vp, vp]
+    L.fa_diarize_cluster_batch_chunks.argtypes = [vp, vp, vp, i32, sz, sz, vp, C.POINTER(ClusterConfig), vp, vp, vp]
     L.fa_diarize_cluster_chunks.argtypes = [vp, vp, sz, sz, sz, vp, C.POINTER(ClusterConfig), vp, vp, vp, vp, i32,
                                             C.POINTER(ClusterInfo)]
     L.fa_hungarian_solve.argtypes = [vp, i32, vp]

@@ -231,7 +231,10 @@ class OfflineClusterer:
         d = {f: getattr(info, f) for f, _ in _lib.ClusterInfo._fields_}
         return ClusterResult(labels, initial, cents[: min(info.centroid_count, max_centroids)].copy(), d)
 
-    def cluster_batch(self, embedding256: np.ndarray, rho128: np.ndarray, set_offsets) -> tuple[np.ndarray, list]:
+    def cluster_batch(self, embedding256: np.ndarray, rho128: np.ndarray, set_offsets,
+                      chunk_indices=None) -> tuple[np.ndarray, list]:
+        """chunk_indices: TimedEmbedding.chunkIndex per row, numbered inside its own set -> the reference's default
+        constrained assignment in every set (as `cluster(..., chunk_indices=...)` does for one)."""
         emb = np.ascontiguousarray(embedding256, np.float32)
         rho = np.ascontiguousarray(rho128, np.float64)
         offs = np.ascontiguousarray(set_offsets, np.int64)
@@ -240,9 +243,18 @@ class OfflineClusterer:
         infos = (_lib.ClusterInfo * max(count, 1))()
         cfg = self.config._c_cluster()
         psi = self.psi if self.psi is not None and self.psi.size == rho.shape[1] else None
-        _lib.check(_lib.load().fa_diarize_cluster_batch(emb.ctypes.data, rho.ctypes.data, offs.ctypes.data, count,
-                                                        emb.shape[1], rho.shape[1], _lib.ptr(psi), C.byref(cfg),
-                                                        labels.ctypes.data, infos), "fa_diarize_cluster_batch")
+        if chunk_indices is None:
+            _lib.check(_lib.load().fa_diarize_cluster_batch(emb.ctypes.data, rho.ctypes.data, offs.ctypes.data, count,
+                                                            emb.shape[1], rho.shape[1], _lib.ptr(psi), C.byref(cfg),
+                                                            labels.ctypes.data, infos), "fa_diarize_cluster_batch")
+        else:
+            chunk = np.ascontiguousarray(chunk_indices, np.int32)
+            if chunk.shape[0] != emb.shape[0]:
+                raise ValueError("chunk_indices needs one entry per embedding")
+            _lib.check(_lib.load().fa_diarize_cluster_batch_chunks(emb.ctypes.data, rho.ctypes.data, offs.ctypes.data,
+                                                                   count, emb.shape[1], rho.shape[1], _lib.ptr(psi),
+                                                                   C.byref(cfg), chunk.ctypes.data, labels.ctypes.data,
+                                                                   infos), "fa_diarize_cluster_batch_chunks")
         out = [{f: getattr(infos[i], f) for f, _ in _lib.ClusterInfo._fields_} for i in range(count)]
         return labels, out
 

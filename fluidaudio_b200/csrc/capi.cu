@@ -1420,9 +1420,10 @@ FA_API fa_status fa_build_chunk_assignments(const int32_t *chunk_index, const in
 
 // Independent sets run on disjoint SM partitions: `lanes` host threads, each leasing a context whose merge kernel
 // is capped at (SMs / lanes) - 1 worker CTAs, pull sets from a shared counter.
-FA_API fa_status fa_diarize_cluster_batch(const float *emb256, const double *rho, const int64_t *set_offsets,
-                                          int32_t set_count, size_t emb_dim, size_t rho_dim, const double *psi,
-                                          const fa_cluster_config *cfg, int32_t *labels, fa_cluster_info *infos) {
+static fa_status cluster_batch_impl(const float *emb256, const double *rho, const int64_t *set_offsets,
+                                    int32_t set_count, size_t emb_dim, size_t rho_dim, const double *psi,
+                                    const fa_cluster_config *cfg, const int32_t *chunk_index, int32_t *labels,
+                                    fa_cluster_info *infos) {
     if (!emb256 || !rho || !set_offsets || !cfg || !labels || set_count < 0 || emb_dim == 0 || rho_dim == 0)
         return FA_STATUS_INVALID_ARGUMENT;
     if (set_count == 0) return FA_STATUS_OK;
@@ -1465,7 +1466,7 @@ FA_API fa_status fa_diarize_cluster_batch(const float *emb256, const double *rho
             if (b <= a) continue;
             const int st = cluster_pipeline(*lease.ctx, emb256 + (size_t)a * emb_dim, rho + (size_t)a * rho_dim,
                                             (size_t)(b - a), emb_dim, rho_dim, psi, *cfg, labels + a, nullptr, nullptr,
-                                            0, infos ? infos + m : nullptr);
+                                            0, infos ? infos + m : nullptr, chunk_index ? chunk_index + a : nullptr);
             if (st != FA_OK) {
                 status[lane] = st;
                 messages[lane] = fa::last_error();
@@ -1515,4 +1516,19 @@ FA_API fa_status fa_diarize_cluster_batch(const float *emb256, const double *rho
         }
     return FA_STATUS_OK;
     FA_GUARD_END
+}
+
+FA_API fa_status fa_diarize_cluster_batch(const float *emb256, const double *rho, const int64_t *set_offsets,
+                                          int32_t set_count, size_t emb_dim, size_t rho_dim, const double *psi,
+                                          const fa_cluster_config *cfg, int32_t *labels, fa_cluster_info *infos) {
+    return cluster_batch_impl(emb256, rho, set_offsets, set_count, emb_dim, rho_dim, psi, cfg, nullptr, labels, infos);
+}
+
+// The reference's default (constrained) assignment per set: chunk_index[row] = TimedEmbedding.chunkIndex of that row,
+// numbered inside its own set.
+FA_API fa_status fa_diarize_cluster_batch_chunks(const float *emb256, const double *rho, const int64_t *set_offsets,
+                                                 int32_t set_count, size_t emb_dim, size_t rho_dim, const double *psi,
+                                                 const fa_cluster_config *cfg, const int32_t *chunk_index,
+                                                 int32_t *labels, fa_cluster_info *infos) {
+    return cluster_batch_impl(emb256, rho, set_offsets, set_count, emb_dim, rho_dim, psi, cfg, chunk_index, labels, infos);
 }

@@ -344,6 +344,13 @@ fa_status fa_diarize_cluster_batch(const float *emb256, const double *rho, const
                                    int32_t set_count, size_t emb_dim, size_t rho_dim, const double *psi,
                                    const fa_cluster_config *cfg, int32_t *labels, fa_cluster_info *infos);
 
+/* Same with the reference's default constrained assignment in every set (OfflineDiarizerManager.swift:357-369):
+ * chunk_index[row] is TimedEmbedding.chunkIndex of that row, numbered inside its own set; NULL = plain argmax. */
+fa_status fa_diarize_cluster_batch_chunks(const float *emb256, const double *rho, const int64_t *set_offsets,
+                                          int32_t set_count, size_t emb_dim, size_t rho_dim, const double *psi,
+                                          const fa_cluster_config *cfg, const int32_t *chunk_index, int32_t *labels,
+                                          fa_cluster_info *infos);
+
 #ifdef __cplusplus
 }
 #endif

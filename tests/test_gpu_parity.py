@@ -628,6 +628,33 @@ def test_batch_of_sets_equals_one_by_one(gpu_lib, oracle):
         assert infos[i]["training_count"] == n
 
 
+def test_batch_with_chunk_indices_equals_one_by_one(gpu_lib, oracle):
+    """fa_diarize_cluster_batch_chunks: the reference's default constrained assignment in every set of a batch equals the
+    single-set entry point and the oracle (chunk indices are numbered inside each set)."""
+    rng = np.random.default_rng(33)
+    sizes = [500, 40, 900]
+    embs, rhos, chunks, offs = [], [], [], [0]
+    psi = None
+    for i, n in enumerate(sizes):
+        e, _ = synth.speaker_embeddings(n, 256, 4, weights=(0.4, 0.3, 0.2, 0.1), seed=200 + i)
+        r, psi = synth.synthetic_plda(e)
+        embs.append(e); rhos.append(r); offs.append(offs[-1] + n)
+        chunks.append(np.sort(rng.integers(0, max(1, n // 2), n)).astype(np.int32))
+    c = cl.OfflineClusterer(psi=psi)
+    labels, _ = c.cluster_batch(np.concatenate(embs), np.concatenate(rhos), offs, chunk_indices=np.concatenate(chunks))
+    plain, _ = c.cluster_batch(np.concatenate(embs), np.concatenate(rhos), offs)
+    differs = False
+    for i, n in enumerate(sizes):
+        single = c.cluster(embs[i], rhos[i], chunk_indices=chunks[i]).labels
+        assert np.array_equal(labels[offs[i]:offs[i + 1]], single)
+        o = oracle.diarize_cluster(embs[i], rhos[i], psi, chunk_indices=chunks[i])
+        assert np.array_equal(single, o.labels)
+        differs |= not np.array_equal(single, plain[offs[i]:offs[i + 1]])
+    assert differs   # the constraint changes at least one label on these inputs (else the test would not see the argument)
+    with pytest.raises(ValueError):
+        c.cluster_batch(np.concatenate(embs), np.concatenate(rhos), offs, chunk_indices=chunks[0])
+
+
 def test_constrained_pipeline_matches_oracle(gpu_lib, oracle):
     """The reference's DEFAULT configuration (constrainedAssignment = true): chunk-wise Hungarian on GPU scores."""
     rng = np.random.default_rng(21)
