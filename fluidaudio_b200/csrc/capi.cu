@@ -801,24 +801,17 @@ FA_API fa_status fa_mel_lseend_features(fa_mel *mel, const float *chunk, size_t 
 FA_API fa_status fa_mel_normalize_per_feature(float *x, int64_t frames, int32_t n_mels, int64_t valid) {
     if (!x || frames < 0 || n_mels <= 0) return FA_STATUS_INVALID_ARGUMENT;
     if (valid > frames) valid = frames;   // UnifiedMelExtractor.swift:66: validFrames = min(validCount / hop, totalFrames)
-    if (valid <= 0) {
-        for (int64_t i = 0; i < frames * n_mels; ++i) x[i] = 0.0f;
+    if (frames == 0) return FA_STATUS_OK;
+    if (valid <= 0) {                     // no valid frame: everything is padding
+        std::memset(x, 0, sizeof(float) * (size_t)frames * n_mels);
         return FA_STATUS_OK;
     }
-    const float denom = (float)(valid > 1 ? valid - 1 : 1);
-    for (int32_t m = 0; m < n_mels; ++m) {
-        float mean = 0.0f;
-        for (int64_t t = 0; t < valid; ++t) mean += x[t * n_mels + m];
-        mean /= (float)valid;
-        float var = 0.0f;
-        for (int64_t t = 0; t < valid; ++t) {
-            const float d = x[t * n_mels + m] - mean;
-            var += d * d;
-        }
-        const float sd = sqrtf(var / denom) + 1e-5f;
-        for (int64_t t = 0; t < frames; ++t) x[t * n_mels + m] = t < valid ? (x[t * n_mels + m] - mean) / sd : 0.0f;
-    }
-    return FA_STATUS_OK;
+    API_REQUIRE_DEVICE();
+    FA_GUARD_BEGIN
+    const int st = mel::normalize_per_feature_host(x, (long long)frames, n_mels, (long long)valid);
+    if (st == FA_OK) ++g_launches;
+    return (fa_status)st;
+    FA_GUARD_END
 }
 
 // ------------------------------------------------------------------------------------------------ AudioConverter stage
@@ -923,35 +916,17 @@ FA_API fa_status fa_audio_to_mel(fa_mel *mel, const void *pcm, int64_t frames, c
 // AudioConverter.linearResample (AudioConverter.swift:388-442): boundary glue for >2-channel input.
 FA_API fa_status fa_linear_resample(const float *in, int64_t frames, int32_t channels, double in_rate, double out_rate,
                                     float *out, int64_t out_cap, int64_t *out_count) {
-    if (!in || frames < 0 || channels <= 0 || !(in_rate > 0) || !(out_rate > 0) || !out_count)
+    if (frames < 0 || channels <= 0 || !(in_rate > 0) || !(out_rate > 0) || !out_count || (out && !in && frames))
         return FA_STATUS_INVALID_ARGUMENT;
-    const float w = 1.0f / (float)channels;
-    auto mono = [&](int64_t f) {
-        float s = 0.0f;
-        for (int32_t c = 0; c < channels; ++c) s += in[(int64_t)c * frames + f];
-        return s * w;
-    };
-    if (in_rate == out_rate) {
-        *out_count = frames;
-        if (!out) return FA_STATUS_OK;
-        if (out_cap < frames) return FA_STATUS_OUTPUT_TOO_SMALL;
-        for (int64_t f = 0; f < frames; ++f) out[f] = mono(f);
-        return FA_STATUS_OK;
-    }
-    const double ratio = in_rate / out_rate;
-    const int64_t n = (int64_t)((double)frames / ratio);
-    *out_count = n;
-    if (!out) return FA_STATUS_OK;
-    if (out_cap < n) return FA_STATUS_OUTPUT_TOO_SMALL;
-    for (int64_t i = 0; i < n; ++i) {
-        const double src = (double)i * ratio;
-        const int64_t idx = (int64_t)src;
-        const float frac = (float)(src - (double)idx);
-        if (idx < frames - 1) out[i] = mono(idx) * (1.0f - frac) + mono(idx + 1) * frac;
-        else if (idx < frames) out[i] = mono(idx);
-        else out[i] = 0.0f;
-    }
-    return FA_STATUS_OK;
+    // planar float32, the two-tap float32 interpolation whatever the channel count: the converter stage's linear kernel
+    fa_audio_format fmt{};
+    fmt.in_rate = in_rate;
+    fmt.out_rate = out_rate;
+    fmt.channels = channels;
+    fmt.format = FA_PCM_F32;
+    fmt.interleaved = 0;
+    fmt.algorithm = FA_RESAMPLE_LINEAR;
+    return fa_audio_resample(in, frames, &fmt, out, out_cap, out_count);
 }
 
 // ------------------------------------------------------------------------------------------------ clustering

@@ -68,6 +68,38 @@ __global__ void __launch_bounds__(kBinsPerCta) per_feature_norm_kernel(const flo
     }
 }
 
+// Same statistics, time-major in place (the standalone UnifiedMelExtractor.normalizePerFeature entry point of the C ABI).
+__global__ void per_feature_norm_inplace_kernel(float *x, long long T, int M, long long valid) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    float mean = 0.0f;
+    for (long long t = 0; t < valid; ++t) mean = __fadd_rn(mean, x[t * M + m]);
+    mean = __fdiv_rn(mean, (float)valid);
+    float var_sum = 0.0f;
+    for (long long t = 0; t < valid; ++t) {
+        const float d = __fsub_rn(x[t * M + m], mean);
+        var_sum = __fadd_rn(var_sum, __fmul_rn(d, d));
+    }
+    const float denom = (float)(valid > 1 ? valid - 1 : 1);
+    const float sd = __fadd_rn(__fsqrt_rn(__fdiv_rn(var_sum, denom)), 1e-5f);
+    for (long long t = 0; t < T; ++t) x[t * M + m] = t < valid ? __fdiv_rn(__fsub_rn(x[t * M + m], mean), sd) : 0.0f;
+}
+
+// host buffer in, host buffer out (x: [T x M] time-major, normalised in place); valid >= 1
+int normalize_per_feature_host(float *x, long long T, int M, long long valid) {
+    struct Buf {
+        float *d = nullptr;
+        ~Buf() { if (d) cudaFree(d); }
+    } b;
+    const size_t bytes = sizeof(float) * (size_t)T * M;
+    FA_CUDA_TRY(cudaMalloc(&b.d, bytes));
+    FA_CUDA_TRY(cudaMemcpy(b.d, x, bytes, cudaMemcpyHostToDevice));
+    per_feature_norm_inplace_kernel<<<(M + kBinsPerCta - 1) / kBinsPerCta, kBinsPerCta>>>(b.d, T, M, valid);
+    FA_CUDA_TRY(cudaGetLastError());
+    FA_CUDA_TRY(cudaMemcpy(x, b.d, bytes, cudaMemcpyDeviceToHost));
+    return FA_OK;
+}
+
 // x: time-major [T x M], in place; state: mean[M] (in/out), count (in: frames seen before this call)
 __global__ void lseend_scale_cmn_kernel(float *x, long long T, int M, float *mean_io, long long count0, float scale) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;

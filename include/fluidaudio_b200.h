@@ -11,7 +11,7 @@
  *   fa_audio_resample / fa_audio_to_mel / fa_resample_output_count
  *                        Sources/FluidAudio/Shared/AudioConverter.swift:60-71 (resample), :299-370 (convertBuffer),
  *                        :388-442 (linearResample) — the converter stage on the GPU, fused ahead of the log-mel kernel
- *   fa_linear_resample   Sources/FluidAudio/Shared/AudioConverter.swift:388-442 (linearResample, host restatement)
+ *   fa_linear_resample   Sources/FluidAudio/Shared/AudioConverter.swift:388-442 (linearResample; the converter stage's linear kernel)
  *   fa_l2_normalize_rows Sources/FluidAudio/Diarizer/Offline/Clustering/AHCClustering.swift:70-105
  *   fastcluster_compute_centroid_linkage  (declared in FastClusterWrapper.h, same symbol as the reference)
  *   fa_ahc_cluster       AHCClustering.swift:20-67  (AHCClustering.cluster)

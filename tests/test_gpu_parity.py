@@ -611,6 +611,31 @@ def test_cluster_pipeline_labels_bit_exact(gpu_lib, oracle):
     assert r.info["training_count"] == 6 and r.info["initial_clusters"] == 6
 
 
+def test_standalone_normalise_and_linear_resample(gpu_lib, oracle):
+    """fa_mel_normalize_per_feature (UnifiedMelExtractor.normalizePerFeature, time-major in place) and fa_linear_resample
+    (AudioConverter.linearResample, :388-442) as standalone C-ABI calls: device kernels, bit-exact against the oracle."""
+    import ctypes as C
+    lib = _lib.load()
+    rng = np.random.default_rng(4)
+    for T, M, valid in ((6, 4, 4), (300, 80, 211), (50, 128, 50), (9, 3, 1)):
+        x = (rng.standard_normal((T, M)) * 3 - 7).astype(np.float32)
+        y = x.copy()
+        assert lib.fa_mel_normalize_per_feature(y.ctypes.data, T, M, valid) == 0
+        assert np.array_equal(y, oracle.normalize_per_feature(x, valid))
+        from fluidaudio_b200 import mel as mel_mod
+        assert np.array_equal(mel_mod.normalize_per_feature(x, valid), y)
+    planar = np.ascontiguousarray(rng.standard_normal((3, 1000)), np.float32)
+    for ch in (1, 3):
+        for rin, rout in ((48000, 16000), (44100, 16000), (8000, 16000), (16000, 16000)):
+            n = C.c_int64()
+            p = np.ascontiguousarray(planar[:ch])
+            assert lib.fa_linear_resample(p.ctypes.data, 1000, ch, rin, rout, None, 0, C.byref(n)) == 0
+            out = np.zeros(n.value, np.float32)
+            assert lib.fa_linear_resample(p.ctypes.data, 1000, ch, rin, rout, out.ctypes.data, out.size, C.byref(n)) == 0
+            assert np.array_equal(out, oracle.linear_resample(p, rin, rout))
+            assert abs(out.size - 1000 * rout / rin) <= 0.01 * 1000 * rout / rin + 1      # AudioConverterTests.swift:129-176
+
+
 def test_batch_of_sets_equals_one_by_one(gpu_lib, oracle):
     sizes = [700, 1200, 300, 2, 950, 1500]
     embs, rhos, offs = [], [], [0]

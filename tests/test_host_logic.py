@@ -100,19 +100,14 @@ def test_product_never_imports_or_links_the_oracle():
 
 
 def test_helpers_that_run_on_the_host(lib, oracle):
-    x = (np.arange(24, dtype=np.float32).reshape(6, 4) ** 1.5)
-    y = x.copy()
-    assert lib.fa_mel_normalize_per_feature(y.ctypes.data, 6, 4, 4) == 0
-    assert np.array_equal(y, oracle.normalize_per_feature(x, 4))
-    planar = np.ascontiguousarray(np.random.default_rng(0).standard_normal((3, 1000)), np.float32)
-    for rin, rout in ((48000, 16000), (44100, 16000), (8000, 16000), (16000, 16000)):
-        n = C.c_int64()
-        assert lib.fa_linear_resample(planar.ctypes.data, 1000, 3, rin, rout, None, 0, C.byref(n)) == 0
-        out = np.zeros(n.value, np.float32)
-        assert lib.fa_linear_resample(planar.ctypes.data, 1000, 3, rin, rout, out.ctypes.data, out.size, C.byref(n)) == 0
-        ref = oracle.linear_resample(planar, rin, rout)
-        assert np.array_equal(out, ref)
-        assert abs(out.size - 1000 * rout / rin) <= 0.01 * 1000 * rout / rin + 1      # AudioConverterTests.swift:129-176
+    # sizing calls and argument checks need no device (the arithmetic of these two entry points runs on the GPU:
+    # tests/test_gpu_parity.py::test_standalone_normalise_and_linear_resample)
+    n = C.c_int64()
+    assert lib.fa_linear_resample(None, 1000, 3, 48000.0, 16000.0, None, 0, C.byref(n)) == 0 and n.value == 333
+    assert lib.fa_linear_resample(None, 1000, 0, 48000.0, 16000.0, None, 0, C.byref(n)) != 0
+    z = np.ones((3, 4), np.float32)
+    assert lib.fa_mel_normalize_per_feature(z.ctypes.data, 3, 4, 0) == 0 and not z.any()   # no valid frame: all padding
+    assert lib.fa_mel_normalize_per_feature(None, 3, 4, 1) != 0
     from fluidaudio_b200.clustering import dendrogram_cut
     rng = np.random.default_rng(5)
     for n in (2, 7, 40):
