@@ -382,17 +382,10 @@ static int cluster_pipeline(ClusterContext &C, const float *emb, const double *r
         if (st != FA_OK) return st;
         st = vbx::onehot_device(d_init, 0, 1, d_gamma, d_pi, s);   // pi[0] = 1
         if (st != FA_OK) return st;
-        // normalise through the finish path: S = 1, gamma unused -> reuse assign with a normalised copy
-        std::vector<double> m(E);
-        FA_CUDA_TRY(cudaMemcpyAsync(m.data(), d_cent, E * sizeof(double), cudaMemcpyDeviceToHost, s));
-        FA_CUDA_TRY(cudaStreamSynchronize(s));
-        double ss = 0;
-        for (size_t k = 0; k < E; ++k) ss += m[k] * m[k];
-        const double sc = ss > 0 ? 1.0 / std::sqrt(ss) : 1.0;
-        std::vector<double> mn(E);
-        for (size_t k = 0; k < E; ++k) mn[k] = m[k] * sc;
-        FA_CUDA_TRY(cudaMemcpyAsync(d_cent_n, mn.data(), E * sizeof(double), cudaMemcpyHostToDevice, s));
-        FA_CUDA_TRY(cudaStreamSynchronize(s));
+        // OfflineDiarizerManager.normalize on the one centroid (:824-860: a zero row is kept)
+        st = ahc::launch_normalize_rows_keep(d_cent, d_cent_n, 1, e, s);
+        if (st != FA_OK) return st;
+        ++lc;
         K = 1;
         lc += 2;
     }
@@ -420,7 +413,25 @@ static int cluster_pipeline(ClusterContext &C, const float *emb, const double *r
         FA_CUDA_TRY(cudaMemcpyAsync(centroids_out, d_cent, (size_t)kc * E * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     FA_CUDA_TRY(cudaEventRecord(C.ev[6], s));
+    // VBxOutput.assignedClusterCount for the caller's info when no speaker-count constraint asked for it above: the
+    // row-argmax winners travel with the final synchronisation
+    std::vector<int> hard_info;
+    const bool count_winners = info && used_vbx && !adjusted && detected == S && Tn > 0 &&
+                               cfg.num_speakers == FA_NO_VALUE && cfg.min_speakers == FA_NO_VALUE && cfg.max_speakers == FA_NO_VALUE;
+    if (count_winners) {
+        hard_info.resize(Tn);
+        FA_CUDA_TRY(cudaMemcpyAsync(hard_info.data(), d_hard, sizeof(int) * Tn, cudaMemcpyDeviceToHost, s));
+    }
     FA_CUDA_TRY(cudaStreamSynchronize(s));
+    if (count_winners) {
+        std::vector<char> seen(S, 0);
+        detected = 0;
+        for (int i = 0; i < Tn; ++i)
+            if (hard_info[i] >= 0 && hard_info[i] < S && !seen[hard_info[i]]) {
+                seen[hard_info[i]] = 1;
+                ++detected;
+            }
+    }
     if (info) {
         info->training_count = Tn;
         info->initial_clusters = S;
@@ -1286,26 +1297,23 @@ FA_API fa_status fa_assign_embeddings(const double *emb, size_t N, size_t dim, c
     Carver sz{nullptr};
     sz.take<double>(N * dim);
     sz.take<double>((size_t)K * dim);
+    sz.take<double>((size_t)K * dim);
     sz.take<int>(N);
     sz.take<double>(scores ? N * (size_t)K : 1);
     int st = C.reserve(sz.off + 1024, 64);
     if (st != FA_OK) return (fa_status)st;
     Carver c{static_cast<char *>(C.d_buf)};
     double *d_emb = c.take<double>(N * dim);
+    double *d_craw = c.take<double>((size_t)K * dim);
     double *d_cn = c.take<double>((size_t)K * dim);
     int *d_labels = c.take<int>(N);
     double *d_scores = c.take<double>(scores ? N * (size_t)K : 1);
-    // centroid normalisation (:793, :824-860) is O(K*dim): host
-    std::vector<double> cn((size_t)K * dim);
-    for (int k = 0; k < K; ++k) {
-        double ss = 0;
-        for (size_t j = 0; j < dim; ++j) ss += centroids[(size_t)k * dim + j] * centroids[(size_t)k * dim + j];
-        const double sc = ss > 0 ? 1.0 / std::sqrt(ss) : 1.0;
-        for (size_t j = 0; j < dim; ++j) cn[(size_t)k * dim + j] = centroids[(size_t)k * dim + j] * sc;
-    }
     API_CUDA_TRY(cudaMemcpyAsync(d_emb, emb, N * dim * sizeof(double), cudaMemcpyHostToDevice, C.stream));
-    API_CUDA_TRY(cudaMemcpyAsync(d_cn, cn.data(), cn.size() * sizeof(double), cudaMemcpyHostToDevice, C.stream));
-    API_CUDA_TRY(cudaStreamSynchronize(C.stream));
+    API_CUDA_TRY(cudaMemcpyAsync(d_craw, centroids, (size_t)K * dim * sizeof(double), cudaMemcpyHostToDevice, C.stream));
+    // centroid normalisation (:793, :824-860; zero rows kept) with the same kernel the pipeline uses
+    st = ahc::launch_normalize_rows_keep(d_craw, d_cn, K, (int)dim, C.stream);
+    if (st != FA_OK) return (fa_status)st;
+    ++g_launches;
     long long lc = 0;
     st = vbx::assign_device(d_emb, (int)N, (int)dim, d_cn, nullptr, K, d_labels, scores ? d_scores : nullptr, C.stream, &lc);
     g_launches += lc;

@@ -603,6 +603,7 @@ def test_cluster_pipeline_labels_bit_exact(gpu_lib, oracle):
         assert np.array_equal(r.initial[o.training_indices], o.initial)
         assert r.info["training_count"] == o.training_indices.size
         assert r.centroids.shape == o.centroids.shape and np.abs(r.centroids - o.centroids).max() <= 1e-9
+        assert r.info["detected_clusters"] == o.detected_clusters and r.info["was_adjusted"] == 0   # assignedClusterCount
     # every row non-finite -> all rows are used (selectTrainingEmbeddings, OfflineDiarizerManager.swift:606-608):
     # AHC then reports NaN and falls back to identity labels exactly like the Swift caller
     emb = np.full((6, 256), np.nan, np.float32)
