@@ -1171,13 +1171,19 @@ int MelPlan::compute_batch_host(const float *audio, const long long *offsets, in
                                 long long *num_frames) {
     if (count <= 0) return FA_OK;
     // device-side packing: clip i starts at a 4-float aligned offset so that every tile can use the TMA path
+    // When every clip already starts at a multiple of four floats in the caller's buffer, the device copy keeps the
+    // caller's layout and a whole group of clips travels in ONE transfer (a bulk copy may read up to three floats past a
+    // clip's end: the neighbour's samples or the pad below, never used: the kernel masks by the clip length).  512 clips
+    // cost 1 024 cudaMemcpyAsync calls otherwise: ~4 ms of host enqueue time on a 25 ms batch.
+    bool same_layout = true;
+    for (int i = 0; i < count; ++i) same_layout = same_layout && ((offsets[i] - offsets[0]) & 3) == 0 && offsets[i + 1] >= offsets[i];
     std::vector<long long> doff(count + 1), dout(count + 1);
     long long a = 0, o = 0;
     std::vector<long long> Ts(count), Tps(count);
     for (int i = 0; i < count; ++i) {
         const long long n = offsets[i + 1] - offsets[i];
-        doff[i] = a;
-        a += ceil_to(n, 4) + 4;
+        doff[i] = same_layout ? offsets[i] - offsets[0] : a;
+        a = same_layout ? ceil_to(offsets[i + 1] - offsets[0], 4) + 4 : a + ceil_to(n, 4) + 4;
         dout[i] = o;
         long long T, Tp;
         if (!shape_of(*this, n, mode, -1, T, Tp)) {
@@ -1222,10 +1228,16 @@ int MelPlan::compute_batch_host(const float *audio, const long long *offsets, in
     FA_CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)o * sizeof(float), s_k));
     for (int g = 0; g < groups; ++g) {
         const int c0 = (int)((long long)count * g / groups), c1 = (int)((long long)count * (g + 1) / groups);
-        for (int i = c0; i < c1; ++i) {
-            const long long n = offsets[i + 1] - offsets[i];
+        if (same_layout) {
+            const long long n = offsets[c1] - offsets[c0];
             if (n > 0)
-                FA_CUDA_TRY(cudaMemcpyAsync(d_audio + doff[i], audio + offsets[i], n * sizeof(float), cudaMemcpyHostToDevice, s_in));
+                FA_CUDA_TRY(cudaMemcpyAsync(d_audio + doff[c0], audio + offsets[c0], n * sizeof(float), cudaMemcpyHostToDevice, s_in));
+        } else {
+            for (int i = c0; i < c1; ++i) {
+                const long long n = offsets[i + 1] - offsets[i];
+                if (n > 0)
+                    FA_CUDA_TRY(cudaMemcpyAsync(d_audio + doff[i], audio + offsets[i], n * sizeof(float), cudaMemcpyHostToDevice, s_in));
+            }
         }
         FA_CUDA_TRY(cudaEventRecord(events[2 * g], s_in));
         FA_CUDA_TRY(cudaStreamWaitEvent(s_k, events[2 * g], 0));
@@ -1233,9 +1245,16 @@ int MelPlan::compute_batch_host(const float *audio, const long long *offsets, in
         if (st != FA_OK) return st;
         FA_CUDA_TRY(cudaEventRecord(events[2 * g + 1], s_k));
         FA_CUDA_TRY(cudaStreamWaitEvent(s_out, events[2 * g + 1], 0));
-        for (int i = c0; i < c1; ++i) {
-            const long long len = dout[i + 1] - dout[i];
-            FA_CUDA_TRY(cudaMemcpyAsync(out + out_offsets[i], d_out + dout[i], len * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+        bool out_contiguous = c1 > c0;   // the caller's output offsets follow the packed device layout: one transfer
+        for (int i = c0; i < c1 && out_contiguous; ++i) out_contiguous = out_offsets[i] - out_offsets[c0] == dout[i] - dout[c0];
+        if (out_contiguous) {
+            FA_CUDA_TRY(cudaMemcpyAsync(out + out_offsets[c0], d_out + dout[c0], (dout[c1] - dout[c0]) * sizeof(float),
+                                        cudaMemcpyDeviceToHost, s_out));
+        } else {
+            for (int i = c0; i < c1; ++i) {
+                const long long len = dout[i + 1] - dout[i];
+                FA_CUDA_TRY(cudaMemcpyAsync(out + out_offsets[i], d_out + dout[i], len * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+            }
         }
     }
     FA_CUDA_TRY(cudaStreamSynchronize(s_out));

@@ -184,6 +184,35 @@ def test_mel_batch_and_device_paths(gpu_lib, oracle):
         assert np.abs(out[offs[i]:offs[i + 1]].reshape(-1, 80) - ref).max() <= MEL_TOL
         single, _, _ = m.compute_flat_transposed(c, last_audio_sample=float(last[i]))
         assert np.array_equal(single, out[offs[i]:offs[i + 1]])                  # batch == one-by-one, bitwise
+    # clips that start at multiples of four floats in the caller's buffer keep that layout on the device and travel one
+    # transfer per group (BASELINE configs[3]: 512 x 480 000): lengths that are not multiples of four sit in aligned slots
+    # with gaps (filled with a sentinel the kernel must never read), plus an empty clip and 40 clips -> several per group
+    lens2 = [480000, 1001, 0, 33333, 6, 4000] + [16000 + 4 * i for i in range(34)]
+    clips2 = [synth.tone_noise_audio(n, seed=50 + i) for i, n in enumerate(lens2)]
+    offs2 = np.zeros(len(lens2) + 1, np.int64)
+    starts = []
+    pos = 0
+    for n in lens2:
+        starts.append(pos)
+        pos += -(-n // 4) * 4 + (8 if n % 8 == 1 else 0)
+    packed = np.full(pos + 4, 1e30, np.float32)
+    for st, c in zip(starts, clips2):
+        packed[st:st + c.size] = c
+    # the C entry point takes offsets[i], offsets[i+1] as the clip's bounds: pass exact ends through a second call shape
+    ends = [st + c.size for st, c in zip(starts, clips2)]
+    for i, (st, en) in enumerate(zip(starts, ends)):
+        single, ml1, nf1 = m.compute_flat_transposed(clips2[i]) if clips2[i].size else (None, 0, 1)
+        if clips2[i].size:
+            # one-clip "batch" at an aligned start inside the sentinel-padded buffer
+            o1, oo1, mlb, nfb = m.compute_batch(None, packed_audio=packed[st:], offsets=np.array([0, en - st], np.int64))
+            assert (mlb[0], nfb[0]) == (ml1, nf1) and np.array_equal(o1[oo1[0]:oo1[1]], single)
+    aligned = [c for c in clips2 if c.size % 4 == 0]                              # contiguous AND aligned: the grouped path
+    outb, offb, mlb, nfb = m.compute_batch(aligned)
+    for i, c in enumerate(aligned):
+        if c.size == 0:
+            continue
+        single, ml1, nf1 = m.compute_flat_transposed(c)
+        assert (mlb[i], nfb[i]) == (ml1, nf1) and np.array_equal(outb[offb[i]:offb[i + 1]], single), i
     # device-resident entry point == host entry point, bitwise; unaligned device pointers take the non-TMA path
     a = clips[0]
     T = m.frame_count(a.size)
