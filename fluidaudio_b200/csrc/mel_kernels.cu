@@ -1202,7 +1202,7 @@ int MelPlan::compute_batch_host(const float *audio, const long long *offsets, in
     if (st != FA_OK) return st;
     st = ensure_units(count);
     if (st != FA_OK) return st;
-    const int groups = std::min(count, 16);
+    const int groups = std::min(count, 32);   // one H2D, one launch, one D2H per group: the last group's kernel + D2H is the pipeline's tail
     st = ensure_events(2 * (size_t)groups);
     if (st != FA_OK) return st;
     cudaStream_t s_in = streams[0], s_k = streams[1], s_out = streams[2];
