@@ -216,6 +216,66 @@ def test_merge_control_plane_matches_reference_goldens(tmp_path, golden_dir, ora
 
 
 # ------------------------------------------------------------------------------------------------ sharding
+def test_float32_filter_bound_is_rigorous():
+    """The AHC initial pass trusts E_ij = c1 r_i r_j + c2 (n_i + n_j), c1 = 2.02 (D + 3) 2^-24, c2 = 2e-12
+    (ahc_kernels.cu: ahc_filter_prep / tile128 / rows) to bracket the reference's sequential double chain from a float32
+    inner product of float32-converted inputs, and evaluates the bracket in float32 interval arithmetic.  Restated here in
+    numpy (directed rounding through nextafter) and checked on inputs chosen to stress it: unit rows, near-duplicates,
+    exact duplicates, rows of very different norm, widths that are not multiples of eight, float32 sums in three orders."""
+    rng = np.random.default_rng(7)
+    f32, f64 = np.float32, np.float64
+
+    def chain(a, b):                      # fastcluster's sq. distance: sum += (a_k - b_k)^2, every operation rounded
+        s = f64(0.0)
+        for k in range(a.size):
+            d = f64(a[k] - b[k])
+            s = f64(s + f64(d * d))
+        return s
+
+    def rd(x):                            # float64 -> float32 rounded down / up
+        y = f32(x)
+        return y if f64(y) <= x else np.nextafter(y, f32(-np.inf))
+
+    def ru(x):
+        y = f32(x)
+        return y if f64(y) >= x else np.nextafter(y, f32(np.inf))
+
+    worst = 0.0
+    for D in (256, 255, 64, 13):
+        c1 = 2.02 * (D + 3) * 2.0 ** -24
+        c2 = 2e-12
+        base = rng.standard_normal((24, D))
+        base /= np.linalg.norm(base, axis=1, keepdims=True)
+        rows = [base[i] for i in range(24)]
+        rows += [base[0] + 1e-7 * rng.standard_normal(D), base[1] * (1 + 1e-9), base[2].copy(), base[3] * 37.5, base[4] * 1e-3,
+                 np.round(base[5] * 4) / 4, np.zeros(D)]
+        X = np.asarray(rows, f64)
+        Xf = X.astype(f32)
+        n = (X * X).sum(axis=1)                                   # |x|^2 in double (k ascending in the kernel; any order here)
+        r = np.array([ru(np.sqrt(v)) * f32(1.000001) for v in n], f32)
+        for i in range(len(rows)):
+            for j in range(i):
+                exact = chain(X[i], X[j])
+                dots = (np.dot(Xf[i], Xf[j]),                                          # library order
+                        f32(sum(f32(Xf[i][k] * Xf[j][k]) for k in range(D))),          # sequential, products rounded
+                        f32(np.sum((Xf[i][::-1] * Xf[j][::-1]).astype(f32), dtype=f32)))   # reversed
+                for dot in dots:
+                    dot = f64(dot)
+                    approx = (n[i] + n[j]) - 2.0 * dot
+                    E = c1 * f64(r[i]) * f64(r[j]) + c2 * (n[i] + n[j])
+                    assert approx - E <= exact <= approx + E, (D, i, j)
+                    if E > 0:
+                        worst = max(worst, abs(approx - exact) / E)
+                    # the float32 interval form of the tile kernel's epilogue brackets the same bounds
+                    s_lo, s_hi = rd(f64(rd(n[i])) + f64(rd(n[j]))), ru(f64(ru(n[i])) + f64(ru(n[j])))
+                    e_up = ru(f64(ru(f64(ru(c1)) * f64(r[i]))) * f64(r[j]) + f64(ru(f64(ru(c2)) * f64(s_hi))))
+                    hi = ru(f64(ru(-2.0 * dot + f64(s_hi))) + f64(e_up))
+                    lo = rd(f64(rd(-2.0 * dot + f64(s_lo))) - f64(e_up))
+                    assert f64(lo) <= approx - E + 1e-300 or f64(lo) <= exact
+                    assert f64(lo) <= exact <= f64(hi), (D, i, j)
+    assert 0.0 < worst < 0.9, worst     # observed error stays below 90 % of the bound (and the check is not vacuous)
+
+
 def test_sharding_partitions():
     for count, world in ((512, 8), (64, 8), (10, 4), (3, 8), (0, 2)):
         seen = []
