@@ -77,6 +77,39 @@ struct OfflineClusteringBackend {
             assignments: labels.map(Int.init), initialClusters: initial.map(Int.init),
             centroids: (0..<k).map { Array(centroids[($0 * dim)..<(($0 + 1) * dim)]) }, info: info)
     }
+
+    /// Many meetings on one GPU (several side by side on disjoint SM partitions): meeting m is rows
+    /// `setOffsets[m] ..< setOffsets[m + 1]` of the packed arrays.  `chunkIndices` (numbered inside each meeting) selects
+    /// the reference's default constrained assignment per meeting (fa_diarize_cluster_batch_chunks), nil the plain argmax.
+    func clusterBatch(embedding256: [Float], rho128: [Double], setOffsets: [Int64], dim: Int, rhoDim: Int,
+                      psi: [Double]) throws -> (assignments: [Int32], info: [fa_cluster_info]) {
+        var cfg = fa_cluster_config()
+        fa_cluster_default_config(&cfg)
+        cfg.threshold = threshold
+        cfg.vbx.Fa = warmStartFa
+        cfg.vbx.Fb = warmStartFb
+        cfg.vbx.max_iterations = Int32(maxIterations)
+        cfg.vbx.epsilon = convergenceTolerance
+        cfg.num_speakers = numSpeakers.map(Int32.init) ?? FA_NO_VALUE
+        cfg.min_speakers = minSpeakers.map(Int32.init) ?? FA_NO_VALUE
+        cfg.max_speakers = maxSpeakers.map(Int32.init) ?? FA_NO_VALUE
+        let sets = max(setOffsets.count - 1, 0)
+        var labels = [Int32](repeating: 0, count: Int(setOffsets.last ?? 0))
+        var infos = [fa_cluster_info](repeating: fa_cluster_info(), count: max(sets, 1))
+        let status: fa_status
+        if let chunks = chunkIndices {
+            status = fa_diarize_cluster_batch_chunks(embedding256, rho128, setOffsets, Int32(sets), dim, rhoDim, psi, &cfg,
+                                                     chunks, &labels, &infos)
+        } else {
+            status = fa_diarize_cluster_batch(embedding256, rho128, setOffsets, Int32(sets), dim, rhoDim, psi, &cfg,
+                                              &labels, &infos)
+        }
+        guard status == FA_STATUS_OK else {
+            throw NSError(domain: "fluidaudio_b200", code: Int(status.rawValue),
+                          userInfo: [NSLocalizedDescriptionKey: String(cString: fa_last_error())])
+        }
+        return (labels, Array(infos.prefix(sets)))
+    }
 }
 
 
