@@ -565,7 +565,12 @@ int MelPlan::init(const MelConfig &c) {
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
         std::vector<std::vector<int>> mine(kWarpsPerCta);
         std::vector<long long> load(kWarpsPerCta, 0);
-        load[0] = 6;   // warp 0's lane 0 also computes the next tile's geometry and issues its bulk copy in this phase
+        // warp 0's lane 0 also computes the next tile's geometry and issues its bulk copy in this phase: measured, that is
+        // worth more than a full share of the filterbank work (handicap 0 / 6 / 12 / 24 quads: 0.3109 / 0.3049 / 0.2996 /
+        // 0.2982 ms per audio-hour, identical output; profiles/r02_mel.md), so warp 0 only takes a group when the others
+        // are this far ahead
+        load[0] = 24;
+        if (const char *h = std::getenv("FA_MEL_ISSUE_HANDICAP")) load[0] = std::atoi(h);   // tuning hook (schedule only)
         for (int g : order) {
             int best = 0;
             for (int wv = 1; wv < kWarpsPerCta; ++wv)
